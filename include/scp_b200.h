@@ -1,0 +1,251 @@
+/* scp_b200 -- C ABI of the B200-native encode-side hot path of SCP.
+ *
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary.  Every function
+ * returns 0 on success and a negative status on failure; scp_last_error() gives the message
+ * (thread-local).  All `d_*` pointers are DEVICE pointers on the current CUDA device, all
+ * `h_*` pointers are HOST pointers.  `stream` is a cudaStream_t passed as void* (0 = default).
+ *
+ * Each entry point names the reference interface it replaces (paths in luoao-kddi/SCP).
+ */
+#ifndef SCP_B200_H
+#define SCP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCP_OK 0
+#define SCP_ERR_ARG (-1)
+#define SCP_ERR_CUDA (-2)
+#define SCP_ERR_RANGE (-3)   /* quantised coordinate does not fit 21 bits / depth > 21 */
+#define SCP_ERR_STATE (-4)
+#define SCP_ERR_INTERNAL (-5)
+
+#define SCP_MAX_DEPTH 21
+#define SCP_MODE_CART 0
+#define SCP_MODE_SPHER 1
+#define SCP_MODE_CYLIN 2
+
+const char* scp_last_error(void);
+int scp_version(void);
+/* 1 if the library was compiled for sm_100a and a device with compute capability 10.x is current. */
+int scp_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Octree construction (A1-A5).  Replaces, for a BATCH of jobs in one call:
+ *   data_preproc/data_preprocess.py:13-92  proc_pc      (cart2spher/cart2cylin :171-207, quantise :42-70)
+ *   data_preproc/data_preprocess.py:95-167 mul_proc_pc  (morton_path filter of Octree.py:188)
+ *   data_preproc/OctreeCPP/Octree_python_lib.so::genOctreeInterface (Octreewarpper.py:28-29)
+ *   data_preproc/Octree.py:102-137,224-272 gen_K_parent_seq[_mullevel]
+ *   dataloaders/encode_dataset_ehem.py:52-105, encode_dataset_ehem_mullevel.py:47-85 (level split, pos normalise)
+ *   dataloaders/encode_dataset.py:32-55 (OctAttention context, via ctx_pos)
+ * A job = one octree over one frame's points: (frame, qs, morton_path, drop_last).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct scp_octree scp_octree;
+
+typedef struct {
+    int32_t frame;        /* index into frame_offsets */
+    int32_t path_len;     /* 0: whole cloud (proc_pc); >0: keep points whose top rho bits == path (Octree.py:188) */
+    int32_t path_bits;    /* bit j = morton_path[j] */
+    int32_t drop_last;    /* 1: drop the last BFS row (Octree.py:259-262) */
+    double  qs;           /* quantisation step of the first axis (data_preprocess.py:44-50) */
+    double  cart_offset;  /* SCP_MODE_CART only: scalar offset (data_preprocess.py:56) */
+    int32_t lidar_level;  /* level clip of the last level block (encode_dataset_ehem.py:86) */
+    int32_t pos_eps_last; /* 1: +1e-9 also in the last block (encode_dataset_ehem.py:92); 0: mullevel dataset (:80) */
+} scp_job;
+
+typedef struct {
+    int32_t depth;                         /* n = ceil(log2(max(q)+1)), Octree.py:58 */
+    int32_t n_points;                      /* points of the frame */
+    int32_t n_voxels;                      /* unique occupied voxels after the path filter */
+    int32_t n_rows;                        /* emitted rows (nodes, minus 1 if drop_last) */
+    int64_t row_start;                     /* first row of this job in the batch outputs */
+    int64_t voxel_start;                   /* first voxel of this job in `voxel_key` */
+    int32_t level_rows[SCP_MAX_DEPTH + 1]; /* rows per level, index 0 = level 1 */
+    float   bin_num;                       /* data_preprocess.py:44/49 (float32 like the reference) */
+    double  steps[3];                      /* quantisation steps per axis */
+    double  offset[3];                     /* offsets per axis (cylin: [0,0,min z]) */
+    int64_t pos_min[SCP_MAX_DEPTH + 1];    /* scalar min of the level's (N_l,3) pos block (encode_dataset_ehem.py:71) */
+    int64_t pos_max[SCP_MAX_DEPTH + 1];
+} scp_job_info;
+
+typedef struct {
+    /* all optional (NULL = skip) except where noted; row-major; N = total rows of the batch */
+    uint8_t*  occ;       /* [N]   occupancy byte 1..255 (Octree.py:175-176)            */
+    uint8_t*  level;     /* [N]   1-based level                                          */
+    uint8_t*  octant;    /* [N]   1..8 (root 1)                                          */
+    uint32_t* parent;    /* [N]   row index of the parent inside the job (root: 0)       */
+    uint32_t* pos;       /* [N,3] origin of the node's cell (Octree.py:140-145)          */
+    uint8_t*  ctx;       /* [N,4,3] EHEM context bytes (level, octant, occ-1), ancestors great-grandparent..self,
+                                   missing ancestor = (0,0,255) (encode_dataset_ehem.py:54,67)            */
+    float*    pos_norm;  /* [N,3] min-max normalised own pos, float32 (encode_dataset_ehem.py:70-72)      */
+    uint32_t* ctx_pos;   /* [N,4,3] pos of the 4 ancestors (0 = missing) (Octree.py:121-122)              */
+    int64_t*  rows_i64;  /* [N,4,6] the reference's .npy layout [occ 1..256, level, octant, x, y, z]
+                                   (data_preprocess.py:74); an expansion for parity dumps / np.save      */
+    uint64_t* voxel_key; /* [V]   Morton keys of the unique voxels per job, ascending                     */
+} scp_octree_out;
+
+scp_octree* scp_octree_create(void);
+void        scp_octree_destroy(scp_octree* t);
+
+/* Phase 1: quantise, Morton keys, segmented radix sort, unique, per-level node counts.
+ * d_xyz: float32 points, `point_stride` floats per point (3, or 4 for KITTI .bin rows, pt.py:190-192).
+ * h_frame_offsets[n_frames+1]: point ranges.  Synchronises `stream` once to return sizes. */
+int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride,
+                    const int64_t* h_frame_offsets, int n_frames,
+                    const scp_job* h_jobs, int n_jobs, int mode, void* stream);
+int     scp_octree_job_info(const scp_octree* t, int job, scp_job_info* out);
+int64_t scp_octree_total_rows(const scp_octree* t);
+int64_t scp_octree_total_voxels(const scp_octree* t);
+/* Phase 2: node records, occupancy, K=4 ancestor context, level-wise normalised positions. Asynchronous. */
+int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream);
+/* After emit + stream sync: fills pos_min/pos_max of every job_info. */
+int scp_octree_finish(scp_octree* t, void* stream);
+/* Device time (ms) of the stages of the last plan+emit, measured with CUDA events on `stream`:
+ * [0] quantise+keys [1] radix sort [2] heads/count [3] emit nodes [4] occupancy [5] context gather */
+int scp_octree_stage_ms(scp_octree* t, float out[6]);
+
+/* Standalone pieces of the above, exposed for tests / profiling --------------------------- */
+/* Segmented LSD radix sort of 64-bit keys (8-bit digits, decoupled look-back), in place.
+ * h_seg_offsets[n_seg+1]; key_bits = number of low bits that take part. */
+int scp_segmented_sort_u64(uint64_t* d_keys, uint64_t* d_tmp, const int64_t* h_seg_offsets, int n_seg,
+                           int key_bits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Legacy symbols of data_preproc/OctreeCPP/Octree_python_lib.so, exactly as bound by
+ * Octreewarpper.py:17-39 (host API; runs the CUDA path above and copies the tree back).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { unsigned nodeid; unsigned octant; unsigned parent; uint8_t oct; unsigned pos[3]; } scp_legacy_node;
+void* new_vector(void);
+void  delete_vector(void* v);
+int   vector_size(void* v);
+void* vector_get(void* v, int i);
+void  vector_push_back(void* v, int i);
+void* genOctreeInterface(void* levels, const double* xyz, int n);
+scp_legacy_node* Nodes_get(void* level, int i);
+int   Nodes_size(void* level);
+int   int_size(void* codes);
+int   int_get(void* codes, int i);
+
+/* ------------------------------------------------------------------------------------------
+ * Coding order + symbols (A7): encode.py:109-136 / encode_mullevel.py:106-133.
+ * For every level (h_level_sizes, rows consecutive) and window of `context_size`: even ids then odd ids.
+ * d_order[N] receives row indices; d_sym[N] (optional) the symbols occ-1 in that order.
+ * ---------------------------------------------------------------------------------------- */
+int scp_coding_order(const int64_t* h_level_sizes, int n_levels, int context_size, int add_base_for_single,
+                     const uint8_t* d_occ, int64_t* d_order, int16_t* d_sym, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PMF / logits -> integer CDF (A13): torch.softmax (encode.py:126-127) +
+ * numpyAc.py:109-114 pdf_convert_to_cdf_and_normalize + :80-107 _convert_to_int_and_normalize.
+ * in: [n,255] float32 (logits if is_logits else PMF).  d_row_of[n] (optional) scatters row i of the
+ * input to CDF row d_row_of[i].  Outputs (each optional): d_cdf [n,256] uint16; d_interval [n,2] uint32
+ * = (c_low, c_high) of symbol d_sym[row] with the coder's 0x10000 substitution (numpyAc_backend.cpp:271-277);
+ * d_pmf [n,255] float32.
+ * ---------------------------------------------------------------------------------------- */
+int scp_pmf_to_cdf(const float* d_in, int64_t n, int is_logits, const int64_t* d_row_of,
+                   const int16_t* d_sym, uint16_t* d_cdf, uint32_t* d_interval, float* d_pmf, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Range coder (A14, host): numpyAc_backend.cpp:245-323 `encode`.  Byte-identical output.
+ * h_interval [n,2] uint32 (c_low,c_high) in coding order.  Returns the number of bytes, or <0.
+ * If h_out is NULL only the size is computed.
+ * ---------------------------------------------------------------------------------------- */
+int64_t scp_range_encode(const uint32_t* h_interval, int64_t n, uint8_t* h_out, int64_t out_cap);
+/* Same from a full CDF table like numpyAc_backend.encode_cdf(cdf[N,Lp], sym[N]) (:327-334). */
+int64_t scp_range_encode_cdf(const uint16_t* h_cdf, const int16_t* h_sym, int64_t n, int Lp,
+                             uint8_t* h_out, int64_t out_cap);
+
+/* ------------------------------------------------------------------------------------------
+ * Entropy-model operators (A8-A12).  Device pointers, float32 activations, row-major [tokens, channels].
+ * ---------------------------------------------------------------------------------------- */
+#define SCP_ACT_NONE 0
+#define SCP_ACT_LEAKY001 1   /* nn.LeakyReLU() default slope 0.01 (ehem.py:36, dgcnn.py:94) */
+#define SCP_ACT_GELU 2       /* exact erf GELU (swin_transformer.py:561, HF ACT2FN["gelu"]) */
+#define SCP_ACT_RELU 3       /* oct_attention.py:26 */
+
+#define SCP_GEMM_AUTO 0
+#define SCP_GEMM_SIMT 1      /* fp32 FFMA tiles */
+#define SCP_GEMM_TF32 2      /* tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators */
+
+/* y[M,N] = act( x[M,K(lda)] @ W[N,K]^T + bias[N] ) (+ residual[M,N(ldr)])   -- nn.Linear (+fused epilogue).
+ * bias, residual may be NULL.  ldx/ldy/ldr = row strides in floats. */
+int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_bias,
+               const float* d_res, int64_t ldr, float* d_y, int64_t ldy,
+               int64_t M, int N, int K, int act, int engine, void* stream);
+
+/* LayerNorm over the last dim (eps 1e-5): swin_transformer.py:591-593, attention_model.py:105-106. */
+int scp_layernorm(const float* d_x, int64_t ldx, const float* d_gamma, const float* d_beta,
+                  float* d_y, int64_t ldy, int64_t M, int C, float eps, void* stream);
+
+/* EHEM token embedding (dgcnn.py:122-129): ctx bytes [n,4,3] (level,octant,occ) -> [n,80]
+ * = [occ_enc(occ of 3 ancestors) 48 | level_enc(4) 16 | octant_enc(4) 16]. */
+int scp_ehem_embed(const uint8_t* d_ctx, int64_t n, const float* d_occ_enc, const float* d_level_enc,
+                   const float* d_octant_enc, float* d_out, int64_t ldo, void* stream);
+
+/* kNN (dgcnn.py:10-28): for every point i of each of `n_win` independent windows the k nearest points
+ * (largest -||xi-xj||^2, self included) of the same window.  x [total, d] (ldx), window w covers rows
+ * [h_win_offsets[w], h_win_offsets[w+1]).  idx [total, k] int32 (window-local indices, ascending distance;
+ * ties -> lower index first). */
+int scp_knn(const float* d_x, int64_t ldx, int d, const int64_t* h_win_offsets, int n_win, int k,
+            int32_t* d_idx, void* stream);
+
+/* Edge convolution (dgcnn.py:48-71 get_graph_feature + :79-87 conv/BN/LeakyReLU(0.2) + :134 max over k),
+ * evaluated as  max_k f(Wa x_nbr + (Wb-Wa) x_i) :  uv [total, 2*C] = x @ [Wa; Wb-Wa]^T computed by
+ * scp_linear, then this gather:  out[i,c] = lrelu02( s[c]*(sel_k uv[nbr_k, c] + uv[i, C+c]) + t[c] ),
+ * sel = max if s[c] >= 0 else min (BatchNorm eval affine s,t). */
+int scp_edge_gather_max(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k,
+                        const int64_t* h_win_offsets, int n_win,
+                        const float* d_bn_scale, const float* d_bn_shift,
+                        float* d_out, int64_t ldo, void* stream);
+
+/* 1-D shifted-window attention (swin_transformer.py:406-501 + :603-652,:684-697).
+ * q,k,v: [n_seq * S, C] with C = heads*64, sequences of S tokens each padded (by the caller, zeros after
+ * LayerNorm) to Sp = ceil(S/512)*512 logical tokens; shift = 0 or 256 (roll by -shift before windowing and
+ * back afterwards); rel-pos bias table [1023, heads]; shift mask -100 on the last window (:603-623).
+ * Rows >= S of the padded sequence are the Linear biases (q_bias/k_bias/v_bias [C]), exactly what the
+ * reference computes for zero-padded tokens.  out [n_seq*S, C]. */
+int scp_swin_attention(const float* d_q, const float* d_k, const float* d_v, int64_t ld,
+                       const float* d_qb, const float* d_kb, const float* d_vb,
+                       const float* d_relpos, int heads, int n_seq, int S, int shift,
+                       float* d_out, int64_t ldo, void* stream);
+
+/* Patch merging input (swin_transformer.py:350-362): out[j] = [x[2j], x[2j+1]] (zero if 2j+1 >= S), j < ceil(S/2). */
+int scp_pair_concat(const float* d_x, int64_t ldx, int n_seq, int S, int C, float* d_out, int64_t ldo, void* stream);
+
+/* out[i, col_off : col_off+C] = src[min(i >> shift, S_src-1)...]: nearest x2^shift upsample used by
+ * EHEM.concat_states (ehem.py:72-86). */
+int scp_upsample_cols(const float* d_src, int64_t lds, int n_seq, int S_src, int S_dst, int shift, int C,
+                      float* d_out, int64_t ldo, int col_off, void* stream);
+
+/* Strided row copy: out[i, col_off:col_off+C] = src[i*row_step + row_off, :C]  (even/odd token split, concat). */
+int scp_copy_cols(const float* d_src, int64_t lds, int64_t row_step, int64_t row_off, int64_t rows, int C,
+                  float* d_out, int64_t ldo, int col_off, void* stream);
+
+/* OctAttention embedding (oct_attention.py:52-79,85-99 + attention_model.py:20-22): writes both streams
+ * embed / embed_unknown [n_win*S, 600] incl. *sqrt(600) and the sinusoidal PE. ctx bytes are (level,octant,occ). */
+int scp_octattn_embed(const uint8_t* d_ctx, const uint32_t* d_ctx_pos, float pos_scale, int level_cap_base,
+                      int max_octree_level, int64_t n_tokens, int S,
+                      const float* d_occ_enc, const float* d_level_enc, const float* d_octant_enc,
+                      const float* d_pos_w, const float* d_pos_b, const float* d_pe,
+                      float* d_embed, float* d_embed_unknown, void* stream);
+
+/* Two-stream causal attention of OctAttention (attention_model.py:58-95), heads x 150.
+ * q_u,k,k_u,v,v_u: [n_win*S, 600]; out, out_u likewise. */
+int scp_octattn_attention(const float* d_qu, const float* d_k, const float* d_ku, const float* d_v,
+                          const float* d_vu, int heads, int head_dim, int n_win, int S,
+                          float* d_out, float* d_out_u, void* stream);
+
+/* y = x + r (elementwise), used for residuals that are not fused. */
+int scp_add(const float* d_a, const float* d_b, float* d_y, int64_t n, void* stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t scp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCP_B200_H */

@@ -1,0 +1,245 @@
+// Coding order (A7), softmax -> integer CDF (A13) and the host range coder (A14).
+//
+// Reference behaviour reproduced: encode.py:109-136, encode_mullevel.py:106-133 (even ids then odd ids per
+// 8192-window); numpyAc/numpyAc.py:109-114 (float32 sequential cumsum, normalise, prepend 0) and :80-107
+// (x 65281, rint, int16 wrap, + arange); numpyAc/backend/numpyAc_backend.cpp:245-323 (32-bit range coder).
+#include <vector>
+#include <string.h>
+#include "common.cuh"
+
+namespace scp {
+
+// ------------------------------------------------------------------------------------------
+// A7 coding order
+// ------------------------------------------------------------------------------------------
+struct Win { long long base; long long start; int len; int single; };
+
+__global__ void __launch_bounds__(256) k_coding_order(const Win* __restrict__ wins, int n_win,
+                                                       const uint8_t* __restrict__ occ, long long* __restrict__ order,
+                                                       int16_t* __restrict__ sym, int add_base_for_single) {
+    for (int w = blockIdx.x; w < n_win; w += gridDim.x) {
+        const Win W = wins[w];
+        const int half = (W.len + 1) >> 1;
+        for (int l = threadIdx.x; l < W.len; l += blockDim.x) {
+            long long row = W.base + W.start + l;
+            long long id = row;
+            int p = (l & 1) ? half + (l >> 1) : (l >> 1);
+            if (W.single) { p = 0; id = add_base_for_single ? row : (row - W.base); }   // encode.py:123 vs encode_mullevel.py:120
+            order[W.base + W.start + p] = id;
+            if (sym) sym[W.base + W.start + p] = (int16_t)((int)occ[id] - 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// A13 logits/PMF -> uint16 CDF
+// ------------------------------------------------------------------------------------------
+constexpr int CDF_R = 64;        // rows per block == threads per block
+constexpr int CDF_LD = 257;      // padded row stride: (257*r + i) % 32 is conflict-free both ways
+
+__global__ void __launch_bounds__(CDF_R) k_pmf_to_cdf(const float* __restrict__ in, long long n, int is_logits,
+                                                       const long long* __restrict__ row_of, const int16_t* __restrict__ sym,
+                                                       uint16_t* __restrict__ cdf, u32* __restrict__ interval,
+                                                       float* __restrict__ pmf) {
+    extern __shared__ float s[];                 // [CDF_R][CDF_LD]
+    const long long row0 = (long long)blockIdx.x * CDF_R;
+    const int rows = (int)min((long long)CDF_R, n - row0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* src = in + row0 * 255;
+    for (int i = threadIdx.x; i < rows * 255; i += CDF_R) {
+        int r = i / 255, c = i - r * 255;
+        s[r * CDF_LD + c] = src[i];
+    }
+    __syncthreads();
+    if (is_logits) {                              // torch.softmax(output, 2)  (encode.py:126-127)
+        for (int r = warp; r < rows; r += CDF_R / 32) {
+            float* x = s + r * CDF_LD;
+            float m = -INFINITY;
+            for (int c = lane; c < 255; c += 32) m = fmaxf(m, x[c]);
+            m = warp_max(m);
+            float e[8];
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int c = lane + 32 * j;
+                e[j] = c < 255 ? expf(x[c] - m) : 0.f;
+                sum += e[j];
+            }
+            sum = warp_sum(sum);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int c = lane + 32 * j;
+                if (c < 255) x[c] = __fdiv_rn(e[j], sum);
+            }
+        }
+        __syncthreads();
+    }
+    if (pmf) {
+        for (int i = threadIdx.x; i < rows * 255; i += CDF_R) {
+            int r = i / 255, c = i - r * 255;
+            long long orow = row_of ? row_of[row0 + r] : row0 + r;
+            pmf[orow * 255 + c] = s[r * CDF_LD + c];
+        }
+    }
+    // np.cumsum(pdf, axis=1) in float32: strictly sequential adds (numpyAc.py:111)
+    if (threadIdx.x < rows) {
+        float* x = s + threadIdx.x * CDF_LD;
+        float acc = x[0];
+#pragma unroll 8
+        for (int c = 1; c < 255; ++c) { acc = __fadd_rn(acc, x[c]); x[c] = acc; }
+    }
+    __syncthreads();
+    // cdfF/cdfF[:, -1:] (float32) -> float64 [0, f...] * 65281 -> rint -> int16 wrap -> + arange(256)
+    for (int i = threadIdx.x; i < rows * 128; i += CDF_R) {
+        int r = i >> 7, c2 = (i & 127) * 2;
+        const float* x = s + r * CDF_LD;
+        const float last = x[254];
+        u32 v[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            int c = c2 + k;                         // position in the 256-long CDF
+            double F = c == 0 ? 0.0 : (double)__fdiv_rn(x[c - 1], last);
+            long long q = (long long)rint(F * 65281.0) + c;
+            v[k] = (u32)(q & 0xffff);
+        }
+        if (cdf) {
+            long long orow = row_of ? row_of[row0 + r] : row0 + r;
+            reinterpret_cast<u32*>(cdf + orow * 256)[c2 >> 1] = v[0] | (v[1] << 16);
+        }
+    }
+    if (interval && threadIdx.x < rows) {
+        const float* x = s + threadIdx.x * CDF_LD;
+        const float last = x[254];
+        long long orow = row_of ? row_of[row0 + threadIdx.x] : row0 + threadIdx.x;
+        int sy = sym[orow];
+        sy = sy < 0 ? 0 : (sy > 254 ? 254 : sy);
+        double Fl = sy == 0 ? 0.0 : (double)__fdiv_rn(x[sy - 1], last);
+        u32 lo = (u32)(((long long)rint(Fl * 65281.0) + sy) & 0xffff);
+        u32 hi = 0x10000u;                          // numpyAc_backend.cpp:277
+        if (sy != 254) hi = (u32)(((long long)rint((double)__fdiv_rn(x[sy], last) * 65281.0) + sy + 1) & 0xffff);
+        interval[2 * orow] = lo;
+        interval[2 * orow + 1] = hi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// A14 range coder (host).  Classic 32-bit low/high coder with E1/E2 shifts and E3 pending bits.
+// ------------------------------------------------------------------------------------------
+struct BitSink {
+    uint8_t* out; long long cap; long long n = 0; uint32_t acc = 0; int fill = 0; bool overflow = false;
+    inline void put(int bit) {
+        acc = (acc << 1) | (uint32_t)bit;
+        if (++fill == 8) { if (out) { if (n < cap) out[n] = (uint8_t)acc; else overflow = true; } ++n; acc = 0; fill = 0; }
+    }
+    inline void put_with_pending(int bit, unsigned long long& pending) {
+        put(bit);
+        for (; pending > 0; --pending) put(!bit);
+    }
+    inline void flush() { while (fill != 0) put(0); }
+};
+
+template <class GetInterval>
+static long long range_encode_impl(long long n, uint8_t* out, long long cap, GetInterval get) {
+    BitSink sink{out, cap};
+    uint32_t low = 0, high = 0xFFFFFFFFu;
+    unsigned long long pending = 0;
+    for (long long i = 0; i < n; ++i) {
+        uint32_t c_low, c_high;
+        get(i, c_low, c_high);
+        const uint64_t span = (uint64_t)high - (uint64_t)low + 1;
+        high = (low - 1) + (uint32_t)((span * (uint64_t)c_high) >> 16);
+        low = low + (uint32_t)((span * (uint64_t)c_low) >> 16);
+        for (;;) {
+            if (high < 0x80000000u) {
+                sink.put_with_pending(0, pending);
+            } else if (low >= 0x80000000u) {
+                sink.put_with_pending(1, pending);
+            } else if (low >= 0x40000000u && high < 0xC0000000u) {
+                ++pending;
+                low = (low << 1) & 0x7FFFFFFFu;
+                high = (high << 1) | 0x80000001u;
+                continue;
+            } else {
+                break;
+            }
+            low <<= 1;
+            high = (high << 1) | 1u;
+        }
+    }
+    ++pending;
+    sink.put_with_pending(low < 0x40000000u ? 0 : 1, pending);
+    sink.flush();
+    if (sink.overflow) { set_error("scp_range_encode: output buffer too small (%lld needed)", sink.n); return SCP_ERR_ARG; }
+    return sink.n;
+}
+
+}  // namespace scp
+
+using namespace scp;
+
+extern "C" {
+
+int scp_coding_order(const int64_t* h_level_sizes, int n_levels, int context_size, int add_base_for_single,
+                     const uint8_t* d_occ, int64_t* d_order, int16_t* d_sym, void* stream) {
+    SCP_REQUIRE(h_level_sizes && d_order && n_levels > 0 && context_size > 0, "scp_coding_order: bad argument");
+    SCP_REQUIRE(!d_sym || d_occ, "scp_coding_order: symbols need d_occ");
+    cudaStream_t st = as_stream(stream);
+    std::vector<Win> wins;
+    long long base = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        long long n = h_level_sizes[l];
+        SCP_REQUIRE(n >= 0, "scp_coding_order: negative level size");
+        for (long long i = 0; i < n; i += context_size)
+            wins.push_back(Win{base, i, (int)std::min<long long>(context_size, n - i), n == 1});
+        base += n;
+    }
+    if (wins.empty()) return SCP_OK;
+    Win* d_w = nullptr;
+    SCP_CUDA(cudaMallocAsync((void**)&d_w, wins.size() * sizeof(Win), st));
+    SCP_CUDA(cudaMemcpyAsync(d_w, wins.data(), wins.size() * sizeof(Win), cudaMemcpyHostToDevice, st));
+    int grid = (int)std::min<size_t>(wins.size(), 148 * 8);
+    k_coding_order<<<grid, 256, 0, st>>>(d_w, (int)wins.size(), d_occ, (long long*)d_order, d_sym, add_base_for_single);
+    SCP_LAUNCHED();
+    SCP_CUDA(cudaStreamSynchronize(st));      // `wins` is pageable host memory
+    SCP_CUDA(cudaFreeAsync(d_w, st));
+    return SCP_OK;
+}
+
+int scp_pmf_to_cdf(const float* d_in, int64_t n, int is_logits, const int64_t* d_row_of, const int16_t* d_sym,
+                   uint16_t* d_cdf, uint32_t* d_interval, float* d_pmf, void* stream) {
+    SCP_REQUIRE(d_in && n >= 0, "scp_pmf_to_cdf: bad argument");
+    SCP_REQUIRE(!d_interval || d_sym, "scp_pmf_to_cdf: intervals need the symbols");
+    if (n == 0) return SCP_OK;
+    static bool attr_done = false;
+    const int smem = CDF_R * CDF_LD * 4;
+    if (!attr_done) {
+        SCP_CUDA(cudaFuncSetAttribute(k_pmf_to_cdf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done = true;
+    }
+    k_pmf_to_cdf<<<(unsigned)cdiv(n, CDF_R), CDF_R, smem, as_stream(stream)>>>(
+        d_in, n, is_logits, (const long long*)d_row_of, d_sym, d_cdf, d_interval, d_pmf);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int64_t scp_range_encode(const uint32_t* h_interval, int64_t n, uint8_t* h_out, int64_t out_cap) {
+    if (!h_interval || n < 0) { set_error("scp_range_encode: bad argument"); return SCP_ERR_ARG; }
+    return range_encode_impl(n, h_out, out_cap, [&](long long i, uint32_t& lo, uint32_t& hi) {
+        lo = h_interval[2 * i]; hi = h_interval[2 * i + 1];
+    });
+}
+
+int64_t scp_range_encode_cdf(const uint16_t* h_cdf, const int16_t* h_sym, int64_t n, int Lp, uint8_t* h_out,
+                             int64_t out_cap) {
+    if (!h_cdf || !h_sym || n < 0 || Lp < 2) { set_error("scp_range_encode_cdf: bad argument"); return SCP_ERR_ARG; }
+    const int max_symbol = Lp - 2;
+    for (int64_t i = 0; i < n; ++i)
+        if (h_sym[i] < 0 || h_sym[i] > max_symbol) { set_error("scp_range_encode_cdf: symbol %d out of range at %lld", (int)h_sym[i], (long long)i); return SCP_ERR_ARG; }
+    return range_encode_impl(n, h_out, out_cap, [&](long long i, uint32_t& lo, uint32_t& hi) {
+        const int s = h_sym[i];
+        lo = h_cdf[i * Lp + s];
+        hi = s == max_symbol ? 0x10000u : h_cdf[i * Lp + s + 1];
+    });
+}
+
+}  // extern "C"

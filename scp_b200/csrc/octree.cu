@@ -1,0 +1,930 @@
+// Batched octree construction on B200.
+//
+//   points (float32) --K1--> per-frame rho max / z min
+//                    --K2--> quantised (r,phi,theta|z) -> 63-bit Morton key per point   [20 B/pt]
+//                    --K3--> segmented LSD radix sort, 8-bit digits, decoupled look-back [(1+2P)*8 B/pt]
+//                    --K4--> "head level" of every sorted key + per-tile level histograms [8 B/pt]
+//                    --K5--> level counts / offsets per job
+//                    --K6--> node records of ALL levels in one pass over the sorted keys   [28 B/node]
+//                    --K7a-> occupancy bytes from the children run of every node
+//                    --K7b-> K=4 ancestor context bytes + level-normalised positions       [60 B/node]
+//
+// One pass over the sorted voxel keys yields every level at once: for consecutive distinct keys the
+// number d of common leading octal digits says that the second key opens a new node on every level
+// L >= d+2 ("head level" h = d+2).  A node's BFS index inside level L is the number of earlier keys
+// with h <= L, i.e. one prefix sum per level, done with warp ballots.
+//
+// Reference behaviour reproduced (paths in luoao-kddi/SCP): data_preprocess.py:13-167,171-207;
+// Octree.py:56-65,102-145,148-272; OctreeCPP/Octreewarpper.py; encode_dataset_ehem.py:52-105;
+// encode_dataset_ehem_mullevel.py:47-85.
+#include <vector>
+#include <algorithm>
+#include <string.h>
+#include "common.cuh"
+
+namespace scp {
+
+constexpr int TPB = 256;
+constexpr int TILE = 2048;            // elements per tile for the streaming kernels
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = TPB * SORT_ITEMS;   // 4096 keys
+constexpr int NBINS = 24;             // head-level histogram bins (0 = not a new voxel, 1..22)
+constexpr int MAXL = SCP_MAX_DEPTH;   // 21
+constexpr u64 SENTINEL = ~0ull;
+
+struct Tile { int job; int begin; int count; int first; };
+
+struct FrameDev { u32 rho_max_bits; u32 zmin_enc; };
+
+struct JobDev {
+    int frame, path_len, path_bits, drop_last;
+    double qs, cart_offset;
+    int lidar_level, pos_eps_last;
+    long long pt_begin;
+    int n_points;
+    long long key_begin;
+    float bin_num;
+    double step[3];
+    double off[3];
+    u32 qmax;
+    u32 overflow;
+    int depth;
+    int n_voxels, n_nodes, n_rows;
+    int level_count[MAXL + 1];   // nodes on level L at [L-1]
+    int level_start[MAXL + 2];   // node offset of level L inside the job at [L-1]
+    long long node_start, row_start, vox_start;
+    u32 pos_min[MAXL + 1];
+    u32 pos_max[MAXL + 1];
+};
+
+// ------------------------------------------------------------------------------------------
+// bit tricks
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 spread3(u32 v) {   // 21 bits -> every third bit
+    u64 x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__host__ __device__ __forceinline__ u32 compact3(u64 x) {
+    x &= 0x1249249249249249ull;
+    x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ull;
+    x = (x ^ (x >> 4)) & 0x100f00f00f00f00full;
+    x = (x ^ (x >> 8)) & 0x1f0000ff0000ffull;
+    x = (x ^ (x >> 16)) & 0x1f00000000ffffull;
+    x = (x ^ (x >> 32)) & 0x1fffffull;
+    return (u32)x;
+}
+__device__ __forceinline__ u32 enc_ordered(float f) {
+    u32 b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(u32 e) {
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: per-frame rho max (and z min for cylindrical)            data_preprocess.py:44-46,49
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rho_of(float x, float y, float z, int mode) {
+    float s = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));          // x**2 + y**2 (float32, no FMA)
+    if (mode == SCP_MODE_SPHER) s = __fadd_rn(s, __fmul_rn(z, z));
+    return __fsqrt_rn(s);
+}
+
+__global__ void k_init_frames(FrameDev* fr, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { fr[i].rho_max_bits = 0u; fr[i].zmin_enc = 0xffffffffu; }
+}
+
+__global__ void __launch_bounds__(TPB) k_frame_stats(const float* __restrict__ xyz, int stride,
+                                                      const Tile* __restrict__ tiles, const long long* __restrict__ frame_begin,
+                                                      FrameDev* fr, int mode) {
+    Tile t = tiles[blockIdx.x];
+    const float* p = xyz + (frame_begin[t.job] + t.begin) * (long long)stride;
+    float rmax = 0.f;
+    u32 zmin = 0xffffffffu;
+    for (int i = threadIdx.x; i < t.count; i += TPB) {
+        float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
+        rmax = fmaxf(rmax, rho_of(x, y, z, mode));
+        zmin = min(zmin, enc_ordered(z));
+    }
+    u32 rb = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
+    u32 zb = __reduce_min_sync(0xffffffffu, zmin);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&fr[t.job].rho_max_bits, rb);
+        atomicMin(&fr[t.job].zmin_enc, zb);
+    }
+}
+
+__global__ void k_job_setup(JobDev* jobs, int n_jobs, const FrameDev* fr, int mode) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    JobDev& J = jobs[j];
+    J.qmax = 0; J.overflow = 0; J.depth = 0;
+    for (int l = 0; l <= MAXL; ++l) { J.pos_min[l] = 0xffffffffu; J.pos_max[l] = 0u; }
+    if (mode == SCP_MODE_CART) {
+        J.bin_num = 0.f;
+        J.step[0] = J.step[1] = J.step[2] = J.qs;
+        J.off[0] = J.off[1] = J.off[2] = J.cart_offset;
+        return;
+    }
+    float rho_max = __uint_as_float(fr[J.frame].rho_max_bits);
+    // bin_num = np.round(rho.max() / qs) + 1   (float32 arithmetic under numpy>=2)
+    float bn = __fadd_rn(rintf(__fdiv_rn(rho_max, (float)J.qs)), 1.0f);
+    J.bin_num = bn;
+    float bm1 = __fsub_rn(bn, 1.0f);
+    J.step[0] = J.qs;
+    J.step[1] = (double)__fdiv_rn(6.2831854820251465f, bm1);     // float32(2*pi) / float32
+    J.off[0] = 0.0; J.off[1] = 0.0; J.off[2] = 0.0;
+    if (mode == SCP_MODE_SPHER) {
+        J.step[2] = (double)__fdiv_rn(3.1415927410125732f, bm1);
+    } else {
+        J.step[2] = J.qs;
+        J.off[2] = (double)dec_ordered(fr[J.frame].zmin_enc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: coordinate transform + quantise + Morton key            data_preprocess.py:171-207, :56,:68-70
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_quantise_keys(const float* __restrict__ xyz, int stride,
+                                                        const Tile* __restrict__ tiles, JobDev* jobs,
+                                                        u64* __restrict__ keys, int mode) {
+    Tile t = tiles[blockIdx.x];
+    JobDev& J = jobs[t.job];
+    const float* p = xyz + (J.pt_begin + t.begin) * (long long)stride;
+    u64* out = keys + J.key_begin + t.begin;
+    const double s0 = J.step[0], s1 = J.step[1], s2 = J.step[2], o2 = J.off[2];
+    const float coff = (float)J.cart_offset, cqs = (float)J.qs;
+    u32 qmax = 0, ovf = 0;
+    for (int i = threadIdx.x; i < t.count; i += TPB) {
+        float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
+        long long q0, q1, q2;
+        if (mode == SCP_MODE_CART) {
+            // float32 chain: (p - offset) / qs with python-float scalars (NEP 50 keeps float32)
+            q0 = (long long)rintf(__fdiv_rn(__fsub_rn(x, coff), cqs));
+            q1 = (long long)rintf(__fdiv_rn(__fsub_rn(y, coff), cqs));
+            q2 = (long long)rintf(__fdiv_rn(__fsub_rn(z, coff), cqs));
+        } else {
+            float rho = rho_of(x, y, z, mode);
+            float xe = __fadd_rn(x, 1e-9f);
+            float phi = (float)atan2((double)y, (double)xe);           // correctly rounded float32 angle
+            if (phi < 0.f) phi = __fadd_rn(phi, 6.2831854820251465f);
+            float third = (mode == SCP_MODE_SPHER) ? (float)acos((double)__fdiv_rn(z, rho)) : z;
+            q0 = (long long)rint((double)rho / s0);
+            q1 = (long long)rint((double)phi / s1);
+            q2 = (long long)rint(((double)third - o2) / s2);
+        }
+        if (q0 < 0 || q1 < 0 || q2 < 0 || q0 >= (1 << 21) || q1 >= (1 << 21) || q2 >= (1 << 21)) {
+            ovf = 1; q0 = q1 = q2 = 0;
+        }
+        qmax = max(qmax, (u32)max(q0, max(q1, q2)));
+        out[i] = (spread3((u32)q0) << 2) | (spread3((u32)q1) << 1) | spread3((u32)q2);
+    }
+    qmax = __reduce_max_sync(0xffffffffu, qmax);
+    ovf = __reduce_max_sync(0xffffffffu, ovf);
+    if ((threadIdx.x & 31) == 0) {
+        if (qmax) atomicMax(&J.qmax, qmax);
+        if (ovf) atomicMax(&J.overflow, 1u);
+    }
+}
+
+__global__ void k_job_depth(JobDev* jobs, int n_jobs) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    u32 m = jobs[j].qmax;
+    jobs[j].depth = m ? 32 - __clz(m) : 0;     // ceil(log2(max+1)), Octree.py:58
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: segmented radix sort (Onesweep: global digit histograms once, then P scatter passes whose
+// tile offsets come from a decoupled look-back over single-word (flag|count) descriptors)
+// ------------------------------------------------------------------------------------------
+constexpr u32 FLAG_AGG = 1u << 30, FLAG_INC = 1u << 31, VAL_MASK = (1u << 30) - 1;
+
+// also applies the morton_path filter of Octree.py:188 by rewriting rejected keys to SENTINEL
+__global__ void __launch_bounds__(TPB) k_sort_hist(u64* __restrict__ keys, const Tile* __restrict__ tiles,
+                                                    const JobDev* __restrict__ jobs, u32* __restrict__ hist,
+                                                    int P, int apply_filter) {
+    __shared__ u32 sh[8 * 256];
+    Tile t = tiles[blockIdx.x];
+    const JobDev& J = jobs[t.job];
+    for (int i = threadIdx.x; i < P * 256; i += TPB) sh[i] = 0;
+    __syncthreads();
+    u64* src = keys + J.key_begin + t.begin;
+    const int n = J.depth, plen = apply_filter ? J.path_len : 0, pbits = J.path_bits;
+    for (int i = threadIdx.x; i < t.count; i += TPB) {
+        u64 k = src[i];
+        if (plen > 0 && k != SENTINEL) {
+            bool keep = true;
+            for (int j = 0; j < plen; ++j) {
+                int b = n - 1 - j;
+                int bit = b >= 0 ? (int)((k >> (3 * b + 2)) & 1) : 0;
+                keep &= (bit == ((pbits >> j) & 1));
+            }
+            if (!keep) { k = SENTINEL; src[i] = k; }
+        }
+        for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + (u32)((k >> (8 * p)) & 0xff)], 1u);
+    }
+    __syncthreads();
+    u32* h = hist + (size_t)t.job * P * 256;
+    for (int i = threadIdx.x; i < P * 256; i += TPB)
+        if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(256) k_scan_hist(u32* hist) {   // one block per (job, pass): exclusive scan of 256 bins
+    __shared__ u32 ws[8];
+    u32* h = hist + (size_t)blockIdx.x * 256;
+    u32 v = h[threadIdx.x];
+    u32 inc = v;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    u32 base = 0;
+    for (int i = 0; i < w; ++i) base += ws[i];
+    h[threadIdx.x] = base + inc - v;
+}
+
+__global__ void __launch_bounds__(TPB) k_onesweep(const u64* __restrict__ in, u64* __restrict__ out,
+                                                   const Tile* __restrict__ tiles, int n_tiles,
+                                                   const JobDev* __restrict__ jobs, const u32* __restrict__ hist,
+                                                   int P, int pass, u32* desc, u32* ticket, u32* err) {
+    __shared__ u64 s_keys[SORT_TILE];
+    __shared__ u32 s_whist[8][257];
+    __shared__ u32 s_dstart[256];
+    __shared__ u32 s_gbase[256];
+    __shared__ u32 s_ws[8];
+    __shared__ int s_tile;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < 8 * 257; i += TPB) (&s_whist[0][0])[i] = 0;
+    __syncthreads();
+    const int t = s_tile;
+    if (t >= n_tiles) return;
+    const Tile tl = tiles[t];
+    const JobDev& J = jobs[tl.job];
+    const u64* src = in + J.key_begin + tl.begin;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int shift = pass * 8;
+    const int wbase = warp * (32 * SORT_ITEMS);
+    u64 key[SORT_ITEMS];
+    u32 rank[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int idx = wbase + i * 32 + lane;
+        key[i] = idx < tl.count ? src[idx] : SENTINEL;
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int idx = wbase + i * 32 + lane;
+        u32 d = idx < tl.count ? (u32)((key[i] >> shift) & 0xff) : 256u;
+        u32 peers = __match_any_sync(0xffffffffu, d);
+        u32 lt = peers & ((1u << lane) - 1u);
+        u32 prev = s_whist[warp][d];
+        __syncwarp();
+        if (lt == 0) s_whist[warp][d] = prev + __popc(peers);
+        __syncwarp();
+        rank[i] = prev + __popc(lt);
+    }
+    __syncthreads();
+    const u32 d = threadIdx.x;
+    u32 total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { u32 c = s_whist[w][d]; s_whist[w][d] = total; total += c; }
+    volatile u32* vdesc = desc + ((size_t)pass * n_tiles) * 256;
+    vdesc[(size_t)t * 256 + d] = total | FLAG_AGG;
+    // exclusive scan of `total` over the 256 digits -> position of the digit's run inside the tile
+    u32 inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { u32 n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) s_ws[warp] = inc;
+    __syncthreads();
+    u32 wb = 0;
+    for (int i = 0; i < warp; ++i) wb += s_ws[i];
+    s_dstart[d] = wb + inc - total;
+    // decoupled look-back over the previous tiles of the same job
+    u32 ex = 0;
+    for (int p = t - 1; p >= tl.first; --p) {
+        u32 v;
+        int spins = 0;
+        do { v = vdesc[(size_t)p * 256 + d]; } while ((v & (FLAG_AGG | FLAG_INC)) == 0 && ++spins < (1 << 22));
+        if ((v & (FLAG_AGG | FLAG_INC)) == 0) { atomicExch(err, 1u); break; }   // never hang the GPU
+        ex += v & VAL_MASK;
+        if (v & FLAG_INC) break;
+    }
+    vdesc[(size_t)t * 256 + d] = ((ex + total) & VAL_MASK) | FLAG_INC;
+    s_gbase[d] = hist[((size_t)tl.job * P + pass) * 256 + d] + ex;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int idx = wbase + i * 32 + lane;
+        if (idx < tl.count) {
+            u32 dg = (u32)((key[i] >> shift) & 0xff);
+            s_keys[s_dstart[dg] + s_whist[warp][dg] + rank[i]] = key[i];
+        }
+    }
+    __syncthreads();
+    u64* dst = out + J.key_begin;
+    for (int s = threadIdx.x; s < tl.count; s += TPB) {
+        u64 k = s_keys[s];
+        u32 dg = (u32)((k >> shift) & 0xff);
+        dst[s_gbase[dg] + ((u32)s - s_dstart[dg])] = k;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: head levels + per-tile histograms
+// ------------------------------------------------------------------------------------------
+// h = 0: not a new voxel (duplicate / filtered); h = 1: first voxel of the job; otherwise d+2 where d is the
+// number of leading octal digits (out of n) shared with the previous key.  h <= n+1.
+__device__ __forceinline__ int head_level(u64 k, u64 prev, bool first, int n) {
+    if (k == SENTINEL) return 0;
+    if (first) return 1;
+    if (k == prev) return 0;
+    int hb = 63 - __clzll((long long)(k ^ prev));
+    return n - hb / 3 + 1;      // d = n-1-hb/3
+}
+
+__global__ void __launch_bounds__(TPB) k_head_hist(const u64* __restrict__ keys, const Tile* __restrict__ tiles,
+                                                    const JobDev* __restrict__ jobs, u32* __restrict__ tile_hist) {
+    __shared__ u32 sh[NBINS];
+    Tile t = tiles[blockIdx.x];
+    const JobDev& J = jobs[t.job];
+    if (threadIdx.x < NBINS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const u64* src = keys + J.key_begin;
+    const int n = J.depth;
+    for (int i0 = 0; i0 < t.count; i0 += TPB) {
+        int i = i0 + threadIdx.x;
+        int h = 0;
+        if (i < t.count) {
+            int g = t.begin + i;
+            u64 k = src[g];
+            u64 prev = g > 0 ? src[g - 1] : 0ull;
+            h = head_level(k, prev, g == 0, n);
+        }
+        u32 peers = __match_any_sync(0xffffffffu, h);
+        if (h > 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&sh[h], (u32)__popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < NBINS) tile_hist[(size_t)blockIdx.x * NBINS + threadIdx.x] = sh[threadIdx.x];
+}
+
+// K5: one warp per job: exclusive scan of the tile histograms, level counts and offsets
+__global__ void k_level_scan(JobDev* jobs, int n_jobs, const int* __restrict__ job_tile_begin,
+                             u32* tile_hist /* in: counts, out: exclusive prefix inside the job */) {
+    int j = blockIdx.x;
+    JobDev& J = jobs[j];
+    __shared__ u32 tot[32];
+    int b = threadIdx.x;
+    u32 run = 0;
+    if (b < NBINS) {
+        for (int t = job_tile_begin[j]; t < job_tile_begin[j + 1]; ++t) {
+            u32 c = tile_hist[(size_t)t * NBINS + b];
+            tile_hist[(size_t)t * NBINS + b] = run;
+            run += c;
+        }
+    }
+    tot[b] = run;
+    __syncwarp();
+    if (b == 0) {
+        int n = J.depth;
+        int nodes = 0, cum = 0, vox = 0;
+        for (int h = 1; h < NBINS; ++h) vox += tot[h];
+        for (int L = 1; L <= MAXL; ++L) {
+            if (L <= n) cum += tot[L];
+            int c = (L <= n) ? cum : 0;
+            J.level_start[L - 1] = nodes;
+            J.level_count[L - 1] = c;
+            nodes += c;
+        }
+        J.level_start[MAXL] = nodes;
+        J.n_voxels = vox;
+        J.n_nodes = nodes;
+        J.n_rows = (J.drop_last && nodes > 0) ? nodes - 1 : nodes;
+    }
+}
+
+__global__ void k_job_offsets(JobDev* jobs, int n_jobs) {
+    if (threadIdx.x || blockIdx.x) return;
+    long long node = 0, row = 0, vox = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        jobs[j].node_start = node; jobs[j].row_start = row; jobs[j].vox_start = vox;
+        node += jobs[j].n_nodes; row += jobs[j].n_rows; vox += jobs[j].n_voxels;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: node records for all levels in one pass
+// ------------------------------------------------------------------------------------------
+struct NodeArrays {
+    uint8_t* level; uint8_t* octant; uint8_t* occ; u32* parent; u32* pos; u32* fc;
+};
+
+__global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys, const Tile* __restrict__ tiles,
+                                                     JobDev* jobs, const u32* __restrict__ tile_base,
+                                                     NodeArrays A, u64* __restrict__ vox_key) {
+    __shared__ u32 s_base[MAXL + 2];        // running count of heads per level (index L), [0] = voxels
+    __shared__ u32 s_wcnt[8][MAXL + 2];
+    __shared__ u32 s_wpre[8][MAXL + 2];
+    __shared__ u32 s_pmin[MAXL + 2], s_pmax[MAXL + 2];
+    const Tile t = tiles[blockIdx.x];
+    JobDev& J = jobs[t.job];
+    const int n = J.depth;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 ltmask = (1u << lane) - 1u;
+    if (threadIdx.x <= MAXL) {
+        int L = threadIdx.x;       // L = 0: voxel counter
+        u32 s = 0;
+        const u32* tb = tile_base + (size_t)blockIdx.x * NBINS;
+        if (L == 0) { for (int h = 1; h < NBINS; ++h) s += tb[h]; }
+        else if (L <= n) { for (int h = 1; h <= L; ++h) s += tb[h]; }
+        s_base[L] = s;
+        s_pmin[L] = 0xffffffffu; s_pmax[L] = 0u;
+    }
+    __syncthreads();
+    const u64* src = keys + J.key_begin;
+    const long long node0 = J.node_start;
+    const int last_cnt = J.level_count[n > 0 ? n - 1 : 0];
+    for (int i0 = 0; i0 < t.count; i0 += TPB) {
+        const int i = i0 + threadIdx.x;
+        int h = 0;
+        u64 k = 0;
+        if (i < t.count) {
+            int g = t.begin + i;
+            k = src[g];
+            u64 prev = g > 0 ? src[g - 1] : 0ull;
+            h = head_level(k, prev, g == 0, n);
+        }
+        const int hh = h == 0 ? 99 : h;
+        u32 rank[MAXL + 2];
+        {
+            u32 b = __ballot_sync(0xffffffffu, h > 0);
+            rank[0] = __popc(b & ltmask);
+            if (lane == 0) s_wcnt[warp][0] = __popc(b);
+        }
+#pragma unroll
+        for (int L = 1; L <= MAXL; ++L) {
+            u32 b = __ballot_sync(0xffffffffu, hh <= L);
+            rank[L] = __popc(b & ltmask);
+            if (lane == 0) s_wcnt[warp][L] = __popc(b);
+        }
+        __syncthreads();
+        if (threadIdx.x <= MAXL) {
+            u32 run = 0;
+            for (int w = 0; w < 8; ++w) { s_wpre[w][threadIdx.x] = run; run += s_wcnt[w][threadIdx.x]; }
+        }
+        __syncthreads();
+        const u32 x = compact3(k >> 2), y = compact3(k >> 1), z = compact3(k);
+        const u32 v = s_base[0] + s_wpre[warp][0] + rank[0];
+        if (h > 0 && vox_key) vox_key[J.vox_start + v] = k;
+#pragma unroll
+        for (int L = 1; L <= MAXL; ++L) {
+            if (L > n) break;                                   // uniform
+            const bool mine = (h > 0) && (L >= h);
+            u32 vmin = 0xffffffffu, vmax = 0u;
+            if (mine) {
+                const u32 kL = s_base[L] + s_wpre[warp][L] + rank[L];
+                const long long r = node0 + J.level_start[L - 1] + kL;
+                A.level[r] = (uint8_t)L;
+                A.octant[r] = (L == 1) ? 1 : (uint8_t)(((k >> (3 * (n - L + 1))) & 7) + 1);
+                u32 par = 0;
+                if (L > 1) {
+                    u32 kp = s_base[L - 1] + s_wpre[warp][L - 1] + rank[L - 1] + ((hh <= L - 1) ? 1u : 0u) - 1u;
+                    par = (u32)J.level_start[L - 2] + kp;
+                }
+                A.parent[r] = par;
+                const u32 m = ~((1u << (n - L + 1)) - 1u);
+                const u32 px = x & m, py = y & m, pz = z & m;
+                A.pos[3 * r] = px; A.pos[3 * r + 1] = py; A.pos[3 * r + 2] = pz;
+                A.fc[r] = (L < n) ? (u32)J.level_start[L] + s_base[L + 1] + s_wpre[warp][L + 1] + rank[L + 1] : v;
+                const bool dropped = J.drop_last && L == n && (int)kL == last_cnt - 1;
+                if (!dropped) { vmin = min(px, min(py, pz)); vmax = max(px, max(py, pz)); }
+            }
+            const u32 any = __ballot_sync(0xffffffffu, mine);
+            if (any) {                                          // warp-uniform
+                vmin = __reduce_min_sync(0xffffffffu, vmin);
+                vmax = __reduce_max_sync(0xffffffffu, vmax);
+                if (lane == 0 && vmin != 0xffffffffu) { atomicMin(&s_pmin[L], vmin); atomicMax(&s_pmax[L], vmax); }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x <= MAXL) {
+            u32 add = 0;
+            for (int w = 0; w < 8; ++w) add += s_wcnt[w][threadIdx.x];
+            s_base[threadIdx.x] += add;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x >= 1 && threadIdx.x <= n && s_pmin[threadIdx.x] != 0xffffffffu) {
+        atomicMin(&J.pos_min[threadIdx.x - 1], s_pmin[threadIdx.x]);
+        atomicMax(&J.pos_max[threadIdx.x - 1], s_pmax[threadIdx.x]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7a: occupancy byte = OR over the node's children run           Octree.py:175-176
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+                                                    NodeArrays A, const u64* __restrict__ vox_key) {
+    const Tile t = tiles[blockIdx.x];
+    const JobDev& J = jobs[t.job];
+    const int n = J.depth;
+    for (int i = threadIdx.x; i < t.count; i += TPB) {
+        const int loc = t.begin + i;
+        const long long r = J.node_start + loc;
+        const int L = A.level[r];
+        const u32 c0 = A.fc[r];
+        const bool last_of_level = (loc + 1 == J.level_start[L]);    // level_start[L] = start of level L+1
+        u32 occ = 0;
+        if (L < n) {
+            const u32 c1 = last_of_level ? (u32)J.level_start[L + 1] : A.fc[r + 1];
+            for (u32 c = c0; c < c1; ++c) occ |= 1u << (A.octant[J.node_start + c] - 1);
+        } else {
+            const u32 c1 = last_of_level ? (u32)J.n_voxels : A.fc[r + 1];
+            for (u32 c = c0; c < c1; ++c) occ |= 1u << (u32)(vox_key[J.vox_start + c] & 7);
+        }
+        A.occ[r] = (uint8_t)occ;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7b: K=4 ancestor context + level-normalised positions (+ optional reference-layout expansion)
+//   Octree.py:102-137 gen_K_parent_seq ; encode_dataset_ehem.py:54,66-72,85-93
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+                                                  NodeArrays A, scp_octree_out O) {
+    const Tile t = tiles[blockIdx.x];
+    const JobDev& J = jobs[t.job];
+    const int n = J.depth;
+    for (int i = threadIdx.x; i < t.count; i += TPB) {
+        const int loc = t.begin + i;
+        if (loc >= J.n_rows) continue;                    // the dropped last row (Octree.py:259-262)
+        const long long r = J.node_start + loc;
+        const long long o = J.row_start + loc;
+        const int L = A.level[r];
+        const bool last_block = (L == n);
+        int lv[4], oc[4], occ[4];
+        u32 px[4], py[4], pz[4];
+        long long a = r;
+        bool have = true;
+#pragma unroll
+        for (int k = 3; k >= 0; --k) {
+            if (have) {
+                lv[k] = A.level[a]; oc[k] = A.octant[a]; occ[k] = A.occ[a];
+                px[k] = A.pos[3 * a]; py[k] = A.pos[3 * a + 1]; pz[k] = A.pos[3 * a + 2];
+                have = lv[k] > 1;
+                a = J.node_start + A.parent[a];
+            } else {
+                lv[k] = 0; oc[k] = 0; occ[k] = 256; px[k] = py[k] = pz[k] = 0;
+            }
+        }
+        if (O.occ) O.occ[o] = (uint8_t)occ[3];
+        if (O.level) O.level[o] = (uint8_t)lv[3];
+        if (O.octant) O.octant[o] = (uint8_t)oc[3];
+        if (O.parent) O.parent[o] = A.parent[r];
+        if (O.pos) { O.pos[3 * o] = px[3]; O.pos[3 * o + 1] = py[3]; O.pos[3 * o + 2] = pz[3]; }
+        if (O.ctx) {
+            uint8_t c[12];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int l = lv[k];
+                if (last_block && l > J.lidar_level) l = J.lidar_level;     // encode_dataset_ehem.py:86
+                c[3 * k] = (uint8_t)l; c[3 * k + 1] = (uint8_t)oc[k]; c[3 * k + 2] = (uint8_t)(occ[k] - 1);
+            }
+            uint32_t* dst = reinterpret_cast<uint32_t*>(O.ctx + 12 * o);
+            dst[0] = c[0] | (c[1] << 8) | (c[2] << 16) | ((u32)c[3] << 24);
+            dst[1] = c[4] | (c[5] << 8) | (c[6] << 16) | ((u32)c[7] << 24);
+            dst[2] = c[8] | (c[9] << 8) | (c[10] << 16) | ((u32)c[11] << 24);
+        }
+        if (O.pos_norm) {
+            const double mn = (double)J.pos_min[L - 1];
+            const double den = (double)(J.pos_max[L - 1] - J.pos_min[L - 1]) +
+                               ((last_block && !J.pos_eps_last) ? 0.0 : 1e-9);
+            O.pos_norm[3 * o] = (float)(((double)px[3] - mn) / den);
+            O.pos_norm[3 * o + 1] = (float)(((double)py[3] - mn) / den);
+            O.pos_norm[3 * o + 2] = (float)(((double)pz[3] - mn) / den);
+        }
+        if (O.ctx_pos) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                O.ctx_pos[12 * o + 3 * k] = px[k]; O.ctx_pos[12 * o + 3 * k + 1] = py[k]; O.ctx_pos[12 * o + 3 * k + 2] = pz[k];
+            }
+        }
+        if (O.rows_i64) {
+            long long* w = reinterpret_cast<long long*>(O.rows_i64) + 24 * o;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w[6 * k] = occ[k]; w[6 * k + 1] = lv[k]; w[6 * k + 2] = oc[k];
+                w[6 * k + 3] = px[k]; w[6 * k + 4] = py[k]; w[6 * k + 5] = pz[k];
+            }
+        }
+    }
+}
+
+}  // namespace scp
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+using namespace scp;
+
+struct scp_octree {
+    DevBuf keys_a, keys_b, tiles_pts, tiles_sort, tiles_node, frames, jobs, frame_begin, hist, desc, misc,
+        tile_hist, job_tile_begin, n_level, n_octant, n_occ, n_parent, n_pos, n_fc, vox;
+    std::vector<JobDev> hjobs;
+    std::vector<Tile> h_tiles_pts, h_tiles_sort, h_tiles_node;
+    int n_jobs = 0, mode = 0, P = 0, nt_frame = 0;
+    long long total_keys = 0, total_nodes = 0, total_rows = 0, total_vox = 0;
+    bool planned = false, emitted = false;
+    cudaEvent_t ev[8] = {};
+    bool ev_ok = false;
+    u64* sorted = nullptr;
+};
+
+static void build_tiles(const std::vector<long long>& counts, int tile, std::vector<Tile>& out, std::vector<int>* job_begin) {
+    out.clear();
+    if (job_begin) job_begin->clear();
+    for (size_t j = 0; j < counts.size(); ++j) {
+        int first = (int)out.size();
+        if (job_begin) job_begin->push_back(first);
+        for (long long b = 0; b < counts[j]; b += tile)
+            out.push_back(Tile{(int)j, (int)b, (int)std::min<long long>(tile, counts[j] - b), first});
+    }
+    if (job_begin) job_begin->push_back((int)out.size());
+}
+
+static int run_sort(u64* keys, u64* tmp, const Tile* d_tiles, int n_tiles, const JobDev* d_jobs, int n_jobs, int P,
+                    int apply_filter, DevBuf& hist, DevBuf& desc, DevBuf& misc, cudaStream_t st, u64** result) {
+    if (P <= 0 || n_tiles == 0) { *result = keys; return SCP_OK; }
+    if (int e = hist.reserve((size_t)n_jobs * P * 256 * 4)) return e;
+    if (int e = desc.reserve((size_t)P * n_tiles * 256 * 4)) return e;
+    if (int e = misc.reserve(64 * 4)) return e;
+    SCP_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)n_jobs * P * 256 * 4, st));
+    SCP_CUDA(cudaMemsetAsync(desc.p, 0, (size_t)P * n_tiles * 256 * 4, st));
+    SCP_CUDA(cudaMemsetAsync(misc.p, 0, 64 * 4, st));
+    k_sort_hist<<<n_tiles, TPB, 0, st>>>(keys, d_tiles, d_jobs, hist.as<u32>(), P, apply_filter);
+    SCP_LAUNCHED();
+    k_scan_hist<<<n_jobs * P, 256, 0, st>>>(hist.as<u32>());
+    SCP_LAUNCHED();
+    u64* a = keys; u64* b = tmp;
+    for (int p = 0; p < P; ++p) {
+        k_onesweep<<<n_tiles, TPB, 0, st>>>(a, b, d_tiles, n_tiles, d_jobs, hist.as<u32>(), P, p, desc.as<u32>(),
+                                            misc.as<u32>() + 1 + p, misc.as<u32>());
+        SCP_LAUNCHED();
+        std::swap(a, b);
+    }
+    *result = a;
+    return SCP_OK;
+}
+
+extern "C" {
+
+scp_octree* scp_octree_create(void) { return new scp_octree(); }
+
+void scp_octree_destroy(scp_octree* t) {
+    if (!t) return;
+    DevBuf* bufs[] = {&t->keys_a, &t->keys_b, &t->tiles_pts, &t->tiles_sort, &t->tiles_node, &t->frames, &t->jobs,
+                      &t->frame_begin, &t->hist, &t->desc, &t->misc, &t->tile_hist, &t->job_tile_begin, &t->n_level,
+                      &t->n_octant, &t->n_occ, &t->n_parent, &t->n_pos, &t->n_fc, &t->vox};
+    for (DevBuf* b : bufs) b->release();
+    if (t->ev_ok) for (auto& e : t->ev) cudaEventDestroy(e);
+    delete t;
+}
+
+int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const int64_t* h_frame_offsets, int n_frames,
+                    const scp_job* h_jobs, int n_jobs, int mode, void* stream) {
+    SCP_REQUIRE(t && d_xyz && h_frame_offsets && h_jobs, "scp_octree_plan: null argument");
+    SCP_REQUIRE(point_stride >= 3, "scp_octree_plan: point_stride must be >= 3");
+    SCP_REQUIRE(n_frames > 0 && n_jobs > 0, "scp_octree_plan: empty batch");
+    SCP_REQUIRE(mode >= 0 && mode <= 2, "scp_octree_plan: bad mode %d", mode);
+    cudaStream_t st = as_stream(stream);
+    t->planned = t->emitted = false;
+    t->mode = mode; t->n_jobs = n_jobs;
+    if (!t->ev_ok) { for (auto& e : t->ev) SCP_CUDA(cudaEventCreate(&e)); t->ev_ok = true; }
+
+    std::vector<long long> fcount(n_frames), fbegin(n_frames);
+    for (int f = 0; f < n_frames; ++f) {
+        fbegin[f] = h_frame_offsets[f];
+        fcount[f] = h_frame_offsets[f + 1] - h_frame_offsets[f];
+        SCP_REQUIRE(fcount[f] > 0 && fcount[f] < (1ll << 30), "scp_octree_plan: frame %d has %lld points", f, fcount[f]);
+    }
+    t->hjobs.assign(n_jobs, JobDev{});
+    std::vector<long long> jcount(n_jobs);
+    long long kb = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const scp_job& s = h_jobs[j];
+        SCP_REQUIRE(s.frame >= 0 && s.frame < n_frames, "scp_octree_plan: job %d frame out of range", j);
+        SCP_REQUIRE(s.path_len >= 0 && s.path_len <= 8, "scp_octree_plan: job %d path_len", j);
+        SCP_REQUIRE(s.qs > 0, "scp_octree_plan: job %d qs must be > 0", j);
+        JobDev& J = t->hjobs[j];
+        J.frame = s.frame; J.path_len = s.path_len; J.path_bits = s.path_bits; J.drop_last = s.drop_last;
+        J.qs = s.qs; J.cart_offset = s.cart_offset; J.lidar_level = s.lidar_level; J.pos_eps_last = s.pos_eps_last;
+        J.pt_begin = fbegin[s.frame]; J.n_points = (int)fcount[s.frame]; J.key_begin = kb;
+        jcount[j] = fcount[s.frame];
+        kb += fcount[s.frame];
+    }
+    t->total_keys = kb;
+
+    std::vector<Tile> ftiles;
+    std::vector<int> jtb;
+    build_tiles(fcount, TILE, ftiles, nullptr);
+    build_tiles(jcount, TILE, t->h_tiles_pts, &jtb);
+    build_tiles(jcount, SORT_TILE, t->h_tiles_sort, nullptr);
+    const int nt_f = (int)ftiles.size(), nt_p = (int)t->h_tiles_pts.size(), nt_s = (int)t->h_tiles_sort.size();
+
+    if (int e = t->keys_a.reserve(kb * 8)) return e;
+    if (int e = t->keys_b.reserve(kb * 8)) return e;
+    if (int e = t->tiles_pts.reserve((size_t)(nt_f + nt_p) * sizeof(Tile))) return e;
+    if (int e = t->tiles_sort.reserve((size_t)nt_s * sizeof(Tile))) return e;
+    if (int e = t->frames.reserve((size_t)n_frames * sizeof(FrameDev))) return e;
+    if (int e = t->frame_begin.reserve((size_t)n_frames * 8)) return e;
+    if (int e = t->jobs.reserve((size_t)n_jobs * sizeof(JobDev))) return e;
+    if (int e = t->tile_hist.reserve((size_t)nt_p * NBINS * 4)) return e;
+    if (int e = t->job_tile_begin.reserve((size_t)(n_jobs + 1) * 4)) return e;
+    Tile* d_ftiles = t->tiles_pts.as<Tile>();
+    t->nt_frame = nt_f;
+    Tile* d_ptiles = d_ftiles + nt_f;
+    SCP_CUDA(cudaMemcpyAsync(d_ftiles, ftiles.data(), nt_f * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    SCP_CUDA(cudaMemcpyAsync(d_ptiles, t->h_tiles_pts.data(), nt_p * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    SCP_CUDA(cudaMemcpyAsync(t->tiles_sort.p, t->h_tiles_sort.data(), nt_s * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    SCP_CUDA(cudaMemcpyAsync(t->frame_begin.p, fbegin.data(), n_frames * 8, cudaMemcpyHostToDevice, st));
+    SCP_CUDA(cudaMemcpyAsync(t->jobs.p, t->hjobs.data(), n_jobs * sizeof(JobDev), cudaMemcpyHostToDevice, st));
+    SCP_CUDA(cudaMemcpyAsync(t->job_tile_begin.p, jtb.data(), (n_jobs + 1) * 4, cudaMemcpyHostToDevice, st));
+    JobDev* d_jobs = t->jobs.as<JobDev>();
+
+    SCP_CUDA(cudaEventRecord(t->ev[0], st));
+    if (mode != SCP_MODE_CART) {
+        k_init_frames<<<(int)cdiv(n_frames, 256), 256, 0, st>>>(t->frames.as<FrameDev>(), n_frames);
+        SCP_LAUNCHED();
+        k_frame_stats<<<nt_f, TPB, 0, st>>>(d_xyz, point_stride, d_ftiles, t->frame_begin.as<long long>(),
+                                            t->frames.as<FrameDev>(), mode);
+        SCP_LAUNCHED();
+    }
+    k_job_setup<<<(int)cdiv(n_jobs, 128), 128, 0, st>>>(d_jobs, n_jobs, t->frames.as<FrameDev>(), mode);
+    SCP_LAUNCHED();
+    k_quantise_keys<<<nt_p, TPB, 0, st>>>(d_xyz, point_stride, d_ptiles, d_jobs, t->keys_a.as<u64>(), mode);
+    SCP_LAUNCHED();
+    k_job_depth<<<(int)cdiv(n_jobs, 128), 128, 0, st>>>(d_jobs, n_jobs);
+    SCP_LAUNCHED();
+    SCP_CUDA(cudaEventRecord(t->ev[1], st));
+    SCP_CUDA(cudaMemcpyAsync(t->hjobs.data(), d_jobs, n_jobs * sizeof(JobDev), cudaMemcpyDeviceToHost, st));
+    SCP_CUDA(cudaStreamSynchronize(st));
+    int max_depth = 0, any_filter = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        if (t->hjobs[j].overflow) { set_error("job %d: quantised coordinate outside [0, 2^21)", j); return SCP_ERR_RANGE; }
+        max_depth = std::max(max_depth, t->hjobs[j].depth);
+        any_filter |= t->hjobs[j].path_len > 0;
+    }
+    SCP_REQUIRE(max_depth >= 1 && max_depth <= MAXL, "octree depth %d outside [1,%d]", max_depth, MAXL);
+    t->P = (3 * max_depth + 1 + 7) / 8;
+    if (int e = run_sort(t->keys_a.as<u64>(), t->keys_b.as<u64>(), t->tiles_sort.as<Tile>(), nt_s, d_jobs, n_jobs, t->P,
+                         any_filter, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
+    SCP_CUDA(cudaEventRecord(t->ev[2], st));
+    k_head_hist<<<nt_p, TPB, 0, st>>>(t->sorted, d_ptiles, d_jobs, t->tile_hist.as<u32>());
+    SCP_LAUNCHED();
+    k_level_scan<<<n_jobs, 32, 0, st>>>(d_jobs, n_jobs, t->job_tile_begin.as<int>(), t->tile_hist.as<u32>());
+    SCP_LAUNCHED();
+    k_job_offsets<<<1, 32, 0, st>>>(d_jobs, n_jobs);
+    SCP_LAUNCHED();
+    SCP_CUDA(cudaEventRecord(t->ev[3], st));
+    u32 err = 0;
+    SCP_CUDA(cudaMemcpyAsync(t->hjobs.data(), d_jobs, n_jobs * sizeof(JobDev), cudaMemcpyDeviceToHost, st));
+    SCP_CUDA(cudaMemcpyAsync(&err, t->misc.p, 4, cudaMemcpyDeviceToHost, st));
+    SCP_CUDA(cudaStreamSynchronize(st));
+    if (err) { set_error("radix sort look-back timed out"); return SCP_ERR_INTERNAL; }
+    t->total_nodes = t->total_rows = t->total_vox = 0;
+    std::vector<long long> ncount(n_jobs);
+    for (int j = 0; j < n_jobs; ++j) {
+        t->total_nodes += t->hjobs[j].n_nodes; t->total_rows += t->hjobs[j].n_rows; t->total_vox += t->hjobs[j].n_voxels;
+        ncount[j] = t->hjobs[j].n_nodes;
+    }
+    build_tiles(ncount, TILE, t->h_tiles_node, nullptr);
+    t->planned = true;
+    return SCP_OK;
+}
+
+int scp_octree_job_info(const scp_octree* t, int job, scp_job_info* out) {
+    SCP_REQUIRE(t && out && t->planned, "scp_octree_job_info: plan first");
+    SCP_REQUIRE(job >= 0 && job < t->n_jobs, "scp_octree_job_info: job out of range");
+    const JobDev& J = t->hjobs[job];
+    memset(out, 0, sizeof(*out));
+    out->depth = J.depth; out->n_points = J.n_points; out->n_voxels = J.n_voxels; out->n_rows = J.n_rows;
+    out->row_start = J.row_start; out->voxel_start = J.vox_start;
+    for (int l = 0; l < MAXL; ++l) {
+        int c = J.level_count[l];
+        if (J.drop_last && l == J.depth - 1 && c > 0) c -= 1;
+        out->level_rows[l] = c;
+        out->pos_min[l] = J.pos_min[l] == 0xffffffffu ? 0 : (int64_t)J.pos_min[l];
+        out->pos_max[l] = (int64_t)J.pos_max[l];
+    }
+    out->bin_num = J.bin_num;
+    for (int c = 0; c < 3; ++c) { out->steps[c] = J.step[c]; out->offset[c] = J.off[c]; }
+    return SCP_OK;
+}
+
+int64_t scp_octree_total_rows(const scp_octree* t) { return t && t->planned ? t->total_rows : -1; }
+int64_t scp_octree_total_voxels(const scp_octree* t) { return t && t->planned ? t->total_vox : -1; }
+
+int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
+    SCP_REQUIRE(t && d_out && t->planned, "scp_octree_emit: plan first");
+    cudaStream_t st = as_stream(stream);
+    const long long N = t->total_nodes + 1;
+    if (int e = t->n_level.reserve(N)) return e;
+    if (int e = t->n_octant.reserve(N)) return e;
+    if (int e = t->n_occ.reserve(N)) return e;
+    if (int e = t->n_parent.reserve(N * 4)) return e;
+    if (int e = t->n_pos.reserve(N * 12)) return e;
+    if (int e = t->n_fc.reserve(N * 4)) return e;
+    u64* vox = reinterpret_cast<u64*>(d_out->voxel_key);
+    if (!vox) { if (int e = t->vox.reserve((t->total_vox + 1) * 8)) return e; vox = t->vox.as<u64>(); }
+    const int nt_n = (int)t->h_tiles_node.size(), nt_p = (int)t->h_tiles_pts.size();
+    if (int e = t->tiles_node.reserve((size_t)(nt_n + 1) * sizeof(Tile))) return e;
+    SCP_CUDA(cudaMemcpyAsync(t->tiles_node.p, t->h_tiles_node.data(), nt_n * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    NodeArrays A{t->n_level.as<uint8_t>(), t->n_octant.as<uint8_t>(), t->n_occ.as<uint8_t>(), t->n_parent.as<u32>(),
+                 t->n_pos.as<u32>(), t->n_fc.as<u32>()};
+    JobDev* d_jobs = t->jobs.as<JobDev>();
+    Tile* d_ptiles = t->tiles_pts.as<Tile>() + t->nt_frame;   // point tiles live behind the frame tiles
+    SCP_CUDA(cudaEventRecord(t->ev[4], st));
+    k_emit_nodes<<<nt_p, TPB, 0, st>>>(t->sorted, d_ptiles, d_jobs, t->tile_hist.as<u32>(), A, vox);
+    SCP_LAUNCHED();
+    SCP_CUDA(cudaEventRecord(t->ev[5], st));
+    if (nt_n) {
+        k_occupancy<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, vox);
+        SCP_LAUNCHED();
+    }
+    SCP_CUDA(cudaEventRecord(t->ev[6], st));
+    if (nt_n) {
+        k_context<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
+        SCP_LAUNCHED();
+    }
+    SCP_CUDA(cudaEventRecord(t->ev[7], st));
+    t->emitted = true;
+    return SCP_OK;
+}
+
+int scp_octree_finish(scp_octree* t, void* stream) {
+    SCP_REQUIRE(t && t->emitted, "scp_octree_finish: emit first");
+    cudaStream_t st = as_stream(stream);
+    SCP_CUDA(cudaMemcpyAsync(t->hjobs.data(), t->jobs.p, t->n_jobs * sizeof(JobDev), cudaMemcpyDeviceToHost, st));
+    SCP_CUDA(cudaStreamSynchronize(st));
+    return SCP_OK;
+}
+
+int scp_octree_stage_ms(scp_octree* t, float out[6]) {
+    SCP_REQUIRE(t && t->emitted, "scp_octree_stage_ms: emit first");
+    SCP_CUDA(cudaEventSynchronize(t->ev[7]));
+    const int a[6] = {0, 1, 2, 4, 5, 6}, b[6] = {1, 2, 3, 5, 6, 7};
+    for (int i = 0; i < 6; ++i) SCP_CUDA(cudaEventElapsedTime(&out[i], t->ev[a[i]], t->ev[b[i]]));
+    return SCP_OK;
+}
+
+int scp_segmented_sort_u64(uint64_t* d_keys, uint64_t* d_tmp, const int64_t* h_seg_offsets, int n_seg, int key_bits,
+                           void* stream) {
+    SCP_REQUIRE(d_keys && d_tmp && h_seg_offsets && n_seg > 0, "scp_segmented_sort_u64: bad argument");
+    SCP_REQUIRE(key_bits > 0 && key_bits <= 64, "scp_segmented_sort_u64: key_bits");
+    cudaStream_t st = as_stream(stream);
+    std::vector<JobDev> jobs(n_seg, JobDev{});
+    std::vector<long long> cnt(n_seg);
+    for (int j = 0; j < n_seg; ++j) {
+        jobs[j].key_begin = h_seg_offsets[j];
+        cnt[j] = h_seg_offsets[j + 1] - h_seg_offsets[j];
+        jobs[j].n_points = (int)cnt[j];
+    }
+    std::vector<Tile> tiles;
+    build_tiles(cnt, SORT_TILE, tiles, nullptr);
+    DevBuf dj, dt, hist, desc, misc;
+    int rc = SCP_OK;
+    u64* res = nullptr;
+    const int P = (key_bits + 7) / 8;
+    do {
+        if ((rc = dj.reserve(n_seg * sizeof(JobDev)))) break;
+        if ((rc = dt.reserve((tiles.size() + 1) * sizeof(Tile)))) break;
+        if (cudaMemcpyAsync(dj.p, jobs.data(), n_seg * sizeof(JobDev), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(dt.p, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            set_error("scp_segmented_sort_u64: upload failed"); rc = SCP_ERR_CUDA; break;
+        }
+        rc = run_sort((u64*)d_keys, (u64*)d_tmp, dt.as<Tile>(), (int)tiles.size(), dj.as<JobDev>(), n_seg, P, 0, hist, desc,
+                      misc, st, &res);
+        if (rc) break;
+        long long total = h_seg_offsets[n_seg] - h_seg_offsets[0];
+        if (res != (u64*)d_keys &&
+            cudaMemcpyAsync(d_keys + h_seg_offsets[0], res + h_seg_offsets[0], total * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            set_error("scp_segmented_sort_u64: copy back failed"); rc = SCP_ERR_CUDA; break;
+        }
+        u32 err = 0;
+        if (cudaMemcpyAsync(&err, misc.p, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { set_error("scp_segmented_sort_u64: sync failed"); rc = SCP_ERR_CUDA; break; }
+        if (err) { set_error("radix sort look-back timed out"); rc = SCP_ERR_INTERNAL; }
+    } while (0);
+    cudaStreamSynchronize(st);
+    dj.release(); dt.release(); hist.release(); desc.release(); misc.release();
+    return rc;
+}
+
+}  // extern "C"
