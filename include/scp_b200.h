@@ -161,7 +161,15 @@ int64_t scp_range_encode_cdf(const uint16_t* h_cdf, const int16_t* h_sym, int64_
 
 /* ------------------------------------------------------------------------------------------
  * Entropy-model operators (A8-A12).  Device pointers, float32 activations, row-major [tokens, channels].
+ * Windows of ANY length are processed together as one ragged batch: a `scp_seqs` describes how the token
+ * stream is cut into sequences (one per context window of encode.py:112-115).
  * ---------------------------------------------------------------------------------------- */
+typedef struct scp_seqs scp_seqs;
+/* h_offsets[n_seq+1]: token ranges of the sequences (host). Uploads the tables the kernels need. */
+scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq);
+void      scp_seqs_destroy(scp_seqs* s);
+int64_t   scp_seqs_total(const scp_seqs* s);
+
 #define SCP_ACT_NONE 0
 #define SCP_ACT_LEAKY001 1   /* nn.LeakyReLU() default slope 0.01 (ehem.py:36, dgcnn.py:94) */
 #define SCP_ACT_GELU 2       /* exact erf GELU (swin_transformer.py:561, HF ACT2FN["gelu"]) */
@@ -171,76 +179,77 @@ int64_t scp_range_encode_cdf(const uint16_t* h_cdf, const int16_t* h_sym, int64_
 #define SCP_GEMM_SIMT 1      /* fp32 FFMA tiles */
 #define SCP_GEMM_TF32 2      /* tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators */
 
-/* y[M,N] = act( x[M,K(lda)] @ W[N,K]^T + bias[N] ) (+ residual[M,N(ldr)])   -- nn.Linear (+fused epilogue).
- * bias, residual may be NULL.  ldx/ldy/ldr = row strides in floats. */
+/* y[M,N] = act( x[M,K] @ W[N,K]^T + bias[N] ) (+ residual[M,N])   -- nn.Linear with fused epilogue.
+ * bias, residual may be NULL.  ldx/ldy/ldr = row strides in floats (W is dense [N,K]). */
 int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_bias,
                const float* d_res, int64_t ldr, float* d_y, int64_t ldy,
                int64_t M, int N, int K, int act, int engine, void* stream);
+/* 1 if the tcgen05 engine can take this shape (alignment rules in DESIGN.md). */
+int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K);
 
-/* LayerNorm over the last dim (eps 1e-5): swin_transformer.py:591-593, attention_model.py:105-106. */
-int scp_layernorm(const float* d_x, int64_t ldx, const float* d_gamma, const float* d_beta,
-                  float* d_y, int64_t ldy, int64_t M, int C, float eps, void* stream);
+/* LayerNorm over the last dim: swin_transformer.py:591-593,340, attention_model.py:105-106.
+ * Optional fused residual: y = LN(x + res) (attention_model.py:114-116). */
+int scp_layernorm(const float* d_x, int64_t ldx, const float* d_res, int64_t ldr, const float* d_gamma,
+                  const float* d_beta, float* d_y, int64_t ldy, int64_t M, int C, float eps, void* stream);
 
 /* EHEM token embedding (dgcnn.py:122-129): ctx bytes [n,4,3] (level,octant,occ) -> [n,80]
- * = [occ_enc(occ of 3 ancestors) 48 | level_enc(4) 16 | octant_enc(4) 16]. */
+ * = [occ_enc(occ of the 3 ancestors) 48 | level_enc(4) 16 | octant_enc(4) 16]. */
 int scp_ehem_embed(const uint8_t* d_ctx, int64_t n, const float* d_occ_enc, const float* d_level_enc,
-                   const float* d_octant_enc, float* d_out, int64_t ldo, void* stream);
+                   int n_level_rows, const float* d_octant_enc, float* d_out, int64_t ldo, void* stream);
+/* occ_enc rows for pre_occ (dgcnn.py:153): out[i,:16] = occ_enc[ctx[2*i][3].occ]  (even tokens). */
+int scp_ehem_embed_occ(const uint8_t* d_ctx, int64_t n_even, const float* d_occ_enc, float* d_out, int64_t ldo,
+                       void* stream);
 
-/* kNN (dgcnn.py:10-28): for every point i of each of `n_win` independent windows the k nearest points
- * (largest -||xi-xj||^2, self included) of the same window.  x [total, d] (ldx), window w covers rows
- * [h_win_offsets[w], h_win_offsets[w+1]).  idx [total, k] int32 (window-local indices, ascending distance;
- * ties -> lower index first). */
-int scp_knn(const float* d_x, int64_t ldx, int d, const int64_t* h_win_offsets, int n_win, int k,
-            int32_t* d_idx, void* stream);
+/* kNN (dgcnn.py:10-28): for every point the k nearest points (largest 2 xi.xj - |xj|^2 - |xi|^2, self
+ * included) inside its own sequence.  x [total, d] (ldx).  idx [total, k] int32, GLOBAL row indices,
+ * descending score; ties -> lower index first; sequences shorter than k repeat the point itself. */
+int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, int32_t* d_idx, void* stream);
 
 /* Edge convolution (dgcnn.py:48-71 get_graph_feature + :79-87 conv/BN/LeakyReLU(0.2) + :134 max over k),
- * evaluated as  max_k f(Wa x_nbr + (Wb-Wa) x_i) :  uv [total, 2*C] = x @ [Wa; Wb-Wa]^T computed by
- * scp_linear, then this gather:  out[i,c] = lrelu02( s[c]*(sel_k uv[nbr_k, c] + uv[i, C+c]) + t[c] ),
- * sel = max if s[c] >= 0 else min (BatchNorm eval affine s,t). */
-int scp_edge_gather_max(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k,
-                        const int64_t* h_win_offsets, int n_win,
-                        const float* d_bn_scale, const float* d_bn_shift,
-                        float* d_out, int64_t ldo, void* stream);
+ * evaluated as max_k f(Wa x_nbr + (Wb-Wa) x_i):  uv [total, 2C] = x @ [Wa; Wb-Wa]^T comes from scp_linear,
+ * then out[i,c] = lrelu02( s[c]*(sel_k uv[nbr_k, c] + uv[i, C+c]) + t[c] ), sel = max if s[c] >= 0 else min
+ * (BatchNorm eval folded to s,t; monotone so the max commutes exactly). */
+int scp_edge_gather_max(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k, int64_t n,
+                        const float* d_bn_scale, const float* d_bn_shift, float* d_out, int64_t ldo, void* stream);
 
-/* 1-D shifted-window attention (swin_transformer.py:406-501 + :603-652,:684-697).
- * q,k,v: [n_seq * S, C] with C = heads*64, sequences of S tokens each padded (by the caller, zeros after
- * LayerNorm) to Sp = ceil(S/512)*512 logical tokens; shift = 0 or 256 (roll by -shift before windowing and
- * back afterwards); rel-pos bias table [1023, heads]; shift mask -100 on the last window (:603-623).
- * Rows >= S of the padded sequence are the Linear biases (q_bias/k_bias/v_bias [C]), exactly what the
- * reference computes for zero-padded tokens.  out [n_seq*S, C]. */
-int scp_swin_attention(const float* d_q, const float* d_k, const float* d_v, int64_t ld,
-                       const float* d_qb, const float* d_kb, const float* d_vb,
-                       const float* d_relpos, int heads, int n_seq, int S, int shift,
-                       float* d_out, int64_t ldo, void* stream);
+/* 1-D shifted-window attention (swin_transformer.py:406-501 + :603-652,:684-697), heads x 64.
+ * q [total, *] (ldq) queries, kv-side k,v [total, *] (ldk, ldv): projected tokens of every sequence.  Each
+ * sequence of S tokens is logically zero-padded AFTER LayerNorm to Sp = ceil(S/512)*512 tokens, so padded
+ * tokens carry exactly the Linear biases qb/kb/vb [heads*64] (what the reference computes); shift = 0 or 256
+ * rolls by -shift before windowing and back afterwards; bias = relpos[(i-j)+511, head]; -100 shift mask on the
+ * last window (:603-623).  out [total, heads*64] (ldo). */
+int scp_swin_attention(const float* d_q, int64_t ldq, const float* d_k, int64_t ldk, const float* d_v, int64_t ldv,
+                       const float* d_qb, const float* d_kb, const float* d_vb, const float* d_relpos, int heads,
+                       const scp_seqs* seqs, int shift, float* d_out, int64_t ldo, void* stream);
 
-/* Patch merging input (swin_transformer.py:350-362): out[j] = [x[2j], x[2j+1]] (zero if 2j+1 >= S), j < ceil(S/2). */
-int scp_pair_concat(const float* d_x, int64_t ldx, int n_seq, int S, int C, float* d_out, int64_t ldo, void* stream);
+/* Patch merging input (swin_transformer.py:350-362): per sequence, out[j] = [x[2j], x[2j+1]] (zeros if 2j+1 >= S),
+ * j < ceil(S/2).  `dst` describes the halved sequences. */
+int scp_pair_concat(const float* d_x, int64_t ldx, const scp_seqs* src, const scp_seqs* dst, int C,
+                    float* d_out, int64_t ldo, void* stream);
 
-/* out[i, col_off : col_off+C] = src[min(i >> shift, S_src-1)...]: nearest x2^shift upsample used by
- * EHEM.concat_states (ehem.py:72-86). */
-int scp_upsample_cols(const float* d_src, int64_t lds, int n_seq, int S_src, int S_dst, int shift, int C,
+/* EHEM.concat_states (ehem.py:72-86): out[t, col_off:col_off+C] = x[seq_start_src + ((t - seq_start_dst) >> shift)]
+ * (nearest x2^shift upsample of a coarser stage, cropped). */
+int scp_upsample_cols(const float* d_src, int64_t lds, const scp_seqs* src, const scp_seqs* dst, int shift, int C,
                       float* d_out, int64_t ldo, int col_off, void* stream);
 
-/* Strided row copy: out[i, col_off:col_off+C] = src[i*row_step + row_off, :C]  (even/odd token split, concat). */
+/* Strided row copy: out[i, col_off:col_off+C] = src[i*row_step + row_off, :C], i < rows (even/odd split, concat). */
 int scp_copy_cols(const float* d_src, int64_t lds, int64_t row_step, int64_t row_off, int64_t rows, int C,
                   float* d_out, int64_t ldo, int col_off, void* stream);
 
-/* OctAttention embedding (oct_attention.py:52-79,85-99 + attention_model.py:20-22): writes both streams
- * embed / embed_unknown [n_win*S, 600] incl. *sqrt(600) and the sinusoidal PE. ctx bytes are (level,octant,occ). */
-int scp_octattn_embed(const uint8_t* d_ctx, const uint32_t* d_ctx_pos, float pos_scale, int level_cap_base,
-                      int max_octree_level, int64_t n_tokens, int S,
+/* OctAttention embedding (oct_attention.py:52-79,85-99 + attention_model.py:20-22): both streams
+ * embed / embed_unknown [n, 600] incl. *sqrt(600) and the sinusoidal PE (row = position inside the sequence).
+ * ctx bytes are (level,octant,occ); ctx_pos u32 [n,4,3]; pos_scale = 1/2^max_level (encode_dataset.py:48). */
+int scp_octattn_embed(const uint8_t* d_ctx, const uint32_t* d_ctx_pos, float pos_scale, int level_base,
+                      int max_octree_level, const scp_seqs* seqs,
                       const float* d_occ_enc, const float* d_level_enc, const float* d_octant_enc,
                       const float* d_pos_w, const float* d_pos_b, const float* d_pe,
                       float* d_embed, float* d_embed_unknown, void* stream);
 
-/* Two-stream causal attention of OctAttention (attention_model.py:58-95), heads x 150.
- * q_u,k,k_u,v,v_u: [n_win*S, 600]; out, out_u likewise. */
+/* Two-stream causal attention of OctAttention (attention_model.py:58-95), heads x head_dim (4 x 150).
+ * qu,k,ku,v,vu: [total, heads*head_dim] with row stride ld; out, out_u likewise (ldo). */
 int scp_octattn_attention(const float* d_qu, const float* d_k, const float* d_ku, const float* d_v,
-                          const float* d_vu, int heads, int head_dim, int n_win, int S,
-                          float* d_out, float* d_out_u, void* stream);
-
-/* y = x + r (elementwise), used for residuals that are not fused. */
-int scp_add(const float* d_a, const float* d_b, float* d_y, int64_t n, void* stream);
+                          const float* d_vu, int64_t ld, int heads, int head_dim, const scp_seqs* seqs,
+                          float* d_out, float* d_out_u, int64_t ldo, void* stream);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t scp_launch_count(void);
