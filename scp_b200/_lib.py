@@ -71,17 +71,22 @@ SIGNATURES = {
     "scp_pmf_to_cdf": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scp_range_encode": (_i64, [_vp, _i64, _vp, _i64]),
     "scp_range_encode_cdf": (_i64, [_vp, _vp, _i64, _i, _vp, _i64]),
+    "scp_seqs_create": (_vp, [C.POINTER(_i64), _i]),
+    "scp_seqs_destroy": (None, [_vp]),
+    "scp_seqs_total": (_i64, [_vp]),
     "scp_linear": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp]),
-    "scp_layernorm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _f, _vp]),
-    "scp_ehem_embed": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "scp_knn": (_i, [_vp, _i64, _i, C.POINTER(_i64), _i, _i, _vp, _vp]),
-    "scp_edge_gather_max": (_i, [_vp, _i64, _i, _vp, _i, C.POINTER(_i64), _i, _vp, _vp, _vp, _i64, _vp]),
-    "scp_swin_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
-    "scp_pair_concat": (_i, [_vp, _i64, _i, _i, _i, _vp, _i64, _vp]),
-    "scp_upsample_cols": (_i, [_vp, _i64, _i, _i, _i, _i, _i, _vp, _i64, _i, _vp]),
+    "scp_linear_tf32_supported": (_i, [_i64, _i64, _i64, _i, _i]),
+    "scp_layernorm": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _f, _vp]),
+    "scp_ehem_embed": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp]),
+    "scp_ehem_embed_occ": (_i, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    "scp_knn": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp]),
+    "scp_edge_gather_max": (_i, [_vp, _i64, _i, _vp, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "scp_swin_attention": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i64, _vp]),
+    "scp_pair_concat": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _i64, _vp]),
+    "scp_upsample_cols": (_i, [_vp, _i64, _vp, _vp, _i, _i, _vp, _i64, _i, _vp]),
     "scp_copy_cols": (_i, [_vp, _i64, _i64, _i64, _i64, _i, _vp, _i64, _i, _vp]),
-    "scp_octattn_embed": (_i, [_vp, _vp, _f, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "scp_octattn_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "scp_octattn_embed": (_i, [_vp, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "scp_octattn_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "scp_add": (_i, [_vp, _vp, _vp, _i64, _vp]),
 }
 

@@ -1,0 +1,871 @@
+// Entropy-model operators, fp32 SIMT engine.
+// Everything here is hand-written CUDA; the tcgen05/TMEM/TMA GEMM lives in gemm_tc.cu.
+//
+// Reference behaviour reproduced (paths in luoao-kddi/SCP): models/dgcnn.py:10-154,
+// models/swin_transformer.py:322-367,406-501,583-706, models/ehem.py:72-136,
+// models/oct_attention.py:48-99, models/attention_model.py:6-155.
+#include <vector>
+#include <algorithm>
+#include <math.h>
+#include "common.cuh"
+
+struct scp_seqs {
+    int n_seq = 0;
+    long long total = 0;
+    std::vector<long long> h_off;
+    long long* d_off = nullptr;     // [n_seq+1]
+    int n_win = 0;                  // 512-token attention windows over all (padded) sequences
+    int* d_win_seq = nullptr;       // [n_win]
+    int* d_win_idx = nullptr;       // [n_win] window index inside its sequence
+    int n_tile = 0;                 // 64-token tiles over all sequences
+    int* d_tile_seq = nullptr;      // [n_tile]
+    int* d_tile_start = nullptr;    // [n_tile] first token of the tile inside its sequence
+};
+
+namespace scp {
+
+int linear_tf32(const float* x, long long ldx, const float* w, const float* bias, const float* res, long long ldr,
+                float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st);   // gemm_tc.cu
+bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, const void* x, const void* w, const void* y);
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case SCP_ACT_LEAKY001: return v > 0.f ? v : 0.01f * v;
+        case SCP_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        case SCP_ACT_RELU: return v > 0.f ? v : 0.f;
+        default: return v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 GEMM  Y[M,N] = act(X[M,K] W[N,K]^T + b) (+ R)
+// ------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) k_linear_simt(const float* __restrict__ X, long long ldx,
+                                                      const float* __restrict__ W, const float* __restrict__ bias,
+                                                      const float* __restrict__ R, long long ldr, float* __restrict__ Y,
+                                                      long long ldy, long long M, int N, int K, int act, int vec4) {
+    constexpr int BK = 16;
+    static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+    __shared__ __align__(16) float Xs[BK][BM + 4];
+    __shared__ __align__(16) float Ws[BK][BN + 4];
+    const int t = threadIdx.x;
+    const long long m0 = (long long)blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+    const int ty = t / (BN / TN), tx = t % (BN / TN);
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        if (vec4) {
+            for (int e = t; e < BM * 4; e += 256) {
+                int r = e >> 2, kq = (e & 3) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m0 + r < M && k0 + kq < K) v = *reinterpret_cast<const float4*>(X + (m0 + r) * ldx + k0 + kq);
+                Xs[kq][r] = v.x; Xs[kq + 1][r] = v.y; Xs[kq + 2][r] = v.z; Xs[kq + 3][r] = v.w;
+            }
+            for (int e = t; e < BN * 4; e += 256) {
+                int r = e >> 2, kq = (e & 3) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n0 + r < N && k0 + kq < K) v = *reinterpret_cast<const float4*>(W + (long long)(n0 + r) * K + k0 + kq);
+                Ws[kq][r] = v.x; Ws[kq + 1][r] = v.y; Ws[kq + 2][r] = v.z; Ws[kq + 3][r] = v.w;
+            }
+        } else {
+            for (int e = t; e < BM * BK; e += 256) {
+                int r = e / BK, kk = e % BK;
+                Xs[kk][r] = (m0 + r < M && k0 + kk < K) ? X[(m0 + r) * ldx + k0 + kk] : 0.f;
+            }
+            for (int e = t; e < BN * BK; e += 256) {
+                int r = e / BK, kk = e % BK;
+                Ws[kk][r] = (n0 + r < N && k0 + kk < K) ? W[(long long)(n0 + r) * K + k0 + kk] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) *reinterpret_cast<float4*>(&a[i]) = *reinterpret_cast<const float4*>(&Xs[kk][ty * TM + i]);
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) *reinterpret_cast<float4*>(&b[j]) = *reinterpret_cast<const float4*>(&Ws[kk][tx * TN + j]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long m = m0 + ty * TM + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (bias) v += bias[n];
+            v = apply_act(v, act);
+            if (R) v += R[m * ldr + n];
+            Y[m * ldy + n] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm (optionally of x + res): one warp per row
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ X, long long ldx, const float* __restrict__ R,
+                                                    long long ldr, const float* __restrict__ g, const float* __restrict__ b,
+                                                    float* __restrict__ Y, long long ldy, long long M, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    constexpr int MAXP = 20;
+    float v[MAXP];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        int c = lane + 32 * i;
+        float x = 0.f;
+        if (c < C) { x = X[row * ldx + c]; if (R) x += R[row * ldr + c]; }
+        v[i] = x;
+        s += x;
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        int c = lane + 32 * i;
+        float dlt = c < C ? v[i] - mean : 0.f;
+        q += dlt * dlt;
+    }
+    const float rs = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        int c = lane + 32 * i;
+        if (c < C) Y[row * ldy + c] = (v[i] - mean) * rs * g[c] + b[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// EHEM embedding
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ehem_embed(const uint8_t* __restrict__ ctx, long long n,
+                                                     const float* __restrict__ occ_enc, const float* __restrict__ level_enc,
+                                                     int n_level_rows, const float* __restrict__ octant_enc,
+                                                     float* __restrict__ out, long long ldo) {
+    const long long total = n * 80;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long tok = e / 80;
+        const int c = (int)(e - tok * 80);
+        const uint8_t* cx = ctx + tok * 12;
+        float v;
+        if (c < 48) { int k = c >> 4; v = occ_enc[(int)cx[3 * k + 2] * 16 + (c & 15)]; }          // ancestors' occupancy
+        else if (c < 64) { int k = (c - 48) >> 2; int l = min((int)cx[3 * k], n_level_rows - 1); v = level_enc[l * 4 + (c & 3)]; }
+        else { int k = (c - 64) >> 2; int o = min((int)cx[3 * k + 1], 8); v = octant_enc[o * 4 + (c & 3)]; }
+        out[tok * ldo + c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ehem_embed_occ(const uint8_t* __restrict__ ctx, long long n_even,
+                                                         const float* __restrict__ occ_enc, float* __restrict__ out,
+                                                         long long ldo) {
+    const long long total = n_even * 16;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long i = e >> 4;
+        const int c = (int)(e & 15);
+        out[i * ldo + c] = occ_enc[(int)ctx[(2 * i) * 12 + 11] * 16 + c];       // data[:, ::2, -1, -1] (ehem.py:104)
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// kNN: scores 2 xi.xj - |xj|^2 - |xi|^2 by fp32 tiles + per-thread sorted top-k lists in shared memory
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_sqnorm(const float* __restrict__ X, long long ldx, int d, long long n,
+                                                     float* __restrict__ xx) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) { float v = X[row * ldx + c]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) xx[row] = s;
+}
+
+constexpr int KQ = 64, KC = 128, KD = 32;
+
+__global__ void __launch_bounds__(256) k_knn(const float* __restrict__ X, long long ldx, int d,
+                                              const float* __restrict__ xx, const long long* __restrict__ seq_off,
+                                              const int* __restrict__ tile_seq, const int* __restrict__ tile_start, int k,
+                                              int* __restrict__ idx_out) {
+    extern __shared__ __align__(16) float sm[];
+    float (*Qs)[KQ + 4] = reinterpret_cast<float (*)[KQ + 4]>(sm);                        // [KD][68]
+    float (*Cs)[KC + 4] = reinterpret_cast<float (*)[KC + 4]>(sm + KD * (KQ + 4));         // [KD][132]
+    float (*S)[KC + 1] = reinterpret_cast<float (*)[KC + 1]>(sm + KD * (KQ + 4) + KD * (KC + 4));   // [KQ][129]
+    float* ls = sm + KD * (KQ + 4) + KD * (KC + 4) + KQ * (KC + 1);                        // [k][256]
+    int* li = reinterpret_cast<int*>(ls + k * 256);                                        // [k][256]
+    const int t = threadIdx.x;
+    const int s = tile_seq[blockIdx.x];
+    const long long base = seq_off[s];
+    const int n = (int)(seq_off[s + 1] - base);
+    const int q0 = tile_start[blockIdx.x];
+    const int tq = t >> 4, tc = t & 15;
+    for (int j = 0; j < k; ++j) { ls[j * 256 + t] = -INFINITY; li[j * 256 + t] = -1; }
+    float thresh = -INFINITY;
+    const int myq = t >> 2, sub = t & 3;
+    for (int c0 = 0; c0 < n; c0 += KC) {
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int d0 = 0; d0 < d; d0 += KD) {
+            __syncthreads();
+            for (int e = t; e < KQ * KD; e += 256) {
+                int r = e >> 5, dd = e & 31;
+                Qs[dd][r] = (q0 + r < n && d0 + dd < d) ? X[(base + q0 + r) * ldx + d0 + dd] : 0.f;
+            }
+            for (int e = t; e < KC * KD; e += 256) {
+                int r = e >> 5, dd = e & 31;
+                Cs[dd][r] = (c0 + r < n && d0 + dd < d) ? X[(base + c0 + r) * ldx + d0 + dd] : 0.f;
+            }
+            __syncthreads();
+            const int dmax = min(KD, d - d0);
+            for (int dd = 0; dd < dmax; ++dd) {
+                float a[4], b[8];
+                *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&Qs[dd][tq * 4]);
+                *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&Cs[dd][tc * 8]);
+                *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(&Cs[dd][tc * 8 + 4]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = q0 + tq * 4 + i;
+            const float xq = q < n ? xx[base + q] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + tc * 8 + j;
+                float sc = -INFINITY;
+                if (q < n && c < n) sc = __fsub_rn(__fsub_rn(2.0f * acc[i][j], xx[base + c]), xq);   // dgcnn.py:18-20
+                S[tq * 4 + i][tc * 8 + j] = sc;
+            }
+        }
+        __syncthreads();
+        // every thread scans a quarter of its query's row and keeps a private sorted top-k
+        for (int c = sub; c < KC; c += 4) {
+            const float sc = S[myq][c];
+            if (sc > thresh) {
+                int j = k - 1;
+                while (j > 0 && ls[(j - 1) * 256 + t] < sc) {
+                    ls[j * 256 + t] = ls[(j - 1) * 256 + t];
+                    li[j * 256 + t] = li[(j - 1) * 256 + t];
+                    --j;
+                }
+                ls[j * 256 + t] = sc;
+                li[j * 256 + t] = c0 + c;
+                thresh = ls[(k - 1) * 256 + t];
+            }
+        }
+    }
+    __syncthreads();
+    if (sub == 0 && q0 + myq < n) {
+        // 4-way merge of the sorted partial lists (score desc, index asc)
+        int p[4] = {0, 0, 0, 0};
+        const long long row = base + q0 + myq;
+        for (int j = 0; j < k; ++j) {
+            int best = -1;
+            float bs = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int u = 0; u < 4; ++u) {
+                if (p[u] >= k) continue;
+                const float sc = ls[p[u] * 256 + t + u];
+                const int id = li[p[u] * 256 + t + u];
+                if (id < 0) continue;
+                if (sc > bs || (sc == bs && id < bi)) { bs = sc; bi = id; best = u; }
+            }
+            if (best < 0) { idx_out[row * k + j] = (int)row; continue; }     // sequence shorter than k: repeat self
+            ++p[best];
+            idx_out[row * k + j] = (int)(base + bi);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// edge conv gather: out = lrelu0.2( s * (sel_k uv[nbr] + uv_self[C:]) + t )
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_edge_gather(const float* __restrict__ uv, long long lduv, int C,
+                                                      const int* __restrict__ idx, int k, long long n,
+                                                      const float* __restrict__ bs, const float* __restrict__ bt,
+                                                      float* __restrict__ out, long long ldo) {
+    const int per = 256 / C;            // points per block iteration (C in {64,128,256})
+    const int c = threadIdx.x % C;
+    const int pl = threadIdx.x / C;
+    const float sc = bs[c], sh = bt[c];
+    for (long long p = (long long)blockIdx.x * per + pl; p < n; p += (long long)gridDim.x * per) {
+        float mx = -INFINITY, mn = INFINITY;
+        for (int j = 0; j < k; ++j) {
+            const int nb = idx[p * k + j];
+            const float u = uv[(long long)nb * lduv + c];
+            mx = fmaxf(mx, u); mn = fminf(mn, u);
+        }
+        const float sel = sc >= 0.f ? mx : mn;
+        float v = fmaf(sc, sel + uv[p * lduv + C + c], sh);
+        out[p * ldo + c] = v > 0.f ? v : 0.2f * v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// shifted-window attention, one block per (window, head, 64-query chunk), online softmax over 8 key tiles
+// ------------------------------------------------------------------------------------------
+constexpr int WS = 512, HD = 64, AQ = 64, AK = 64, ALD = 68;
+
+__global__ void __launch_bounds__(256) k_swin_attn(const float* __restrict__ Q, long long ldq, const float* __restrict__ K,
+                                                    long long ldk, const float* __restrict__ V, long long ldv,
+                                                    const float* __restrict__ qb, const float* __restrict__ kb,
+                                                    const float* __restrict__ vb, const float* __restrict__ relpos, int heads,
+                                                    const long long* __restrict__ seq_off, const int* __restrict__ win_seq,
+                                                    const int* __restrict__ win_idx, int shift, float* __restrict__ O,
+                                                    long long ldo) {
+    extern __shared__ __align__(16) float sm[];
+    float (*Qt)[ALD] = reinterpret_cast<float (*)[ALD]>(sm);                  // [d][q]
+    float (*Kt)[ALD] = reinterpret_cast<float (*)[ALD]>(sm + HD * ALD);       // [d][key]
+    float (*Vs)[ALD] = reinterpret_cast<float (*)[ALD]>(sm + 2 * HD * ALD);   // [key][d]
+    float (*Pt)[ALD] = reinterpret_cast<float (*)[ALD]>(sm + 3 * HD * ALD);   // [key][q]
+    __shared__ float s_bias[2 * WS];                                          // relpos[:, head], index (i-j)+511
+    const int t = threadIdx.x;
+    const int h = blockIdx.x % heads, qc = blockIdx.x / heads;
+    const int gw = blockIdx.y;
+    const int s = win_seq[gw], w = win_idx[gw];
+    const long long base = seq_off[s];
+    const int S = (int)(seq_off[s + 1] - base);
+    const int Sp = ((S + WS - 1) / WS) * WS;
+    const bool last_win = (w == Sp / WS - 1) && shift > 0;
+    for (int e = t; e < 2 * WS - 1; e += 256) s_bias[e] = relpos[e * heads + h];
+    // Q tile (scaled by 1/sqrt(64) = 0.125, exact)
+    for (int e = t; e < AQ * HD; e += 256) {
+        int r = e >> 6, dd = e & 63;
+        int u = (w * WS + qc * AQ + r + shift) % Sp;
+        float v = u < S ? Q[(base + u) * ldq + h * HD + dd] : qb[h * HD + dd];
+        Qt[dd][r] = v * 0.125f;
+    }
+    const int ty = t >> 4, tx = t & 15;
+    float o[4][4], m[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m[i] = -INFINITY; l[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    }
+    for (int kt = 0; kt < WS / AK; ++kt) {
+        __syncthreads();
+        for (int e = t; e < AK * HD; e += 256) {
+            int r = e >> 6, dd = e & 63;
+            int u = (w * WS + kt * AK + r + shift) % Sp;
+            float kv = u < S ? K[(base + u) * ldk + h * HD + dd] : kb[h * HD + dd];
+            float vv = u < S ? V[(base + u) * ldv + h * HD + dd] : vb[h * HD + dd];
+            Kt[dd][r] = kv;
+            Vs[r][dd] = vv;
+        }
+        __syncthreads();
+        float sc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sc[i][j] = 0.f;
+#pragma unroll 8
+        for (int dd = 0; dd < HD; ++dd) {
+            float a[4], b[4];
+            *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&Qt[dd][ty * 4]);
+            *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&Kt[dd][tx * 4]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sc[i][j] = fmaf(a[i], b[j], sc[i][j]);
+        }
+        float alpha[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pi = qc * AQ + ty * 4 + i;
+            float rmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int pj = kt * AK + tx * 4 + j;
+                float v = sc[i][j] + s_bias[pi - pj + WS - 1];
+                if (last_win && ((pi < WS / 2) != (pj < WS / 2))) v += -100.0f;     // swin_transformer.py:620
+                sc[i][j] = v;
+                rmax = fmaxf(rmax, v);
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, off));
+            const float mnew = fmaxf(m[i], rmax);
+            alpha[i] = expf(m[i] - mnew);
+            float rsum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sc[i][j] = expf(sc[i][j] - mnew); rsum += sc[i][j]; }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, off);
+            l[i] = l[i] * alpha[i] + rsum;
+            m[i] = mnew;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Pt[tx * 4 + j][ty * 4 + i] = sc[i][j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[i][j] *= alpha[i];
+#pragma unroll 8
+        for (int kk = 0; kk < AK; ++kk) {
+            float a[4], b[4];
+            *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&Pt[kk][ty * 4]);
+            *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&Vs[kk][tx * 4]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[i][j] = fmaf(a[i], b[j], o[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int u = (w * WS + qc * AQ + ty * 4 + i + shift) % Sp;
+        if (u >= S) continue;
+        const float inv = 1.0f / l[i];
+        float4 r = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+        *reinterpret_cast<float4*>(O + (base + u) * ldo + h * HD + tx * 4) = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// small data-movement kernels
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pair_concat(const float* __restrict__ X, long long ldx,
+                                                      const long long* __restrict__ soff, const long long* __restrict__ doff,
+                                                      const int* __restrict__ tile_seq, const int* __restrict__ tile_start,
+                                                      int C, float* __restrict__ out, long long ldo) {
+    const int s = tile_seq[blockIdx.x];
+    const int S = (int)(soff[s + 1] - soff[s]);
+    const int Sd = (int)(doff[s + 1] - doff[s]);
+    const int j0 = tile_start[blockIdx.x];
+    const int C4 = C >> 2;
+    for (int e = threadIdx.x; e < 64 * 2 * C4; e += 256) {
+        const int r = e / (2 * C4), c4 = e % (2 * C4);
+        const int j = j0 + r;
+        if (j >= Sd) break;
+        const int src = 2 * j + (c4 >= C4 ? 1 : 0);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src < S) v = *reinterpret_cast<const float4*>(X + (soff[s] + src) * ldx + (c4 % C4) * 4);
+        *reinterpret_cast<float4*>(out + (doff[s] + j) * ldo + c4 * 4) = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_upsample_cols(const float* __restrict__ X, long long ldx,
+                                                        const long long* __restrict__ soff, const long long* __restrict__ doff,
+                                                        const int* __restrict__ tile_seq, const int* __restrict__ tile_start,
+                                                        int shift, int C, float* __restrict__ out, long long ldo, int col_off) {
+    const int s = tile_seq[blockIdx.x];
+    const int Sd = (int)(doff[s + 1] - doff[s]);
+    const int j0 = tile_start[blockIdx.x];
+    const int C4 = C >> 2;
+    for (int e = threadIdx.x; e < 64 * C4; e += 256) {
+        const int r = e / C4, c4 = e % C4;
+        const int j = j0 + r;
+        if (j >= Sd) break;
+        const float4 v = *reinterpret_cast<const float4*>(X + (soff[s] + (j >> shift)) * ldx + c4 * 4);
+        *reinterpret_cast<float4*>(out + (doff[s] + j) * ldo + col_off + c4 * 4) = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_copy_cols(const float* __restrict__ X, long long ldx, long long row_step,
+                                                    long long row_off, long long rows, int C, float* __restrict__ out,
+                                                    long long ldo, int col_off) {
+    const long long total = rows * C;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long r = e / C;
+        const int c = (int)(e - r * C);
+        out[r * ldo + col_off + c] = X[(r * row_step + row_off) * ldx + c];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_add(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                              long long n) {
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) y[e] = a[e] + b[e];
+}
+
+// ------------------------------------------------------------------------------------------
+// OctAttention: embedding of both streams, and two-stream causal attention
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_octattn_embed(const uint8_t* __restrict__ ctx, const u32* __restrict__ ctx_pos,
+                                                        float pos_scale, int level_base, int max_lvl,
+                                                        const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
+                                                        const int* __restrict__ tile_start,
+                                                        const float* __restrict__ occ_enc, const float* __restrict__ level_enc,
+                                                        const float* __restrict__ octant_enc, const float* __restrict__ pw,
+                                                        const float* __restrict__ pb, const float* __restrict__ pe,
+                                                        float* __restrict__ E, float* __restrict__ EU) {
+    const int s = tile_seq[blockIdx.x];
+    const long long base = seq_off[s];
+    const int S = (int)(seq_off[s + 1] - base);
+    const int j0 = tile_start[blockIdx.x];
+    const float scale = sqrtf(600.0f);
+    for (int e = threadIdx.x; e < 64 * 600; e += 256) {
+        const int r = e / 600, c = e % 600;
+        const int j = j0 + r;
+        if (j >= S) break;
+        const long long tok = base + j;
+        const int k = c / 150, f = c % 150;
+        const uint8_t* cx = ctx + tok * 12 + 3 * k;
+        const int self_level = ctx[tok * 12 + 9];
+        const int sh = max(self_level - level_base, 0);                       // oct_attention.py:57-60
+        int lvl = min(max((int)cx[0] - sh, 0), max_lvl);                      // :61
+        float v, vu;
+        if (f < 128) { v = occ_enc[(int)cx[2] * 128 + f]; vu = (k == 3) ? occ_enc[255 * 128 + f] : v; }
+        else if (f < 134) { v = vu = level_enc[lvl * 6 + (f - 128)]; }
+        else if (f < 138) { v = vu = octant_enc[min((int)cx[1], 8) * 4 + (f - 134)]; }
+        else {
+            const int o = f - 138;
+            const u32* p = ctx_pos + tok * 12 + 3 * k;
+            const float x = (float)p[0] * pos_scale, y = (float)p[1] * pos_scale, z = (float)p[2] * pos_scale;
+            v = vu = pw[o * 3] * x + pw[o * 3 + 1] * y + pw[o * 3 + 2] * z + pb[o];
+        }
+        const float pos = pe[(long long)j * 600 + c];
+        E[tok * 600 + c] = v * scale + pos;
+        EU[tok * 600 + c] = vu * scale + pos;
+    }
+}
+
+// one warp per query row; keys in tiles of 32 staged in shared memory; both streams share the scores except
+// on the diagonal (attention_model.py:82-93)
+constexpr int OA_Q = 16, OA_K = 32, OA_LD = 151;
+__global__ void __launch_bounds__(128) k_octattn_attn(const float* __restrict__ QU, const float* __restrict__ K,
+                                                       const float* __restrict__ KU, const float* __restrict__ V,
+                                                       const float* __restrict__ VU, long long ld, int heads, int hd,
+                                                       const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
+                                                       const int* __restrict__ tile_start, float* __restrict__ O,
+                                                       float* __restrict__ OU, long long ldo) {
+    __shared__ float Ks[OA_K][OA_LD];
+    __shared__ float Vs[OA_K][OA_LD];
+    __shared__ float Qs[OA_Q][OA_LD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = blockIdx.y;
+    // 64-token tiles are split into 4 sub-tiles of 16 queries
+    const int tile = blockIdx.x >> 2, subt = blockIdx.x & 3;
+    const int s = tile_seq[tile];
+    const long long base = seq_off[s];
+    const int S = (int)(seq_off[s + 1] - base);
+    const int q0 = tile_start[tile] + subt * OA_Q;
+    if (q0 >= S) return;
+    const float inv = rsqrtf((float)hd);
+    for (int e = threadIdx.x; e < OA_Q * hd; e += 128) {
+        int r = e / hd, dd = e % hd;
+        Qs[r][dd] = q0 + r < S ? QU[(base + q0 + r) * ld + h * hd + dd] : 0.f;
+    }
+    float m[4], l[4], mu[4], lu[4], o[4][5], ou[4][5];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m[i] = mu[i] = -INFINITY; l[i] = lu[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) o[i][j] = ou[i][j] = 0.f;
+    }
+    const int qlast = min(q0 + OA_Q, S) - 1;
+    for (int k0 = 0; k0 <= qlast; k0 += OA_K) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < OA_K * hd; e += 128) {
+            int r = e / hd, dd = e % hd;
+            bool ok = k0 + r < S;
+            Ks[r][dd] = ok ? K[(base + k0 + r) * ld + h * hd + dd] : 0.f;
+            Vs[r][dd] = ok ? V[(base + k0 + r) * ld + h * hd + dd] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int qi = q0 + warp * 4 + i;
+            if (qi >= S || k0 > qi) continue;                      // warp-uniform
+            const float* qrow = Qs[warp * 4 + i];
+            const int kj = k0 + lane;
+            float sc = 0.f;
+            for (int dd = 0; dd < hd; ++dd) sc = fmaf(qrow[dd], Ks[lane][dd], sc);
+            sc *= inv;
+            float scu = sc;
+            const bool diag = (kj == qi);
+            if (diag) {                                             // unknown stream: own key/value have no occupancy
+                float z = 0.f;
+                for (int dd = 0; dd < hd; ++dd) z = fmaf(qrow[dd], KU[(base + qi) * ld + h * hd + dd], z);
+                scu = z * inv;
+            }
+            const bool ok = kj <= qi;                               // causal mask (oct_attention.py:38-46)
+            if (!ok) { sc = -INFINITY; scu = -INFINITY; }
+            const float tmax = warp_max(sc), tmaxu = warp_max(scu);
+            const float mn = fmaxf(m[i], tmax), mnu = fmaxf(mu[i], tmaxu);
+            const float a = expf(m[i] - mn), au = expf(mu[i] - mnu);
+            const float p = ok ? expf(sc - mn) : 0.f, pu = ok ? expf(scu - mnu) : 0.f;
+            l[i] = l[i] * a + warp_sum(p);
+            lu[i] = lu[i] * au + warp_sum(pu);
+            m[i] = mn; mu[i] = mnu;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { o[i][j] *= a; ou[i][j] *= au; }
+            for (int kk = 0; kk < OA_K; ++kk) {
+                const float pk = __shfl_sync(0xffffffffu, p, kk), pku = __shfl_sync(0xffffffffu, pu, kk);
+                if (pk == 0.f && pku == 0.f) continue;
+                const bool dg = (k0 + kk == qi);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int dd = lane + 32 * j;
+                    if (dd < hd) {
+                        const float vv = Vs[kk][dd];
+                        o[i][j] = fmaf(pk, vv, o[i][j]);
+                        const float vvu = dg ? VU[(base + qi) * ld + h * hd + dd] : vv;
+                        ou[i][j] = fmaf(pku, vvu, ou[i][j]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int qi = q0 + warp * 4 + i;
+        if (qi >= S) continue;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int dd = lane + 32 * j;
+            if (dd < hd) {
+                O[(base + qi) * ldo + h * hd + dd] = o[i][j] / l[i];
+                OU[(base + qi) * ldo + h * hd + dd] = ou[i][j] / lu[i];
+            }
+        }
+    }
+}
+
+static inline int grid_for(long long work, int per_block, int cap = 148 * 16) {
+    return (int)std::max<long long>(1, std::min<long long>(cdiv(work, per_block), cap));
+}
+
+}  // namespace scp
+
+using namespace scp;
+
+extern "C" {
+
+scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq) {
+    if (!h_offsets || n_seq <= 0) { set_error("scp_seqs_create: bad argument"); return nullptr; }
+    auto* s = new scp_seqs();
+    s->n_seq = n_seq;
+    s->h_off.assign(h_offsets, h_offsets + n_seq + 1);
+    s->total = h_offsets[n_seq] - h_offsets[0];
+    std::vector<int> wseq, widx, tseq, tstart;
+    for (int i = 0; i < n_seq; ++i) {
+        long long len = h_offsets[i + 1] - h_offsets[i];
+        if (len < 0 || len > (1 << 24)) { set_error("scp_seqs_create: sequence %d has length %lld", i, len); delete s; return nullptr; }
+        for (long long w = 0; w < cdiv(len, 512); ++w) { wseq.push_back(i); widx.push_back((int)w); }
+        for (long long t = 0; t < len; t += 64) { tseq.push_back(i); tstart.push_back((int)t); }
+    }
+    s->n_win = (int)wseq.size();
+    s->n_tile = (int)tseq.size();
+    bool ok = cudaMalloc((void**)&s->d_off, (n_seq + 1) * 8) == cudaSuccess &&
+              cudaMalloc((void**)&s->d_win_seq, std::max(1, s->n_win) * 4) == cudaSuccess &&
+              cudaMalloc((void**)&s->d_win_idx, std::max(1, s->n_win) * 4) == cudaSuccess &&
+              cudaMalloc((void**)&s->d_tile_seq, std::max(1, s->n_tile) * 4) == cudaSuccess &&
+              cudaMalloc((void**)&s->d_tile_start, std::max(1, s->n_tile) * 4) == cudaSuccess;
+    ok = ok && cudaMemcpy(s->d_off, s->h_off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && s->n_win) {
+        ok = cudaMemcpy(s->d_win_seq, wseq.data(), s->n_win * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(s->d_win_idx, widx.data(), s->n_win * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (ok && s->n_tile) {
+        ok = cudaMemcpy(s->d_tile_seq, tseq.data(), s->n_tile * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(s->d_tile_start, tstart.data(), s->n_tile * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) { set_error("scp_seqs_create: CUDA allocation/upload failed"); scp_seqs_destroy(s); return nullptr; }
+    return s;
+}
+
+void scp_seqs_destroy(scp_seqs* s) {
+    if (!s) return;
+    cudaFree(s->d_off); cudaFree(s->d_win_seq); cudaFree(s->d_win_idx); cudaFree(s->d_tile_seq); cudaFree(s->d_tile_start);
+    delete s;
+}
+
+int64_t scp_seqs_total(const scp_seqs* s) { return s ? s->total : -1; }
+
+int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K) {
+    return linear_tf32_ok(ldx, ldy, M, N, K, nullptr, nullptr, nullptr) ? 1 : 0;
+}
+
+int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_bias, const float* d_res, int64_t ldr,
+               float* d_y, int64_t ldy, int64_t M, int N, int K, int act, int engine, void* stream) {
+    SCP_REQUIRE(d_x && d_w && d_y && M >= 0 && N > 0 && K > 0, "scp_linear: bad argument");
+    SCP_REQUIRE(ldx >= K && ldy >= N && (!d_res || ldr >= N), "scp_linear: leading dimension too small");
+    if (M == 0) return SCP_OK;
+    cudaStream_t st = as_stream(stream);
+    const bool tc_ok = linear_tf32_ok(ldx, ldy, M, N, K, d_x, d_w, d_y);
+    if (engine == SCP_GEMM_TF32) {
+        SCP_REQUIRE(tc_ok, "scp_linear: shape M=%lld N=%d K=%d ldx=%lld not supported by the tcgen05 engine", (long long)M, N, K, (long long)ldx);
+        return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st);
+    }
+    const int vec4 = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(d_w) & 15) == 0);
+    if (N > 64 && M > 2048) {
+        dim3 grid((unsigned)cdiv(N, 128), (unsigned)cdiv(M, 128));
+        k_linear_simt<128, 128, 8, 8><<<grid, 256, 0, st>>>(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, vec4);
+    } else {
+        dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64));
+        k_linear_simt<64, 64, 4, 4><<<grid, 256, 0, st>>>(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, vec4);
+    }
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_layernorm(const float* d_x, int64_t ldx, const float* d_res, int64_t ldr, const float* d_gamma,
+                  const float* d_beta, float* d_y, int64_t ldy, int64_t M, int C, float eps, void* stream) {
+    SCP_REQUIRE(d_x && d_gamma && d_beta && d_y && C > 0 && C <= 640, "scp_layernorm: bad argument (C<=640)");
+    if (M == 0) return SCP_OK;
+    k_layernorm<<<(unsigned)cdiv(M, 8), 256, 0, as_stream(stream)>>>(d_x, ldx, d_res, ldr, d_gamma, d_beta, d_y, ldy, M, C, eps);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_ehem_embed(const uint8_t* d_ctx, int64_t n, const float* d_occ_enc, const float* d_level_enc, int n_level_rows,
+                   const float* d_octant_enc, float* d_out, int64_t ldo, void* stream) {
+    SCP_REQUIRE(d_ctx && d_occ_enc && d_level_enc && d_octant_enc && d_out && ldo >= 80, "scp_ehem_embed: bad argument");
+    if (n == 0) return SCP_OK;
+    k_ehem_embed<<<grid_for(n * 80, 256 * 4), 256, 0, as_stream(stream)>>>(d_ctx, n, d_occ_enc, d_level_enc, n_level_rows,
+                                                                           d_octant_enc, d_out, ldo);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_ehem_embed_occ(const uint8_t* d_ctx, int64_t n_even, const float* d_occ_enc, float* d_out, int64_t ldo,
+                       void* stream) {
+    SCP_REQUIRE(d_ctx && d_occ_enc && d_out && ldo >= 16, "scp_ehem_embed_occ: bad argument");
+    if (n_even == 0) return SCP_OK;
+    k_ehem_embed_occ<<<grid_for(n_even * 16, 256 * 4), 256, 0, as_stream(stream)>>>(d_ctx, n_even, d_occ_enc, d_out, ldo);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, int32_t* d_idx, void* stream) {
+    SCP_REQUIRE(d_x && seqs && d_idx && d > 0 && k > 0 && k <= 32, "scp_knn: bad argument (k<=32)");
+    if (seqs->total == 0) return SCP_OK;
+    cudaStream_t st = as_stream(stream);
+    float* xx = nullptr;
+    SCP_CUDA(cudaMallocAsync((void**)&xx, seqs->total * 4, st));
+    const float* x0 = d_x + seqs->h_off[0] * ldx;
+    k_row_sqnorm<<<(unsigned)cdiv(seqs->total, 8), 256, 0, st>>>(x0, ldx, d, seqs->total, xx);
+    SCP_LAUNCHED();
+    const int smem = (KD * (KQ + 4) + KD * (KC + 4) + KQ * (KC + 1) + 2 * k * 256) * 4;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        SCP_CUDA(cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    // xx is indexed by global row: shift so that xx[row] works for rows starting at h_off[0]
+    k_knn<<<seqs->n_tile, 256, smem, st>>>(d_x, ldx, d, xx - seqs->h_off[0], seqs->d_off, seqs->d_tile_seq,
+                                           seqs->d_tile_start, k, d_idx);
+    SCP_LAUNCHED();
+    SCP_CUDA(cudaFreeAsync(xx, st));
+    return SCP_OK;
+}
+
+int scp_edge_gather_max(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k, int64_t n,
+                        const float* d_bn_scale, const float* d_bn_shift, float* d_out, int64_t ldo, void* stream) {
+    SCP_REQUIRE(d_uv && d_idx && d_bn_scale && d_bn_shift && d_out, "scp_edge_gather_max: null argument");
+    SCP_REQUIRE(C == 64 || C == 128 || C == 256, "scp_edge_gather_max: C must be 64, 128 or 256");
+    if (n == 0) return SCP_OK;
+    k_edge_gather<<<grid_for(n, 256 / C, 148 * 32), 256, 0, as_stream(stream)>>>(d_uv, lduv, C, d_idx, k, n, d_bn_scale,
+                                                                                 d_bn_shift, d_out, ldo);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_swin_attention(const float* d_q, int64_t ldq, const float* d_k, int64_t ldk, const float* d_v, int64_t ldv,
+                       const float* d_qb, const float* d_kb, const float* d_vb, const float* d_relpos, int heads,
+                       const scp_seqs* seqs, int shift, float* d_out, int64_t ldo, void* stream) {
+    SCP_REQUIRE(d_q && d_k && d_v && d_qb && d_kb && d_vb && d_relpos && seqs && d_out, "scp_swin_attention: null argument");
+    SCP_REQUIRE(heads > 0 && heads <= 16 && (shift == 0 || shift == 256), "scp_swin_attention: heads/shift");
+    SCP_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "scp_swin_attention: out must be 16B aligned");
+    if (seqs->n_win == 0) return SCP_OK;
+    const int smem = 4 * HD * ALD * 4;
+    static bool attr = false;
+    if (!attr) { SCP_CUDA(cudaFuncSetAttribute(k_swin_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    dim3 grid((WS / AQ) * heads, seqs->n_win);
+    k_swin_attn<<<grid, 256, smem, as_stream(stream)>>>(d_q, ldq, d_k, ldk, d_v, ldv, d_qb, d_kb, d_vb, d_relpos, heads,
+                                                        seqs->d_off, seqs->d_win_seq, seqs->d_win_idx, shift, d_out, ldo);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_pair_concat(const float* d_x, int64_t ldx, const scp_seqs* src, const scp_seqs* dst, int C, float* d_out,
+                    int64_t ldo, void* stream) {
+    SCP_REQUIRE(d_x && src && dst && d_out && src->n_seq == dst->n_seq && C % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0,
+                "scp_pair_concat: bad argument");
+    if (dst->n_tile == 0) return SCP_OK;
+    k_pair_concat<<<dst->n_tile, 256, 0, as_stream(stream)>>>(d_x, ldx, src->d_off, dst->d_off, dst->d_tile_seq,
+                                                              dst->d_tile_start, C, d_out, ldo);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_upsample_cols(const float* d_src, int64_t lds, const scp_seqs* src, const scp_seqs* dst, int shift, int C,
+                      float* d_out, int64_t ldo, int col_off, void* stream) {
+    SCP_REQUIRE(d_src && src && dst && d_out && src->n_seq == dst->n_seq && C % 4 == 0 && lds % 4 == 0 && ldo % 4 == 0 &&
+                col_off % 4 == 0 && shift >= 0 && shift < 16, "scp_upsample_cols: bad argument");
+    if (dst->n_tile == 0) return SCP_OK;
+    k_upsample_cols<<<dst->n_tile, 256, 0, as_stream(stream)>>>(d_src, lds, src->d_off, dst->d_off, dst->d_tile_seq,
+                                                                dst->d_tile_start, shift, C, d_out, ldo, col_off);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_copy_cols(const float* d_src, int64_t lds, int64_t row_step, int64_t row_off, int64_t rows, int C, float* d_out,
+                  int64_t ldo, int col_off, void* stream) {
+    SCP_REQUIRE(d_src && d_out && rows >= 0 && C > 0, "scp_copy_cols: bad argument");
+    if (rows == 0) return SCP_OK;
+    k_copy_cols<<<grid_for(rows * C, 1024), 256, 0, as_stream(stream)>>>(d_src, lds, row_step, row_off, rows, C, d_out, ldo, col_off);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_add(const float* d_a, const float* d_b, float* d_y, int64_t n, void* stream) {
+    SCP_REQUIRE(d_a && d_b && d_y && n >= 0, "scp_add: bad argument");
+    if (n == 0) return SCP_OK;
+    k_add<<<grid_for(n, 1024), 256, 0, as_stream(stream)>>>(d_a, d_b, d_y, n);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_octattn_embed(const uint8_t* d_ctx, const uint32_t* d_ctx_pos, float pos_scale, int level_base,
+                      int max_octree_level, const scp_seqs* seqs, const float* d_occ_enc, const float* d_level_enc,
+                      const float* d_octant_enc, const float* d_pos_w, const float* d_pos_b, const float* d_pe,
+                      float* d_embed, float* d_embed_unknown, void* stream) {
+    SCP_REQUIRE(d_ctx && d_ctx_pos && seqs && d_occ_enc && d_level_enc && d_octant_enc && d_pos_w && d_pos_b && d_pe &&
+                d_embed && d_embed_unknown, "scp_octattn_embed: null argument");
+    if (seqs->n_tile == 0) return SCP_OK;
+    k_octattn_embed<<<seqs->n_tile, 256, 0, as_stream(stream)>>>(d_ctx, d_ctx_pos, pos_scale, level_base, max_octree_level,
+                                                                 seqs->d_off, seqs->d_tile_seq, seqs->d_tile_start, d_occ_enc,
+                                                                 d_level_enc, d_octant_enc, d_pos_w, d_pos_b, d_pe, d_embed,
+                                                                 d_embed_unknown);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int scp_octattn_attention(const float* d_qu, const float* d_k, const float* d_ku, const float* d_v, const float* d_vu,
+                          int64_t ld, int heads, int head_dim, const scp_seqs* seqs, float* d_out, float* d_out_u,
+                          int64_t ldo, void* stream) {
+    SCP_REQUIRE(d_qu && d_k && d_ku && d_v && d_vu && seqs && d_out && d_out_u, "scp_octattn_attention: null argument");
+    SCP_REQUIRE(head_dim > 0 && head_dim <= 150 && heads > 0, "scp_octattn_attention: head_dim must be <= 150");
+    if (seqs->n_tile == 0) return SCP_OK;
+    dim3 grid(seqs->n_tile * 4, heads);
+    k_octattn_attn<<<grid, 128, 0, as_stream(stream)>>>(d_qu, d_k, d_ku, d_v, d_vu, ld, heads, head_dim, seqs->d_off,
+                                                        seqs->d_tile_seq, seqs->d_tile_start, d_out, d_out_u, ldo);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+}  // extern "C"

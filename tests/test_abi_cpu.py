@@ -13,6 +13,7 @@ from scp_b200 import _lib
 def header_symbols():
     src = open(os.path.join(ROOT, "include", "scp_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = "\n".join(l for l in src.splitlines() if not l.lstrip().startswith("#"))
     names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", src)
     return sorted(set(n for n in names if n not in ("defined",)))
 
@@ -50,7 +51,7 @@ def test_range_coder_matches_numpyac_bitstream():
     assert np.array_equal(out[:n], g["bitstream"])
     # interval form gives the same bytes
     lo = cdf[np.arange(len(sym)), sym].astype(np.uint32)
-    hi = np.where(sym == 254, 0x10000, cdf[np.arange(len(sym)), np.minimum(sym + 1, 255)]).astype(np.uint32)
+    hi = np.where(sym == 254, 0x10000, cdf[np.arange(len(sym)), np.minimum(sym + 1, 255)].astype(np.int64)).astype(np.uint32)
     iv = np.ascontiguousarray(np.stack([lo, hi], 1))
     out2 = np.zeros(cap, np.uint8)
     n2 = lib.scp_range_encode(_lib.ptr(iv), len(sym), _lib.ptr(out2), cap)
