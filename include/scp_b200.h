@@ -86,6 +86,7 @@ typedef struct {
     int64_t*  rows_i64;  /* [N,4,6] the reference's .npy layout [occ 1..256, level, octant, x, y, z]
                                    (data_preprocess.py:74); an expansion for parity dumps / np.save      */
     uint64_t* voxel_key; /* [V]   Morton keys of the unique voxels per job, ascending                     */
+    int16_t*  sym;       /* [N]   coder symbol of the node = occ-1 (encode.py:98,148)                             */
 } scp_octree_out;
 
 scp_octree* scp_octree_create(void);
@@ -135,14 +136,26 @@ int   int_get(void* codes, int i);
  * For every level (h_level_sizes, rows consecutive) and window of `context_size`: even ids then odd ids.
  * d_order[N] receives row indices; d_sym[N] (optional) the symbols occ-1 in that order.
  * ---------------------------------------------------------------------------------------- */
-int scp_coding_order(const int64_t* h_level_sizes, int n_levels, int context_size, int add_base_for_single,
-                     const uint8_t* d_occ, int64_t* d_order, int16_t* d_sym, void* stream);
+int scp_coding_order(const int64_t* h_level_sizes, const uint8_t* h_level_restart, int n_levels, int context_size,
+                     int add_base_for_single, const uint8_t* d_occ, int64_t* d_order, int16_t* d_sym, void* stream);
+/* h_level_restart (optional): 1 where a level starts a new frame -- the reference restarts `coded_cnt` per frame,
+ * which matters only for its single-node-level quirk (encode.py:123). */
+
+/* Context-window assembly (encode.py:112-115 + the odd-length pad token of ehem.py:92-99) for ALL windows of a
+ * batch: window w covers rows [h_win_row[w], h_win_row[w]+h_win_len[w]) and lands at token h_win_tok[w] of the
+ * padded stream (every window padded to even length with ctx (0,0,255), pos 0).  Writes ctx [T,12], pos [T,3]
+ * and, for the even / odd tokens, the row each logits row belongs to (-1 for the pad token). */
+int scp_gather_windows(const uint8_t* d_ctx, const float* d_pos, const int64_t* h_win_row, const int32_t* h_win_len,
+                       const int64_t* h_win_tok, int n_win, uint8_t* d_ctx_out, float* d_pos_out,
+                       int64_t* d_row_even, int64_t* d_row_odd, void* stream);
+/* out[i, :] = in[idx[i], :] for 8-byte rows (coding-order gather of the (c_low,c_high) intervals). */
+int scp_gather_rows8(const void* d_in, const int64_t* d_idx, int64_t n, void* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * PMF / logits -> integer CDF (A13): torch.softmax (encode.py:126-127) +
  * numpyAc.py:109-114 pdf_convert_to_cdf_and_normalize + :80-107 _convert_to_int_and_normalize.
  * in: [n,255] float32 (logits if is_logits else PMF).  d_row_of[n] (optional) scatters row i of the
- * input to CDF row d_row_of[i].  Outputs (each optional): d_cdf [n,256] uint16; d_interval [n,2] uint32
+ * input to CDF row d_row_of[i] (negative = skip the row).  Outputs (each optional): d_cdf [n,256] uint16; d_interval [n,2] uint32
  * = (c_low, c_high) of symbol d_sym[row] with the coder's 0x10000 substitution (numpyAc_backend.cpp:271-277);
  * d_pmf [n,255] float32.
  * ---------------------------------------------------------------------------------------- */

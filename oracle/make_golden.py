@@ -161,6 +161,17 @@ def gen_ehem_logits(ns):
             out[f"{tag}_logits1"] = o1[0].numpy()
             out[f"{tag}_logits2"] = o2[0].numpy()
             print("ehem", tag, o1.shape, o2.shape, float(torch.softmax(o1, 2).max()))
+        # tie-free variants: same context bytes, positions replaced by seeded uniform noise so that every
+        # neighbour set is unambiguous (grid positions make torch.topk's tie order part of the output)
+        for tag, (a, b) in {"j600": (s0, s0 + 600), "j1100": (s0 + 100, s0 + 1200)}.items():
+            d = torch.from_numpy(data_all[a:b])[None]
+            pj = np.random.RandomState(b).random_sample((3, b - a)).astype(np.float32)
+            o1, o2 = model(d, torch.from_numpy(pj)[None], enc=True)
+            out[f"{tag}_data"] = data_all[a:b].astype(np.int16)
+            out[f"{tag}_pos"] = pj
+            out[f"{tag}_logits1"] = o1[0].numpy()
+            out[f"{tag}_logits2"] = o2[0].numpy()
+            print("ehem", tag, o1.shape, o2.shape, float(torch.softmax(o1, 2).max()))
     np.savez_compressed(os.path.join(GOLD, "ehem_logits.npz"), **out)
 
     # one full 8192-token window on a denser frame; logits stored at every 16th token
@@ -175,6 +186,11 @@ def gen_ehem_logits(ns):
     p = torch.from_numpy(poss[li][:, :8192].copy())[None]
     with torch.no_grad():
         o1, o2 = model(d, p, enc=True)
+    pj = np.random.RandomState(8192).random_sample((3, 8192)).astype(np.float32)
+    with torch.no_grad():
+        j1, j2 = model(d, torch.from_numpy(pj)[None], enc=True)
+    np.savez_compressed(os.path.join(GOLD, "ehem_logits_full_jit.npz"), pos=pj,
+                        logits1_s16=j1[0, ::16].numpy(), logits2_s16=j2[0, ::16].numpy())
     np.savez_compressed(os.path.join(GOLD, "ehem_logits_full.npz"),
                         data=data[li][:8192].astype(np.int16), pos=poss[li][:, :8192].copy(),
                         logits1_s16=o1[0, ::16].numpy(), logits2_s16=o2[0, ::16].numpy(),

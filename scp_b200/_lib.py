@@ -31,7 +31,7 @@ class JobInfo(C.Structure):
 
 class OctreeOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("occ", "level", "octant", "parent", "pos", "ctx", "pos_norm", "ctx_pos",
-                                           "rows_i64", "voxel_key")]
+                                           "rows_i64", "voxel_key", "sym")]
 
 
 class LegacyNode(C.Structure):      # Octreewarpper.py:6-14
@@ -67,7 +67,9 @@ SIGNATURES = {
     "Nodes_size": (_i, [_vp]),
     "int_size": (_i, [_vp]),
     "int_get": (_i, [_vp, _i]),
-    "scp_coding_order": (_i, [C.POINTER(_i64), _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "scp_coding_order": (_i, [C.POINTER(_i64), _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "scp_gather_windows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "scp_gather_rows8": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "scp_pmf_to_cdf": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scp_range_encode": (_i64, [_vp, _i64, _vp, _i64]),
     "scp_range_encode_cdf": (_i64, [_vp, _vp, _i64, _i, _vp, _i64]),

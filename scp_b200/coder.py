@@ -7,7 +7,7 @@ import torch
 from . import _lib
 
 
-def coding_order(level_sizes, context_size, occ, mullevel=False):
+def coding_order(level_sizes, context_size, occ, mullevel=False, level_restart=None):
     """encode.py:109-136 / encode_mullevel.py:106-133.  occ: CUDA uint8 [N] occupancy bytes 1..255.
     Returns (order int64 [N], symbols int16 [N]) on the device."""
     lib = _lib.require_device()
@@ -15,7 +15,8 @@ def coding_order(level_sizes, context_size, occ, mullevel=False):
     order = torch.zeros(n, dtype=torch.int64, device=occ.device)
     sym = torch.zeros(n, dtype=torch.int16, device=occ.device)
     sizes = (C.c_int64 * len(level_sizes))(*[int(s) for s in level_sizes])
-    _lib.check(lib.scp_coding_order(sizes, len(level_sizes), context_size, int(mullevel), _lib.ptr(occ),
+    restart = None if level_restart is None else np.ascontiguousarray(np.asarray(level_restart, np.uint8))
+    _lib.check(lib.scp_coding_order(sizes, _lib.ptr(restart), len(level_sizes), context_size, int(mullevel), _lib.ptr(occ),
                                     _lib.ptr(order), _lib.ptr(sym), _lib.stream_ptr()), "scp_coding_order")
     return order, sym
 

@@ -12,7 +12,7 @@ namespace scp {
 // ------------------------------------------------------------------------------------------
 // A7 coding order
 // ------------------------------------------------------------------------------------------
-struct Win { long long base; long long start; int len; int single; };
+struct Win { long long base; long long start; long long frame_base; int len; int single; };
 
 __global__ void __launch_bounds__(256) k_coding_order(const Win* __restrict__ wins, int n_win,
                                                        const uint8_t* __restrict__ occ, long long* __restrict__ order,
@@ -24,11 +24,45 @@ __global__ void __launch_bounds__(256) k_coding_order(const Win* __restrict__ wi
             long long row = W.base + W.start + l;
             long long id = row;
             int p = (l & 1) ? half + (l >> 1) : (l >> 1);
-            if (W.single) { p = 0; id = add_base_for_single ? row : (row - W.base); }   // encode.py:123 vs encode_mullevel.py:120
+            if (W.single) { p = 0; id = add_base_for_single ? row : (row - W.base + W.frame_base); }   // encode.py:123 vs encode_mullevel.py:120
             order[W.base + W.start + p] = id;
             if (sym) sym[W.base + W.start + p] = (int16_t)((int)occ[id] - 1);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// context-window assembly (all windows of a batch, odd windows get the pad token of ehem.py:92-99)
+// ------------------------------------------------------------------------------------------
+struct GWin { long long row; long long tok; int len; int pad; };
+
+__global__ void __launch_bounds__(256) k_gather_windows(const GWin* __restrict__ wins, const uint8_t* __restrict__ ctx,
+                                                         const float* __restrict__ pos, uint8_t* __restrict__ ctx_out,
+                                                         float* __restrict__ pos_out, long long* __restrict__ row_even,
+                                                         long long* __restrict__ row_odd) {
+    const GWin W = wins[blockIdx.y];
+    const int plen = W.len + (W.len & 1);
+    const u32* ci = reinterpret_cast<const u32*>(ctx);
+    u32* co = reinterpret_cast<u32*>(ctx_out);
+    for (int l = blockIdx.x * 256 + threadIdx.x; l < plen; l += gridDim.x * 256) {
+        const long long t = W.tok + l;
+        const bool real = l < W.len;
+        const long long r = W.row + l;
+        if (real) {
+            co[3 * t] = ci[3 * r]; co[3 * t + 1] = ci[3 * r + 1]; co[3 * t + 2] = ci[3 * r + 2];
+            pos_out[3 * t] = pos[3 * r]; pos_out[3 * t + 1] = pos[3 * r + 1]; pos_out[3 * t + 2] = pos[3 * r + 2];
+        } else {
+            co[3 * t] = 0x00ff0000u; co[3 * t + 1] = 0x0000ff00u; co[3 * t + 2] = 0xff0000ffu;   // 4 x (0,0,255)
+            pos_out[3 * t] = 0.f; pos_out[3 * t + 1] = 0.f; pos_out[3 * t + 2] = 0.f;
+        }
+        long long* dst = (l & 1) ? row_odd : row_even;
+        if (dst) dst[t >> 1] = real ? r : -1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_rows8(const u64* __restrict__ in, const long long* __restrict__ idx,
+                                                       long long n, u64* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = in[idx[i]];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -78,6 +112,7 @@ __global__ void __launch_bounds__(CDF_R) k_pmf_to_cdf(const float* __restrict__ 
         for (int i = threadIdx.x; i < rows * 255; i += CDF_R) {
             int r = i / 255, c = i - r * 255;
             long long orow = row_of ? row_of[row0 + r] : row0 + r;
+            if (orow < 0) continue;
             pmf[orow * 255 + c] = s[r * CDF_LD + c];
         }
     }
@@ -104,6 +139,7 @@ __global__ void __launch_bounds__(CDF_R) k_pmf_to_cdf(const float* __restrict__ 
         }
         if (cdf) {
             long long orow = row_of ? row_of[row0 + r] : row0 + r;
+            if (orow < 0) continue;
             reinterpret_cast<u32*>(cdf + orow * 256)[c2 >> 1] = v[0] | (v[1] << 16);
         }
     }
@@ -111,6 +147,7 @@ __global__ void __launch_bounds__(CDF_R) k_pmf_to_cdf(const float* __restrict__ 
         const float* x = s + threadIdx.x * CDF_LD;
         const float last = x[254];
         long long orow = row_of ? row_of[row0 + threadIdx.x] : row0 + threadIdx.x;
+        if (orow < 0) return;
         int sy = sym[orow];
         sy = sy < 0 ? 0 : (sy > 254 ? 254 : sy);
         double Fl = sy == 0 ? 0.0 : (double)__fdiv_rn(x[sy - 1], last);
@@ -179,18 +216,19 @@ using namespace scp;
 
 extern "C" {
 
-int scp_coding_order(const int64_t* h_level_sizes, int n_levels, int context_size, int add_base_for_single,
-                     const uint8_t* d_occ, int64_t* d_order, int16_t* d_sym, void* stream) {
+int scp_coding_order(const int64_t* h_level_sizes, const uint8_t* h_level_restart, int n_levels, int context_size,
+                     int add_base_for_single, const uint8_t* d_occ, int64_t* d_order, int16_t* d_sym, void* stream) {
     SCP_REQUIRE(h_level_sizes && d_order && n_levels > 0 && context_size > 0, "scp_coding_order: bad argument");
     SCP_REQUIRE(!d_sym || d_occ, "scp_coding_order: symbols need d_occ");
     cudaStream_t st = as_stream(stream);
     std::vector<Win> wins;
-    long long base = 0;
+    long long base = 0, frame_base = 0;
     for (int l = 0; l < n_levels; ++l) {
         long long n = h_level_sizes[l];
         SCP_REQUIRE(n >= 0, "scp_coding_order: negative level size");
+        if (h_level_restart && h_level_restart[l]) frame_base = base;
         for (long long i = 0; i < n; i += context_size)
-            wins.push_back(Win{base, i, (int)std::min<long long>(context_size, n - i), n == 1});
+            wins.push_back(Win{base, i, frame_base, (int)std::min<long long>(context_size, n - i), n == 1});
         base += n;
     }
     if (wins.empty()) return SCP_OK;
@@ -202,6 +240,40 @@ int scp_coding_order(const int64_t* h_level_sizes, int n_levels, int context_siz
     SCP_LAUNCHED();
     SCP_CUDA(cudaStreamSynchronize(st));      // `wins` is pageable host memory
     SCP_CUDA(cudaFreeAsync(d_w, st));
+    return SCP_OK;
+}
+
+int scp_gather_windows(const uint8_t* d_ctx, const float* d_pos, const int64_t* h_win_row, const int32_t* h_win_len,
+                       const int64_t* h_win_tok, int n_win, uint8_t* d_ctx_out, float* d_pos_out, int64_t* d_row_even,
+                       int64_t* d_row_odd, void* stream) {
+    SCP_REQUIRE(d_ctx && d_pos && h_win_row && h_win_len && h_win_tok && d_ctx_out && d_pos_out && n_win >= 0,
+                "scp_gather_windows: bad argument");
+    if (n_win == 0) return SCP_OK;
+    cudaStream_t st = as_stream(stream);
+    std::vector<GWin> wins(n_win);
+    int maxlen = 0;
+    for (int w = 0; w < n_win; ++w) {
+        SCP_REQUIRE(h_win_len[w] > 0 && (h_win_tok[w] & 1) == 0, "scp_gather_windows: window %d (len>0, even token start)", w);
+        wins[w] = GWin{h_win_row[w], h_win_tok[w], h_win_len[w], 0};
+        maxlen = std::max(maxlen, h_win_len[w] + 1);
+    }
+    GWin* d_w = nullptr;
+    SCP_CUDA(cudaMallocAsync((void**)&d_w, wins.size() * sizeof(GWin), st));
+    SCP_CUDA(cudaMemcpyAsync(d_w, wins.data(), wins.size() * sizeof(GWin), cudaMemcpyHostToDevice, st));
+    dim3 grid((unsigned)std::min<long long>(cdiv(maxlen, 256), 32), (unsigned)n_win);
+    k_gather_windows<<<grid, 256, 0, st>>>(d_w, d_ctx, d_pos, d_ctx_out, d_pos_out, (long long*)d_row_even, (long long*)d_row_odd);
+    SCP_LAUNCHED();
+    SCP_CUDA(cudaStreamSynchronize(st));
+    SCP_CUDA(cudaFreeAsync(d_w, st));
+    return SCP_OK;
+}
+
+int scp_gather_rows8(const void* d_in, const int64_t* d_idx, int64_t n, void* d_out, void* stream) {
+    SCP_REQUIRE(d_in && d_idx && d_out && n >= 0, "scp_gather_rows8: bad argument");
+    if (n == 0) return SCP_OK;
+    k_gather_rows8<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 16), 256, 0, as_stream(stream)>>>(
+        (const u64*)d_in, (const long long*)d_idx, n, (u64*)d_out);
+    SCP_LAUNCHED();
     return SCP_OK;
 }
 

@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles,
             }
         }
         if (O.occ) O.occ[o] = (uint8_t)occ[3];
+        if (O.sym) O.sym[o] = (int16_t)(occ[3] - 1);
         if (O.level) O.level[o] = (uint8_t)lv[3];
         if (O.octant) O.octant[o] = (uint8_t)oc[3];
         if (O.parent) O.parent[o] = A.parent[r];

@@ -20,6 +20,9 @@ struct scp_seqs {
     int n_tile = 0;                 // 64-token tiles over all sequences
     int* d_tile_seq = nullptr;      // [n_tile]
     int* d_tile_start = nullptr;    // [n_tile] first token of the tile inside its sequence
+    int n_tile128 = 0;              // 128-token tiles
+    int* d_tile128_seq = nullptr;
+    int* d_tile128_start = nullptr;
 };
 
 namespace scp {
@@ -294,6 +297,65 @@ __global__ void __launch_bounds__(256) k_knn(const float* __restrict__ X, long l
             if (best < 0) { idx_out[row * k + j] = (int)row; continue; }     // sequence shorter than k: repeat self
             ++p[best];
             idx_out[row * k + j] = (int)(base + bi);
+        }
+    }
+}
+
+// d <= 4 (the 3-D position kNN): octree positions lie on a grid, so EXACT distance ties are the rule, and the
+// reference's pick among tied neighbours is whatever torch.topk returns.  Here the rule is canonical: exact
+// float64 squared distance ((dx^2 + dy^2) + dz^2, no FMA contraction), ties -> lowest index.  One thread per query.
+constexpr int KS_Q = 128, KS_C = 256;
+__global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X, long long ldx, int d,
+                                                     const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
+                                                     const int* __restrict__ tile_start, int k, int* __restrict__ idx_out) {
+    extern __shared__ __align__(16) double smd[];
+    double* cs = smd;                                   // [KS_C][4]
+    double* ls = smd + KS_C * 4;                        // [k][KS_Q]
+    int* li = reinterpret_cast<int*>(ls + k * KS_Q);    // [k][KS_Q]
+    const int t = threadIdx.x;
+    const int s = tile_seq[blockIdx.x];
+    const long long base = seq_off[s];
+    const int n = (int)(seq_off[s + 1] - base);
+    const int q = tile_start[blockIdx.x] + t;
+    const bool active = q < n;
+    double xq[4] = {0, 0, 0, 0};
+    if (active) for (int c = 0; c < d; ++c) xq[c] = (double)X[(base + q) * ldx + c];
+    for (int j = 0; j < k; ++j) { ls[j * KS_Q + t] = INFINITY; li[j * KS_Q + t] = -1; }
+    double worst = INFINITY;
+    for (int c0 = 0; c0 < n; c0 += KS_C) {
+        __syncthreads();
+        for (int e = t; e < KS_C * 4; e += KS_Q) {
+            int r = e >> 2, c = e & 3;
+            cs[e] = (c0 + r < n && c < d) ? (double)X[(base + c0 + r) * ldx + c] : 0.0;
+        }
+        __syncthreads();
+        if (!active) continue;
+        const int cmax = min(KS_C, n - c0);
+        for (int r = 0; r < cmax; ++r) {
+            double dist = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double df = __dsub_rn(xq[c], cs[r * 4 + c]);
+                dist = __dadd_rn(dist, __dmul_rn(df, df));
+            }
+            if (dist < worst) {
+                int j = k - 1;
+                while (j > 0 && ls[(j - 1) * KS_Q + t] > dist) {
+                    ls[j * KS_Q + t] = ls[(j - 1) * KS_Q + t];
+                    li[j * KS_Q + t] = li[(j - 1) * KS_Q + t];
+                    --j;
+                }
+                ls[j * KS_Q + t] = dist;
+                li[j * KS_Q + t] = c0 + r;
+                worst = ls[(k - 1) * KS_Q + t];
+            }
+        }
+    }
+    if (active) {
+        const long long row = base + q;
+        for (int j = 0; j < k; ++j) {
+            const int id = li[j * KS_Q + t];
+            idx_out[row * k + j] = id < 0 ? (int)row : (int)(base + id);
         }
     }
 }
@@ -659,20 +721,24 @@ scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq) {
     s->n_seq = n_seq;
     s->h_off.assign(h_offsets, h_offsets + n_seq + 1);
     s->total = h_offsets[n_seq] - h_offsets[0];
-    std::vector<int> wseq, widx, tseq, tstart;
+    std::vector<int> wseq, widx, tseq, tstart, t2seq, t2start;
     for (int i = 0; i < n_seq; ++i) {
         long long len = h_offsets[i + 1] - h_offsets[i];
         if (len < 0 || len > (1 << 24)) { set_error("scp_seqs_create: sequence %d has length %lld", i, len); delete s; return nullptr; }
         for (long long w = 0; w < cdiv(len, 512); ++w) { wseq.push_back(i); widx.push_back((int)w); }
         for (long long t = 0; t < len; t += 64) { tseq.push_back(i); tstart.push_back((int)t); }
+        for (long long t = 0; t < len; t += 128) { t2seq.push_back(i); t2start.push_back((int)t); }
     }
     s->n_win = (int)wseq.size();
     s->n_tile = (int)tseq.size();
+    s->n_tile128 = (int)t2seq.size();
     bool ok = cudaMalloc((void**)&s->d_off, (n_seq + 1) * 8) == cudaSuccess &&
               cudaMalloc((void**)&s->d_win_seq, std::max(1, s->n_win) * 4) == cudaSuccess &&
               cudaMalloc((void**)&s->d_win_idx, std::max(1, s->n_win) * 4) == cudaSuccess &&
               cudaMalloc((void**)&s->d_tile_seq, std::max(1, s->n_tile) * 4) == cudaSuccess &&
-              cudaMalloc((void**)&s->d_tile_start, std::max(1, s->n_tile) * 4) == cudaSuccess;
+              cudaMalloc((void**)&s->d_tile_start, std::max(1, s->n_tile) * 4) == cudaSuccess &&
+              cudaMalloc((void**)&s->d_tile128_seq, std::max(1, s->n_tile128) * 4) == cudaSuccess &&
+              cudaMalloc((void**)&s->d_tile128_start, std::max(1, s->n_tile128) * 4) == cudaSuccess;
     ok = ok && cudaMemcpy(s->d_off, s->h_off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     if (ok && s->n_win) {
         ok = cudaMemcpy(s->d_win_seq, wseq.data(), s->n_win * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -680,7 +746,9 @@ scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq) {
     }
     if (ok && s->n_tile) {
         ok = cudaMemcpy(s->d_tile_seq, tseq.data(), s->n_tile * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(s->d_tile_start, tstart.data(), s->n_tile * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+             cudaMemcpy(s->d_tile_start, tstart.data(), s->n_tile * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(s->d_tile128_seq, t2seq.data(), s->n_tile128 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(s->d_tile128_start, t2start.data(), s->n_tile128 * 4, cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) { set_error("scp_seqs_create: CUDA allocation/upload failed"); scp_seqs_destroy(s); return nullptr; }
     return s;
@@ -689,6 +757,7 @@ scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq) {
 void scp_seqs_destroy(scp_seqs* s) {
     if (!s) return;
     cudaFree(s->d_off); cudaFree(s->d_win_seq); cudaFree(s->d_win_idx); cudaFree(s->d_tile_seq); cudaFree(s->d_tile_start);
+    cudaFree(s->d_tile128_seq); cudaFree(s->d_tile128_start);
     delete s;
 }
 
@@ -754,6 +823,17 @@ int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, i
     SCP_REQUIRE(d_x && seqs && d_idx && d > 0 && k > 0 && k <= 32, "scp_knn: bad argument (k<=32)");
     if (seqs->total == 0) return SCP_OK;
     cudaStream_t st = as_stream(stream);
+    if (d <= 4) {
+        const int smem_s = KS_C * 4 * 8 + k * KS_Q * 12;
+        static int attr_s = 0;
+        if (smem_s > attr_s) {
+            SCP_CUDA(cudaFuncSetAttribute(k_knn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
+            attr_s = smem_s;
+        }
+        k_knn_small<<<seqs->n_tile128, KS_Q, smem_s, st>>>(d_x, ldx, d, seqs->d_off, seqs->d_tile128_seq, seqs->d_tile128_start, k, d_idx);
+        SCP_LAUNCHED();
+        return SCP_OK;
+    }
     float* xx = nullptr;
     SCP_CUDA(cudaMallocAsync((void**)&xx, seqs->total * 4, st));
     const float* x0 = d_x + seqs->h_off[0] * ldx;

@@ -1,0 +1,196 @@
+"""End-to-end encode path: LiDAR points -> bitstream, for batches of frames on one GPU.
+
+Replaces the per-frame, per-window Python loops of the reference's ``encode.py`` (compress_ehem :85-160,
+compress :23-82) and ``encode_mullevel.py`` (:88-157, :23-85) together with the dataset/pre-processing they
+drive (dataloaders/encode_dataset_ehem*.py, data_preproc/data_preprocess.py):
+
+  points (host or device) --> octree rows / context bytes / normalised positions   (scp_octree_*)
+                          --> all context windows of all frames as ONE ragged batch  (scp_gather_windows)
+                          --> EHEM / OctAttention logits                              (models.*)
+                          --> softmax -> integer CDF -> (c_low, c_high) of the true symbol   (scp_pmf_to_cdf)
+                          --> coding order gather                                     (scp_coding_order, scp_gather_rows8)
+                          --> range coder, one stream per frame                       (scp_range_encode, host threads)
+
+Only 8 bytes per node leave the GPU (the reference copies 1020 B/node of PMFs, encode.py:133).
+"""
+import ctypes as C
+import os
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, coder, octree
+from .synth import FORD_QS, KITTI_QS
+
+
+@dataclass
+class FrameResult:
+    n_points: int
+    n_nodes: int
+    n_levels: int
+    bin_num: int
+    z_offset: float
+    bitstream: bytes
+    bpp: float
+    pos_mm: list = field(default_factory=list)
+
+
+class Encoder:
+    """``Encoder(model, lidar_level, mode, mullevel)`` then ``encode(frames)``.
+
+    mode 'spher' | 'cylin' | 'cart'; ``mullevel`` = the three sub-octrees of encode_mullevel.py;
+    ``kind`` 'kitti' | 'ford' picks the quantisation step like encode_dataset_ehem.py:164."""
+
+    def __init__(self, model, lidar_level=12, mode="spher", mullevel=False, kind="kitti", max_tokens=1 << 19,
+                 coder_threads=None):
+        self.model = model
+        self.level = lidar_level
+        self.mode = mode
+        self.mullevel = mullevel
+        self.kind = kind
+        self.is_ehem = model.__class__.__name__ == "EHEM"
+        self.context = model.cfg.model.context_size
+        self.max_tokens = max_tokens
+        self.builder = octree.OctreeBuilder()
+        self.lib = _lib.require_device()
+        self.pool = ThreadPoolExecutor(coder_threads or min(32, os.cpu_count() or 1))
+        self.timings = {}
+
+    # -- stage 1: octrees ---------------------------------------------------------------------
+    def _jobs(self, n_frames):
+        qf = KITTI_QS if self.kind == "kitti" else FORD_QS
+        if self.mullevel:
+            return [j for f in range(n_frames) for j in octree.mullevel_jobs(f, self.level, self.kind)], 3
+        clip = self.level if self.is_ehem else 255          # encode_dataset.py (OctAttention) does not clip levels
+        return [octree.JobSpec(f, qf(self.level), None, lidar_level=clip) for f in range(n_frames)], 1
+
+    def build_context(self, xyz, frame_offsets):
+        jobs, per_frame = self._jobs(len(frame_offsets) - 1)
+        b = self.builder.plan(xyz, frame_offsets, jobs, self.mode)
+        outs = ("occ", "sym", "ctx", "pos_norm") if self.is_ehem else ("occ", "sym", "ctx", "ctx_pos")
+        t = b.emit(outs, finish=False)
+        return b, t, per_frame
+
+    # -- stage 2: windows ---------------------------------------------------------------------
+    def _ehem_windows(self, infos):
+        """(row, len, token) of every context window (encode.py:112-115), level by level."""
+        rows, lens = [], []
+        for i in infos:
+            r = i.row_start
+            for n in i.level_rows:
+                for s in range(0, n, self.context):
+                    rows.append(r + s)
+                    lens.append(min(self.context, n - s))
+                r += n
+        lens = np.asarray(lens, np.int32)
+        toks = np.concatenate([[0], np.cumsum(lens + (lens & 1))]).astype(np.int64)
+        return np.asarray(rows, np.int64), lens, toks
+
+    def _ehem_logits_to_intervals(self, t, infos, interval_row):
+        rows, lens, toks = self._ehem_windows(infos)
+        ctx, pos, sym = t["ctx"], t["pos_norm"], t["sym"]
+        dev = ctx.device
+        w0 = 0
+        st = _lib.stream_ptr()
+        while w0 < len(rows):                               # chunks of windows bounded by max_tokens
+            w1 = w0 + 1
+            while w1 < len(rows) and toks[w1 + 1] - toks[w0] <= self.max_tokens:
+                w1 += 1
+            T = int(toks[w1] - toks[w0])
+            ctxp = torch.empty((T, 4, 3), dtype=torch.uint8, device=dev)
+            posp = torch.empty((T, 3), dtype=torch.float32, device=dev)
+            re = torch.empty(T // 2, dtype=torch.int64, device=dev)
+            ro = torch.empty(T // 2, dtype=torch.int64, device=dev)
+            tk = np.ascontiguousarray(toks[w0:w1] - toks[w0])
+            _lib.check(self.lib.scp_gather_windows(_lib.ptr(ctx), _lib.ptr(pos), _lib.ptr(np.ascontiguousarray(rows[w0:w1])),
+                                                   _lib.ptr(np.ascontiguousarray(lens[w0:w1])), _lib.ptr(tk), w1 - w0,
+                                                   _lib.ptr(ctxp), _lib.ptr(posp), _lib.ptr(re), _lib.ptr(ro), st),
+                       "scp_gather_windows")
+            l1, l2 = self.model.forward_ragged(ctxp, posp, [int(x) for x in np.append(tk, T)])
+            coder.pmf_to_cdf(l1, sym=sym, is_logits=True, row_of=re, out={"interval": interval_row})
+            coder.pmf_to_cdf(l2, sym=sym, is_logits=True, row_of=ro, out={"interval": interval_row})
+            w0 = w1
+
+    def _octattn_logits_to_intervals(self, t, infos, per_frame, interval_row):
+        """encode.py:23-82 (non level-wise): per frame one sequence [1023 pad rows ; nodes] cut into windows of 1024."""
+        ctx, cpos, sym = t["ctx"], t["ctx_pos"], t["sym"]
+        dev = ctx.device
+        cs = self.context
+        for f in range(len(infos) // per_frame):
+            fi = infos[f * per_frame:(f + 1) * per_frame]
+            r0, n = fi[0].row_start, sum(i.n_rows for i in fi)
+            max_level = max(i.depth for i in fi)
+            padc = torch.zeros((cs - 1, 4, 3), dtype=torch.uint8, device=dev)
+            padc[:, :, 2] = 255
+            seq_ctx = torch.cat([padc, ctx[r0:r0 + n]])
+            seq_pos = torch.cat([torch.zeros((cs - 1, 4, 3), dtype=torch.int32, device=dev), cpos[r0:r0 + n]])
+            row_of = torch.cat([torch.full((cs - 1,), -1, dtype=torch.int64, device=dev),
+                                torch.arange(r0, r0 + n, dtype=torch.int64, device=dev)])
+            L = seq_ctx.shape[0]
+            offs = list(range(0, L, cs)) + [L]
+            step = max(1, self.max_tokens // cs)
+            for a in range(0, len(offs) - 1, step):
+                o = offs[a:a + step + 1]
+                lo, hi = o[0], o[-1]
+                logits = self.model.forward_ragged(seq_ctx[lo:hi].contiguous(), seq_pos[lo:hi].contiguous(),
+                                                   [x - lo for x in o], 1.0 / float(1 << max_level))
+                coder.pmf_to_cdf(logits, sym=sym, is_logits=True, row_of=row_of[lo:hi].contiguous(),
+                                 out={"interval": interval_row})
+
+    # -- public API ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode_device(self, xyz, frame_offsets):
+        """xyz: CUDA float32 (n,3|4); returns (interval tensor int32 [N,2] in coding order on the device,
+        per-frame (row_start, n_rows), job infos)."""
+        b, t, per_frame = self.build_context(xyz, frame_offsets)
+        infos = b.infos
+        N = b.total_rows
+        interval_row = torch.empty((N, 2), dtype=torch.int32, device=xyz.device)
+        if self.is_ehem:
+            self._ehem_logits_to_intervals(t, infos, interval_row)
+            sizes, restart = [], []
+            for j, i in enumerate(infos):
+                for l, n in enumerate(i.level_rows):
+                    sizes.append(n)
+                    restart.append(1 if (j % per_frame == 0 and l == 0) else 0)
+            order, _ = coder.coding_order(sizes, self.context, t["occ"], mullevel=self.mullevel, level_restart=restart)
+            interval = torch.empty_like(interval_row)
+            _lib.check(self.lib.scp_gather_rows8(_lib.ptr(interval_row), _lib.ptr(order), N, _lib.ptr(interval),
+                                                 _lib.stream_ptr()), "scp_gather_rows8")
+        else:
+            self._octattn_logits_to_intervals(t, infos, per_frame, interval_row)
+            interval = interval_row                              # OctAttention codes in BFS order (encode.py:67-69)
+        frames = []
+        for f in range(len(frame_offsets) - 1):
+            fi = infos[f * per_frame:(f + 1) * per_frame]
+            frames.append((fi[0].row_start, sum(i.n_rows for i in fi)))
+        return interval, frames, infos, per_frame
+
+    @torch.no_grad()
+    def encode(self, frames_xyz: List[np.ndarray]) -> List[FrameResult]:
+        """frames_xyz: list of host float32 (n,3|4) arrays (KITTI .bin rows).  Returns one FrameResult per frame."""
+        offs = np.concatenate([[0], np.cumsum([len(f) for f in frames_xyz])]).astype(np.int64)
+        host = torch.from_numpy(np.ascontiguousarray(np.concatenate(frames_xyz, 0), dtype=np.float32))
+        if not host.is_pinned():
+            host = host.pin_memory()
+        xyz = host.cuda(non_blocking=True)
+        interval, frames, infos, per_frame = self.encode_device(xyz, offs)
+        iv = torch.empty(interval.shape, dtype=torch.int32).pin_memory()
+        iv.copy_(interval, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _lib.check(self.lib.scp_octree_finish(self.builder.h, _lib.stream_ptr()), "scp_octree_finish")
+        self.builder._read_infos()
+        infos = self.builder.infos
+        ivn = iv.numpy().view(np.uint32)
+        streams = list(self.pool.map(lambda fr: coder.range_encode(ivn[fr[0]:fr[0] + fr[1]]), frames))
+        out = []
+        for f, ((r0, n), bs) in enumerate(zip(frames, streams)):
+            fi = infos[f * per_frame:(f + 1) * per_frame]
+            npts = int(offs[f + 1] - offs[f])
+            out.append(FrameResult(npts, n, sum(len(i.level_rows) for i in fi), int(fi[0].bin_num),
+                                   float(fi[0].offset[2]), bs, 8.0 * len(bs) / npts,
+                                   [p for i in fi for p in i.pos_mm]))
+        return out

@@ -55,10 +55,11 @@ def mullevel_jobs(frame, level, kind="kitti"):
 class OctreeBuilder:
     """Reusable builder (keeps its device workspace between batches)."""
 
-    ALL_OUTPUTS = ("occ", "level", "octant", "parent", "pos", "ctx", "pos_norm", "ctx_pos", "rows_i64", "voxel_key")
+    ALL_OUTPUTS = ("occ", "level", "octant", "parent", "pos", "ctx", "pos_norm", "ctx_pos", "rows_i64", "voxel_key", "sym")
     _SHAPES = {"occ": ((), torch.uint8), "level": ((), torch.uint8), "octant": ((), torch.uint8),
                "parent": ((), torch.int32), "pos": ((3,), torch.int32), "ctx": ((4, 3), torch.uint8),
-               "pos_norm": ((3,), torch.float32), "ctx_pos": ((4, 3), torch.int32), "rows_i64": ((4, 6), torch.int64)}
+               "pos_norm": ((3,), torch.float32), "ctx_pos": ((4, 3), torch.int32), "rows_i64": ((4, 6), torch.int64),
+               "sym": ((), torch.int16)}
 
     def __init__(self):
         self.lib = _lib.require_device()

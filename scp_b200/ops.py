@@ -51,12 +51,33 @@ def V(t, col=0, ncol=None):
     return (t, col, t.shape[1] - col if ncol is None else ncol)
 
 
+class _Rec:
+    def __init__(self, ops, tag, flops, nbytes):
+        self.ops, self.tag, self.flops, self.nbytes = ops, tag, flops, nbytes
+
+    def __enter__(self):
+        if self.ops.prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.ops.prof is not None:
+            self.e1.record()
+            self.ops.prof.append((self.tag, self.flops, self.nbytes, self.e0, self.e1))
+
+
 class CudaOps:
     name = "cuda"
 
     def __init__(self, engine="auto"):
         self.lib = _lib.require_device()
         self.engine = ENGINE[engine]
+        self.prof = None          # bench.py: list of (kernel tag, flops, bytes, start event, end event)
+
+    def _rec(self, tag, flops, nbytes):
+        """Context manager that brackets one launch with CUDA events on the current stream when profiling is on."""
+        return _Rec(self, tag, flops, nbytes)
 
     # -- plumbing ---------------------------------------------------------------------------
     def _seqs_create(self, offsets):
@@ -95,16 +116,18 @@ class CudaOps:
         rp, ldr = (None, 0) if res is None else self._p(res)
         N, K = w.shape
         assert x[2] == K and y[2] == N, (x[2], K, y[2], N)
-        _lib.check(self.lib.scp_linear(xp, ldx, _lib.ptr(w), _lib.ptr(b), rp, ldr, yp, ldy, M, N, K, ACT[act],
-                                       self.engine if engine is None else ENGINE[engine], _lib.stream_ptr()),
-                   "scp_linear")
+        with self._rec("linear", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (2 if res is not None else 1))):
+            _lib.check(self.lib.scp_linear(xp, ldx, _lib.ptr(w), _lib.ptr(b), rp, ldr, yp, ldy, M, N, K, ACT[act],
+                                           self.engine if engine is None else ENGINE[engine], _lib.stream_ptr()),
+                       "scp_linear")
 
     def layernorm(self, x, g, b, y, res=None, eps=1e-5):
         xp, ldx = self._p(x)
         yp, ldy = self._p(y)
         rp, ldr = (None, 0) if res is None else self._p(res)
-        _lib.check(self.lib.scp_layernorm(xp, ldx, rp, ldr, _lib.ptr(g), _lib.ptr(b), yp, ldy, x[0].shape[0], x[2],
-                                          eps, _lib.stream_ptr()), "scp_layernorm")
+        with self._rec("layernorm", 8.0 * x[0].shape[0] * x[2], 4.0 * x[0].shape[0] * x[2] * (3 if res is not None else 2)):
+            _lib.check(self.lib.scp_layernorm(xp, ldx, rp, ldr, _lib.ptr(g), _lib.ptr(b), yp, ldy, x[0].shape[0], x[2],
+                                              eps, _lib.stream_ptr()), "scp_layernorm")
 
     def ehem_embed(self, ctx, occ_enc, level_enc, octant_enc, y):
         yp, ldy = self._p(y)
@@ -120,24 +143,30 @@ class CudaOps:
     def knn(self, x, seqs, k):
         xp, ldx = self._p(x)
         idx = torch.empty((x[0].shape[0], k), dtype=torch.int32, device=x[0].device)
-        _lib.check(self.lib.scp_knn(xp, ldx, x[2], seqs.handle, k, _lib.ptr(idx), _lib.stream_ptr()), "scp_knn")
+        fl = sum(2.0 * n * n * x[2] for n in seqs.lengths)
+        with self._rec("knn", fl, 4.0 * x[0].shape[0] * (x[2] + k)):
+            _lib.check(self.lib.scp_knn(xp, ldx, x[2], seqs.handle, k, _lib.ptr(idx), _lib.stream_ptr()), "scp_knn")
         return idx
 
     def edge_gather_max(self, uv, C_, idx, bn_scale, bn_shift, y):
         up, ldu = self._p(uv)
         yp, ldy = self._p(y)
-        _lib.check(self.lib.scp_edge_gather_max(up, ldu, C_, _lib.ptr(idx), idx.shape[1], idx.shape[0],
-                                                _lib.ptr(bn_scale), _lib.ptr(bn_shift), yp, ldy, _lib.stream_ptr()),
-                   "scp_edge_gather_max")
+        n = idx.shape[0]
+        with self._rec("edge_gather", 2.0 * n * C_ * idx.shape[1], 4.0 * n * (C_ * (idx.shape[1] + 2) + idx.shape[1])):
+            _lib.check(self.lib.scp_edge_gather_max(up, ldu, C_, _lib.ptr(idx), idx.shape[1], n,
+                                                    _lib.ptr(bn_scale), _lib.ptr(bn_shift), yp, ldy, _lib.stream_ptr()),
+                       "scp_edge_gather_max")
 
     def swin_attention(self, q, k, v, qb, kb, vb, relpos, heads, seqs, shift, y):
         qp, ldq = self._p(q)
         kp, ldk = self._p(k)
         vp, ldv = self._p(v)
         yp, ldy = self._p(y)
-        _lib.check(self.lib.scp_swin_attention(qp, ldq, kp, ldk, vp, ldv, _lib.ptr(qb), _lib.ptr(kb), _lib.ptr(vb),
-                                               _lib.ptr(relpos), heads, seqs.handle, shift, yp, ldy,
-                                               _lib.stream_ptr()), "scp_swin_attention")
+        nwin = sum((n + 511) // 512 for n in seqs.lengths)
+        with self._rec("swin_attention", 4.0 * nwin * heads * 512 * 512 * 64, 4.0 * 4 * seqs.total * heads * 64):
+            _lib.check(self.lib.scp_swin_attention(qp, ldq, kp, ldk, vp, ldv, _lib.ptr(qb), _lib.ptr(kb), _lib.ptr(vb),
+                                                   _lib.ptr(relpos), heads, seqs.handle, shift, yp, ldy,
+                                                   _lib.stream_ptr()), "scp_swin_attention")
 
     def pair_concat(self, x, src, dst, y):
         xp, ldx = self._p(x)
