@@ -197,6 +197,8 @@ int64_t   scp_seqs_total(const scp_seqs* s);
 int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_bias,
                const float* d_res, int64_t ldr, float* d_y, int64_t ldy,
                int64_t M, int N, int K, int act, int engine, void* stream);
+/* What SCP_GEMM_AUTO means: 0 = fp32 SIMT everywhere, 1 = tcgen05 TF32 for the large layers. Returns the old value. */
+int scp_set_auto_engine(int use_tf32);
 /* 1 if the tcgen05 engine can take this shape (alignment rules in DESIGN.md). */
 int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K);
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "scp_seqs_destroy": (None, [_vp]),
     "scp_seqs_total": (_i64, [_vp]),
     "scp_linear": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp]),
+    "scp_set_auto_engine": (_i, [_i]),
     "scp_linear_tf32_supported": (_i, [_i64, _i64, _i64, _i, _i]),
     "scp_layernorm": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _f, _vp]),
     "scp_ehem_embed": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _vp, _i64, _vp]),

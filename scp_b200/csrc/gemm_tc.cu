@@ -1,10 +1,334 @@
-// tcgen05 / TMEM / TMA GEMM engine (placeholder until the kernel below is validated on hardware).
+// tcgen05 / TMEM / TMA GEMM engine for nn.Linear:  Y[M,N] = act(X[M,K] W[N,K]^T + b) (+ R)   (sm_100a only)
+//
+// Both operands are K-major (row-major with K contiguous), which is exactly tcgen05's "K-major A, K-major B"
+// form, so no transposes are needed.  Persistent, warp-specialised CTA (256 threads):
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled [128 x 32] A tiles and [BN x 32] B tiles
+//   warp 1   MMA issuer     one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8), fp32 accumulate in TMEM
+//   warp 2   TMEM allocator (2 accumulator stages x BN columns, so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 4-7 epilogue      tcgen05.ld 32x32b.x32 -> bias / activation / residual -> global
+// smem ring of STAGES x (A 16 KB + B BN*128 B) with full/empty mbarriers; tcgen05.commit releases stages.
+// Operands are read as fp32 and rounded to TF32 by the tensor core (10-bit mantissa), accumulation is fp32.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
+
 namespace scp {
-bool linear_tf32_ok(long long, long long, long long, int, int, const void*, const void*, const void*) { return false; }
-int linear_tf32(const float*, long long, const float*, const float*, const float*, long long, float*, long long,
-                long long, int, int, int, cudaStream_t) {
-    set_error("tcgen05 engine not built");
-    return SCP_ERR_STATE;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > 8000000000ll) __trap();      // never hang the GPU on a protocol bug
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(tile) >> 4) & 0x3fff);     // start address
+    d |= (uint64_t)1 << 16;                               // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+    switch (act) {
+        case SCP_ACT_LEAKY001: return v > 0.f ? v : 0.01f * v;
+        case SCP_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        case SCP_ACT_RELU: return v > 0.f ? v : 0.f;
+        default: return v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CUtensorMap tmA,
+                                                       const __grid_constant__ CUtensorMap tmB,
+                                                       const float* __restrict__ bias, const float* __restrict__ R,
+                                                       long long ldr, float* __restrict__ Y, long long ldy, long long M, int N,
+                                                       int K, int act) {
+    constexpr int BM = 128, BK = 32;
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles_n = (N + BN - 1) / BN;
+    const long long n_tiles = ((M + BM - 1) / BM) * n_tiles_n;
+    const int n_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    uint8_t* a = smem + stage * STAGE_BYTES;
+                    tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(a + A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint8_t* a = smem + stage * STAGE_BYTES;
+                    const uint64_t da = make_smem_desc(a), db = make_smem_desc(a + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)       // 8 tf32 = 32 bytes = 2 descriptor units per MMA
+                        tc_mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    tc_commit(&empty[stage]);              // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[acc]);                    // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const int w = warp - 4;                            // TMEM lane quarter this warp may read
+        int acc = 0; uint32_t acc_phase = 0;
+        const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
+                            (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0)));
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * BM + w * 32 + lane;
+            const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tc_ld32(t_row + (uint32_t)c0, r);
+                const int n0 = n_blk * BN + c0;
+                if (row < M && n0 < N) {
+                    float* yrow = Y + row * ldy + n0;
+                    const float* rrow = R ? R + row * ldr + n0 : nullptr;
+                    if (vec_ok && n0 + 32 <= N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 v;
+                            v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
+                            v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+                            if (bias) { const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + j); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+                            v.x = tc_act(v.x, act); v.y = tc_act(v.y, act); v.z = tc_act(v.z, act); v.w = tc_act(v.w, act);
+                            if (rrow) { const float4 q = *reinterpret_cast<const float4*>(rrow + j); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+                            *reinterpret_cast<float4*>(yrow + j) = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (n0 + j < N) {
+                                float v = __uint_as_float(r[j]);
+                                if (bias) v += bias[n0 + j];
+                                v = tc_act(v, act);
+                                if (rrow) v += rrow[j];
+                                yrow[j] = v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps (cached) + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* p; long long ld; long long rows; int cols; int box_rows;
+    bool operator==(const MapKey& o) const { return p == o.p && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+};
+struct MapHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.p);
+        h ^= (size_t)k.ld * 0x9e3779b97f4a7c15ull; h ^= (size_t)k.rows * 0xc2b2ae3d27d4eb4full;
+        h ^= ((size_t)k.cols << 20) ^ (size_t)k.box_rows;
+        return h;
+    }
+};
+
+static int get_map(const float* p, long long ld, long long rows, int cols, int box_rows, CUtensorMap* out) {
+    static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+    static std::mutex mu;
+    MapKey key{p, ld, rows, cols, box_rows};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return SCP_OK; }
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SCP_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d ld=%lld", (int)r, rows, cols, ld); return SCP_ERR_CUDA; }
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return SCP_OK;
+}
+
+bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, const void* x, const void* w, const void* y) {
+    (void)ldy; (void)y;
+    if (M < 1 || N < 8 || K < 32) return false;
+    if (K % 4 || ldx % 4) return false;
+    if (x && (reinterpret_cast<uintptr_t>(x) & 15)) return false;
+    if (w && (reinterpret_cast<uintptr_t>(w) & 15)) return false;
+    return true;
+}
+
+template <int BN, int STAGES>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* res, long long ldr, float* y,
+                  long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
+    constexpr int smem = STAGES * (128 * 128 + BN * 128) + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        SCP_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    const long long tiles = cdiv(M, 128) * cdiv(N, BN);
+    const int grid = (int)std::min<long long>(tiles, n_sm);
+    k_gemm_tf32<BN, STAGES><<<grid, 256, smem, st>>>(ma, mb, bias, res, ldr, y, ldy, M, N, K, act);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+int linear_tf32(const float* x, long long ldx, const float* w, const float* bias, const float* res, long long ldr, float* y,
+                long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
+    const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    CUtensorMap ma, mb;
+    if (int e = get_map(x, ldx, M, K, 128, &ma)) return e;
+    if (int e = get_map(w, K, N, K, BN, &mb)) return e;
+    if (BN == 256) return launch<256, 4>(ma, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
+    if (BN == 128) return launch<128, 6>(ma, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
+    return launch<64, 8>(ma, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
+}
+
 }  // namespace scp

@@ -705,6 +705,8 @@ __global__ void __launch_bounds__(128) k_octattn_attn(const float* __restrict__ 
     }
 }
 
+static int g_auto_tf32 = 0;      // flipped by scp_set_auto_engine once the tcgen05 engine is validated on the device
+
 static inline int grid_for(long long work, int per_block, int cap = 148 * 16) {
     return (int)std::max<long long>(1, std::min<long long>(cdiv(work, per_block), cap));
 }
@@ -763,6 +765,8 @@ void scp_seqs_destroy(scp_seqs* s) {
 
 int64_t scp_seqs_total(const scp_seqs* s) { return s ? s->total : -1; }
 
+int scp_set_auto_engine(int use_tf32) { int old = g_auto_tf32; g_auto_tf32 = use_tf32 ? 1 : 0; return old; }
+
 int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K) {
     return linear_tf32_ok(ldx, ldy, M, N, K, nullptr, nullptr, nullptr) ? 1 : 0;
 }
@@ -774,10 +778,10 @@ int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b
     if (M == 0) return SCP_OK;
     cudaStream_t st = as_stream(stream);
     const bool tc_ok = linear_tf32_ok(ldx, ldy, M, N, K, d_x, d_w, d_y);
-    if (engine == SCP_GEMM_TF32) {
-        SCP_REQUIRE(tc_ok, "scp_linear: shape M=%lld N=%d K=%d ldx=%lld not supported by the tcgen05 engine", (long long)M, N, K, (long long)ldx);
+    // SCP_GEMM_TF32: tensor cores wherever the shape allows (tiny / unaligned layers stay on the fp32 tiles);
+    // SCP_GEMM_AUTO: tensor cores for the large layers only
+    if (tc_ok && (engine == SCP_GEMM_TF32 || (engine == SCP_GEMM_AUTO && g_auto_tf32 && M >= 512 && N >= 64)))
         return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st);
-    }
     const int vec4 = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_w) & 15) == 0);
     if (N > 64 && M > 2048) {

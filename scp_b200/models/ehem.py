@@ -102,15 +102,16 @@ class EHEM(nn.Module):
         """nn.Sequential(Linear, LeakyReLU, Linear, LeakyReLU, Linear); ``out`` is the view to write."""
         ops, sd = self.ops, self._prep["sd"]
         rows = kw.get("rows", x[0].shape[0])
+        eng = kw.pop("engine", None)
         cur, first = x, True
         for li, act in zip((0, 2, 4), acts):
             w, b = sd[f"{prefix}.{li}.weight"], sd[f"{prefix}.{li}.bias"]
             dst = out if li == 4 else V(ops.empty(rows, w.shape[0], x[0]))
             if first:
-                ops.linear(cur, w, b, dst, act=act, **kw)
+                ops.linear(cur, w, b, dst, act=act, engine=eng, **kw)
                 first = False
             else:
-                ops.linear(cur, w, b, dst, act=act)
+                ops.linear(cur, w, b, dst, act=act, engine=eng)
             cur = dst
         return out
 
@@ -207,10 +208,10 @@ class EHEM(nn.Module):
         ops.copy_cols(V(P123, 0, 64), V(F2, 0, 64))
         idx = ops.knn(V(F2), seqs, k)
         uv = ops.empty(T, 256, pos)
-        ops.linear(V(F2), P["conv2.w"], None, V(uv))
+        ops.linear(V(F2), P["conv2.w"], None, V(uv), engine="simt")      # feeds kNN #3: keep fp32 (neighbour sets)
         ops.edge_gather_max(V(uv), 128, idx, P["conv2.s"], P["conv2.t"], V(P123, 64, 128))
         ops.copy_cols(V(P123, 64, 128), V(F3, 0, 128))
-        self._mlp(f"{g}.mlp2", V(F2, 64, 80), V(F3, 128, 64))
+        self._mlp(f"{g}.mlp2", V(F2, 64, 80), V(F3, 128, 64), engine="simt")
         idx = ops.knn(V(F3), seqs, k)
         uv = ops.empty(T, 512, pos)
         ops.linear(V(F3), P["conv3.w"], None, V(uv))

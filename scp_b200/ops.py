@@ -4,6 +4,7 @@
 Tensors are views into caller-owned buffers: every op takes (tensor, column offset, columns) style
 arguments through ``View`` so that concatenations are written in place instead of copied."""
 import ctypes as C
+import os
 
 import torch
 
@@ -70,9 +71,9 @@ class _Rec:
 class CudaOps:
     name = "cuda"
 
-    def __init__(self, engine="auto"):
+    def __init__(self, engine=None):
         self.lib = _lib.require_device()
-        self.engine = ENGINE[engine]
+        self.engine = ENGINE[engine or os.environ.get("SCP_GEMM", "auto")]
         self.prof = None          # bench.py: list of (kernel tag, flops, bytes, start event, end event)
 
     def _rec(self, tag, flops, nbytes):
