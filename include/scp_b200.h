@@ -190,15 +190,18 @@ int64_t   scp_seqs_total(const scp_seqs* s);
 
 #define SCP_GEMM_AUTO 0
 #define SCP_GEMM_SIMT 1      /* fp32 FFMA tiles */
-#define SCP_GEMM_TF32 2      /* tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators */
+#define SCP_GEMM_TF32 2      /* tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators (10-bit mantissa operands) */
+#define SCP_GEMM_TF32X3 3    /* same engine, error-compensated split (x_hi + x_lo): fp32-class accuracy */
 
 /* y[M,N] = act( x[M,K] @ W[N,K]^T + bias[N] ) (+ residual[M,N])   -- nn.Linear with fused epilogue.
  * bias, residual may be NULL.  ldx/ldy/ldr = row strides in floats (W is dense [N,K]). */
 int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_bias,
                const float* d_res, int64_t ldr, float* d_y, int64_t ldy,
                int64_t M, int N, int K, int act, int engine, void* stream);
-/* What SCP_GEMM_AUTO means: 0 = fp32 SIMT everywhere, 1 = tcgen05 TF32 for the large layers. Returns the old value. */
+/* What SCP_GEMM_AUTO means: 0 = fp32 SIMT everywhere, 1 = tcgen05 3xTF32 for the large layers. Returns the old value. */
 int scp_set_auto_engine(int use_tf32);
+/* Drops the cached hi/lo splits of weight matrices (call after weights changed in place). */
+void scp_gemm_cache_clear(void);
 /* 1 if the tcgen05 engine can take this shape (alignment rules in DESIGN.md). */
 int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K);
 

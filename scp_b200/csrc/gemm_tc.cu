@@ -8,6 +8,12 @@
 //   warps 4-7 epilogue      tcgen05.ld 32x32b.x32 -> bias / activation / residual -> global
 // smem ring of STAGES x (A 16 KB + B BN*128 B) with full/empty mbarriers; tcgen05.commit releases stages.
 // Operands are read as fp32 and rounded to TF32 by the tensor core (10-bit mantissa), accumulation is fp32.
+//
+// SPLIT = true is the error-compensated "3xTF32" mode that keeps fp32-class accuracy (needed for the 1e-3 PMF
+// parity bound): x = x_hi + x_lo with x_hi = x & 0xffffe000 (exactly representable in TF32) and
+//     D += A_hi B_hi + A_lo B_hi + A_hi B_lo          (the dropped A_lo B_lo term is ~2^-22 relative).
+// W_hi / W_lo are split once per weight matrix (cached); A tiles are split in shared memory by warps 2-3 between the
+// TMA arrival and the MMA (generic-proxy writes + fence.proxy.async), so activations are still read once from HBM.
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
@@ -96,14 +102,18 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CUtensorMap tmA,
                                                        const __grid_constant__ CUtensorMap tmB,
+                                                       const __grid_constant__ CUtensorMap tmBlo,
                                                        const float* __restrict__ bias, const float* __restrict__ R,
                                                        long long ldr, float* __restrict__ Y, long long ldy, long long M, int N,
                                                        int K, int act) {
     constexpr int BM = 128, BK = 32;
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr int STAGE_BYTES = SPLIT ? 2 * (A_BYTES + B_BYTES) : (A_BYTES + B_BYTES);   // [A | B] or [A_hi | A_lo | B_hi | B_lo]
+    constexpr int TX_BYTES = SPLIT ? (A_BYTES + 2 * B_BYTES) : (A_BYTES + B_BYTES);
+    constexpr int OFF_ALO = A_BYTES, OFF_B = SPLIT ? 2 * A_BYTES : A_BYTES, OFF_BLO = OFF_B + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -111,7 +121,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* ready = tempty + 2;                        // SPLIT: A tile split done (2 splitter warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = (N + BN - 1) / BN;
@@ -123,7 +134,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 2); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -144,10 +155,11 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
                 const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], TX_BYTES);
                     uint8_t* a = smem + stage * STAGE_BYTES;
                     tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(a + A_BYTES, &tmB, &full[stage], kb * BK, n_blk * BN);
+                    tma_load_2d(a + OFF_B, &tmB, &full[stage], kb * BK, n_blk * BN);
+                    if (SPLIT) tma_load_2d(a + OFF_BLO, &tmBlo, &full[stage], kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -163,18 +175,50 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
                     tc_fence_after();
                     const uint8_t* a = smem + stage * STAGE_BYTES;
-                    const uint64_t da = make_smem_desc(a), db = make_smem_desc(a + A_BYTES);
+                    const uint64_t da = make_smem_desc(a), db = make_smem_desc(a + OFF_B);
+                    const uint64_t dal = make_smem_desc(a + OFF_ALO), dbl = make_smem_desc(a + OFF_BLO);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)       // 8 tf32 = 32 bytes = 2 descriptor units per MMA
-                        tc_mma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < BK / 8; ++k) {     // 8 tf32 = 32 bytes = 2 descriptor units per MMA
+                        const uint64_t o = (uint64_t)(2 * k);
+                        tc_mma_tf32(d_tmem, da + o, db + o, idesc, (kb | k) ? 1u : 0u);
+                        if (SPLIT) {
+                            tc_mma_tf32(d_tmem, dal + o, db + o, idesc, 1u);
+                            tc_mma_tf32(d_tmem, da + o, dbl + o, idesc, 1u);
+                        }
+                    }
                     tc_commit(&empty[stage]);              // frees the smem stage when these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(&tfull[acc]);                    // accumulator ready for the epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (SPLIT && (warp == 2 || warp == 3)) {
+        // split the freshly landed A tile in place: A <- A_hi, A_lo tile next to it (same swizzled layout)
+        const int tsp = (warp - 2) * 32 + lane;            // 0..63
+        int stage = 0; uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                uint4* hi = reinterpret_cast<uint4*>(smem + stage * STAGE_BYTES);
+                uint4* lo = reinterpret_cast<uint4*>(smem + stage * STAGE_BYTES + OFF_ALO);
+#pragma unroll 4
+                for (int i = tsp; i < A_BYTES / 16; i += 64) {
+                    uint4 v = hi[i], h, l;
+                    h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+                    l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+                    l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+                    l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+                    l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+                    hi[i] = h; lo[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -293,6 +337,42 @@ static int get_map(const float* p, long long ld, long long rows, int cols, int b
     return SCP_OK;
 }
 
+// W -> [W_hi ; W_lo] (two [N,K] matrices back to back), cached per weight pointer
+__global__ void __launch_bounds__(256) k_split_weights(const float* __restrict__ w, long long n, float* __restrict__ hi,
+                                                        float* __restrict__ lo) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float v = w[i];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        hi[i] = h; lo[i] = v - h;
+    }
+}
+
+struct WKey { const void* p; int n, k; bool operator==(const WKey& o) const { return p == o.p && n == o.n && k == o.k; } };
+struct WHash { size_t operator()(const WKey& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.n << 40) ^ ((size_t)k.k << 20); } };
+static std::unordered_map<WKey, float*, WHash> g_wsplit;
+static std::mutex g_wmu;
+
+void gemm_cache_clear() {
+    std::lock_guard<std::mutex> g(g_wmu);
+    for (auto& kv : g_wsplit) cudaFree(kv.second);
+    g_wsplit.clear();
+}
+
+static int get_weight_split(const float* w, int N, int K, cudaStream_t st, float** out) {
+    std::lock_guard<std::mutex> g(g_wmu);
+    WKey key{w, N, K};
+    auto it = g_wsplit.find(key);
+    if (it != g_wsplit.end()) { *out = it->second; return SCP_OK; }
+    float* buf = nullptr;
+    const long long n = (long long)N * K;
+    SCP_CUDA(cudaMalloc((void**)&buf, 2 * n * 4));
+    k_split_weights<<<(unsigned)std::min<long long>(cdiv(n, 256), 1184), 256, 0, st>>>(w, n, buf, buf + n);
+    SCP_LAUNCHED();
+    g_wsplit[key] = buf;
+    *out = buf;
+    return SCP_OK;
+}
+
 bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, const void* x, const void* w, const void* y) {
     (void)ldy; (void)y;
     if (M < 1 || N < 8 || K < 32) return false;
@@ -302,33 +382,42 @@ bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, con
     return true;
 }
 
-template <int BN, int STAGES>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const float* bias, const float* res, long long ldr, float* y,
-                  long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
-    constexpr int smem = STAGES * (128 * 128 + BN * 128) + 1024 + 256;
+template <int BN, int STAGES, bool SPLIT>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, const float* res,
+                  long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
+    constexpr int smem = STAGES * (128 * 128 + BN * 128) * (SPLIT ? 2 : 1) + 1024 + 512;
     static bool attr = false;
     if (!attr) {
-        SCP_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SCP_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const long long tiles = cdiv(M, 128) * cdiv(N, BN);
     const int grid = (int)std::min<long long>(tiles, n_sm);
-    k_gemm_tf32<BN, STAGES><<<grid, 256, smem, st>>>(ma, mb, bias, res, ldr, y, ldy, M, N, K, act);
+    k_gemm_tf32<BN, STAGES, SPLIT><<<grid, 256, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act);
     SCP_LAUNCHED();
     return SCP_OK;
 }
 
 int linear_tf32(const float* x, long long ldx, const float* w, const float* bias, const float* res, long long ldr, float* y,
-                long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
-    const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
-    CUtensorMap ma, mb;
+                long long ldy, long long M, int N, int K, int act, cudaStream_t st, int split) {
+    CUtensorMap ma, mb, mbl;
     if (int e = get_map(x, ldx, M, K, 128, &ma)) return e;
+    if (split) {
+        float* ws = nullptr;
+        if (int e = get_weight_split(w, N, K, st, &ws)) return e;
+        const int BN = N > 64 ? 128 : 64;
+        if (int e = get_map(ws, K, N, K, BN, &mb)) return e;
+        if (int e = get_map(ws + (long long)N * K, K, N, K, BN, &mbl)) return e;
+        if (BN == 128) return launch<128, 3, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
+        return launch<64, 4, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
+    }
+    const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
     if (int e = get_map(w, K, N, K, BN, &mb)) return e;
-    if (BN == 256) return launch<256, 4>(ma, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
-    if (BN == 128) return launch<128, 6>(ma, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
-    return launch<64, 8>(ma, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
+    if (BN == 256) return launch<256, 4, false>(ma, mb, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
+    if (BN == 128) return launch<128, 6, false>(ma, mb, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
+    return launch<64, 8, false>(ma, mb, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
 }
 
 }  // namespace scp

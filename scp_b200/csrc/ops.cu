@@ -28,7 +28,8 @@ struct scp_seqs {
 namespace scp {
 
 int linear_tf32(const float* x, long long ldx, const float* w, const float* bias, const float* res, long long ldr,
-                float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st);   // gemm_tc.cu
+                float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st, int split);   // gemm_tc.cu
+void gemm_cache_clear();
 bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, const void* x, const void* w, const void* y);
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -765,6 +766,8 @@ void scp_seqs_destroy(scp_seqs* s) {
 
 int64_t scp_seqs_total(const scp_seqs* s) { return s ? s->total : -1; }
 
+void scp_gemm_cache_clear(void) { gemm_cache_clear(); }
+
 int scp_set_auto_engine(int use_tf32) { int old = g_auto_tf32; g_auto_tf32 = use_tf32 ? 1 : 0; return old; }
 
 int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K) {
@@ -778,10 +781,11 @@ int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b
     if (M == 0) return SCP_OK;
     cudaStream_t st = as_stream(stream);
     const bool tc_ok = linear_tf32_ok(ldx, ldy, M, N, K, d_x, d_w, d_y);
-    // SCP_GEMM_TF32: tensor cores wherever the shape allows (tiny / unaligned layers stay on the fp32 tiles);
-    // SCP_GEMM_AUTO: tensor cores for the large layers only
-    if (tc_ok && (engine == SCP_GEMM_TF32 || (engine == SCP_GEMM_AUTO && g_auto_tf32 && M >= 512 && N >= 64)))
-        return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st);
+    // SCP_GEMM_TF32 / SCP_GEMM_TF32X3: tensor cores wherever the shape allows (tiny / unaligned layers stay on the fp32
+    // tiles); SCP_GEMM_AUTO: error-compensated tensor cores for the large layers only (once enabled)
+    if (tc_ok && engine == SCP_GEMM_TF32) return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st, 0);
+    if (tc_ok && (engine == SCP_GEMM_TF32X3 || (engine == SCP_GEMM_AUTO && g_auto_tf32 && M >= 512 && N >= 64)))
+        return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st, 1);
     const int vec4 = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_w) & 15) == 0);
     if (N > 64 && M > 2048) {

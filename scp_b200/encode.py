@@ -1,0 +1,181 @@
+"""Drop-in for the reference's ``encode.py``: same ``compress_ehem(batch, outputfile, model, args)`` /
+``compress(batch, outputfile, model, args)`` contracts (encode.py:85-160, :23-82), same output files
+(``<name>[_spher|_cylin]_<levels>_<bin_num>_<z_offset>.bin`` + ``.dat``), same printed report, same CLI flags
+(:315-336).  The per-window Python loop, softmax, PMF download and numpyAc call are replaced by one ragged batch
+on the GPU (scp_b200.encoder).  No checkpoints / hydra offline: ``--ckpt_path`` is optional and, when absent,
+the seeded "random-init+" weights are used."""
+import argparse
+import glob
+import os
+import time
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .dataloaders.encode_dataset import EncodeDataset
+from .dataloaders.encode_dataset_ehem import EncodeEHEMDataset
+from .encoder import Encoder
+from .models import EHEM, OctAttention
+from . import coder
+
+MULLEVEL = False
+
+
+def _report(outputfile, elapsed, pt_num, oct_len, real_rate):
+    np.set_printoptions(formatter={"float": "{: 0.4f}".format})
+    print("outputfile                  :", outputfile)
+    print("time(s)                     :", elapsed)
+    print("pt num                      :", pt_num)
+    print("oct num                     :", oct_len)
+    print("total binsize               :", real_rate)
+    print("bit per oct                 :", real_rate / oct_len)
+    print("bit per pixel               :", real_rate / pt_num)
+
+
+def _unbatch(x):
+    x = torch.as_tensor(x)
+    return x[0] if x.dim() and x.shape[0] == 1 else x
+
+
+def compress_ehem(batch, outputfile, model, args, mullevel=MULLEVEL):
+    """encode.py:85-160 / encode_mullevel.py:88-157."""
+    model.eval()
+    ids, pos, pos_mm, data, oct_seq, pt_num, pc, bin_num, z_offset = batch
+    pt_num, bin_num, z_offset = int(pt_num), int(bin_num), int(z_offset)
+    oct_len = int(_unbatch(oct_seq).shape[0])
+    enc = Encoder(model, getattr(args, "lidar_level", 12), "spher", mullevel=mullevel)
+    t0 = time.time()
+    ctx = torch.cat([_unbatch(d).to(torch.uint8) for d in data]).cuda()                 # (N,4,3) level, octant, occ
+    p = torch.cat([_unbatch(q).transpose(0, 1) for q in pos]).to(torch.float32).cuda()  # (3,N_l) -> (N,3)
+    sizes = [int(_unbatch(d).shape[0]) for d in data]
+    restart = [1] + [0] * (len(sizes) - 1)
+    interval = enc.encode_context(ctx, p, sizes, restart)
+    torch.cuda.synchronize()
+    elapsed = time.time() - t0
+    stream = coder.range_encode(interval.cpu().numpy())
+    if getattr(args, "spher", False):
+        outputfile += '_spher'
+    elif getattr(args, "cylin", False):
+        outputfile += '_cylin'
+    outputfile += '_' + str(len(data)) + '_' + str(bin_num) + '_' + str(z_offset) + '.bin'
+    if os.path.dirname(outputfile) and not os.path.exists(os.path.dirname(outputfile)):
+        os.makedirs(os.path.dirname(outputfile))
+    with open(outputfile, 'wb') as f:
+        f.write(stream)
+    torch.save(torch.Tensor(np.array([[float(a), float(b)] for a, b in pos_mm])), outputfile + '.dat')
+    real_rate = len(stream) * 8
+    _report(outputfile, elapsed, pt_num, oct_len, real_rate)
+    return real_rate / pt_num, elapsed
+
+
+def compress(batch, outputfile, model, args):
+    """encode.py:23-82 (OctAttention, non level-wise, window = context_size)."""
+    if getattr(args, "sequential", False):
+        raise NotImplementedError("--sequential (stride-1 windows) is not part of the accelerated path")
+    model.eval()
+    ids, pos, data, oct_seq, pt_num, bin_num = batch
+    outputfile += '.bin'
+    oct_len = int(_unbatch(oct_seq).shape[0])
+    cs = model.cfg.model.context_size
+    t0 = time.time()
+    intervals = []
+    for d, p in zip(data, pos):
+        d, p = _unbatch(d).cuda(), _unbatch(p).cuda()
+        L = d.shape[0]
+        offs = list(range(0, L, cs)) + [L]
+        ctx = torch.stack((d[..., 1], d[..., 2], d[..., 0]), -1).to(torch.uint8)
+        ipos = torch.round(p.double() * (1 << 21)).to(torch.int32)
+        logits = model.forward_ragged(ctx, ipos, offs, 1.0 / float(1 << 21))
+        sym = d[:, 3, 0].to(torch.int16).contiguous()
+        iv = coder.pmf_to_cdf(logits, sym=sym, is_logits=True, want_interval=True)["interval"]
+        intervals.append(iv[cs - 1:] if len(data) == 1 else iv[cs - 1:])
+    interval = torch.cat(intervals)[:oct_len]
+    torch.cuda.synchronize()
+    elapsed = time.time() - t0
+    stream = coder.range_encode(interval.cpu().numpy())
+    if os.path.dirname(outputfile) and not os.path.exists(os.path.dirname(outputfile)):
+        os.makedirs(os.path.dirname(outputfile))
+    with open(outputfile, 'wb') as f:
+        f.write(stream)
+    real_rate = len(stream) * 8
+    _report(outputfile, elapsed, int(pt_num), oct_len, real_rate)
+    return real_rate / int(pt_num), elapsed
+
+
+def make_cfg(model_name, data_type):
+    NS = types.SimpleNamespace
+    if model_name == "EHEM":
+        m = NS(class_name="EHEM", context_size=8192, token_num=255, level_k=4, max_level=19)
+    else:
+        m = NS(class_name="OctAttention", max_octree_level=12, context_size=1024, token_num=255, layer_num=3, head_num=4,
+               abs_pos_embed_dim=12, occ_embed_dim=128, level_embed_dim=6, octant_embed_dim=4, hidden_dimension=300,
+               level_k=4, pos_embed=True)
+    return NS(model=m, train=NS(type=data_type, dropout=0.0), data=NS(extra_pos=False))
+
+
+def build_model(args):
+    cfg = make_cfg(args.model, args.type)
+    model = (EHEM if args.model == "EHEM" else OctAttention)(cfg)
+    if args.ckpt_path:
+        sd = torch.load(args.ckpt_path, map_location="cpu")
+        model.load_state_dict(sd.get("state_dict", sd), strict=True)      # Lightning checkpoints keep 'state_dict'
+    return model.cuda()
+
+
+def main(args, mullevel=MULLEVEL):
+    model = build_model(args)
+    test_files = args.test_files
+    if '*' in test_files[0]:
+        test_files = sorted(glob.glob(test_files[0]))
+    test_output_path = args.out_dir.rstrip('/') + '/'
+    if args.model == "EHEM":
+        if mullevel:
+            from .dataloaders.encode_dataset_ehem_mullevel import EncodeEHEMDataset as DS
+            testset = DS(test_files, 8192, args.type, True, args.lidar_level, args.cylin, args.spher, args.preproc_path)
+        else:
+            testset = EncodeEHEMDataset(test_files, 8192, args.type, True, args.lidar_level, args.cylin,
+                                        args.spher or args.spher_circle, args.spher_circle, False, args.preproc_path)
+    else:
+        testset = EncodeDataset(test_files, 1024, args.type, args.level_wise, args.lidar_level, args.spher, args.preproc_path)
+    bpps, times = [], []
+    print("Encoding with", args.model)
+    for i, cur_file in enumerate(test_files):
+        print("Encoding ", cur_file, i, '/', len(test_files))
+        batch = testset[i]
+        name = (cur_file.split('/')[-2] + Path(cur_file).stem) if args.type == 'kitti' and cur_file.count('/') >= 2 else Path(cur_file).stem
+        if args.model == "EHEM":
+            bpp, t = compress_ehem(batch[:-2], test_output_path + name, model, args, mullevel)
+        else:
+            bpp, t = compress(batch[:-2], test_output_path + Path(cur_file).stem, model, args)
+        bpps.append(bpp)
+        times.append(t)
+    print('bpps:', bpps)
+    print('sample number:', len(bpps))
+    print('times:', float(np.array(times).mean()))
+    with open(f"test_results_{'mul' if mullevel else 'same'}_{args.type}_{args.lidar_level}.txt", 'a') as f:
+        f.write(f"{'mul' if mullevel else 'same'} {args.lidar_level} {args.test_files} {args.ckpt_path}\\nsample number: {len(bpps)}\\n"
+                f"times: {float(np.array(times).mean())}\\nbpp: {float(np.array(bpps).mean())}\\n\\n")
+    return bpps
+
+
+def get_args(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--ckpt_path", type=str, default="", help="optional state_dict / Lightning checkpoint")
+    parser.add_argument("--model", type=str, default="EHEM", choices=["EHEM", "OctAttention"])
+    parser.add_argument("--test_files", nargs="*", required=True)
+    parser.add_argument("--out_dir", type=str, default="test_output")
+    parser.add_argument("--sequential", action="store_true")
+    parser.add_argument("--type", type=str, default='kitti', choices=['obj', 'kitti', 'ford'])
+    parser.add_argument("--lidar_level", type=int, default=12)
+    parser.add_argument("--level_wise", action="store_true")
+    parser.add_argument("--cylin", action="store_true")
+    parser.add_argument("--spher", action="store_true")
+    parser.add_argument("--spher_circle", action="store_true")
+    parser.add_argument("--preproc_path", type=str, default="")
+    return parser.parse_args(argv)
+
+
+if __name__ == "__main__":
+    main(get_args())

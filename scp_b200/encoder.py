@@ -78,13 +78,13 @@ class Encoder:
     def _ehem_windows(self, infos):
         """(row, len, token) of every context window (encode.py:112-115), level by level."""
         rows, lens = [], []
-        for i in infos:
-            r = i.row_start
-            for n in i.level_rows:
-                for s in range(0, n, self.context):
-                    rows.append(r + s)
-                    lens.append(min(self.context, n - s))
-                r += n
+        r = infos[0].row_start if infos and hasattr(infos[0], "row_start") else 0
+        sizes = [n for i in infos for n in i.level_rows] if infos and hasattr(infos[0], "level_rows") else list(infos)
+        for n in sizes:
+            for s in range(0, n, self.context):
+                rows.append(r + s)
+                lens.append(min(self.context, n - s))
+            r += n
         lens = np.asarray(lens, np.int32)
         toks = np.concatenate([[0], np.cumsum(lens + (lens & 1))]).astype(np.int64)
         return np.asarray(rows, np.int64), lens, toks
@@ -139,6 +139,24 @@ class Encoder:
                                                    [x - lo for x in o], 1.0 / float(1 << max_level))
                 coder.pmf_to_cdf(logits, sym=sym, is_logits=True, row_of=row_of[lo:hi].contiguous(),
                                  out={"interval": interval_row})
+
+    @torch.no_grad()
+    def encode_context(self, ctx, pos, level_sizes, level_restart=None):
+        """Entropy-model + CDF + coding order for context tensors that already exist (the ``batch`` a reference
+        ``EncodeEHEMDataset`` yields): ctx uint8 [N,4,3] (level, octant, occ 0..254|255), pos float32 [N,3].
+        Returns the (c_low, c_high) intervals in coding order, int32 [N,2] on the device."""
+        assert self.is_ehem
+        N = ctx.shape[0]
+        occ = (ctx[:, 3, 2].to(torch.int16) + 1).to(torch.uint8).contiguous()
+        t = {"ctx": ctx.contiguous(), "pos_norm": pos.contiguous(), "sym": ctx[:, 3, 2].to(torch.int16).contiguous()}
+        interval_row = torch.empty((N, 2), dtype=torch.int32, device=ctx.device)
+        self._ehem_logits_to_intervals(t, [int(n) for n in level_sizes], interval_row)
+        order, _ = coder.coding_order([int(n) for n in level_sizes], self.context, occ, mullevel=self.mullevel,
+                                      level_restart=level_restart)
+        interval = torch.empty_like(interval_row)
+        _lib.check(self.lib.scp_gather_rows8(_lib.ptr(interval_row), _lib.ptr(order), N, _lib.ptr(interval),
+                                             _lib.stream_ptr()), "scp_gather_rows8")
+        return interval
 
     # -- public API ---------------------------------------------------------------------------
     @torch.no_grad()

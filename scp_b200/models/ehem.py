@@ -75,6 +75,8 @@ class EHEM(nn.Module):
         """Derived weights: folded BatchNorm, [Wa; Wb-Wa] edge-conv weights, fused QKV."""
         if self._prep is not None:
             return self._prep
+        if self._ops is not None and hasattr(self._ops, "lib"):
+            self._ops.lib.scp_gemm_cache_clear()              # weights may have changed in place
         sd = {k: v.detach() for k, v in self.state_dict().items()}
         P = {"sd": sd}
         g = "geo_feat_generator"
