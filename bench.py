@@ -190,9 +190,24 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = lib.scp_launch_count() - launches0
     prof, model.ops.prof = model.ops.prof, None
-    octree_ms = enc.builder.stage_ms()
     clocks = sampler.stop() if sampler else None
     n_nodes = sum(f[1] for f in fr)
+
+    # octree / gather kernels alone on a batch large enough to fill the GPU (64 frames = 192 jobs, > L2)
+    OB = 64
+    big = torch.cat([xyz] * (OB // F + 1))[: 0 + sum(len(f) for f in frames) * (OB // F)] if F <= OB else xyz
+    reps = OB // F if F <= OB else 1
+    boffs = np.concatenate([[0], np.cumsum([len(f) for f in frames] * reps)]).astype(np.int64)
+    octree_ms = None
+    for _ in range(4):
+        bb, tt_, _pf = enc.build_context(big, boffs)
+        torch.cuda.synchronize()
+        m = enc.builder.stage_ms()
+        octree_ms = m if octree_ms is None else {k: min(octree_ms[k], v) for k, v in m.items()}
+    o_pts = int(boffs[-1]) * 3
+    o_nodes = bb.total_rows
+    o_depth = max(i.depth for i in bb.infos)
+    del big, tt_
 
     # end to end through the public API: pinned host points in, bitstreams out
     enc.encode(frames)
@@ -233,10 +248,9 @@ def run_ours(args):
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[3] // args.steps,
                    "TFLOPs": v[1] / v[0] / 1e9 if v[0] else None, "GBps": v[2] / v[0] / 1e6 if v[0] else None}
                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
-    npts = int(offs[-1]) * 3
-    P = (3 * max(i.depth for i in infos) + 1 + 7) // 8
-    bm = {"quantise": 20 * npts, "sort": (1 + 2 * P) * 8 * npts, "heads": 8 * npts, "emit": 28 * n_nodes,
-          "occupancy": 6 * n_nodes, "context": 60 * n_nodes}
+    P = (3 * o_depth + 1 + 7) // 8
+    bm = {"quantise": 20 * o_pts, "sort": (1 + 2 * P) * 8 * o_pts, "heads": 8 * o_pts, "emit": 28 * o_nodes,
+          "occupancy": 6 * o_nodes, "context": 60 * o_nodes}
     oct_rep = {k: {"ms": round(v, 4), "GBps": round(bm[k] / v / 1e6, 1) if v > 0 else None,
                    "frac_of_hbm_peak": round(bm[k] / v / 1e6 / hbm_peak, 3) if v > 0 else None} for k, v in octree_ms.items()}
 
@@ -256,7 +270,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
         "kernels": kernels,
-        "octree_stages": oct_rep,
+        "octree_stages": {"batch_frames": reps * F, "points": o_pts, "nodes": o_nodes, "stages": oct_rep},
         "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
                          "sample": cpu_desc},
     }

@@ -145,7 +145,7 @@ class CudaOps:
         xp, ldx = self._p(x)
         idx = torch.empty((x[0].shape[0], k), dtype=torch.int32, device=x[0].device)
         fl = sum(2.0 * n * n * x[2] for n in seqs.lengths)
-        with self._rec("knn", fl, 4.0 * x[0].shape[0] * (x[2] + k)):
+        with self._rec("knn_d%d" % x[2], fl, 4.0 * x[0].shape[0] * (x[2] + k)):
             _lib.check(self.lib.scp_knn(xp, ldx, x[2], seqs.handle, k, _lib.ptr(idx), _lib.stream_ptr()), "scp_knn")
         return idx
 

@@ -1,0 +1,32 @@
+"""Frame-wise multi-GPU partition: frames are independent, so rank r of R encodes frames
+r, r+R, ... in its own process/GPU with replicated weights; there is NO collective on the hot path.  The only
+communication is the final gather of the per-frame (bytes, points) records."""
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def frames_for_rank(n_frames: int, rank: int, world: int) -> List[int]:
+    """Static round-robin: frame counts differ by at most one between ranks."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    return list(range(rank, n_frames, world))
+
+
+def gather_frame_records(local_ids: Sequence[int], local_bytes: Sequence[int], local_points: Sequence[int], n_frames: int,
+                         device="cpu"):
+    """All ranks end up with int64 [n_frames, 2] = (stream bytes, points) for every frame.  Works on gloo (CPU) and
+    nccl (device='cuda'); a single all_reduce over a zero-initialised table, since each frame has exactly one owner."""
+    table = torch.zeros((n_frames, 2), dtype=torch.int64, device=device)
+    for i, b, p in zip(local_ids, local_bytes, local_points):
+        table[i, 0] = int(b)
+        table[i, 1] = int(p)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(table, op=dist.ReduceOp.SUM)
+    return table
+
+
+def mean_bpp(table: torch.Tensor) -> float:
+    """encode.py:294: mean over frames of 8*bytes/points."""
+    return float((8.0 * table[:, 0].double() / table[:, 1].double()).mean())

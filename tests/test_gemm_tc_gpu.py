@@ -15,7 +15,7 @@ def V(t, col=0, ncol=None):
     (4096, 1024, 1280, "leaky", False, 1), (2500, 255, 512, "none", False, 1), (640, 240, 256, "relu", False, 2),
     (300, 64, 80, "leaky", False, 1), (3000, 256, 1024, "none", True, 1), (2500, 1024, 256, "gelu", False, 1),
     (70000, 256, 256, "none", True, 1), (33, 128, 448, "none", False, 1)])
-@pytest.mark.parametrize("engine,tol", [("tf32", 4e-3), ("tf32x3", 2e-6)])
+@pytest.mark.parametrize("engine,tol", [("tf32", 4e-3), ("tf32x3", 1e-5)])
 def test_linear_tensor_core_engines(M, N, K, act, res, step, engine, tol):
     from scp_b200.ops import CudaOps
     cu = CudaOps(engine=engine)
