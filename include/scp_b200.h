@@ -222,6 +222,8 @@ int scp_ehem_embed_occ(const uint8_t* d_ctx, int64_t n_even, const float* d_occ_
  * included) inside its own sequence.  x [total, d] (ldx).  idx [total, k] int32, GLOBAL row indices,
  * descending score; ties -> lower index first; sequences shorter than k repeat the point itself. */
 int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, int32_t* d_idx, void* stream);
+/* d > 4: 1 (default) = tcgen05 3xTF32 Gram tiles + fused top-k, 0 = fp32 SIMT tiles.  Returns the old value. */
+int scp_set_knn_engine(int use_tensor_cores);
 
 /* Edge convolution (dgcnn.py:48-71 get_graph_feature + :79-87 conv/BN/LeakyReLU(0.2) + :134 max over k),
  * evaluated as max_k f(Wa x_nbr + (Wb-Wa) x_i):  uv [total, 2C] = x @ [Wa; Wb-Wa]^T comes from scp_linear,

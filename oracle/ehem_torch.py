@@ -8,7 +8,7 @@ Follows: models/ehem.py:72-136; models/dgcnn.py:10-71,121-154; models/swin_trans
 
 ``knn`` is pluggable because the reference's neighbour choice under EXACT distance ties is whatever
 ``torch.topk`` (libstdc++ partial_sort / nth_element) happens to return; ``knn_torch_topk`` restates that,
-``knn_canonical`` is the deterministic rule of the CUDA path (exact float64 distance for the 3-D kNN,
+``knn_canonical`` is the deterministic rule of the CUDA path (exact float64 distance of the float32 rows,
 ties -> lowest index)."""
 import math
 
@@ -28,21 +28,15 @@ def knn_torch_topk(x, k):
 
 
 def knn_canonical(x, k):
-    """Deterministic rule used by scp_knn: d<=4 -> exact float64 squared distance (diff form, axis order),
-    else the float32 score 2 x.y - |y|^2 - |x|^2 with |.|^2 accumulated by fma in channel order; ties ->
-    lowest index."""
+    """Deterministic rule of scp_knn: the k nearest rows by the EXACT squared distance of the float32 rows (float64
+    accumulation of (a-b)^2 in channel order), ties -> lowest index."""
     C, N = x.shape
-    if C <= 4:
-        xd = x.double().t().contiguous()
-        d = torch.zeros(N, N, dtype=torch.float64)
-        for c in range(C):
-            diff = xd[:, None, c] - xd[None, :, c]
-            d = d + diff * diff
-        score = -d
-    else:
-        xt = x.t().contiguous()
-        score = 2 * (xt @ xt.t()) - (xt * xt).sum(1)[None, :] - (xt * xt).sum(1)[:, None]
-    return torch.argsort(score, dim=1, descending=True, stable=True)[:, :k]
+    xd = x.double().t().contiguous()
+    d = torch.zeros(N, N, dtype=torch.float64)
+    for c in range(C):
+        diff = xd[:, None, c] - xd[None, :, c]
+        d = d + diff * diff
+    return torch.argsort(d, dim=1, stable=True)[:, :k]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -14,81 +14,11 @@
 //     D += A_hi B_hi + A_lo B_hi + A_hi B_lo          (the dropped A_lo B_lo term is ~2^-22 relative).
 // W_hi / W_lo are split once per weight matrix (cached); A tiles are split in shared memory by warps 2-3 between the
 // TMA arrival and the MMA (generic-proxy writes + fence.proxy.async), so activations are still read once from HBM.
-#include <cuda.h>
 #include <mutex>
 #include <unordered_map>
-#include "common.cuh"
+#include "tc.cuh"
 
 namespace scp {
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) return;
-        if (clock64() - t0 > 8000000000ll) __trap();      // never hang the GPU on a protocol bug
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_u32(tile) >> 4) & 0x3fff);     // start address
-    d |= (uint64_t)1 << 16;                               // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: 8 rows x 128 B
-    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
-    return d;
-}
 
 __device__ __forceinline__ float tc_act(float v, int act) {
     switch (act) {
@@ -312,7 +242,7 @@ struct MapHash {
     }
 };
 
-static int get_map(const float* p, long long ld, long long rows, int cols, int box_rows, CUtensorMap* out) {
+int get_tensor_map_2d(const float* p, long long ld, long long rows, int cols, int box_rows, CUtensorMap* out) {
     static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
     static std::mutex mu;
     MapKey key{p, ld, rows, cols, box_rows};
@@ -403,18 +333,18 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
 int linear_tf32(const float* x, long long ldx, const float* w, const float* bias, const float* res, long long ldr, float* y,
                 long long ldy, long long M, int N, int K, int act, cudaStream_t st, int split) {
     CUtensorMap ma, mb, mbl;
-    if (int e = get_map(x, ldx, M, K, 128, &ma)) return e;
+    if (int e = get_tensor_map_2d(x, ldx, M, K, 128, &ma)) return e;
     if (split) {
         float* ws = nullptr;
         if (int e = get_weight_split(w, N, K, st, &ws)) return e;
         const int BN = N > 64 ? 128 : 64;
-        if (int e = get_map(ws, K, N, K, BN, &mb)) return e;
-        if (int e = get_map(ws + (long long)N * K, K, N, K, BN, &mbl)) return e;
+        if (int e = get_tensor_map_2d(ws, K, N, K, BN, &mb)) return e;
+        if (int e = get_tensor_map_2d(ws + (long long)N * K, K, N, K, BN, &mbl)) return e;
         if (BN == 128) return launch<128, 3, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
         return launch<64, 4, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
     }
     const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
-    if (int e = get_map(w, K, N, K, BN, &mb)) return e;
+    if (int e = get_tensor_map_2d(w, K, N, K, BN, &mb)) return e;
     if (BN == 256) return launch<256, 4, false>(ma, mb, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
     if (BN == 128) return launch<128, 6, false>(ma, mb, mb, bias, res, ldr, y, ldy, M, N, K, act, st);
     return launch<64, 8, false>(ma, mb, mb, bias, res, ldr, y, ldy, M, N, K, act, st);

@@ -1,0 +1,276 @@
+// kNN in learned feature space (dgcnn.py:10-28 on 144-/192-d activations) on the 5th-gen tensor cores.
+//
+// score(i,j) = 2 x_i.x_j - |x_j|^2 - |x_i|^2; the Gram tile x_i.x_j is a K-major x K-major tcgen05 GEMM of the
+// token matrix with itself.  Neighbour sets must not move, so the dot products use the error-compensated 3xTF32
+// split (x = x_hi + x_lo, hi.hi + lo.hi + hi.lo: fp32-class accuracy); X is split ONCE per call by an elementwise
+// kernel (the tiles are re-read ~64x from L2, so the extra copy is free) and |x|^2 is fp32.
+//
+// One persistent CTA per (window, 128-query tile): the candidate tiles of the window stream through a TMA -> smem
+// ring -> tcgen05.mma -> TMEM (2 accumulator stages), and the epilogue warps (one thread per query row) read the
+// 128x128 score tile back with tcgen05.ld and keep a sorted top-k list per row in shared memory.  Candidates are
+// visited in index order with a strict ">" insert, so exact ties go to the lowest index (the canonical rule).
+#include <algorithm>
+#include "tc.cuh"
+
+struct scp_seqs;
+
+namespace scp {
+
+constexpr int KT_BM = 128, KT_BN = 128, KT_BK = 32, KT_STAGES = 3;
+constexpr int KT_EXTRA = 8;                                    // approximate top-(k+8) is re-ranked exactly
+constexpr int KT_TILE_BYTES = 128 * KT_BK * 4;                 // 16 KB
+constexpr int KT_STAGE_BYTES = 4 * KT_TILE_BYTES;              // A_hi | A_lo | B_hi | B_lo
+
+__global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X, long long ldx, int d, long long n,
+                                                     float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ xx) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        const float v = X[row * ldx + c];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        hi[row * d + c] = h;
+        lo[row * d + c] = v - h;
+        s = fmaf(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) xx[row] = s;
+}
+
+__global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUtensorMap tmHi,
+                                                    const __grid_constant__ CUtensorMap tmLo,
+                                                    const float* __restrict__ xx, const long long* __restrict__ seq_off,
+                                                    const int* __restrict__ tile_seq, const int* __restrict__ tile_start,
+                                                    int n_work, long long row0, int d, int k, int* __restrict__ idx_out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + KT_STAGES * KT_STAGE_BYTES);
+    uint64_t* empty = full + KT_STAGES;
+    uint64_t* tfull = empty + KT_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* ls = reinterpret_cast<float*>(tmem_slot + 4);        // [k][128] scores, descending per column
+    int* li = reinterpret_cast<int*>(ls + k * 128);              // [k][128] window-local candidate index
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_kb = (d + KT_BK - 1) / KT_BK;
+    constexpr uint32_t TMEM_COLS = 2 * KT_BN;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmHi)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmLo)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < KT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+                const int s = tile_seq[wk];
+                const long long base = seq_off[s] - row0;               // row of the window inside the split copies
+                const int n = (int)(seq_off[s + 1] - seq_off[s]);
+                const int q0 = tile_start[wk];
+                for (int c0 = 0; c0 < n; c0 += KT_BN) {
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], KT_STAGE_BYTES);
+                        uint8_t* a = smem + stage * KT_STAGE_BYTES;
+                        tma_load_2d(a, &tmHi, &full[stage], kb * KT_BK, (int)(base + q0));
+                        tma_load_2d(a + KT_TILE_BYTES, &tmLo, &full[stage], kb * KT_BK, (int)(base + q0));
+                        tma_load_2d(a + 2 * KT_TILE_BYTES, &tmHi, &full[stage], kb * KT_BK, (int)(base + c0));
+                        tma_load_2d(a + 3 * KT_TILE_BYTES, &tmLo, &full[stage], kb * KT_BK, (int)(base + c0));
+                        if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT_BN >> 3) << 17) | ((uint32_t)(KT_BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+                const int s = tile_seq[wk];
+                const int n = (int)(seq_off[s + 1] - seq_off[s]);
+                for (int c0 = 0; c0 < n; c0 += KT_BN) {
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * KT_BN);
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint8_t* a = smem + stage * KT_STAGE_BYTES;
+                        const uint64_t dah = make_smem_desc(a), dal = make_smem_desc(a + KT_TILE_BYTES);
+                        const uint64_t dbh = make_smem_desc(a + 2 * KT_TILE_BYTES), dbl = make_smem_desc(a + 3 * KT_TILE_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < KT_BK / 8; ++kk) {
+                            const uint64_t o = (uint64_t)(2 * kk);
+                            tc_mma_tf32(d_tmem, dah + o, dbh + o, idesc, (kb | kk) ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, dal + o, dbh + o, idesc, 1u);
+                            tc_mma_tf32(d_tmem, dah + o, dbl + o, idesc, 1u);
+                        }
+                        tc_commit(&empty[stage]);
+                        if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&tfull[acc]);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int w = warp - 4;
+        const int t = w * 32 + lane;                                    // query row inside the tile == TMEM lane
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+            const int s = tile_seq[wk];
+            const long long gbase = seq_off[s];
+            const int n = (int)(seq_off[s + 1] - gbase);
+            const int q = tile_start[wk] + t;
+            const bool qok = q < n;
+            const float xq = qok ? xx[gbase - row0 + q] : 0.f;
+            for (int j = 0; j < k; ++j) { ls[j * 128 + t] = -INFINITY; li[j * 128 + t] = -1; }
+            float thresh = -INFINITY;
+            for (int c0 = 0; c0 < n; c0 += KT_BN) {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * KT_BN);
+#pragma unroll 1
+                for (int cc = 0; cc < KT_BN; cc += 32) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tc_ld32(t_row + (uint32_t)cc, r);
+                    if (!qok) continue;
+                    const float* xc = xx + (gbase - row0) + c0 + cc;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int c = c0 + cc + j;
+                        if (c >= n) break;
+                        const float sc = __fsub_rn(__fsub_rn(2.0f * __uint_as_float(r[j]), __ldg(xc + j)), xq);
+                        if (sc > thresh) {
+                            int p = k - 1;
+                            while (p > 0 && ls[(p - 1) * 128 + t] < sc) {
+                                ls[p * 128 + t] = ls[(p - 1) * 128 + t];
+                                li[p * 128 + t] = li[(p - 1) * 128 + t];
+                                --p;
+                            }
+                            ls[p * 128 + t] = sc;
+                            li[p * 128 + t] = c;
+                            thresh = ls[(k - 1) * 128 + t];
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (qok) {
+                const long long row = gbase + q;
+                for (int j = 0; j < k; ++j) {
+                    const int id = li[j * 128 + t];
+                    idx_out[(row - row0) * k + j] = id < 0 ? -1 : (int)(gbase + id);   // candidates for the exact re-rank
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// Exact re-rank: the tensor-core scores are accurate to ~1e-6 relative, which is enough to find the top-(k+8) but
+// not to order near-ties reproducibly.  The final neighbour list is defined by the EXACT squared distance of the
+// float32 rows (float64 accumulation in channel order), ties -> lowest index, independent of the engine.
+__global__ void __launch_bounds__(256) k_knn_rerank(const float* __restrict__ X, long long ldx, int d, long long row0,
+                                                     long long n, const int* __restrict__ cand, int kc, int k,
+                                                     int* __restrict__ idx_out) {
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per query, one lane per candidate
+    if (r >= n) return;
+    const long long row = row0 + r;
+    const int c = lane < kc ? cand[r * kc + lane] : -1;
+    double dist = INFINITY;
+    if (c >= 0) {
+        const float* a = X + row * ldx;
+        const float* b = X + (long long)c * ldx;
+        double acc = 0.0;
+        const bool v4 = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (d % 4 == 0);
+        if (v4) {
+            for (int j = 0; j < d; j += 4) {
+                const float4 fa = *reinterpret_cast<const float4*>(a + j), fb = *reinterpret_cast<const float4*>(b + j);
+                double df = (double)fa.x - (double)fb.x; acc = __dadd_rn(acc, __dmul_rn(df, df));
+                df = (double)fa.y - (double)fb.y; acc = __dadd_rn(acc, __dmul_rn(df, df));
+                df = (double)fa.z - (double)fb.z; acc = __dadd_rn(acc, __dmul_rn(df, df));
+                df = (double)fa.w - (double)fb.w; acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+        } else {
+            for (int j = 0; j < d; ++j) { const double df = (double)a[j] - (double)b[j]; acc = __dadd_rn(acc, __dmul_rn(df, df)); }
+        }
+        dist = acc;
+    }
+    // rank of this candidate among the warp's candidates by (dist, index)
+    int rank = 0;
+    for (int o = 0; o < 32; ++o) {
+        const double od = __shfl_sync(0xffffffffu, dist, o);
+        const int oc = __shfl_sync(0xffffffffu, c, o);
+        if (oc >= 0 && (od < dist || (od == dist && oc < c))) ++rank;
+    }
+    if (c >= 0 && rank < k) idx_out[row * k + rank] = c;
+    const int valid = __popc(__ballot_sync(0xffffffffu, c >= 0));
+    if (lane >= valid && lane < k) idx_out[row * k + lane] = (int)row;         // short window: repeat self
+}
+
+// host ------------------------------------------------------------------------------------------
+bool knn_tc_ok(int d, int k) { return d >= 32 && d % 4 == 0 && k >= 1 && k + KT_EXTRA <= 32; }
+
+int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n_seq, const long long* d_off,
+           const int* d_tile_seq, const int* d_tile_start, int n_work, int k, int* d_idx, cudaStream_t st) {
+    const long long row0 = h_off[0], total = h_off[n_seq] - h_off[0];
+    float *hi = nullptr, *lo = nullptr, *xx = nullptr;
+    int* cand = nullptr;
+    const int kc = k + KT_EXTRA;
+    SCP_CUDA(cudaMallocAsync((void**)&cand, (size_t)total * kc * 4 + 1024, st));
+    SCP_CUDA(cudaMallocAsync((void**)&hi, (size_t)total * d * 4 + 1024, st));
+    SCP_CUDA(cudaMallocAsync((void**)&lo, (size_t)total * d * 4 + 1024, st));
+    SCP_CUDA(cudaMallocAsync((void**)&xx, (size_t)total * 4 + 1024, st));
+    k_split_rows<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x + row0 * ldx, ldx, d, total, hi, lo, xx);
+    SCP_LAUNCHED();
+    CUtensorMap mh, ml;
+    // the split buffers are transient: encode their maps every call (pointer reuse would alias a cached map only
+    // when shape and address are identical, which is then also correct)
+    if (int e = get_tensor_map_2d(hi, d, total, d, 128, &mh)) return e;
+    if (int e = get_tensor_map_2d(lo, d, total, d, 128, &ml)) return e;
+    const int smem = KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + 2 * kc * 128 * 4;
+    static int attr = 0;
+    if (smem > attr) { SCP_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    k_knn_tc<<<std::min(n_work, n_sm), 256, smem, st>>>(mh, ml, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand);
+    SCP_LAUNCHED();
+    k_knn_rerank<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x, ldx, d, row0, total, cand, kc, k, d_idx);
+    SCP_LAUNCHED();
+    SCP_CUDA(cudaFreeAsync(cand, st));
+    SCP_CUDA(cudaFreeAsync(hi, st));
+    SCP_CUDA(cudaFreeAsync(lo, st));
+    SCP_CUDA(cudaFreeAsync(xx, st));
+    return SCP_OK;
+}
+
+}  // namespace scp

@@ -46,6 +46,8 @@ struct JobDev {
     float bin_num;
     double step[3];
     double off[3];
+    double inv_step[3];          // fast-path reciprocal steps
+    double margin[3];            // fast-path safety margin (bins) around a .5 rounding boundary
     u32 qmax;
     u32 overflow;
     int depth;
@@ -146,21 +148,55 @@ __global__ void k_job_setup(JobDev* jobs, int n_jobs, const FrameDev* fr, int mo
         J.step[2] = J.qs;
         J.off[2] = (double)dec_ordered(fr[J.frame].zmin_enc);
     }
+    // Fast path of k_quantise_keys: float32 atan2f/acosf are within 2 ulp of the correctly rounded float32 angle the
+    // slow (float64) path produces; with the +2*pi fold that is < 1.5e-6 rad, and multiplying by the reciprocal step
+    // instead of dividing moves the bin coordinate by < 1e-10 bins.  Points whose fast bin coordinate is closer than
+    // `margin` to a .5 boundary are recomputed exactly, everything else is provably identical.
+    for (int c = 0; c < 3; ++c) J.inv_step[c] = 1.0 / J.step[c];
+    J.margin[0] = 1e-7;
+    J.margin[1] = 1.5e-6 * J.inv_step[1] + 1e-7;
+    J.margin[2] = (mode == SCP_MODE_SPHER) ? 1.5e-6 * J.inv_step[2] + 1e-7 : 1e-7;
 }
 
 // ------------------------------------------------------------------------------------------
 // K2: coordinate transform + quantise + Morton key            data_preprocess.py:171-207, :56,:68-70
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool quantise_exact(float x, float y, float z, int mode, double s0, double s1, double s2, double o2,
+                                               long long& q0, long long& q1, long long& q2) {
+    float rho = rho_of(x, y, z, mode);
+    float xe = __fadd_rn(x, 1e-9f);
+    float phi = (float)atan2((double)y, (double)xe);           // correctly rounded float32 angle
+    if (phi < 0.f) phi = __fadd_rn(phi, 6.2831854820251465f);
+    float third = (mode == SCP_MODE_SPHER) ? (float)acos((double)__fdiv_rn(z, rho)) : z;
+    q0 = (long long)rint((double)rho / s0);
+    q1 = (long long)rint((double)phi / s1);
+    q2 = (long long)rint(((double)third - o2) / s2);
+    return true;
+}
+
 __global__ void __launch_bounds__(TPB) k_quantise_keys(const float* __restrict__ xyz, int stride,
                                                         const Tile* __restrict__ tiles, JobDev* jobs,
                                                         u64* __restrict__ keys, int mode) {
+    __shared__ int s_slow[TILE];
+    __shared__ int s_nslow;
     Tile t = tiles[blockIdx.x];
     JobDev& J = jobs[t.job];
     const float* p = xyz + (J.pt_begin + t.begin) * (long long)stride;
     u64* out = keys + J.key_begin + t.begin;
     const double s0 = J.step[0], s1 = J.step[1], s2 = J.step[2], o2 = J.off[2];
+    const double i0 = J.inv_step[0], i1 = J.inv_step[1], i2 = J.inv_step[2];
+    const double m0 = J.margin[0], m1 = J.margin[1], m2 = J.margin[2];
     const float coff = (float)J.cart_offset, cqs = (float)J.qs;
     u32 qmax = 0, ovf = 0;
+    if (threadIdx.x == 0) s_nslow = 0;
+    __syncthreads();
+    auto emit = [&](int i, long long q0, long long q1, long long q2) {
+        if (q0 < 0 || q1 < 0 || q2 < 0 || q0 >= (1 << 21) || q1 >= (1 << 21) || q2 >= (1 << 21)) {
+            ovf = 1; q0 = q1 = q2 = 0;
+        }
+        qmax = max(qmax, (u32)max(q0, max(q1, q2)));
+        out[i] = (spread3((u32)q0) << 2) | (spread3((u32)q1) << 1) | spread3((u32)q2);
+    };
     for (int i = threadIdx.x; i < t.count; i += TPB) {
         float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
         long long q0, q1, q2;
@@ -170,20 +206,28 @@ __global__ void __launch_bounds__(TPB) k_quantise_keys(const float* __restrict__
             q1 = (long long)rintf(__fdiv_rn(__fsub_rn(y, coff), cqs));
             q2 = (long long)rintf(__fdiv_rn(__fsub_rn(z, coff), cqs));
         } else {
-            float rho = rho_of(x, y, z, mode);
-            float xe = __fadd_rn(x, 1e-9f);
-            float phi = (float)atan2((double)y, (double)xe);           // correctly rounded float32 angle
+            const float rho = rho_of(x, y, z, mode);
+            const float xe = __fadd_rn(x, 1e-9f);
+            float phi = atan2f(y, xe);
             if (phi < 0.f) phi = __fadd_rn(phi, 6.2831854820251465f);
-            float third = (mode == SCP_MODE_SPHER) ? (float)acos((double)__fdiv_rn(z, rho)) : z;
-            q0 = (long long)rint((double)rho / s0);
-            q1 = (long long)rint((double)phi / s1);
-            q2 = (long long)rint(((double)third - o2) / s2);
+            const float third = (mode == SCP_MODE_SPHER) ? acosf(__fdiv_rn(z, rho)) : z;
+            const double u0 = (double)rho * i0, u1 = (double)phi * i1, u2 = ((double)third - o2) * i2;
+            const double r0 = rint(u0), r1 = rint(u1), r2 = rint(u2);
+            const bool safe = (0.5 - fabs(u0 - r0) > m0) && (0.5 - fabs(u1 - r1) > m1) && (0.5 - fabs(u2 - r2) > m2) &&
+                              (phi > 1e-3f) && (phi < 6.28f);      // keep clear of the 0 / 2*pi fold
+            if (!safe) { s_slow[atomicAdd(&s_nslow, 1)] = i; continue; }
+            q0 = (long long)r0; q1 = (long long)r1; q2 = (long long)r2;
         }
-        if (q0 < 0 || q1 < 0 || q2 < 0 || q0 >= (1 << 21) || q1 >= (1 << 21) || q2 >= (1 << 21)) {
-            ovf = 1; q0 = q1 = q2 = 0;
-        }
-        qmax = max(qmax, (u32)max(q0, max(q1, q2)));
-        out[i] = (spread3((u32)q0) << 2) | (spread3((u32)q1) << 1) | spread3((u32)q2);
+        emit(i, q0, q1, q2);
+    }
+    __syncthreads();
+    // exact float64 path for the few points near a rounding boundary, densely packed over the threads
+    for (int e = threadIdx.x; e < s_nslow; e += TPB) {
+        const int i = s_slow[e];
+        float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
+        long long q0, q1, q2;
+        quantise_exact(x, y, z, mode, s0, s1, s2, o2, q0, q1, q2);
+        emit(i, q0, q1, q2);
     }
     qmax = __reduce_max_sync(0xffffffffu, qmax);
     ovf = __reduce_max_sync(0xffffffffu, ovf);

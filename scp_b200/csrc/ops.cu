@@ -30,6 +30,9 @@ namespace scp {
 int linear_tf32(const float* x, long long ldx, const float* w, const float* bias, const float* res, long long ldr,
                 float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st, int split);   // gemm_tc.cu
 void gemm_cache_clear();
+bool knn_tc_ok(int d, int k);                                                                      // knn_tc.cu
+int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n_seq, const long long* d_off,
+           const int* d_tile_seq, const int* d_tile_start, int n_work, int k, int* d_idx, cudaStream_t st);
 bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, const void* x, const void* w, const void* y);
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -706,6 +709,7 @@ __global__ void __launch_bounds__(128) k_octattn_attn(const float* __restrict__ 
     }
 }
 
+static int g_knn_tc = 1;         // learned-feature kNN on the tensor cores (3xTF32 Gram + fused top-k); 0 = fp32 SIMT tiles
 static int g_auto_tf32 = 1;      // SCP_GEMM_AUTO = 3xTF32 tcgen05 engine for the large layers (validated: PMF err 7e-5)
 
 static inline int grid_for(long long work, int per_block, int cap = 148 * 16) {
@@ -767,6 +771,8 @@ void scp_seqs_destroy(scp_seqs* s) {
 int64_t scp_seqs_total(const scp_seqs* s) { return s ? s->total : -1; }
 
 void scp_gemm_cache_clear(void) { gemm_cache_clear(); }
+
+int scp_set_knn_engine(int use_tensor_cores) { int old = g_knn_tc; g_knn_tc = use_tensor_cores ? 1 : 0; return old; }
 
 int scp_set_auto_engine(int use_tf32) { int old = g_auto_tf32; g_auto_tf32 = use_tf32 ? 1 : 0; return old; }
 
@@ -842,6 +848,9 @@ int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, i
         SCP_LAUNCHED();
         return SCP_OK;
     }
+    if (g_knn_tc && knn_tc_ok(d, k))
+        return knn_tc(d_x, ldx, d, seqs->h_off.data(), seqs->n_seq, seqs->d_off, seqs->d_tile128_seq, seqs->d_tile128_start,
+                      seqs->n_tile128, k, d_idx, st);
     float* xx = nullptr;
     SCP_CUDA(cudaMallocAsync((void**)&xx, seqs->total * 4, st));
     const float* x0 = d_x + seqs->h_off[0] * ldx;

@@ -88,10 +88,12 @@ def test_ehem_embeddings(ops):
     assert torch.equal(zc.cpu(), z)
 
 
-@pytest.mark.parametrize("d,lens,grid", [(3, [2, 700, 64, 37 + 1, 8192], True), (144, [600, 130], False),
-                                         (192, [2100], False)])
-def test_knn(ops, d, lens, grid):
+@pytest.mark.parametrize("tensor_cores", [1, 0])
+@pytest.mark.parametrize("d,lens,grid", [(3, [2, 700, 64, 37 + 1, 8192], True), (144, [600, 130, 2, 8192], False),
+                                         (192, [2100, 129], False)])
+def test_knn(ops, d, lens, grid, tensor_cores):
     cu, _ = ops
+    old = cu.lib.scp_set_knn_engine(tensor_cores)
     offs = np.concatenate([[0], np.cumsum(lens)])
     g = torch.Generator().manual_seed(d)
     x = torch.randn(offs[-1], d, generator=g)
@@ -99,6 +101,7 @@ def test_knn(ops, d, lens, grid):
         x = torch.randint(0, 40, (offs[-1], d), generator=g).float() / 40
     k = 20
     idx = cu.knn(V(x.cuda()), cu.seqs(list(offs)), k).cpu().long()
+    cu.lib.scp_set_knn_engine(old)
     xd = x.double()
     for a, b in zip(offs[:-1], offs[1:]):
         s = xd[a:b]
