@@ -179,6 +179,7 @@ def run_ours(args):
         enc.encode_device(xyz, offs)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    model.ops.reserve_events(2 * 700 * F * args.steps + 4096)
     model.ops.prof = []
     launches0 = lib.scp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

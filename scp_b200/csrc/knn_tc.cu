@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
     uint64_t* tfull = empty + KT_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* ls = reinterpret_cast<float*>(tmem_slot + 4);        // [k][128] scores, descending per column
-    int* li = reinterpret_cast<int*>(ls + k * 128);              // [k][128] window-local candidate index
+    float* stage = reinterpret_cast<float*>(tmem_slot + 4);     // 4 warps x [32][33] transpose tiles
+    const int kc = k;                                            // candidates kept per row (k + KT_EXTRA <= 32)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (d + KT_BK - 1) / KT_BK;
@@ -132,18 +132,25 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
             }
         }
     } else if (warp >= 4) {
+        // Epilogue: warp w owns query rows 32w..32w+31 of the tile.  tcgen05.ld hands lane i the 32 scores of ROW i; a
+        // [32][33] smem transpose lets the whole warp look at one row at a time (lane j = candidate j).  Each row's
+        // top-kc list lives in registers, one entry per lane (sorted descending); a candidate is inserted with one
+        // ballot + shuffle-shift, so the common case "nothing beats the threshold" costs one compare + ballot per row.
         const int w = warp - 4;
-        const int t = w * 32 + lane;                                    // query row inside the tile == TMEM lane
+        float* st = stage + w * (32 * 33);
         int acc = 0; uint32_t acc_phase = 0;
         for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
             const int s = tile_seq[wk];
             const long long gbase = seq_off[s];
             const int n = (int)(seq_off[s + 1] - gbase);
-            const int q = tile_start[wk] + t;
-            const bool qok = q < n;
-            const float xq = qok ? xx[gbase - row0 + q] : 0.f;
-            for (int j = 0; j < k; ++j) { ls[j * 128 + t] = -INFINITY; li[j * 128 + t] = -1; }
-            float thresh = -INFINITY;
+            const int qw0 = tile_start[wk] + w * 32;                      // first query row of this warp
+            float lsc[32]; int lid[32];                                    // lsc[q] on lane l = l-th best score of row q
+            float xq[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) { lsc[q] = -INFINITY; lid[q] = -1; }
+            const float xq_l = (qw0 + lane < n) ? xx[gbase - row0 + qw0 + lane] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) xq[q] = __shfl_sync(0xffffffffu, xq_l, q);
             for (int c0 = 0; c0 < n; c0 += KT_BN) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
@@ -153,36 +160,43 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                     uint32_t r[32];
                     __syncwarp();
                     tc_ld32(t_row + (uint32_t)cc, r);
-                    if (!qok) continue;
-                    const float* xc = xx + (gbase - row0) + c0 + cc;
+                    if (c0 + cc >= n) continue;                            // warp-uniform
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int c = c0 + cc + j;
-                        if (c >= n) break;
-                        const float sc = __fsub_rn(__fsub_rn(2.0f * __uint_as_float(r[j]), __ldg(xc + j)), xq);
-                        if (sc > thresh) {
-                            int p = k - 1;
-                            while (p > 0 && ls[(p - 1) * 128 + t] < sc) {
-                                ls[p * 128 + t] = ls[(p - 1) * 128 + t];
-                                li[p * 128 + t] = li[(p - 1) * 128 + t];
-                                --p;
-                            }
-                            ls[p * 128 + t] = sc;
-                            li[p * 128 + t] = c;
-                            thresh = ls[(k - 1) * 128 + t];
+                    for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
+                    __syncwarp();
+                    const int c = c0 + cc + lane;                          // this lane's candidate
+                    const float xc = c < n ? __ldg(xx + (gbase - row0) + c) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        if (qw0 + q >= n) break;                           // warp-uniform
+                        const float sc = c < n ? __fsub_rn(__fsub_rn(2.0f * st[q * 33 + lane], xc), xq[q]) : -INFINITY;
+                        float th = __shfl_sync(0xffffffffu, lsc[q], kc - 1);
+                        unsigned m = __ballot_sync(0xffffffffu, sc > th);
+                        while (m) {
+                            const int j = __ffs(m) - 1;
+                            const float sj = __shfl_sync(0xffffffffu, sc, j);
+                            // entries with score >= sj stay ahead (earlier = lower index wins ties)
+                            const int pos = __popc(__ballot_sync(0xffffffffu, lsc[q] >= sj));
+                            const float us = __shfl_up_sync(0xffffffffu, lsc[q], 1);
+                            const int ui = __shfl_up_sync(0xffffffffu, lid[q], 1);
+                            if (lane > pos) { lsc[q] = us; lid[q] = ui; }
+                            if (lane == pos) { lsc[q] = sj; lid[q] = c0 + cc + j; }
+                            th = __shfl_sync(0xffffffffu, lsc[q], kc - 1);
+                            m = __ballot_sync(0xffffffffu, sc > th) & ~((2u << j) - 1u);
                         }
                     }
+                    __syncwarp();
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (qok) {
-                const long long row = gbase + q;
-                for (int j = 0; j < k; ++j) {
-                    const int id = li[j * 128 + t];
-                    idx_out[(row - row0) * k + j] = id < 0 ? -1 : (int)(gbase + id);   // candidates for the exact re-rank
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                if (qw0 + q < n && lane < kc) {
+                    const long long row = gbase + qw0 + q;
+                    idx_out[(row - row0) * kc + lane] = lid[q] < 0 ? -1 : (int)(gbase + lid[q]);   // candidates for the re-rank
                 }
             }
         }
@@ -257,7 +271,7 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     // when shape and address are identical, which is then also correct)
     if (int e = get_tensor_map_2d(hi, d, total, d, 128, &mh)) return e;
     if (int e = get_tensor_map_2d(lo, d, total, d, 128, &ml)) return e;
-    const int smem = KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + 2 * kc * 128 * 4;
+    const int smem = KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + 4 * 32 * 33 * 4;
     static int attr = 0;
     if (smem > attr) { SCP_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
     static int n_sm = 0;

@@ -788,9 +788,10 @@ int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b
     cudaStream_t st = as_stream(stream);
     const bool tc_ok = linear_tf32_ok(ldx, ldy, M, N, K, d_x, d_w, d_y);
     // SCP_GEMM_TF32 / SCP_GEMM_TF32X3: tensor cores wherever the shape allows (tiny / unaligned layers stay on the fp32
-    // tiles); SCP_GEMM_AUTO: error-compensated tensor cores for the large layers only (once enabled)
+    // tiles); SCP_GEMM_AUTO: error-compensated tensor cores for every layer with N >= 64.  The choice must not depend on
+    // M: a window has to produce bit-identical logits whatever batch it is encoded in (frame partition = multi-GPU)
     if (tc_ok && engine == SCP_GEMM_TF32) return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st, 0);
-    if (tc_ok && (engine == SCP_GEMM_TF32X3 || (engine == SCP_GEMM_AUTO && g_auto_tf32 && M >= 512 && N >= 64)))
+    if (tc_ok && (engine == SCP_GEMM_TF32X3 || (engine == SCP_GEMM_AUTO && g_auto_tf32 && N >= 64)))
         return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st, 1);
     const int vec4 = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_w) & 15) == 0);

@@ -58,8 +58,9 @@ class _Rec:
 
     def __enter__(self):
         if self.ops.prof is not None:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e1 = torch.cuda.Event(enable_timing=True)
+            pool = self.ops.event_pool
+            self.e0 = pool.pop() if pool else torch.cuda.Event(enable_timing=True)
+            self.e1 = pool.pop() if pool else torch.cuda.Event(enable_timing=True)
             self.e0.record()
 
     def __exit__(self, *a):
@@ -75,6 +76,10 @@ class CudaOps:
         self.lib = _lib.require_device()
         self.engine = ENGINE[engine or os.environ.get("SCP_GEMM", "auto")]
         self.prof = None          # bench.py: list of (kernel tag, flops, bytes, start event, end event)
+        self.event_pool = []      # pre-created timing events (creating them inside the timed region is slow)
+
+    def reserve_events(self, n):
+        self.event_pool = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
 
     def _rec(self, tag, flops, nbytes):
         """Context manager that brackets one launch with CUDA events on the current stream when profiling is on."""
