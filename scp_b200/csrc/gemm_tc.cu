@@ -53,7 +53,6 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
     uint64_t* tempty = tfull + 2;
     uint64_t* ready = tempty + 2;                        // SPLIT: A tile split done (2 splitter warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + STAGES);
-    float* stage_out = reinterpret_cast<float*>(tmem_slot + 4);   // 4 warps x [32][33] epilogue transpose tiles
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = (N + BN - 1) / BN;
@@ -155,34 +154,44 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
     } else if (warp >= 4) {
         const int w = warp - 4;                            // TMEM lane quarter this warp may read
         int acc = 0; uint32_t acc_phase = 0;
+        const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
+                            (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0)));
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
+            const long long row = (long long)m_blk * BM + w * 32 + lane;
             const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tc_ld32(t_row + (uint32_t)c0, r);
                 const int n0 = n_blk * BN + c0;
-                // transpose through a per-warp smem tile so that every global store / residual load of the warp is one
-                // contiguous 128-byte row segment (the TMEM read gives each lane 32 columns of ITS row)
-                float* st = stage_out + w * (32 * 33);
-                __syncwarp();
+                if (row < M && n0 < N) {
+                    float* yrow = Y + row * ldy + n0;
+                    const float* rrow = R ? R + row * ldr + n0 : nullptr;
+                    if (vec_ok && n0 + 32 <= N) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
-                __syncwarp();
-                const int n = n0 + lane;
-                if (n < N) {
-                    const float bv = bias ? bias[n] : 0.f;
-                    const long long row_base = (long long)m_blk * BM + w * 32;
-#pragma unroll 4
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const long long row_i = row_base + rr;
-                        if (row_i >= M) break;
-                        float v = tc_act(st[rr * 33 + lane] + bv, act);
-                        if (R) v += R[row_i * ldr + n];
-                        Y[row_i * ldy + n] = v;
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 v;
+                            v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
+                            v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+                            if (bias) { const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + j); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+                            v.x = tc_act(v.x, act); v.y = tc_act(v.y, act); v.z = tc_act(v.z, act); v.w = tc_act(v.w, act);
+                            if (rrow) { const float4 q = *reinterpret_cast<const float4*>(rrow + j); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+                            *reinterpret_cast<float4*>(yrow + j) = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (n0 + j < N) {
+                                float v = __uint_as_float(r[j]);
+                                if (bias) v += bias[n0 + j];
+                                v = tc_act(v, act);
+                                if (rrow) v += rrow[j];
+                                yrow[j] = v;
+                            }
+                        }
                     }
                 }
             }
@@ -306,7 +315,7 @@ bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, con
 template <int BN, int STAGES, bool SPLIT>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, const float* res,
                   long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
-    constexpr int smem = STAGES * (128 * 128 + BN * 128) * (SPLIT ? 2 : 1) + 1024 + 512 + 4 * 32 * 33 * 4;
+    constexpr int smem = STAGES * (128 * 128 + BN * 128) * (SPLIT ? 2 : 1) + 1024 + 512;
     static bool attr = false;
     if (!attr) {
         SCP_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -309,6 +309,17 @@ __global__ void __launch_bounds__(256) k_knn(const float* __restrict__ X, long l
 // reference's pick among tied neighbours is whatever torch.topk returns.  Here the rule is canonical: exact
 // float64 squared distance ((dx^2 + dy^2) + dz^2, no FMA contraction), ties -> lowest index.  One thread per query.
 constexpr int KS_Q = 128, KS_C = 256;
+__host__ __device__ __forceinline__ int knn_tile_order(int i, int t0, int nt) {     // same rule as knn_tc.cu
+    const int a = t0 > 0 ? t0 - 1 : 0, b = t0 + 1 < nt ? t0 + 1 : nt - 1;
+    const int first[3] = {t0, t0 - 1, t0 + 1};
+    int nf = 0;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+        if (first[u] >= 0 && first[u] < nt) { if (i == nf) return first[u]; ++nf; }
+    }
+    const int j = i - nf;
+    return j < a ? j : j + (b - a + 1);
+}
 __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X, long long ldx, int d,
                                                      const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
                                                      const int* __restrict__ tile_start, int k, int* __restrict__ idx_out) {
@@ -326,7 +337,10 @@ __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X,
     if (active) for (int c = 0; c < d; ++c) xq[c] = (double)X[(base + q) * ldx + c];
     for (int j = 0; j < k; ++j) { ls[j * KS_Q + t] = INFINITY; li[j * KS_Q + t] = -1; }
     double worst = INFINITY;
-    for (int c0 = 0; c0 < n; c0 += KS_C) {
+    const int nchunk = (n + KS_C - 1) / KS_C;
+    for (int ci = 0; ci < nchunk; ++ci) {
+        // own neighbourhood first, then ascending (see knn_tile_order): ties are still resolved by (distance, index)
+        const int c0 = knn_tile_order(ci, tile_start[blockIdx.x] / KS_C, nchunk) * KS_C;
         __syncthreads();
         for (int e = t; e < KS_C * 4; e += KS_Q) {
             int r = e >> 2, c = e & 3;
@@ -342,15 +356,16 @@ __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X,
                 const double df = __dsub_rn(xq[c], cs[r * 4 + c]);
                 dist = __dadd_rn(dist, __dmul_rn(df, df));
             }
-            if (dist < worst) {
+            const int cidx = c0 + r;
+            if (dist < worst || (dist == worst && cidx < li[(k - 1) * KS_Q + t])) {
                 int j = k - 1;
-                while (j > 0 && ls[(j - 1) * KS_Q + t] > dist) {
+                while (j > 0 && (ls[(j - 1) * KS_Q + t] > dist || (ls[(j - 1) * KS_Q + t] == dist && li[(j - 1) * KS_Q + t] > cidx))) {
                     ls[j * KS_Q + t] = ls[(j - 1) * KS_Q + t];
                     li[j * KS_Q + t] = li[(j - 1) * KS_Q + t];
                     --j;
                 }
                 ls[j * KS_Q + t] = dist;
-                li[j * KS_Q + t] = c0 + r;
+                li[j * KS_Q + t] = cidx;
                 worst = ls[(k - 1) * KS_Q + t];
             }
         }
