@@ -242,6 +242,9 @@ int scp_swin_attention(const float* d_q, int64_t ldq, const float* d_k, int64_t 
                        const float* d_qb, const float* d_kb, const float* d_vb, const float* d_relpos, int heads,
                        const scp_seqs* seqs, int shift, float* d_out, int64_t ldo, void* stream);
 
+/* 1 (default) = tcgen05 3xTF32 window attention (attn_tc.cu), 0 = fp32 SIMT tiles.  Returns the old value. */
+int scp_set_attn_engine(int use_tensor_cores);
+
 /* Patch merging input (swin_transformer.py:350-362): per sequence, out[j] = [x[2j], x[2j+1]] (zeros if 2j+1 >= S),
  * j < ceil(S/2).  `dst` describes the halved sequences. */
 int scp_pair_concat(const float* d_x, int64_t ldx, const scp_seqs* src, const scp_seqs* dst, int C,

@@ -17,6 +17,24 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+cudaError_t malloc_async(void** p, size_t bytes, cudaStream_t st) {
+    static std::atomic<unsigned long long> configured{0};          // bit per device
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load() & bit)) {
+        cudaMemPool_t pool;
+        e = cudaDeviceGetDefaultMemPool(&pool, dev);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        configured.fetch_or(bit);
+    }
+    return cudaMallocAsync(p, bytes, st);
+}
+
 }  // namespace scp
 
 using namespace scp;

@@ -1,0 +1,361 @@
+// 1-D shifted-window attention (swin_transformer.py:406-501,603-697) on the 5th-gen tensor cores.
+//
+// One CTA per (window, head, 128-query block); the 512 keys of the window stream through in 16 chunks of 32:
+//     S_c = Q K_c^T          tcgen05.mma M128 x N32 x K64   (3xTF32: Q_hi K_hi + Q_lo K_hi + Q_hi K_lo), fp32 accum in TMEM
+//     P_c = exp(S_c + bias + mask - m)      one query row per thread (tcgen05.ld), online softmax in registers
+//     O_c = P_c V_c          tcgen05.mma M128 x N64 x K32   (P_hi V_hi + P_lo V_hi + P_hi V_lo), accum in TMEM,
+//                            rescaled and added to the running output in registers
+// Warp roles (288 threads):  warps 0-3 softmax / output (TMEM lane quarter = warp), warp 4 MMA issuer + TMEM owner,
+// warps 5-6 K loader, warps 7-8 V loader.  Everything is double-buffered (S, O_c in TMEM; K, V, P in shared memory) and
+// handed over through mbarriers, so the MMAs of chunk i+1 overlap the softmax of chunk i and the staging of chunk i+2.
+// Operand tiles are written by the loader warps in the canonical K-major 128B-swizzled layout: the roll by -shift, the
+// zero padding of the sequence (padded tokens carry exactly the Linear biases), the hi/lo split and the V transpose
+// happen on the way, so no TMA descriptor is needed for the gathered rows and HBM/L2 is read once in fp32.
+#include "tc.cuh"
+
+struct scp_seqs;
+
+namespace scp {
+
+constexpr int AT_WS = 512, AT_HD = 64, AT_BQ = 128, AT_BK = 32, AT_NC = AT_WS / AT_BK;
+constexpr int AT_Q_ATOM = AT_BQ * 128;           // [128 rows x 128 B] one 32-float K-atom of the Q operand (16 KB)
+constexpr int AT_K_ATOM = AT_BK * 128;           // [32 keys x 128 B]                                        ( 4 KB)
+// shared memory map (bytes, from a 1024-aligned base)
+constexpr int AT_OFF_QH = 0;                     // Q_hi: 2 atoms
+constexpr int AT_OFF_QL = 2 * AT_Q_ATOM;         // Q_lo: 2 atoms
+constexpr int AT_OFF_K = 4 * AT_Q_ATOM;          // 2 stages x [K_hi 8K | K_lo 8K]
+constexpr int AT_K_STAGE = 4 * AT_K_ATOM;
+constexpr int AT_OFF_V = AT_OFF_K + 2 * AT_K_STAGE;   // 2 stages x [Vt_hi 8K | Vt_lo 8K]   (rows = dims, K extent = 32 keys)
+constexpr int AT_V_TILE = AT_HD * 128;
+constexpr int AT_V_STAGE = 2 * AT_V_TILE;
+constexpr int AT_OFF_P = AT_OFF_V + 2 * AT_V_STAGE;   // 2 buffers x [P_hi 16K | P_lo 16K]
+constexpr int AT_P_TILE = AT_BQ * 128;
+constexpr int AT_P_BUF = 2 * AT_P_TILE;
+constexpr int AT_OFF_BIAS = AT_OFF_P + 2 * AT_P_BUF;  // 1023 floats
+constexpr int AT_OFF_BAR = AT_OFF_BIAS + 4096;
+constexpr int AT_SMEM = AT_OFF_BAR + 256 + 1024;
+constexpr int AT_THREADS = 288;
+constexpr uint32_t AT_TMEM_COLS = 256;           // S0 [0,32) S1 [32,64) O0 [64,128) O1 [128,192)
+
+__device__ __forceinline__ void split_tf32(const float4 v, uint4& hi, uint4& lo) {
+    hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
+    hi.z = __float_as_uint(v.z) & 0xffffe000u; hi.w = __float_as_uint(v.w) & 0xffffe000u;
+    lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+    lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __restrict__ Q, long long ldq,
+                                                                 const float* __restrict__ K, long long ldk,
+                                                                 const float* __restrict__ V, long long ldv,
+                                                                 const float* __restrict__ qb, const float* __restrict__ kb,
+                                                                 const float* __restrict__ vb, const float* __restrict__ relpos,
+                                                                 int heads, const long long* __restrict__ seq_off,
+                                                                 const int* __restrict__ win_seq, const int* __restrict__ win_idx,
+                                                                 int shift, float* __restrict__ O, long long ldo) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* s_bias = reinterpret_cast<float*>(sm + AT_OFF_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AT_OFF_BAR);
+    uint64_t* k_full = bars;            // [2] K chunk staged              (2 loader warps)
+    uint64_t* v_full = bars + 2;        // [2] V chunk staged              (2 loader warps)
+    uint64_t* s_full = bars + 4;        // [2] S chunk in TMEM, K stage free (tcgen05.commit)
+    uint64_t* s_empty = bars + 6;       // [2] S chunk read back           (4 softmax warps)
+    uint64_t* p_full = bars + 8;        // [2] P chunk written             (4 softmax warps)
+    uint64_t* pv_done = bars + 10;      // [2] O_c in TMEM, V stage and P buffer free (tcgen05.commit)
+    uint64_t* o_empty = bars + 12;      // [2] O_c read back               (4 softmax warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int h = blockIdx.x % heads, qblk = blockIdx.x / heads;
+    const int gw = blockIdx.y;
+    const int s = win_seq[gw], w = win_idx[gw];
+    const long long base = seq_off[s];
+    const int S = (int)(seq_off[s + 1] - base);
+    const int Sp = ((S + AT_WS - 1) / AT_WS) * AT_WS;
+    const bool last_win = (w == Sp / AT_WS - 1) && shift > 0;
+    // rolled position of this block's first query row; blocks are 128-aligned inside the 512-aligned padded sequence,
+    // so a block never wraps and it has real (stored) rows iff its first row is real
+    int q_start = w * AT_WS + qblk * AT_BQ + shift;
+    if (q_start >= Sp) q_start -= Sp;
+    if (q_start >= S) return;                                              // CTA-uniform, before any barrier / TMEM use
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&k_full[b], 2); mbar_init(&v_full[b], 2); mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4);
+                mbar_init(&p_full[b], 4); mbar_init(&pv_done[b], 1); mbar_init(&o_empty[b], 4);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(AT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int e = t; e < 2 * AT_WS - 1; e += AT_THREADS) s_bias[e] = relpos[e * heads + h];
+    // Q block: rolled rows, 1/sqrt(64) scale (exact), hi/lo split, swizzled K-major
+    for (int f = t; f < AT_BQ * 16; f += AT_THREADS) {
+        const int r = f >> 4, c4 = (f & 15) << 2;
+        const int u = q_start + r;
+        float4 v = u < S ? *reinterpret_cast<const float4*>(Q + (base + u) * ldq + h * AT_HD + c4)
+                         : *reinterpret_cast<const float4*>(qb + h * AT_HD + c4);
+        v.x *= 0.125f; v.y *= 0.125f; v.z *= 0.125f; v.w *= 0.125f;
+        uint4 hi, lo;
+        split_tf32(v, hi, lo);
+        const uint32_t o = (uint32_t)((c4 >> 5) * AT_Q_ATOM + r * 128 + (((((c4 & 31) >> 2) ^ (r & 7))) << 4));
+        *reinterpret_cast<uint4*>(sm + AT_OFF_QH + o) = hi;
+        *reinterpret_cast<uint4*>(sm + AT_OFF_QL + o) = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ---------------- softmax + output: thread t owns query row t of the block ----------------
+        float o_acc[AT_HD];
+#pragma unroll
+        for (int d = 0; d < AT_HD; ++d) o_acc[d] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, m_acc = -INFINITY, m_hist0 = 0.f, m_hist1 = 0.f;
+        const int pi = qblk * AT_BQ + t;                                   // window position of this row
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t prow = (uint32_t)(t * 128);
+        const int sw = t & 7;
+#pragma unroll 1
+        for (int i = 0; i < AT_NC; ++i) {
+            const int b = i & 1, n = i >> 1;
+            mbar_wait(&s_full[b], n & 1);
+            tc_fence_after();
+            uint32_t r[32];
+            tc_ld32(trow + (uint32_t)(b * 32), r);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[b]);
+            const bool masked = last_win && ((pi < AT_WS / 2) != (i < AT_NC / 2));     // swin_transformer.py:620
+            const float* bp = s_bias + (pi - i * AT_BK + AT_WS - 1);
+            float mx = m_run;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float v = __uint_as_float(r[j]) + bp[-j];
+                if (masked) v += -100.0f;
+                r[j] = __float_as_uint(v);
+                mx = fmaxf(mx, v);
+            }
+            const float alpha = __expf(m_run - mx);
+            m_run = mx;
+            const float m_old = b ? m_hist1 : m_hist0;                     // max the in-flight O_c of this buffer refers to
+            if (b) m_hist1 = mx; else m_hist0 = mx;
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float p = __expf(__uint_as_float(r[j]) - mx);
+                sum += p;
+                r[j] = __float_as_uint(p);
+            }
+            l_run = fmaf(l_run, alpha, sum);
+            if (i >= 2) {
+                // O_c of chunk i-2 is complete; that also frees P buffer b
+                mbar_wait(&pv_done[b], (n - 1) & 1);
+                tc_fence_after();
+                const float sc = __expf(m_acc - m_old);
+                m_acc = m_old;
+                uint32_t q0[32];
+                tc_ld32(trow + 64u + (uint32_t)(b * 64), q0);
+#pragma unroll
+                for (int d = 0; d < 32; ++d) o_acc[d] = fmaf(o_acc[d], sc, __uint_as_float(q0[d]));
+                tc_ld32(trow + 64u + (uint32_t)(b * 64) + 32u, q0);
+#pragma unroll
+                for (int d = 0; d < 32; ++d) o_acc[32 + d] = fmaf(o_acc[32 + d], sc, __uint_as_float(q0[d]));
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&o_empty[b]);
+            }
+            uint8_t* ph = sm + AT_OFF_P + b * AT_P_BUF + prow;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 pv = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                              __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+                uint4 hi, lo;
+                split_tf32(pv, hi, lo);
+                const uint32_t o = (uint32_t)((c ^ sw) << 4);
+                *reinterpret_cast<uint4*>(ph + o) = hi;
+                *reinterpret_cast<uint4*>(ph + AT_P_TILE + o) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[b]);
+        }
+#pragma unroll 1
+        for (int j = AT_NC - 2; j < AT_NC; ++j) {                          // drain the two in-flight O_c
+            const int b = j & 1;
+            mbar_wait(&pv_done[b], (j >> 1) & 1);
+            tc_fence_after();
+            const float m_j = b ? m_hist1 : m_hist0;
+            const float sc = __expf(m_acc - m_j);
+            m_acc = m_j;
+            uint32_t q0[32];
+            tc_ld32(trow + 64u + (uint32_t)(b * 64), q0);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o_acc[d] = fmaf(o_acc[d], sc, __uint_as_float(q0[d]));
+            tc_ld32(trow + 64u + (uint32_t)(b * 64) + 32u, q0);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o_acc[32 + d] = fmaf(o_acc[32 + d], sc, __uint_as_float(q0[d]));
+        }
+        const int u = q_start + t;
+        if (u < S) {
+            const float inv = 1.0f / l_run;                               // m_acc == m_run here
+            float* dst = O + (base + u) * ldo + h * AT_HD;
+#pragma unroll
+            for (int d = 0; d < AT_HD; d += 4)
+                *reinterpret_cast<float4*>(dst + d) = make_float4(o_acc[d] * inv, o_acc[d + 1] * inv, o_acc[d + 2] * inv, o_acc[d + 3] * inv);
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+#pragma unroll 1
+            for (int i = 0; i <= AT_NC; ++i) {
+                if (i < AT_NC) {                                           // S(i) = Q K_i^T
+                    const int b = i & 1, n = i >> 1;
+                    mbar_wait(&k_full[b], n & 1);
+                    if (n > 0) mbar_wait(&s_empty[b], (n - 1) & 1);
+                    tc_fence_after();
+                    const uint8_t* ks_ = sm + AT_OFF_K + b * AT_K_STAGE;
+                    const uint32_t d_tmem = tmem + (uint32_t)(b * 32);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t qo = (ks >> 2) * AT_Q_ATOM, ko = (ks >> 2) * AT_K_ATOM;
+                        const uint64_t adv = (uint64_t)(2 * (ks & 3));
+                        const uint64_t qh = make_smem_desc(sm + AT_OFF_QH + qo) + adv, ql = make_smem_desc(sm + AT_OFF_QL + qo) + adv;
+                        const uint64_t kh = make_smem_desc(ks_ + ko) + adv, kl = make_smem_desc(ks_ + 2 * AT_K_ATOM + ko) + adv;
+                        tc_mma_tf32(d_tmem, qh, kh, idesc_s, ks ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, ql, kh, idesc_s, 1u);
+                        tc_mma_tf32(d_tmem, qh, kl, idesc_s, 1u);
+                    }
+                    tc_commit(&s_full[b]);
+                }
+                if (i >= 1) {                                              // O_c(j) = P_j V_j
+                    const int j = i - 1, b = j & 1, n = j >> 1;
+                    mbar_wait(&v_full[b], n & 1);
+                    mbar_wait(&p_full[b], n & 1);
+                    if (n > 0) mbar_wait(&o_empty[b], (n - 1) & 1);
+                    tc_fence_after();
+                    const uint8_t* pb = sm + AT_OFF_P + b * AT_P_BUF;
+                    const uint8_t* vs_ = sm + AT_OFF_V + b * AT_V_STAGE;
+                    const uint32_t d_tmem = tmem + 64u + (uint32_t)(b * 64);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t adv = (uint64_t)(2 * ks);
+                        const uint64_t ph = make_smem_desc(pb) + adv, pl = make_smem_desc(pb + AT_P_TILE) + adv;
+                        const uint64_t vh = make_smem_desc(vs_) + adv, vl = make_smem_desc(vs_ + AT_V_TILE) + adv;
+                        tc_mma_tf32(d_tmem, ph, vh, idesc_o, ks ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, pl, vh, idesc_o, 1u);
+                        tc_mma_tf32(d_tmem, ph, vl, idesc_o, 1u);
+                    }
+                    tc_commit(&pv_done[b]);
+                }
+            }
+        }
+    } else if (warp < 7) {
+        // ---------------- K loader (64 threads): chunk rows = keys, 64 dims = 2 atoms ----------------
+        const int L = t - 160;
+        const int c4 = (L & 15) << 2, r0 = L >> 4;
+        const uint32_t col_off = (uint32_t)((c4 >> 5) * AT_K_ATOM);
+        const int chunk = (c4 & 31) >> 2;
+#pragma unroll 1
+        for (int i = 0; i < AT_NC; ++i) {
+            const int b = i & 1, n = i >> 1;
+            float4 kv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int r = r0 + 4 * e;
+                int u = w * AT_WS + i * AT_BK + r + shift;
+                if (u >= Sp) u -= Sp;
+                kv[e] = u < S ? *reinterpret_cast<const float4*>(K + (base + u) * ldk + h * AT_HD + c4)
+                              : *reinterpret_cast<const float4*>(kb + h * AT_HD + c4);
+            }
+            if (n > 0) mbar_wait(&s_full[b], (n - 1) & 1);               // S(i-2) retired: K stage b is free
+            uint8_t* dst = sm + AT_OFF_K + b * AT_K_STAGE + col_off;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int r = r0 + 4 * e;
+                uint4 hi, lo;
+                split_tf32(kv[e], hi, lo);
+                const uint32_t o = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+                *reinterpret_cast<uint4*>(dst + o) = hi;
+                *reinterpret_cast<uint4*>(dst + 2 * AT_K_ATOM + o) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&k_full[b]);
+        }
+    } else {
+        // ---------------- V loader (64 threads): transposed tile, rows = dims, cols = keys ----------------
+        const int L = t - 224;
+        const int kg = L & 7;                                              // 4 consecutive keys
+#pragma unroll 1
+        for (int i = 0; i < AT_NC; ++i) {
+            const int b = i & 1, n = i >> 1;
+            float4 vv[2][4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int d4 = (L >> 3) + 8 * e;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int u = w * AT_WS + i * AT_BK + 4 * kg + q + shift;
+                    if (u >= Sp) u -= Sp;
+                    vv[e][q] = u < S ? *reinterpret_cast<const float4*>(V + (base + u) * ldv + h * AT_HD + 4 * d4)
+                                     : *reinterpret_cast<const float4*>(vb + h * AT_HD + 4 * d4);
+                }
+            }
+            if (n > 0) mbar_wait(&pv_done[b], (n - 1) & 1);              // PV(i-2) retired: V stage b is free
+            uint8_t* dst = sm + AT_OFF_V + b * AT_V_STAGE;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int d4 = (L >> 3) + 8 * e;
+                const float4 a0 = vv[e][0], a1 = vv[e][1], a2 = vv[e][2], a3 = vv[e][3];
+                const float4 rows[4] = {make_float4(a0.x, a1.x, a2.x, a3.x), make_float4(a0.y, a1.y, a2.y, a3.y),
+                                        make_float4(a0.z, a1.z, a2.z, a3.z), make_float4(a0.w, a1.w, a2.w, a3.w)};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int row = 4 * d4 + c;
+                    uint4 hi, lo;
+                    split_tf32(rows[c], hi, lo);
+                    const uint32_t o = (uint32_t)(row * 128 + ((kg ^ (row & 7)) << 4));
+                    *reinterpret_cast<uint4*>(dst + o) = hi;
+                    *reinterpret_cast<uint4*>(dst + AT_V_TILE + o) = lo;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&v_full[b]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AT_TMEM_COLS) : "memory");
+    }
+}
+
+bool swin_attn_tc_ok(long long ldq, long long ldk, long long ldv, long long ldo, const void* q, const void* k, const void* v,
+                     const void* o, const void* b0, const void* b1, const void* b2) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && al(q) && al(k) && al(v) && al(o) && al(b0) && al(b1) && al(b2);
+}
+
+int swin_attn_tc(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, const float* qb,
+                 const float* kb, const float* vb, const float* relpos, int heads, const long long* d_off, const int* d_win_seq,
+                 const int* d_win_idx, int n_win, int shift, float* out, long long ldo, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { SCP_CUDA(cudaFuncSetAttribute(k_swin_attn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr = true; }
+    dim3 grid((AT_WS / AT_BQ) * heads, n_win);
+    k_swin_attn_tc<<<grid, AT_THREADS, AT_SMEM, st>>>(q, ldq, k, ldk, v, ldv, qb, kb, vb, relpos, heads, d_off, d_win_seq,
+                                                      d_win_idx, shift, out, ldo);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
+}  // namespace scp

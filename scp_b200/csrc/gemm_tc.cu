@@ -152,36 +152,56 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
             }
         }
     } else if (warp >= 4) {
+        // Epilogue.  tcgen05.ld gives lane i the 32 consecutive columns of ROW i, but a row-per-lane global store touches
+        // 32 different cache lines per instruction (the L1 pipe then costs more than the MMAs of a K=256 tile).  So the
+        // chunk goes through a per-warp [32][36] shared-memory tile: bias + activation on the way in (lane = row), residual
+        // add + 128-byte coalesced stores on the way out (8 lanes per row, 4 rows per instruction).
         const int w = warp - 4;                            // TMEM lane quarter this warp may read
+        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 512) + w * (32 * 36);
         int acc = 0; uint32_t acc_phase = 0;
         const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
-                            (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0)));
+                            (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0))) &&
+                            (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
+        const int sub_r = lane >> 3, sub_c = (lane & 7) << 2;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const long long row = (long long)m_blk * BM + w * 32 + lane;
+            const long long row0 = (long long)m_blk * BM + w * 32;
             const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tc_ld32(t_row + (uint32_t)c0, r);
                 const int n0 = n_blk * BN + c0;
-                if (row < M && n0 < N) {
-                    float* yrow = Y + row * ldy + n0;
-                    const float* rrow = R ? R + row * ldr + n0 : nullptr;
-                    if (vec_ok && n0 + 32 <= N) {
+                if (row0 >= M || n0 >= N) continue;          // warp-uniform
+                if (vec_ok && n0 + 32 <= N) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 v;
-                            v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
-                            v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-                            if (bias) { const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + j); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
-                            v.x = tc_act(v.x, act); v.y = tc_act(v.y, act); v.z = tc_act(v.z, act); v.w = tc_act(v.w, act);
-                            if (rrow) { const float4 q = *reinterpret_cast<const float4*>(rrow + j); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-                            *reinterpret_cast<float4*>(yrow + j) = v;
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v;
+                        v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
+                        v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
+                        if (bias) { const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + j); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+                        v.x = tc_act(v.x, act); v.y = tc_act(v.y, act); v.z = tc_act(v.z, act); v.w = tc_act(v.w, act);
+                        *reinterpret_cast<float4*>(stg + lane * 36 + j) = v;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + sub_r;
+                        const long long row = row0 + rr;
+                        if (row < M) {
+                            float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + sub_c);
+                            if (R) { const float4 q = *reinterpret_cast<const float4*>(R + row * ldr + n0 + sub_c); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+                            *reinterpret_cast<float4*>(Y + row * ldy + n0 + sub_c) = v;
                         }
-                    } else {
+                    }
+                    __syncwarp();
+                } else {
+                    const long long row = row0 + lane;
+                    if (row < M) {
+                        float* yrow = Y + row * ldy + n0;
+                        const float* rrow = R ? R + row * ldr + n0 : nullptr;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (n0 + j < N) {
@@ -315,7 +335,7 @@ bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, con
 template <int BN, int STAGES, bool SPLIT>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, const float* res,
                   long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
-    constexpr int smem = STAGES * (128 * 128 + BN * 128) * (SPLIT ? 2 : 1) + 1024 + 512;
+    constexpr int smem = STAGES * (128 * 128 + BN * 128) * (SPLIT ? 2 : 1) + 1024 + 512 + 4 * 32 * 36 * 4;
     static bool attr = false;
     if (!attr) {
         SCP_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

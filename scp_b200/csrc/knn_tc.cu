@@ -20,6 +20,7 @@ constexpr int KT_BM = 128, KT_BN = 128, KT_BK = 32, KT_STAGES = 3;
 constexpr int KT_EXTRA = 8;                                    // approximate top-(k+8) is re-ranked exactly
 constexpr int KT_TILE_BYTES = 128 * KT_BK * 4;                 // 16 KB
 constexpr int KT_STAGE_BYTES = 4 * KT_TILE_BYTES;              // A_hi | A_lo | B_hi | B_lo
+constexpr int KT_CAP = 256;                                    // per-row scratch list (score, candidate) entries
 
 // Candidate-tile visiting order for a query tile t0: its own neighbourhood first (tokens are in Morton order, so the
 // nearest neighbours are mostly index-local and the top-k threshold tightens at once), then the rest ascending.
@@ -54,11 +55,80 @@ __global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X,
     if (lane == 0) xx[row] = s;
 }
 
+
+// Warp-cooperative compaction of one row's scratch list (cq entries, kc <= cq <= KT_CAP) to its top-kc by
+// (score desc, candidate index asc), written back to the front of the list.  Returns the kc-th best score, the row's
+// new threshold.  Selection = MSB-first radix select of the kc-th largest order-preserving key, 8 entries per lane.
+__device__ __forceinline__ float knn_compact_row(float* bs, int* bi, int cq, int kc, int lane) {
+    __syncwarp();                                                          // the owner lane's appends are visible
+    uint32_t key[KT_CAP / 32];
+    int id[KT_CAP / 32];
+#pragma unroll
+    for (int m = 0; m < KT_CAP / 32; ++m) {
+        const int e = lane + 32 * m;
+        key[m] = 0u; id[m] = 0x7fffffff;
+        if (e < cq) {
+            const uint32_t u = __float_as_uint(__ldcg(bs + e));
+            key[m] = u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);          // ascending uint order == ascending float order
+            id[m] = __ldcg(bi + e);
+        }
+    }
+    uint32_t prefix = 0u;
+    int rem = kc;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t sel = ~((1u << bit) - 1u);                          // this bit and everything above it
+        const uint32_t want = prefix | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int m = 0; m < KT_CAP / 32; ++m) c += ((key[m] & sel) == want) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= rem) prefix = want; else rem -= c;
+    }
+    // prefix = kc-th largest key; keep everything above it and `rem` of the entries equal to it (lowest candidate first)
+    int n_eq = 0;
+#pragma unroll
+    for (int m = 0; m < KT_CAP / 32; ++m) n_eq += (key[m] == prefix) ? 1 : 0;
+    n_eq = __reduce_add_sync(0xffffffffu, n_eq);
+    bool keep[KT_CAP / 32];
+#pragma unroll
+    for (int m = 0; m < KT_CAP / 32; ++m) keep[m] = key[m] >= prefix && prefix != 0u;
+    if (n_eq > rem) {                                                      // exact ties at the cut: lowest candidates first
+#pragma unroll
+        for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix) keep[m] = false;
+#pragma unroll 1
+        for (int it = 0; it < rem; ++it) {
+            int best = 0x7fffffff;
+#pragma unroll
+            for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix && !keep[m]) best = min(best, id[m]);
+            best = __reduce_min_sync(0xffffffffu, best);
+#pragma unroll
+            for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix && id[m] == best) keep[m] = true;
+        }
+    }
+    __syncwarp();
+    int basep = 0;
+#pragma unroll
+    for (int m = 0; m < KT_CAP / 32; ++m) {
+        const unsigned bal = __ballot_sync(0xffffffffu, keep[m]);
+        if (keep[m]) {
+            const int pos = basep + __popc(bal & ((1u << lane) - 1u));
+            const uint32_t u = key[m] ^ ((key[m] >> 31) ? 0x80000000u : 0xffffffffu);
+            __stcg(bs + pos, __uint_as_float(u));
+            __stcg(bi + pos, id[m]);
+        }
+        basep += __popc(bal);
+    }
+    __syncwarp();
+    return __uint_as_float(prefix ^ ((prefix >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
 __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUtensorMap tmHi,
                                                     const __grid_constant__ CUtensorMap tmLo,
                                                     const float* __restrict__ xx, const long long* __restrict__ seq_off,
                                                     const int* __restrict__ tile_seq, const int* __restrict__ tile_start,
-                                                    int n_work, long long row0, int d, int k, int* __restrict__ idx_out) {
+                                                    int n_work, long long row0, int d, int k, int* __restrict__ idx_out,
+                                                    float* __restrict__ scr_s, int* __restrict__ scr_i) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + KT_STAGES * KT_STAGE_BYTES);
@@ -151,75 +221,80 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
             }
         }
     } else if (warp >= 4) {
-        // Epilogue: warp w owns query rows 32w..32w+31 of the tile.  tcgen05.ld hands lane i the 32 scores of ROW i; a
-        // [32][33] smem transpose lets the whole warp look at one row at a time (lane j = candidate j).  Each row's
-        // top-kc list lives in registers, one entry per lane (sorted descending); a candidate is inserted with one
-        // ballot + shuffle-shift, so the common case "nothing beats the threshold" costs one compare + ballot per row.
+        // Epilogue: warp w owns query rows 32w..32w+31 of the tile and tcgen05.ld hands lane i the scores of ROW i, so every
+        // lane scans its own row: score, compare with the row's running threshold (the kc-th best seen so far) and, on the
+        // rare hit, append (score, candidate) to the row's scratch list.  No cross-lane traffic in the common case; when a
+        // list is about to overflow the warp compacts it to the exact top-kc with a radix select and tightens the threshold.
         const int w = warp - 4;
-        float* st = stage + w * (32 * 33);
+        float* xcs = stage + w * 128;                                     // this warp's copy of the tile's candidate norms
+        float* bs = scr_s + ((size_t)blockIdx.x * 128 + w * 32) * KT_CAP;
+        int* bi = scr_i + ((size_t)blockIdx.x * 128 + w * 32) * KT_CAP;
+        float* my_s = bs + (size_t)lane * KT_CAP;
+        int* my_i = bi + (size_t)lane * KT_CAP;
         int acc = 0; uint32_t acc_phase = 0;
         for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
             const int s = tile_seq[wk];
             const long long gbase = seq_off[s];
             const int n = (int)(seq_off[s + 1] - gbase);
             const int qw0 = tile_start[wk] + w * 32;                      // first query row of this warp
-            float lsc[32]; int lid[32];                                    // lsc[q] on lane l = l-th best score of row q
-            float xq[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) { lsc[q] = -INFINITY; lid[q] = -1; }
-            const float xq_l = (qw0 + lane < n) ? xx[gbase - row0 + qw0 + lane] : 0.f;
-#pragma unroll
-            for (int q = 0; q < 32; ++q) xq[q] = __shfl_sync(0xffffffffu, xq_l, q);
+            const bool rowv = qw0 + lane < n;
+            const float xq = rowv ? xx[gbase - row0 + qw0 + lane] : 0.f;
+            float th = rowv ? -INFINITY : INFINITY;                        // rows past the window never take a candidate
+            int cnt = 0;
             const int nt = (n + KT_BN - 1) / KT_BN;
             for (int ci = 0; ci < nt; ++ci) {
                 const int c0 = knn_tile_order(ci, tile_start[wk] / KT_BN, nt) * KT_BN;
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int c = c0 + lane + 32 * m;
+                    xcs[lane + 32 * m] = c < n ? __ldg(xx + (gbase - row0) + c) : INFINITY;   // +inf norm -> score -inf
+                }
+                __syncwarp();
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * KT_BN);
 #pragma unroll 1
                 for (int cc = 0; cc < KT_BN; cc += 32) {
+                    if (c0 + cc >= n) break;                               // warp-uniform
                     uint32_t r[32];
-                    __syncwarp();
                     tc_ld32(t_row + (uint32_t)cc, r);
-                    if (c0 + cc >= n) continue;                            // warp-uniform
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
-                    __syncwarp();
-                    const int c = c0 + cc + lane;                          // this lane's candidate
-                    const float xc = c < n ? __ldg(xx + (gbase - row0) + c) : 0.f;
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const float4 xc = *reinterpret_cast<const float4*>(xcs + cc + j4);
+                        const float xcv[4] = {xc.x, xc.y, xc.z, xc.w};
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        if (qw0 + q >= n) break;                           // warp-uniform
-                        const float sc = c < n ? __fsub_rn(__fsub_rn(2.0f * st[q * 33 + lane], xc), xq[q]) : -INFINITY;
-                        float th = __shfl_sync(0xffffffffu, lsc[q], kc - 1);
-                        unsigned m = __ballot_sync(0xffffffffu, sc > th);
-                        while (m) {
-                            const int j = __ffs(m) - 1;
-                            const float sj = __shfl_sync(0xffffffffu, sc, j);
-                            // entries with score >= sj stay ahead (earlier = lower index wins ties)
-                            const int pos = __popc(__ballot_sync(0xffffffffu, lsc[q] >= sj));
-                            const float us = __shfl_up_sync(0xffffffffu, lsc[q], 1);
-                            const int ui = __shfl_up_sync(0xffffffffu, lid[q], 1);
-                            if (lane > pos) { lsc[q] = us; lid[q] = ui; }
-                            if (lane == pos) { lsc[q] = sj; lid[q] = c0 + cc + j; }
-                            th = __shfl_sync(0xffffffffu, lsc[q], kc - 1);
-                            m = __ballot_sync(0xffffffffu, sc > th) & ~((2u << j) - 1u);
+                        for (int e = 0; e < 4; ++e) {
+                            // == (2 g - |c|^2) - |q|^2 with one rounding per subtraction (2 g is exact)
+                            const float sc = __fsub_rn(fmaf(2.0f, __uint_as_float(r[j4 + e]), -xcv[e]), xq);
+                            if (sc > th) { my_s[cnt] = sc; my_i[cnt] = c0 + cc + j4 + e; ++cnt; }
                         }
                     }
-                    __syncwarp();
+                    unsigned need = __ballot_sync(0xffffffffu, cnt > KT_CAP - 32);
+                    while (need) {
+                        const int q = __ffs(need) - 1;
+                        need &= need - 1;
+                        const float pv = knn_compact_row(bs + (size_t)q * KT_CAP, bi + (size_t)q * KT_CAP,
+                                                         __shfl_sync(0xffffffffu, cnt, q), kc, lane);
+                        if (lane == q) { th = pv; cnt = kc; }
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-#pragma unroll
             for (int q = 0; q < 32; ++q) {
-                if (qw0 + q < n && lane < kc) {
+                if (qw0 + q >= n) break;                                   // warp-uniform
+                int cq = __shfl_sync(0xffffffffu, cnt, q);
+                if (cq > kc) { knn_compact_row(bs + (size_t)q * KT_CAP, bi + (size_t)q * KT_CAP, cq, kc, lane); cq = kc; }
+                __syncwarp();
+                if (lane < kc) {
                     const long long row = gbase + qw0 + q;
-                    idx_out[(row - row0) * kc + lane] = lid[q] < 0 ? -1 : (int)(gbase + lid[q]);   // candidates for the re-rank
+                    idx_out[(row - row0) * kc + lane] = lane < cq ? (int)(gbase + __ldcg(bi + (size_t)q * KT_CAP + lane)) : -1;
                 }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -281,10 +356,10 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     float *hi = nullptr, *lo = nullptr, *xx = nullptr;
     int* cand = nullptr;
     const int kc = k + KT_EXTRA;
-    SCP_CUDA(cudaMallocAsync((void**)&cand, (size_t)total * kc * 4 + 1024, st));
-    SCP_CUDA(cudaMallocAsync((void**)&hi, (size_t)total * d * 4 + 1024, st));
-    SCP_CUDA(cudaMallocAsync((void**)&lo, (size_t)total * d * 4 + 1024, st));
-    SCP_CUDA(cudaMallocAsync((void**)&xx, (size_t)total * 4 + 1024, st));
+    SCP_CUDA(malloc_async((void**)&cand, (size_t)total * kc * 4 + 1024, st));
+    SCP_CUDA(malloc_async((void**)&hi, (size_t)total * d * 4 + 1024, st));
+    SCP_CUDA(malloc_async((void**)&lo, (size_t)total * d * 4 + 1024, st));
+    SCP_CUDA(malloc_async((void**)&xx, (size_t)total * 4 + 1024, st));
     k_split_rows<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x + row0 * ldx, ldx, d, total, hi, lo, xx);
     SCP_LAUNCHED();
     CUtensorMap mh, ml;
@@ -297,10 +372,17 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     if (smem > attr) { SCP_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-    k_knn_tc<<<std::min(n_work, n_sm), 256, smem, st>>>(mh, ml, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand);
+    const int grid = std::min(n_work, n_sm);
+    float* scr_s = nullptr;
+    int* scr_i = nullptr;
+    SCP_CUDA(malloc_async((void**)&scr_s, (size_t)grid * 128 * KT_CAP * 4, st));
+    SCP_CUDA(malloc_async((void**)&scr_i, (size_t)grid * 128 * KT_CAP * 4, st));
+    k_knn_tc<<<grid, 256, smem, st>>>(mh, ml, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, scr_s, scr_i);
     SCP_LAUNCHED();
     k_knn_rerank<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x, ldx, d, row0, total, cand, kc, k, d_idx);
     SCP_LAUNCHED();
+    SCP_CUDA(cudaFreeAsync(scr_s, st));
+    SCP_CUDA(cudaFreeAsync(scr_i, st));
     SCP_CUDA(cudaFreeAsync(cand, st));
     SCP_CUDA(cudaFreeAsync(hi, st));
     SCP_CUDA(cudaFreeAsync(lo, st));

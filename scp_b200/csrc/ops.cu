@@ -34,6 +34,11 @@ bool knn_tc_ok(int d, int k);                                                   
 int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n_seq, const long long* d_off,
            const int* d_tile_seq, const int* d_tile_start, int n_work, int k, int* d_idx, cudaStream_t st);
 bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, const void* x, const void* w, const void* y);
+bool swin_attn_tc_ok(long long ldq, long long ldk, long long ldv, long long ldo, const void* q, const void* k, const void* v,
+                     const void* o, const void* b0, const void* b1, const void* b2);                      // attn_tc.cu
+int swin_attn_tc(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, const float* qb,
+                 const float* kb, const float* vb, const float* relpos, int heads, const long long* d_off, const int* d_win_seq,
+                 const int* d_win_idx, int n_win, int shift, float* out, long long ldo, cudaStream_t st);
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
@@ -155,6 +160,52 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ X, 
     for (int i = 0; i < MAXP; ++i) {
         int c = lane + 32 * i;
         if (c < C) Y[row * ldy + c] = (v[i] - mean) * rs * g[c] + b[c];
+    }
+}
+
+// vectorised variant for C = 128 * V4 (256 / 512 channel rows, 16-byte aligned): one warp per row, V4 float4 per lane,
+// all loads of a row issued before the first reduction
+template <int V4>
+__global__ void __launch_bounds__(256) k_layernorm_v4(const float* __restrict__ X, long long ldx, const float* __restrict__ R,
+                                                       long long ldr, const float* __restrict__ g, const float* __restrict__ b,
+                                                       float* __restrict__ Y, long long ldy, long long M, float eps) {
+    constexpr int C = 128 * V4;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float4 v[V4];
+    const float4* x4 = reinterpret_cast<const float4*>(X + row * ldx);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) v[i] = __ldcs(x4 + lane + 32 * i);
+    if (R) {
+        const float4* r4 = reinterpret_cast<const float4*>(R + row * ldr);
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            const float4 r = __ldcs(r4 + lane + 32 * i);
+            v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rs = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+    float4* y4 = reinterpret_cast<float4*>(Y + row * ldy);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float4 gg = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+        float4 o;
+        o.x = v[i].x * rs * gg.x + bb.x; o.y = v[i].y * rs * gg.y + bb.y;
+        o.z = v[i].z * rs * gg.z + bb.z; o.w = v[i].w * rs * gg.w + bb.w;
+        y4[lane + 32 * i] = o;
     }
 }
 
@@ -725,6 +776,7 @@ __global__ void __launch_bounds__(128) k_octattn_attn(const float* __restrict__ 
 }
 
 static int g_knn_tc = 1;         // learned-feature kNN on the tensor cores (3xTF32 Gram + fused top-k); 0 = fp32 SIMT tiles
+static int g_attn_tc = 1;        // window attention on the tensor cores (3xTF32 QK^T and PV, fused online softmax); 0 = fp32 SIMT
 static int g_auto_tf32 = 1;      // SCP_GEMM_AUTO = 3xTF32 tcgen05 engine for the large layers (validated: PMF err 7e-5)
 
 static inline int grid_for(long long work, int per_block, int cap = 148 * 16) {
@@ -789,6 +841,8 @@ void scp_gemm_cache_clear(void) { gemm_cache_clear(); }
 
 int scp_set_knn_engine(int use_tensor_cores) { int old = g_knn_tc; g_knn_tc = use_tensor_cores ? 1 : 0; return old; }
 
+int scp_set_attn_engine(int use_tensor_cores) { int old = g_attn_tc; g_attn_tc = use_tensor_cores ? 1 : 0; return old; }
+
 int scp_set_auto_engine(int use_tf32) { int old = g_auto_tf32; g_auto_tf32 = use_tf32 ? 1 : 0; return old; }
 
 int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K) {
@@ -825,6 +879,19 @@ int scp_layernorm(const float* d_x, int64_t ldx, const float* d_res, int64_t ldr
                   const float* d_beta, float* d_y, int64_t ldy, int64_t M, int C, float eps, void* stream) {
     SCP_REQUIRE(d_x && d_gamma && d_beta && d_y && C > 0 && C <= 640, "scp_layernorm: bad argument (C<=640)");
     if (M == 0) return SCP_OK;
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool v4 = (C == 256 || C == 512) && ldx % 4 == 0 && ldy % 4 == 0 && al(d_x) && al(d_y) && al(d_gamma) && al(d_beta) &&
+                    (!d_res || (ldr % 4 == 0 && al(d_res)));
+    if (v4 && C == 256) {
+        k_layernorm_v4<2><<<(unsigned)cdiv(M, 8), 256, 0, as_stream(stream)>>>(d_x, ldx, d_res, ldr, d_gamma, d_beta, d_y, ldy, M, eps);
+        SCP_LAUNCHED();
+        return SCP_OK;
+    }
+    if (v4 && C == 512) {
+        k_layernorm_v4<4><<<(unsigned)cdiv(M, 8), 256, 0, as_stream(stream)>>>(d_x, ldx, d_res, ldr, d_gamma, d_beta, d_y, ldy, M, eps);
+        SCP_LAUNCHED();
+        return SCP_OK;
+    }
     k_layernorm<<<(unsigned)cdiv(M, 8), 256, 0, as_stream(stream)>>>(d_x, ldx, d_res, ldr, d_gamma, d_beta, d_y, ldy, M, C, eps);
     SCP_LAUNCHED();
     return SCP_OK;
@@ -868,7 +935,7 @@ int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, i
         return knn_tc(d_x, ldx, d, seqs->h_off.data(), seqs->n_seq, seqs->d_off, seqs->d_tile128_seq, seqs->d_tile128_start,
                       seqs->n_tile128, k, d_idx, st);
     float* xx = nullptr;
-    SCP_CUDA(cudaMallocAsync((void**)&xx, seqs->total * 4, st));
+    SCP_CUDA(malloc_async((void**)&xx, seqs->total * 4, st));
     const float* x0 = d_x + seqs->h_off[0] * ldx;
     k_row_sqnorm<<<(unsigned)cdiv(seqs->total, 8), 256, 0, st>>>(x0, ldx, d, seqs->total, xx);
     SCP_LAUNCHED();
@@ -904,6 +971,9 @@ int scp_swin_attention(const float* d_q, int64_t ldq, const float* d_k, int64_t 
     SCP_REQUIRE(heads > 0 && heads <= 16 && (shift == 0 || shift == 256), "scp_swin_attention: heads/shift");
     SCP_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "scp_swin_attention: out must be 16B aligned");
     if (seqs->n_win == 0) return SCP_OK;
+    if (g_attn_tc && heads * 64 <= 1024 && swin_attn_tc_ok(ldq, ldk, ldv, ldo, d_q, d_k, d_v, d_out, d_qb, d_kb, d_vb))
+        return swin_attn_tc(d_q, ldq, d_k, ldk, d_v, ldv, d_qb, d_kb, d_vb, d_relpos, heads, seqs->d_off, seqs->d_win_seq,
+                            seqs->d_win_idx, seqs->n_win, shift, d_out, ldo, as_stream(stream));
     const int smem = 4 * HD * ALD * 4;
     static bool attr = false;
     if (!attr) { SCP_CUDA(cudaFuncSetAttribute(k_swin_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }

@@ -136,10 +136,12 @@ def test_edge_gather(ops):
         close(yc, y, 1e-6)
 
 
+@pytest.mark.parametrize("tensor_cores", [1, 0])
 @pytest.mark.parametrize("lens,shift", [([37], 0), ([37], 256), ([600, 2, 512], 256), ([1100], 0), ([1100, 300], 256),
-                                        ([2048], 256)])
-def test_swin_attention(ops, lens, shift):
+                                        ([2048], 256), ([8192, 130], 0)])
+def test_swin_attention(ops, lens, shift, tensor_cores):
     cu, em = ops
+    old = cu.lib.scp_set_attn_engine(tensor_cores)
     offs = [0] + list(np.cumsum(lens))
     T = offs[-1]
     qkv, qkvc = both(T, 768, 1)
@@ -149,6 +151,7 @@ def test_swin_attention(ops, lens, shift):
     em.swin_attention(V(qkv, 0, 256), V(qkv, 256, 256), V(qkv, 512, 256), b[0], b[1], b[2], rel, 4, em.seqs(offs), shift, V(y))
     cu.swin_attention(V(qkvc, 0, 256), V(qkvc, 256, 256), V(qkvc, 512, 256), bc[0], bc[1], bc[2], relc, 4,
                       cu.seqs(offs), shift, V(yc))
+    cu.lib.scp_set_attn_engine(old)
     close(yc, y, 2e-5)
 
 
