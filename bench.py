@@ -179,8 +179,6 @@ def run_ours(args):
         enc.encode_device(xyz, offs)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    model.ops.reserve_events(2 * 700 * F * args.steps + 4096)
-    model.ops.prof = []
     launches0 = lib.scp_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -190,9 +188,21 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.scp_launch_count() - launches0
-    prof, model.ops.prof = model.ops.prof, None
     clocks = sampler.stop() if sampler else None
     n_nodes = sum(f[1] for f in fr)
+
+    # per-kernel durations: the same K steps again with every operator launch bracketed by CUDA events on the launching
+    # stream.  Kept out of the headline loop because ~1700 timing events per step cost 15-20 % of the step.
+    model.ops.reserve_events(2 * 700 * F * args.steps + 4096)
+    model.ops.prof = []
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        enc.encode_device(xyz, offs)
+    p1.record()
+    barrier()
+    prof_ms = p0.elapsed_time(p1)
+    prof, model.ops.prof = model.ops.prof, None
 
     # octree / gather kernels alone on a batch large enough to fill the GPU (64 frames = 192 jobs, > L2)
     OB = 64
@@ -238,14 +248,17 @@ def run_ours(args):
     top = max(agg.items(), key=lambda kv: kv[1][0])
     hbm_peak, tf_peak, src = peaks()
     tag, (tms, tfl, tby, cnt) = top
-    intensity = tfl / max(tby, 1.0)
-    if intensity > tf_peak * 1e3 / hbm_peak:
-        roof = {"bound": "tensor", "achieved": tfl / tms / 1e9, "peak": tf_peak, "unit": "TFLOP/s"}
+    # Dense contractions run as error-compensated 3xTF32 (three tcgen05.mma per product, fp32-class result), so the
+    # tensor-pipe work is 3x the nominal 2MNK and the pipe's TF32 rate is half the measured bf16 rate.
+    tensor_kernel = tag in ("linear", "swin_attention") or tag.startswith("knn_d1")
+    if tensor_kernel:
+        roof = {"bound": "tensor", "achieved": 3.0 * tfl / tms / 1e9, "peak": tf_peak / 2.0, "unit": "TFLOP/s",
+                "note": "TF32 MMA flops issued (3 per fp32-class product) vs TF32 peak = measured sustained bf16 / 2"}
     else:
         roof = {"bound": "hbm", "achieved": tby / tms / 1e6, "peak": hbm_peak, "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update({"kernel": tag, "launches": cnt, "avg_ms": tms / cnt, "share_of_step": tms / ms, "peak_source": src,
-                 "traffic": None})
+    roof.update({"kernel": tag, "launches": cnt, "avg_ms": tms / cnt, "share_of_step": tms / prof_ms, "peak_source": src,
+                 "traffic": None, "timed_in": "instrumented repeat of the timed steps (events around every launch)"})
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[3] // args.steps,
                    "TFLOPs": v[1] / v[0] / 1e9 if v[0] else None, "GBps": v[2] / v[0] / 1e6 if v[0] else None}
                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}

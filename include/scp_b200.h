@@ -180,6 +180,8 @@ int64_t scp_range_encode_cdf(const uint16_t* h_cdf, const int16_t* h_sym, int64_
 typedef struct scp_seqs scp_seqs;
 /* h_offsets[n_seq+1]: token ranges of the sequences (host). Uploads the tables the kernels need. */
 scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq);
+/* Same, with the table upload ordered on `stream` (no host synchronisation; use the stream the operators run on). */
+scp_seqs* scp_seqs_create_async(const int64_t* h_offsets, int n_seq, void* stream);
 void      scp_seqs_destroy(scp_seqs* s);
 int64_t   scp_seqs_total(const scp_seqs* s);
 

@@ -74,6 +74,7 @@ SIGNATURES = {
     "scp_range_encode": (_i64, [_vp, _i64, _vp, _i64]),
     "scp_range_encode_cdf": (_i64, [_vp, _vp, _i64, _i, _vp, _i64]),
     "scp_seqs_create": (_vp, [C.POINTER(_i64), _i]),
+    "scp_seqs_create_async": (_vp, [C.POINTER(_i64), _i, _vp]),
     "scp_seqs_destroy": (None, [_vp]),
     "scp_seqs_total": (_i64, [_vp]),
     "scp_linear": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp]),
@@ -125,10 +126,18 @@ def check(status, what=""):
     return status
 
 
+_device_ok = {}
+
+
 def require_device():
     lib = load()
+    import torch
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    if _device_ok.get(dev):                 # cudaGetDeviceProperties costs ~20 ms per call: ask once per device
+        return lib
     if not lib.scp_device_ok():
         raise ScpError("scp_b200 needs a B200 (sm_100) CUDA device: " + lib.scp_last_error().decode(errors="replace"))
+    _device_ok[dev] = True
     return lib
 
 

@@ -1,6 +1,7 @@
 // Library-wide plumbing of the C ABI: error strings, version, device check, launch counter, and the
 // legacy symbols of data_preproc/OctreeCPP/Octree_python_lib.so (Octreewarpper.py:17-39).
 #include <vector>
+#include <mutex>
 #include <string>
 #include <string.h>
 #include "common.cuh"
@@ -33,6 +34,46 @@ cudaError_t malloc_async(void** p, size_t bytes, cudaStream_t st) {
         configured.fetch_or(bit);
     }
     return cudaMallocAsync(p, bytes, st);
+}
+
+static std::mutex g_pin_mu;
+static std::vector<PinnedBlock> g_pin_free;
+
+bool pinned_get(size_t bytes, PinnedBlock* out) {
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        for (size_t i = 0; i < g_pin_free.size(); ++i) {
+            if (g_pin_free[i].bytes >= bytes && g_pin_free[i].bytes <= 4 * bytes + 4096) {
+                *out = g_pin_free[i];
+                g_pin_free.erase(g_pin_free.begin() + i);
+                cudaEventSynchronize(out->ev);
+                return true;
+            }
+        }
+    }
+    PinnedBlock b{nullptr, bytes < 4096 ? (size_t)4096 : bytes, nullptr};
+    if (cudaMallocHost(&b.p, b.bytes) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(b.p); return false; }
+    *out = b;
+    return true;
+}
+
+void pinned_put(const PinnedBlock& b) {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    if (g_pin_free.size() < 256) { g_pin_free.push_back(b); return; }
+    cudaEventDestroy(b.ev);
+    cudaFreeHost(b.p);
+}
+
+cudaError_t upload_async(void** d, const void* h, size_t bytes, cudaStream_t st) {
+    PinnedBlock pb;
+    if (!pinned_get(bytes, &pb)) return cudaErrorMemoryAllocation;
+    memcpy(pb.p, h, bytes);
+    cudaError_t e = malloc_async(d, bytes, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(*d, pb.p, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(pb.ev, st);
+    pinned_put(pb);
+    return e;
 }
 
 }  // namespace scp

@@ -1,41 +1,42 @@
 // 1-D shifted-window attention (swin_transformer.py:406-501,603-697) on the 5th-gen tensor cores.
 //
-// One CTA per (window, head, 128-query block); the 512 keys of the window stream through in 16 chunks of 32:
-//     S_c = Q K_c^T          tcgen05.mma M128 x N32 x K64   (3xTF32: Q_hi K_hi + Q_lo K_hi + Q_hi K_lo), fp32 accum in TMEM
+// One CTA per (window, head, 128-query block); the 512 keys of the window stream through in 8 chunks of 64:
+//     S_c = Q K_c^T          tcgen05.mma M128 x N64 x K64   (3xTF32: Q_hi K_hi + Q_lo K_hi + Q_hi K_lo), fp32 accum in TMEM
 //     P_c = exp(S_c + bias + mask - m)      one query row per thread (tcgen05.ld), online softmax in registers
-//     O_c = P_c V_c          tcgen05.mma M128 x N64 x K32   (P_hi V_hi + P_lo V_hi + P_hi V_lo), accum in TMEM,
+//     O_c = P_c V_c          tcgen05.mma M128 x N64 x K64   (P_hi V_hi + P_lo V_hi + P_hi V_lo), accum in TMEM,
 //                            rescaled and added to the running output in registers
-// Warp roles (288 threads):  warps 0-3 softmax / output (TMEM lane quarter = warp), warp 4 MMA issuer + TMEM owner,
-// warps 5-6 K loader, warps 7-8 V loader.  Everything is double-buffered (S, O_c in TMEM; K, V, P in shared memory) and
-// handed over through mbarriers, so the MMAs of chunk i+1 overlap the softmax of chunk i and the staging of chunk i+2.
-// Operand tiles are written by the loader warps in the canonical K-major 128B-swizzled layout: the roll by -shift, the
-// zero padding of the sequence (padded tokens carry exactly the Linear biases), the hi/lo split and the V transpose
-// happen on the way, so no TMA descriptor is needed for the gathered rows and HBM/L2 is read once in fp32.
+// The A operands live in TENSOR MEMORY (the "TS" form of tcgen05.mma): Q_hi/Q_lo are written there once with tcgen05.st,
+// and the softmax threads write P_hi over the S columns they just read and P_lo next to them.  An MMA with N = 64 reads
+// its 4 KB A slice from shared memory in 32 cycles but computes in 32: with A in TMEM only the 2 KB B slice crosses the
+// shared-memory port and the kernel is MMA-bound instead of shared-memory-bound.
+//
+// TMEM map (512 columns): Q_hi [0,64) | Q_lo [64,128) | buffer b: S / P_hi [128+128b, +64), P_lo [+64, +128) | O_c b [384+64b, +64)
+// Warp roles (288 threads): warps 0-3 softmax / output (TMEM lane quarter = warp), warp 4 MMA issuer + TMEM owner,
+// warps 5-6 K loader, warps 7-8 V loader.  S/P, O_c, K and V stages are double-buffered and handed over through
+// mbarriers, so the MMAs of chunk i+1 overlap the softmax of chunk i and the staging of chunk i+2.
+// The loader warps write K_c and V_c^T in the canonical K-major 128B-swizzled layout: the roll by -shift, the zero
+// padding of the sequence (padded tokens carry exactly the Linear biases), the hi/lo split and the V transpose happen
+// on the way, so HBM/L2 is read once, in fp32, without a TMA descriptor for the gathered rows.
 #include "tc.cuh"
 
 struct scp_seqs;
 
 namespace scp {
 
-constexpr int AT_WS = 512, AT_HD = 64, AT_BQ = 128, AT_BK = 32, AT_NC = AT_WS / AT_BK;
-constexpr int AT_Q_ATOM = AT_BQ * 128;           // [128 rows x 128 B] one 32-float K-atom of the Q operand (16 KB)
-constexpr int AT_K_ATOM = AT_BK * 128;           // [32 keys x 128 B]                                        ( 4 KB)
+constexpr int AT_WS = 512, AT_HD = 64, AT_BQ = 128, AT_BK = 64, AT_NC = AT_WS / AT_BK;
+constexpr int AT_K_ATOM = AT_BK * 128;           // [64 keys x 128 B] one 32-float K-atom of the K operand      (8 KB)
+constexpr int AT_V_ATOM = AT_HD * 128;           // [64 dims x 128 B] one 32-key  K-atom of the V^T operand     (8 KB)
 // shared memory map (bytes, from a 1024-aligned base)
-constexpr int AT_OFF_QH = 0;                     // Q_hi: 2 atoms
-constexpr int AT_OFF_QL = 2 * AT_Q_ATOM;         // Q_lo: 2 atoms
-constexpr int AT_OFF_K = 4 * AT_Q_ATOM;          // 2 stages x [K_hi 8K | K_lo 8K]
-constexpr int AT_K_STAGE = 4 * AT_K_ATOM;
-constexpr int AT_OFF_V = AT_OFF_K + 2 * AT_K_STAGE;   // 2 stages x [Vt_hi 8K | Vt_lo 8K]   (rows = dims, K extent = 32 keys)
-constexpr int AT_V_TILE = AT_HD * 128;
-constexpr int AT_V_STAGE = 2 * AT_V_TILE;
-constexpr int AT_OFF_P = AT_OFF_V + 2 * AT_V_STAGE;   // 2 buffers x [P_hi 16K | P_lo 16K]
-constexpr int AT_P_TILE = AT_BQ * 128;
-constexpr int AT_P_BUF = 2 * AT_P_TILE;
-constexpr int AT_OFF_BIAS = AT_OFF_P + 2 * AT_P_BUF;  // 1023 floats
+constexpr int AT_K_STAGE = 4 * AT_K_ATOM;        // K_hi (2 atoms) | K_lo (2 atoms)
+constexpr int AT_V_STAGE = 4 * AT_V_ATOM;        // Vt_hi (2 atoms) | Vt_lo (2 atoms)
+constexpr int AT_OFF_K = 0;
+constexpr int AT_OFF_V = AT_OFF_K + 2 * AT_K_STAGE;
+constexpr int AT_OFF_BIAS = AT_OFF_V + 2 * AT_V_STAGE;   // 1023 floats
 constexpr int AT_OFF_BAR = AT_OFF_BIAS + 4096;
 constexpr int AT_SMEM = AT_OFF_BAR + 256 + 1024;
 constexpr int AT_THREADS = 288;
-constexpr uint32_t AT_TMEM_COLS = 256;           // S0 [0,32) S1 [32,64) O0 [64,128) O1 [128,192)
+constexpr uint32_t AT_TMEM_COLS = 512;
+constexpr uint32_t AT_T_QH = 0, AT_T_QL = 64, AT_T_SP = 128, AT_T_O = 384;
 
 __device__ __forceinline__ void split_tf32(const float4 v, uint4& hi, uint4& lo) {
     hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
@@ -43,6 +44,33 @@ __device__ __forceinline__ void split_tf32(const float4 v, uint4& hi, uint4& lo)
     lo.x = __float_as_uint(v.x - __uint_as_float(hi.x)); lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
     lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
 }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+          "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+          "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __restrict__ Q, long long ldq,
                                                                  const float* __restrict__ K, long long ldk,
@@ -53,17 +81,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
                                                                  const int* __restrict__ win_seq, const int* __restrict__ win_idx,
                                                                  int shift, float* __restrict__ O, long long ldo) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by an OFFSET from the shared-space symbol: a pointer rebuilt from an integer would be generic
+    // (LD/ST instead of LDS/STS and no alias information against global memory)
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* s_bias = reinterpret_cast<float*>(sm + AT_OFF_BIAS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AT_OFF_BAR);
-    uint64_t* k_full = bars;            // [2] K chunk staged              (2 loader warps)
-    uint64_t* v_full = bars + 2;        // [2] V chunk staged              (2 loader warps)
-    uint64_t* s_full = bars + 4;        // [2] S chunk in TMEM, K stage free (tcgen05.commit)
-    uint64_t* s_empty = bars + 6;       // [2] S chunk read back           (4 softmax warps)
-    uint64_t* p_full = bars + 8;        // [2] P chunk written             (4 softmax warps)
-    uint64_t* pv_done = bars + 10;      // [2] O_c in TMEM, V stage and P buffer free (tcgen05.commit)
-    uint64_t* o_empty = bars + 12;      // [2] O_c read back               (4 softmax warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* k_full = bars;            // [2] K chunk staged                         (2 loader warps)
+    uint64_t* v_full = bars + 2;        // [2] V chunk staged                         (2 loader warps)
+    uint64_t* s_full = bars + 4;        // [2] S chunk in TMEM, K stage free          (tcgen05.commit)
+    uint64_t* p_full = bars + 6;        // [2] P chunk written to TMEM                (4 softmax warps)
+    uint64_t* pv_done = bars + 8;       // [2] O_c in TMEM, V stage and P_lo columns free (tcgen05.commit)
+    uint64_t* o_empty = bars + 10;      // [2] O_c read back                          (4 softmax warps)
+    uint64_t* q_full = bars + 12;       // [1] Q_hi/Q_lo written to TMEM              (4 softmax warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int h = blockIdx.x % heads, qblk = blockIdx.x / heads;
@@ -82,9 +112,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
     if (warp == 4) {
         if (lane == 0) {
             for (int b = 0; b < 2; ++b) {
-                mbar_init(&k_full[b], 2); mbar_init(&v_full[b], 2); mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4);
+                mbar_init(&k_full[b], 2); mbar_init(&v_full[b], 2); mbar_init(&s_full[b], 1);
                 mbar_init(&p_full[b], 4); mbar_init(&pv_done[b], 1); mbar_init(&o_empty[b], 4);
             }
+            mbar_init(q_full, 4);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -92,20 +123,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int e = t; e < 2 * AT_WS - 1; e += AT_THREADS) s_bias[e] = relpos[e * heads + h];
-    // Q block: rolled rows, 1/sqrt(64) scale (exact), hi/lo split, swizzled K-major
-    for (int f = t; f < AT_BQ * 16; f += AT_THREADS) {
-        const int r = f >> 4, c4 = (f & 15) << 2;
-        const int u = q_start + r;
-        float4 v = u < S ? *reinterpret_cast<const float4*>(Q + (base + u) * ldq + h * AT_HD + c4)
-                         : *reinterpret_cast<const float4*>(qb + h * AT_HD + c4);
-        v.x *= 0.125f; v.y *= 0.125f; v.z *= 0.125f; v.w *= 0.125f;
-        uint4 hi, lo;
-        split_tf32(v, hi, lo);
-        const uint32_t o = (uint32_t)((c4 >> 5) * AT_Q_ATOM + r * 128 + (((((c4 & 31) >> 2) ^ (r & 7))) << 4));
-        *reinterpret_cast<uint4*>(sm + AT_OFF_QH + o) = hi;
-        *reinterpret_cast<uint4*>(sm + AT_OFF_QL + o) = lo;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -113,33 +130,54 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
 
     if (warp < 4) {
         // ---------------- softmax + output: thread t owns query row t of the block ----------------
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        {   // Q row -> TMEM: 1/sqrt(64) scale (exact), hi/lo split
+            const int u = q_start + t;
+            const float4* src = reinterpret_cast<const float4*>(u < S ? Q + (base + u) * ldq + h * AT_HD : qb + h * AT_HD);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 v = src[half * 8 + c];
+                    v.x *= 0.125f; v.y *= 0.125f; v.z *= 0.125f; v.w *= 0.125f;
+                    uint4 h4, l4;
+                    split_tf32(v, h4, l4);
+                    hi[4 * c] = h4.x; hi[4 * c + 1] = h4.y; hi[4 * c + 2] = h4.z; hi[4 * c + 3] = h4.w;
+                    lo[4 * c] = l4.x; lo[4 * c + 1] = l4.y; lo[4 * c + 2] = l4.z; lo[4 * c + 3] = l4.w;
+                }
+                tc_st32(trow + AT_T_QH + (uint32_t)(half * 32), hi);
+                tc_st32(trow + AT_T_QL + (uint32_t)(half * 32), lo);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_full);
+        }
         float o_acc[AT_HD];
 #pragma unroll
         for (int d = 0; d < AT_HD; ++d) o_acc[d] = 0.f;
         float m_run = -INFINITY, l_run = 0.f, m_acc = -INFINITY, m_hist0 = 0.f, m_hist1 = 0.f;
         const int pi = qblk * AT_BQ + t;                                   // window position of this row
-        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-        const uint32_t prow = (uint32_t)(t * 128);
-        const int sw = t & 7;
 #pragma unroll 1
         for (int i = 0; i < AT_NC; ++i) {
             const int b = i & 1, n = i >> 1;
+            const uint32_t t_sp = trow + AT_T_SP + (uint32_t)(b * 128);
             mbar_wait(&s_full[b], n & 1);
             tc_fence_after();
-            uint32_t r[32];
-            tc_ld32(trow + (uint32_t)(b * 32), r);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[b]);
+            uint32_t r0[32], r1[32];
+            tc_ld32(t_sp, r0);
+            tc_ld32(t_sp + 32u, r1);
             const bool masked = last_win && ((pi < AT_WS / 2) != (i < AT_NC / 2));     // swin_transformer.py:620
             const float* bp = s_bias + (pi - i * AT_BK + AT_WS - 1);
             float mx = m_run;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float v = __uint_as_float(r[j]) + bp[-j];
-                if (masked) v += -100.0f;
-                r[j] = __float_as_uint(v);
-                mx = fmaxf(mx, v);
+                float v0 = __uint_as_float(r0[j]) + bp[-j];
+                float v1 = __uint_as_float(r1[j]) + bp[-j - 32];
+                if (masked) { v0 += -100.0f; v1 += -100.0f; }
+                r0[j] = __float_as_uint(v0); r1[j] = __float_as_uint(v1);
+                mx = fmaxf(mx, fmaxf(v0, v1));
             }
             const float alpha = __expf(m_run - mx);
             m_run = mx;
@@ -148,42 +186,45 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float p = __expf(__uint_as_float(r[j]) - mx);
-                sum += p;
-                r[j] = __float_as_uint(p);
+                const float p0 = __expf(__uint_as_float(r0[j]) - mx), p1 = __expf(__uint_as_float(r1[j]) - mx);
+                sum += p0 + p1;
+                r0[j] = __float_as_uint(p0); r1[j] = __float_as_uint(p1);
             }
             l_run = fmaf(l_run, alpha, sum);
-            if (i >= 2) {
-                // O_c of chunk i-2 is complete; that also frees P buffer b
-                mbar_wait(&pv_done[b], (n - 1) & 1);
-                tc_fence_after();
+            // PV(i-2) retired: its O_c is complete and the P_lo columns of buffer b are free again
+            if (i >= 2) { mbar_wait(&pv_done[b], (n - 1) & 1); tc_fence_after(); }
+            // P_hi over the S columns, P_lo next to them (first, so that the MMA warp can go on), 16 columns at a time
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t* src = q < 2 ? r0 + 16 * q : r1 + 16 * (q - 2);
+                uint32_t lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t hi = src[j] & 0xffffe000u;
+                    lo[j] = __float_as_uint(__uint_as_float(src[j]) - __uint_as_float(hi));
+                    src[j] = hi;
+                }
+                tc_st16(t_sp + (uint32_t)(16 * q), src);
+                tc_st16(t_sp + 64u + (uint32_t)(16 * q), lo);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[b]);
+            if (i >= 2) {                                                  // fold O_c(i-2) into the running output
                 const float sc = __expf(m_acc - m_old);
                 m_acc = m_old;
                 uint32_t q0[32];
-                tc_ld32(trow + 64u + (uint32_t)(b * 64), q0);
+                tc_ld32(trow + AT_T_O + (uint32_t)(b * 64), q0);
 #pragma unroll
                 for (int d = 0; d < 32; ++d) o_acc[d] = fmaf(o_acc[d], sc, __uint_as_float(q0[d]));
-                tc_ld32(trow + 64u + (uint32_t)(b * 64) + 32u, q0);
+                tc_ld32(trow + AT_T_O + (uint32_t)(b * 64) + 32u, q0);
 #pragma unroll
                 for (int d = 0; d < 32; ++d) o_acc[32 + d] = fmaf(o_acc[32 + d], sc, __uint_as_float(q0[d]));
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&o_empty[b]);
             }
-            uint8_t* ph = sm + AT_OFF_P + b * AT_P_BUF + prow;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 pv = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
-                                              __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
-                uint4 hi, lo;
-                split_tf32(pv, hi, lo);
-                const uint32_t o = (uint32_t)((c ^ sw) << 4);
-                *reinterpret_cast<uint4*>(ph + o) = hi;
-                *reinterpret_cast<uint4*>(ph + AT_P_TILE + o) = lo;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[b]);
         }
 #pragma unroll 1
         for (int j = AT_NC - 2; j < AT_NC; ++j) {                          // drain the two in-flight O_c
@@ -194,10 +235,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
             const float sc = __expf(m_acc - m_j);
             m_acc = m_j;
             uint32_t q0[32];
-            tc_ld32(trow + 64u + (uint32_t)(b * 64), q0);
+            tc_ld32(trow + AT_T_O + (uint32_t)(b * 64), q0);
 #pragma unroll
             for (int d = 0; d < 32; ++d) o_acc[d] = fmaf(o_acc[d], sc, __uint_as_float(q0[d]));
-            tc_ld32(trow + 64u + (uint32_t)(b * 64) + 32u, q0);
+            tc_ld32(trow + AT_T_O + (uint32_t)(b * 64) + 32u, q0);
 #pragma unroll
             for (int d = 0; d < 32; ++d) o_acc[32 + d] = fmaf(o_acc[32 + d], sc, __uint_as_float(q0[d]));
         }
@@ -212,26 +253,24 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
     } else if (warp == 4) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
-            const uint32_t idesc_o = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AT_HD >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+            mbar_wait(q_full, 0);
 #pragma unroll 1
             for (int i = 0; i <= AT_NC; ++i) {
-                if (i < AT_NC) {                                           // S(i) = Q K_i^T
-                    const int b = i & 1, n = i >> 1;
+                if (i < AT_NC) {                                           // S(i) = Q K_i^T  (after PV(i-2) in program order,
+                    const int b = i & 1, n = i >> 1;                       //  which read P_hi from the same columns)
                     mbar_wait(&k_full[b], n & 1);
-                    if (n > 0) mbar_wait(&s_empty[b], (n - 1) & 1);
                     tc_fence_after();
                     const uint8_t* ks_ = sm + AT_OFF_K + b * AT_K_STAGE;
-                    const uint32_t d_tmem = tmem + (uint32_t)(b * 32);
+                    const uint32_t d_tmem = tmem + AT_T_SP + (uint32_t)(b * 128);
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t qo = (ks >> 2) * AT_Q_ATOM, ko = (ks >> 2) * AT_K_ATOM;
+                        const uint32_t ko = (ks >> 2) * AT_K_ATOM;
                         const uint64_t adv = (uint64_t)(2 * (ks & 3));
-                        const uint64_t qh = make_smem_desc(sm + AT_OFF_QH + qo) + adv, ql = make_smem_desc(sm + AT_OFF_QL + qo) + adv;
                         const uint64_t kh = make_smem_desc(ks_ + ko) + adv, kl = make_smem_desc(ks_ + 2 * AT_K_ATOM + ko) + adv;
-                        tc_mma_tf32(d_tmem, qh, kh, idesc_s, ks ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, ql, kh, idesc_s, 1u);
-                        tc_mma_tf32(d_tmem, qh, kl, idesc_s, 1u);
+                        tc_mma_tf32_ts(d_tmem, tmem + AT_T_QH + 8u * ks, kh, idesc, ks ? 1u : 0u);
+                        tc_mma_tf32_ts(d_tmem, tmem + AT_T_QL + 8u * ks, kh, idesc, 1u);
+                        tc_mma_tf32_ts(d_tmem, tmem + AT_T_QH + 8u * ks, kl, idesc, 1u);
                     }
                     tc_commit(&s_full[b]);
                 }
@@ -241,17 +280,17 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
                     mbar_wait(&p_full[b], n & 1);
                     if (n > 0) mbar_wait(&o_empty[b], (n - 1) & 1);
                     tc_fence_after();
-                    const uint8_t* pb = sm + AT_OFF_P + b * AT_P_BUF;
                     const uint8_t* vs_ = sm + AT_OFF_V + b * AT_V_STAGE;
-                    const uint32_t d_tmem = tmem + 64u + (uint32_t)(b * 64);
+                    const uint32_t p_tmem = tmem + AT_T_SP + (uint32_t)(b * 128);
+                    const uint32_t d_tmem = tmem + AT_T_O + (uint32_t)(b * 64);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t adv = (uint64_t)(2 * ks);
-                        const uint64_t ph = make_smem_desc(pb) + adv, pl = make_smem_desc(pb + AT_P_TILE) + adv;
-                        const uint64_t vh = make_smem_desc(vs_) + adv, vl = make_smem_desc(vs_ + AT_V_TILE) + adv;
-                        tc_mma_tf32(d_tmem, ph, vh, idesc_o, ks ? 1u : 0u);
-                        tc_mma_tf32(d_tmem, pl, vh, idesc_o, 1u);
-                        tc_mma_tf32(d_tmem, ph, vl, idesc_o, 1u);
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t vo = (ks >> 2) * AT_V_ATOM;
+                        const uint64_t adv = (uint64_t)(2 * (ks & 3));
+                        const uint64_t vh = make_smem_desc(vs_ + vo) + adv, vl = make_smem_desc(vs_ + 2 * AT_V_ATOM + vo) + adv;
+                        tc_mma_tf32_ts(d_tmem, p_tmem + 8u * ks, vh, idesc, ks ? 1u : 0u);
+                        tc_mma_tf32_ts(d_tmem, p_tmem + 64u + 8u * ks, vh, idesc, 1u);
+                        tc_mma_tf32_ts(d_tmem, p_tmem + 8u * ks, vl, idesc, 1u);
                     }
                     tc_commit(&pv_done[b]);
                 }
@@ -266,9 +305,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
 #pragma unroll 1
         for (int i = 0; i < AT_NC; ++i) {
             const int b = i & 1, n = i >> 1;
-            float4 kv[8];
+            float4 kv[16];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < 16; ++e) {
                 const int r = r0 + 4 * e;
                 int u = w * AT_WS + i * AT_BK + r + shift;
                 if (u >= Sp) u -= Sp;
@@ -278,7 +317,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
             if (n > 0) mbar_wait(&s_full[b], (n - 1) & 1);               // S(i-2) retired: K stage b is free
             uint8_t* dst = sm + AT_OFF_K + b * AT_K_STAGE + col_off;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < 16; ++e) {
                 const int r = r0 + 4 * e;
                 uint4 hi, lo;
                 split_tf32(kv[e], hi, lo);
@@ -291,40 +330,46 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
             if (lane == 0) mbar_arrive(&k_full[b]);
         }
     } else {
-        // ---------------- V loader (64 threads): transposed tile, rows = dims, cols = keys ----------------
+        // ---------------- V loader (64 threads): transposed tile, rows = dims, cols = keys (2 atoms of 32 keys) ----------------
         const int L = t - 224;
-        const int kg = L & 7;                                              // 4 consecutive keys
+        const int kg = L & 7;                                              // 4 consecutive keys inside a 32-key atom
 #pragma unroll 1
         for (int i = 0; i < AT_NC; ++i) {
             const int b = i & 1, n = i >> 1;
-            float4 vv[2][4];
+            float4 vv[2][2][4];                                            // [32-key atom][dim group][key]
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int d4 = (L >> 3) + 8 * e;
+            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    int u = w * AT_WS + i * AT_BK + 4 * kg + q + shift;
-                    if (u >= Sp) u -= Sp;
-                    vv[e][q] = u < S ? *reinterpret_cast<const float4*>(V + (base + u) * ldv + h * AT_HD + 4 * d4)
-                                     : *reinterpret_cast<const float4*>(vb + h * AT_HD + 4 * d4);
+                for (int e = 0; e < 2; ++e) {
+                    const int d4 = (L >> 3) + 8 * e;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int u = w * AT_WS + i * AT_BK + half * 32 + 4 * kg + q + shift;
+                        if (u >= Sp) u -= Sp;
+                        vv[half][e][q] = u < S ? *reinterpret_cast<const float4*>(V + (base + u) * ldv + h * AT_HD + 4 * d4)
+                                               : *reinterpret_cast<const float4*>(vb + h * AT_HD + 4 * d4);
+                    }
                 }
             }
             if (n > 0) mbar_wait(&pv_done[b], (n - 1) & 1);              // PV(i-2) retired: V stage b is free
-            uint8_t* dst = sm + AT_OFF_V + b * AT_V_STAGE;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int d4 = (L >> 3) + 8 * e;
-                const float4 a0 = vv[e][0], a1 = vv[e][1], a2 = vv[e][2], a3 = vv[e][3];
-                const float4 rows[4] = {make_float4(a0.x, a1.x, a2.x, a3.x), make_float4(a0.y, a1.y, a2.y, a3.y),
-                                        make_float4(a0.z, a1.z, a2.z, a3.z), make_float4(a0.w, a1.w, a2.w, a3.w)};
+            for (int half = 0; half < 2; ++half) {
+                uint8_t* dst = sm + AT_OFF_V + b * AT_V_STAGE + half * AT_V_ATOM;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int row = 4 * d4 + c;
-                    uint4 hi, lo;
-                    split_tf32(rows[c], hi, lo);
-                    const uint32_t o = (uint32_t)(row * 128 + ((kg ^ (row & 7)) << 4));
-                    *reinterpret_cast<uint4*>(dst + o) = hi;
-                    *reinterpret_cast<uint4*>(dst + AT_V_TILE + o) = lo;
+                for (int e = 0; e < 2; ++e) {
+                    const int d4 = (L >> 3) + 8 * e;
+                    const float4 a0 = vv[half][e][0], a1 = vv[half][e][1], a2 = vv[half][e][2], a3 = vv[half][e][3];
+                    const float4 rows[4] = {make_float4(a0.x, a1.x, a2.x, a3.x), make_float4(a0.y, a1.y, a2.y, a3.y),
+                                            make_float4(a0.z, a1.z, a2.z, a3.z), make_float4(a0.w, a1.w, a2.w, a3.w)};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int row = 4 * d4 + c;
+                        uint4 hi, lo;
+                        split_tf32(rows[c], hi, lo);
+                        const uint32_t o = (uint32_t)(row * 128 + ((kg ^ (row & 7)) << 4));
+                        *reinterpret_cast<uint4*>(dst + o) = hi;
+                        *reinterpret_cast<uint4*>(dst + 2 * AT_V_ATOM + o) = lo;
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

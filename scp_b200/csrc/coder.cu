@@ -233,12 +233,10 @@ int scp_coding_order(const int64_t* h_level_sizes, const uint8_t* h_level_restar
     }
     if (wins.empty()) return SCP_OK;
     Win* d_w = nullptr;
-    SCP_CUDA(malloc_async((void**)&d_w, wins.size() * sizeof(Win), st));
-    SCP_CUDA(cudaMemcpyAsync(d_w, wins.data(), wins.size() * sizeof(Win), cudaMemcpyHostToDevice, st));
+    SCP_CUDA(upload_async((void**)&d_w, wins.data(), wins.size() * sizeof(Win), st));
     int grid = (int)std::min<size_t>(wins.size(), 148 * 8);
     k_coding_order<<<grid, 256, 0, st>>>(d_w, (int)wins.size(), d_occ, (long long*)d_order, d_sym, add_base_for_single);
     SCP_LAUNCHED();
-    SCP_CUDA(cudaStreamSynchronize(st));      // `wins` is pageable host memory
     SCP_CUDA(cudaFreeAsync(d_w, st));
     return SCP_OK;
 }
@@ -258,12 +256,10 @@ int scp_gather_windows(const uint8_t* d_ctx, const float* d_pos, const int64_t* 
         maxlen = std::max(maxlen, h_win_len[w] + 1);
     }
     GWin* d_w = nullptr;
-    SCP_CUDA(malloc_async((void**)&d_w, wins.size() * sizeof(GWin), st));
-    SCP_CUDA(cudaMemcpyAsync(d_w, wins.data(), wins.size() * sizeof(GWin), cudaMemcpyHostToDevice, st));
+    SCP_CUDA(upload_async((void**)&d_w, wins.data(), wins.size() * sizeof(GWin), st));
     dim3 grid((unsigned)std::min<long long>(cdiv(maxlen, 256), 32), (unsigned)n_win);
     k_gather_windows<<<grid, 256, 0, st>>>(d_w, d_ctx, d_pos, d_ctx_out, d_pos_out, (long long*)d_row_even, (long long*)d_row_odd);
     SCP_LAUNCHED();
-    SCP_CUDA(cudaStreamSynchronize(st));
     SCP_CUDA(cudaFreeAsync(d_w, st));
     return SCP_OK;
 }

@@ -20,6 +20,15 @@ extern std::atomic<long long> g_launches;
 // pays for re-mapping gigabytes of workspace (measured: +60 % step time, erratic).
 cudaError_t malloc_async(void** p, size_t bytes, cudaStream_t st);
 
+// Pinned host staging blocks, recycled: pinned_get() hands out a block whose previous upload has completed (its event
+// is synchronised, normally long done); the user copies into it, issues cudaMemcpyAsync + cudaEventRecord(ev) on its
+// stream and gives it back with pinned_put() at any later time.
+struct PinnedBlock { void* p; size_t bytes; cudaEvent_t ev; };
+bool pinned_get(size_t bytes, PinnedBlock* out);
+void pinned_put(const PinnedBlock& b);
+// host array -> fresh stream-ordered device buffer without synchronising the stream; free with cudaFreeAsync(*d, st)
+cudaError_t upload_async(void** d, const void* h, size_t bytes, cudaStream_t st);
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 #define SCP_CUDA(expr)                                                                         \

@@ -1,11 +1,12 @@
 // tcgen05 / TMEM / TMA GEMM engine for nn.Linear:  Y[M,N] = act(X[M,K] W[N,K]^T + b) (+ R)   (sm_100a only)
 //
 // Both operands are K-major (row-major with K contiguous), which is exactly tcgen05's "K-major A, K-major B"
-// form, so no transposes are needed.  Persistent, warp-specialised CTA (256 threads):
+// form, so no transposes are needed.  Persistent, warp-specialised CTA (384 threads):
 //   warp 0   TMA producer   cp.async.bulk.tensor.2d, 128B-swizzled [128 x 32] A tiles and [BN x 32] B tiles
 //   warp 1   MMA issuer     one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8), fp32 accumulate in TMEM
 //   warp 2   TMEM allocator (2 accumulator stages x BN columns, so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 4-7 epilogue      tcgen05.ld 32x32b.x32 -> bias / activation / residual -> global
+//   warps 4-11 epilogue     tcgen05.ld 32x32b.x32 -> bias / activation -> smem tile -> residual -> coalesced global stores
+//                           (two warps per TMEM lane quarter: the epilogue is instruction-bound, esp. with erf-GELU)
 // smem ring of STAGES x (A 16 KB + B BN*128 B) with full/empty mbarriers; tcgen05.commit releases stages.
 // Operands are read as fp32 and rounded to TF32 by the tensor core (10-bit mantissa), accumulation is fp32.
 //
@@ -33,7 +34,7 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 // kernel
 // ---------------------------------------------------------------------------------------------
 template <int BN, int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CUtensorMap tmA,
                                                        const __grid_constant__ CUtensorMap tmB,
                                                        const __grid_constant__ CUtensorMap tmBlo,
                                                        const float* __restrict__ bias, const float* __restrict__ R,
@@ -46,7 +47,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
     constexpr int OFF_ALO = A_BYTES, OFF_B = SPLIT ? 2 * A_BYTES : A_BYTES, OFF_BLO = OFF_B + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by an OFFSET from the shared-space symbol: a pointer rebuilt from an integer would be generic
+    // (LD/ST instead of LDS/STS and no alias information against global memory)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 2); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -156,8 +159,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
         // 32 different cache lines per instruction (the L1 pipe then costs more than the MMAs of a K=256 tile).  So the
         // chunk goes through a per-warp [32][36] shared-memory tile: bias + activation on the way in (lane = row), residual
         // add + 128-byte coalesced stores on the way out (8 lanes per row, 4 rows per instruction).
-        const int w = warp - 4;                            // TMEM lane quarter this warp may read
-        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 512) + w * (32 * 36);
+        const int w = (warp - 4) & 3;                      // TMEM lane quarter this warp may read (warp id mod 4)
+        const int half = (warp - 4) >> 2;                  // two warps per quarter: even / odd 32-column chunks
+        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 512) + (warp - 4) * (32 * 32);
         int acc = 0; uint32_t acc_phase = 0;
         const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
                             (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0))) &&
@@ -165,16 +169,28 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
         const int sub_r = lane >> 3, sub_c = (lane & 7) << 2;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+            const long long row0 = (long long)m_blk * BM + w * 32;
+            // residual rows of the first 32-column chunk: issued before the accumulator wait, later chunks one chunk ahead,
+            // so the (HBM-latency) loads never sit between the shared-memory tile and the stores
+            float4 q[8];
+            auto load_res = [&](int n0, float4 (&dst)[8]) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const long long row = row0 + it * 4 + sub_r;
+                    dst[it] = (row < M) ? __ldcs(reinterpret_cast<const float4*>(R + row * ldr + n0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            const bool res_vec = R && vec_ok && row0 < M;
+            if (res_vec && n_blk * BN + half * 32 + 32 <= N) load_res(n_blk * BN + half * 32, q);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const long long row0 = (long long)m_blk * BM + w * 32;
             const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tc_ld32(t_row + (uint32_t)c0, r);
+#pragma unroll
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 const int n0 = n_blk * BN + c0;
                 if (row0 >= M || n0 >= N) continue;          // warp-uniform
+                uint32_t r[32];
+                tc_ld32(t_row + (uint32_t)c0, r);
                 if (vec_ok && n0 + 32 <= N) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -183,20 +199,27 @@ __global__ void __launch_bounds__(256, 1) k_gemm_tf32(const __grid_constant__ CU
                         v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
                         if (bias) { const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + j); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
                         v.x = tc_act(v.x, act); v.y = tc_act(v.y, act); v.z = tc_act(v.z, act); v.w = tc_act(v.w, act);
-                        *reinterpret_cast<float4*>(stg + lane * 36 + j) = v;
+                        *reinterpret_cast<float4*>(stg + lane * 32 + ((((j >> 2) ^ lane) & 7) << 2)) = v;
                     }
                     __syncwarp();
+                    float4 qn[8];
+                    const bool more = res_vec && c0 + 64 < BN && n0 + 96 <= N;
+                    if (more) load_res(n0 + 64, qn);
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + sub_r;
                         const long long row = row0 + rr;
                         if (row < M) {
-                            float4 v = *reinterpret_cast<const float4*>(stg + rr * 36 + sub_c);
-                            if (R) { const float4 q = *reinterpret_cast<const float4*>(R + row * ldr + n0 + sub_c); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-                            *reinterpret_cast<float4*>(Y + row * ldy + n0 + sub_c) = v;
+                            float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((((sub_c >> 2) ^ rr) & 7) << 2));
+                            if (R) { v.x += q[it].x; v.y += q[it].y; v.z += q[it].z; v.w += q[it].w; }
+                            __stcs(reinterpret_cast<float4*>(Y + row * ldy + n0 + sub_c), v);
                         }
                     }
                     __syncwarp();
+                    if (more) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) q[it] = qn[it];
+                    }
                 } else {
                     const long long row = row0 + lane;
                     if (row < M) {
@@ -335,7 +358,7 @@ bool linear_tf32_ok(long long ldx, long long ldy, long long M, int N, int K, con
 template <int BN, int STAGES, bool SPLIT>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, const float* res,
                   long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
-    constexpr int smem = STAGES * (128 * 128 + BN * 128) * (SPLIT ? 2 : 1) + 1024 + 512 + 4 * 32 * 36 * 4;
+    constexpr int smem = STAGES * (128 * 128 + BN * 128) * (SPLIT ? 2 : 1) + 1024 + 512 + 8 * 32 * 32 * 4;
     static bool attr = false;
     if (!attr) {
         SCP_CUDA(cudaFuncSetAttribute(k_gemm_tf32<BN, STAGES, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -345,7 +368,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const long long tiles = cdiv(M, 128) * cdiv(N, BN);
     const int grid = (int)std::min<long long>(tiles, n_sm);
-    k_gemm_tf32<BN, STAGES, SPLIT><<<grid, 256, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act);
+    k_gemm_tf32<BN, STAGES, SPLIT><<<grid, 384, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act);
     SCP_LAUNCHED();
     return SCP_OK;
 }

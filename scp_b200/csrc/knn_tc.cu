@@ -56,10 +56,13 @@ __global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X,
 }
 
 
-// Warp-cooperative compaction of one row's scratch list (cq entries, kc <= cq <= KT_CAP) to its top-kc by
-// (score desc, candidate index asc), written back to the front of the list.  Returns the kc-th best score, the row's
-// new threshold.  Selection = MSB-first radix select of the kc-th largest order-preserving key, 8 entries per lane.
-__device__ __forceinline__ float knn_compact_row(float* bs, int* bi, int cq, int kc, int lane) {
+// Warp-cooperative compaction of one row's scratch list (cq entries, kc <= cq <= KT_CAP) to AT MOST 32 entries that
+// contain its top-kc by (score desc, candidate index asc), written back to the front of the list; *kept = how many.
+// Returns a valid new threshold for the row: at least kc kept entries score >= it.
+// Selection = MSB-first radix select on order-preserving keys, 8 entries per lane, stopped as soon as "everything
+// above the current bucket + the bucket" fits in 32 slots (usually after 12-18 of the 32 bits): the exact kc-th value
+// is not needed, the exact re-rank sees every kept candidate.
+__device__ __forceinline__ float knn_compact_row(float* bs, int* bi, int cq, int kc, int lane, int* kept) {
     __syncwarp();                                                          // the owner lane's appends are visible
     uint32_t key[KT_CAP / 32];
     int id[KT_CAP / 32];
@@ -74,30 +77,30 @@ __device__ __forceinline__ float knn_compact_row(float* bs, int* bi, int cq, int
         }
     }
     uint32_t prefix = 0u;
-    int rem = kc;
+    int rem = kc;                                                          // rank of the kc-th best inside the current bucket
+    int bucket = cq;                                                       // entries matching `prefix` on the decided bits
+    int bit = 31;
 #pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
+    for (; bit >= 0 && (kc - rem) + bucket > 32; --bit) {
         const uint32_t sel = ~((1u << bit) - 1u);                          // this bit and everything above it
         const uint32_t want = prefix | (1u << bit);
         int c = 0;
 #pragma unroll
         for (int m = 0; m < KT_CAP / 32; ++m) c += ((key[m] & sel) == want) ? 1 : 0;
         c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= rem) prefix = want; else rem -= c;
+        if (c >= rem) { prefix = want; bucket = c; } else { rem -= c; bucket -= c; }
     }
-    // prefix = kc-th largest key; keep everything above it and `rem` of the entries equal to it (lowest candidate first)
-    int n_eq = 0;
-#pragma unroll
-    for (int m = 0; m < KT_CAP / 32; ++m) n_eq += (key[m] == prefix) ? 1 : 0;
-    n_eq = __reduce_add_sync(0xffffffffu, n_eq);
+    // keep every entry >= prefix (the bucket's lower edge): (kc - rem) above the bucket + the bucket itself
     bool keep[KT_CAP / 32];
 #pragma unroll
-    for (int m = 0; m < KT_CAP / 32; ++m) keep[m] = key[m] >= prefix && prefix != 0u;
-    if (n_eq > rem) {                                                      // exact ties at the cut: lowest candidates first
+    for (int m = 0; m < KT_CAP / 32; ++m) keep[m] = key[m] >= prefix && key[m] != 0u;
+    int total = (kc - rem) + bucket;
+    if (total > 32) {                                                      // all 32 bits used: > 32 - above exact ties; lowest candidates first
+        const int take = 32 - (kc - rem);
 #pragma unroll
         for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix) keep[m] = false;
 #pragma unroll 1
-        for (int it = 0; it < rem; ++it) {
+        for (int it = 0; it < take; ++it) {
             int best = 0x7fffffff;
 #pragma unroll
             for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix && !keep[m]) best = min(best, id[m]);
@@ -105,6 +108,7 @@ __device__ __forceinline__ float knn_compact_row(float* bs, int* bi, int cq, int
 #pragma unroll
             for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix && id[m] == best) keep[m] = true;
         }
+        total = 32;
     }
     __syncwarp();
     int basep = 0;
@@ -120,6 +124,8 @@ __device__ __forceinline__ float knn_compact_row(float* bs, int* bi, int cq, int
         basep += __popc(bal);
     }
     __syncwarp();
+    *kept = total;
+    if (prefix == 0u) return -INFINITY;                                    // no bit decided: keep accepting everything
     return __uint_as_float(prefix ^ ((prefix >> 31) ? 0x80000000u : 0xffffffffu));
 }
 
@@ -130,7 +136,9 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                                                     int n_work, long long row0, int d, int k, int* __restrict__ idx_out,
                                                     float* __restrict__ scr_s, int* __restrict__ scr_i) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by an OFFSET from the shared-space symbol: a pointer rebuilt from an integer would be generic
+    // (LD/ST instead of LDS/STS and no alias information against global memory)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + KT_STAGES * KT_STAGE_BYTES);
     uint64_t* empty = full + KT_STAGES;
     uint64_t* tfull = empty + KT_STAGES;
@@ -254,29 +262,48 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * KT_BN);
+                // two 32-candidate chunks per round: both tcgen05.ld in flight before the first score is touched
 #pragma unroll 1
-                for (int cc = 0; cc < KT_BN; cc += 32) {
+                for (int cc = 0; cc < KT_BN; cc += 64) {
                     if (c0 + cc >= n) break;                               // warp-uniform
-                    uint32_t r[32];
-                    tc_ld32(t_row + (uint32_t)cc, r);
+                    uint32_t r[2][32];
+                    tc_ld32_nowait(t_row + (uint32_t)cc, r[0]);
+                    tc_ld32_nowait(t_row + (uint32_t)cc + 32u, r[1]);
+                    tc_wait_ld();
 #pragma unroll
-                    for (int j4 = 0; j4 < 32; j4 += 4) {
-                        const float4 xc = *reinterpret_cast<const float4*>(xcs + cc + j4);
-                        const float xcv[4] = {xc.x, xc.y, xc.z, xc.w};
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int cb = cc + 32 * hh;
+                        if (c0 + cb >= n) break;                           // warp-uniform
+                        // scores in place; branch-free maximum first: after the first tiles almost no chunk holds a hit
+                        float smax = -INFINITY;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            // == (2 g - |c|^2) - |q|^2 with one rounding per subtraction (2 g is exact)
-                            const float sc = __fsub_rn(fmaf(2.0f, __uint_as_float(r[j4 + e]), -xcv[e]), xq);
-                            if (sc > th) { my_s[cnt] = sc; my_i[cnt] = c0 + cc + j4 + e; ++cnt; }
+                        for (int j4 = 0; j4 < 32; j4 += 4) {
+                            const float4 xc = *reinterpret_cast<const float4*>(xcs + cb + j4);
+                            const float xcv[4] = {xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                // == (2 g - |c|^2) - |q|^2 with one rounding per subtraction (2 g is exact)
+                                const float sc = __fsub_rn(fmaf(2.0f, __uint_as_float(r[hh][j4 + e]), -xcv[e]), xq);
+                                r[hh][j4 + e] = __float_as_uint(sc);
+                                smax = fmaxf(smax, sc);
+                            }
                         }
-                    }
-                    unsigned need = __ballot_sync(0xffffffffu, cnt > KT_CAP - 32);
-                    while (need) {
-                        const int q = __ffs(need) - 1;
-                        need &= need - 1;
-                        const float pv = knn_compact_row(bs + (size_t)q * KT_CAP, bi + (size_t)q * KT_CAP,
-                                                         __shfl_sync(0xffffffffu, cnt, q), kc, lane);
-                        if (lane == q) { th = pv; cnt = kc; }
+                        if (smax > th) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float sc = __uint_as_float(r[hh][j]);
+                                if (sc > th) { my_s[cnt] = sc; my_i[cnt] = c0 + cb + j; ++cnt; }
+                            }
+                        }
+                        unsigned need = __ballot_sync(0xffffffffu, cnt > KT_CAP - 32);
+                        while (need) {
+                            const int q = __ffs(need) - 1;
+                            need &= need - 1;
+                            int kept;
+                            const float pv = knn_compact_row(bs + (size_t)q * KT_CAP, bi + (size_t)q * KT_CAP,
+                                                             __shfl_sync(0xffffffffu, cnt, q), kc, lane, &kept);
+                            if (lane == q) { th = pv; cnt = kept; }
+                        }
                     }
                 }
                 tc_fence_before();
@@ -287,12 +314,10 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
             for (int q = 0; q < 32; ++q) {
                 if (qw0 + q >= n) break;                                   // warp-uniform
                 int cq = __shfl_sync(0xffffffffu, cnt, q);
-                if (cq > kc) { knn_compact_row(bs + (size_t)q * KT_CAP, bi + (size_t)q * KT_CAP, cq, kc, lane); cq = kc; }
+                if (cq > 32) knn_compact_row(bs + (size_t)q * KT_CAP, bi + (size_t)q * KT_CAP, cq, kc, lane, &cq);
                 __syncwarp();
-                if (lane < kc) {
-                    const long long row = gbase + qw0 + q;
-                    idx_out[(row - row0) * kc + lane] = lane < cq ? (int)(gbase + __ldcg(bi + (size_t)q * KT_CAP + lane)) : -1;
-                }
+                const long long row = gbase + qw0 + q;                     // up to 32 candidates per row for the exact re-rank
+                idx_out[(row - row0) * 32 + lane] = lane < cq ? (int)(gbase + __ldcg(bi + (size_t)q * KT_CAP + lane)) : -1;
             }
             __syncwarp();
         }
@@ -356,7 +381,7 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     float *hi = nullptr, *lo = nullptr, *xx = nullptr;
     int* cand = nullptr;
     const int kc = k + KT_EXTRA;
-    SCP_CUDA(malloc_async((void**)&cand, (size_t)total * kc * 4 + 1024, st));
+    SCP_CUDA(malloc_async((void**)&cand, (size_t)total * 32 * 4 + 1024, st));
     SCP_CUDA(malloc_async((void**)&hi, (size_t)total * d * 4 + 1024, st));
     SCP_CUDA(malloc_async((void**)&lo, (size_t)total * d * 4 + 1024, st));
     SCP_CUDA(malloc_async((void**)&xx, (size_t)total * 4 + 1024, st));
@@ -379,7 +404,7 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     SCP_CUDA(malloc_async((void**)&scr_i, (size_t)grid * 128 * KT_CAP * 4, st));
     k_knn_tc<<<grid, 256, smem, st>>>(mh, ml, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, scr_s, scr_i);
     SCP_LAUNCHED();
-    k_knn_rerank<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x, ldx, d, row0, total, cand, kc, k, d_idx);
+    k_knn_rerank<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x, ldx, d, row0, total, cand, 32, k, d_idx);
     SCP_LAUNCHED();
     SCP_CUDA(cudaFreeAsync(scr_s, st));
     SCP_CUDA(cudaFreeAsync(scr_i, st));

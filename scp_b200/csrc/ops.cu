@@ -7,6 +7,8 @@
 #include <vector>
 #include <algorithm>
 #include <math.h>
+#include <mutex>
+#include <string.h>
 #include "common.cuh"
 
 struct scp_seqs {
@@ -23,6 +25,11 @@ struct scp_seqs {
     int n_tile128 = 0;              // 128-token tiles
     int* d_tile128_seq = nullptr;
     int* d_tile128_start = nullptr;
+    void* d_arena = nullptr;        // one stream-ordered allocation behind all the tables above
+    void* h_pinned = nullptr;       // pinned staging block (returned to the pool on destroy)
+    size_t pinned_bytes = 0;
+    cudaEvent_t copied = nullptr;   // H2D of the tables finished: the staging block may be rewritten
+    cudaStream_t stream = nullptr;
 };
 
 namespace scp {
@@ -789,10 +796,14 @@ using namespace scp;
 
 extern "C" {
 
-scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq) {
+// Creation must not synchronise: a cudaMalloc / pageable cudaMemcpy here drains the stream ~12 times per forward pass and
+// runs host and GPU in lock-step.  The tables go through a recycled pinned staging block (common.cuh) instead.
+scp_seqs* scp_seqs_create_async(const int64_t* h_offsets, int n_seq, void* stream) {
     if (!h_offsets || n_seq <= 0) { set_error("scp_seqs_create: bad argument"); return nullptr; }
+    cudaStream_t st = as_stream(stream);
     auto* s = new scp_seqs();
     s->n_seq = n_seq;
+    s->stream = st;
     s->h_off.assign(h_offsets, h_offsets + n_seq + 1);
     s->total = h_offsets[n_seq] - h_offsets[0];
     std::vector<int> wseq, widx, tseq, tstart, t2seq, t2start;
@@ -806,32 +817,38 @@ scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq) {
     s->n_win = (int)wseq.size();
     s->n_tile = (int)tseq.size();
     s->n_tile128 = (int)t2seq.size();
-    bool ok = cudaMalloc((void**)&s->d_off, (n_seq + 1) * 8) == cudaSuccess &&
-              cudaMalloc((void**)&s->d_win_seq, std::max(1, s->n_win) * 4) == cudaSuccess &&
-              cudaMalloc((void**)&s->d_win_idx, std::max(1, s->n_win) * 4) == cudaSuccess &&
-              cudaMalloc((void**)&s->d_tile_seq, std::max(1, s->n_tile) * 4) == cudaSuccess &&
-              cudaMalloc((void**)&s->d_tile_start, std::max(1, s->n_tile) * 4) == cudaSuccess &&
-              cudaMalloc((void**)&s->d_tile128_seq, std::max(1, s->n_tile128) * 4) == cudaSuccess &&
-              cudaMalloc((void**)&s->d_tile128_start, std::max(1, s->n_tile128) * 4) == cudaSuccess;
-    ok = ok && cudaMemcpy(s->d_off, s->h_off.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (ok && s->n_win) {
-        ok = cudaMemcpy(s->d_win_seq, wseq.data(), s->n_win * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(s->d_win_idx, widx.data(), s->n_win * 4, cudaMemcpyHostToDevice) == cudaSuccess;
-    }
-    if (ok && s->n_tile) {
-        ok = cudaMemcpy(s->d_tile_seq, tseq.data(), s->n_tile * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(s->d_tile_start, tstart.data(), s->n_tile * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(s->d_tile128_seq, t2seq.data(), s->n_tile128 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(s->d_tile128_start, t2start.data(), s->n_tile128 * 4, cudaMemcpyHostToDevice) == cudaSuccess;
-    }
-    if (!ok) { set_error("scp_seqs_create: CUDA allocation/upload failed"); scp_seqs_destroy(s); return nullptr; }
+    // layout of the single arena: offsets (8-byte), then the six int tables, each 16-byte aligned
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_off = 0, o_ws = al((size_t)(n_seq + 1) * 8), o_wi = o_ws + al((size_t)s->n_win * 4),
+                 o_ts = o_wi + al((size_t)s->n_win * 4), o_tt = o_ts + al((size_t)s->n_tile * 4),
+                 o_2s = o_tt + al((size_t)s->n_tile * 4), o_2t = o_2s + al((size_t)s->n_tile128 * 4),
+                 bytes = o_2t + al((size_t)s->n_tile128 * 4) + 16;
+    PinnedBlock pb;
+    if (!pinned_get(bytes, &pb)) { set_error("scp_seqs_create: pinned staging allocation failed"); delete s; return nullptr; }
+    uint8_t* h = static_cast<uint8_t*>(pb.p);
+    memcpy(h + o_off, s->h_off.data(), (size_t)(n_seq + 1) * 8);
+    if (s->n_win) { memcpy(h + o_ws, wseq.data(), (size_t)s->n_win * 4); memcpy(h + o_wi, widx.data(), (size_t)s->n_win * 4); }
+    if (s->n_tile) { memcpy(h + o_ts, tseq.data(), (size_t)s->n_tile * 4); memcpy(h + o_tt, tstart.data(), (size_t)s->n_tile * 4); }
+    if (s->n_tile128) { memcpy(h + o_2s, t2seq.data(), (size_t)s->n_tile128 * 4); memcpy(h + o_2t, t2start.data(), (size_t)s->n_tile128 * 4); }
+    s->h_pinned = pb.p; s->pinned_bytes = pb.bytes; s->copied = pb.ev;
+    bool ok = malloc_async(&s->d_arena, bytes, st) == cudaSuccess &&
+              cudaMemcpyAsync(s->d_arena, h, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+              cudaEventRecord(pb.ev, st) == cudaSuccess;
+    if (!ok) { set_error("scp_seqs_create: CUDA allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError())); scp_seqs_destroy(s); return nullptr; }
+    uint8_t* d = static_cast<uint8_t*>(s->d_arena);
+    s->d_off = reinterpret_cast<long long*>(d + o_off);
+    s->d_win_seq = reinterpret_cast<int*>(d + o_ws); s->d_win_idx = reinterpret_cast<int*>(d + o_wi);
+    s->d_tile_seq = reinterpret_cast<int*>(d + o_ts); s->d_tile_start = reinterpret_cast<int*>(d + o_tt);
+    s->d_tile128_seq = reinterpret_cast<int*>(d + o_2s); s->d_tile128_start = reinterpret_cast<int*>(d + o_2t);
     return s;
 }
 
+scp_seqs* scp_seqs_create(const int64_t* h_offsets, int n_seq) { return scp_seqs_create_async(h_offsets, n_seq, nullptr); }
+
 void scp_seqs_destroy(scp_seqs* s) {
     if (!s) return;
-    cudaFree(s->d_off); cudaFree(s->d_win_seq); cudaFree(s->d_win_idx); cudaFree(s->d_tile_seq); cudaFree(s->d_tile_start);
-    cudaFree(s->d_tile128_seq); cudaFree(s->d_tile128_start);
+    if (s->d_arena) cudaFreeAsync(s->d_arena, s->stream);                  // stream-ordered: later kernels of the stream are unaffected
+    if (s->h_pinned) pinned_put(PinnedBlock{s->h_pinned, s->pinned_bytes, s->copied});
     delete s;
 }
 

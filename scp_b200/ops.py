@@ -88,7 +88,7 @@ class CudaOps:
     # -- plumbing ---------------------------------------------------------------------------
     def _seqs_create(self, offsets):
         arr = (C.c_int64 * len(offsets))(*offsets)
-        h = self.lib.scp_seqs_create(arr, len(offsets) - 1)
+        h = self.lib.scp_seqs_create_async(arr, len(offsets) - 1, _lib.stream_ptr())
         if not h:
             raise _lib.ScpError("scp_seqs_create: " + self.lib.scp_last_error().decode())
         return h
