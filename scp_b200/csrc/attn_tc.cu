@@ -37,6 +37,7 @@ constexpr int AT_SMEM = AT_OFF_BAR + 256 + 1024;
 constexpr int AT_THREADS = 288;
 constexpr uint32_t AT_TMEM_COLS = 512;
 constexpr uint32_t AT_T_QH = 0, AT_T_QL = 64, AT_T_SP = 128, AT_T_O = 384;
+constexpr float AT_LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void split_tf32(const float4 v, uint4& hi, uint4& lo) {
     hi.x = __float_as_uint(v.x) & 0xffffe000u; hi.y = __float_as_uint(v.y) & 0xffffe000u;
@@ -45,32 +46,11 @@ __device__ __forceinline__ void split_tf32(const float4 v, uint4& hi, uint4& lo)
     lo.z = __float_as_uint(v.z - __uint_as_float(hi.z)); lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
 }
 
-// D[tmem] (+)= A[tmem] * B[smem]^T
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
-          "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
-          "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
-}
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __restrict__ Q, long long ldq,
                                                                  const float* __restrict__ K, long long ldk,
@@ -122,7 +102,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(AT_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int e = t; e < 2 * AT_WS - 1; e += AT_THREADS) s_bias[e] = relpos[e * heads + h];
+    for (int e = t; e < 2 * AT_WS - 1; e += AT_THREADS) s_bias[e] = relpos[e * heads + h] * AT_LOG2E;   // scores live in the log2 domain
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -140,7 +120,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float4 v = src[half * 8 + c];
-                    v.x *= 0.125f; v.y *= 0.125f; v.z *= 0.125f; v.w *= 0.125f;
+                    // 1/sqrt(64) and log2(e) folded into Q: softmax(x) = 2^(x log2e - max) / sum, one ex2 per score
+                    const float qs = 0.125f * AT_LOG2E;
+                    v.x *= qs; v.y *= qs; v.z *= qs; v.w *= qs;
                     uint4 h4, l4;
                     split_tf32(v, h4, l4);
                     hi[4 * c] = h4.x; hi[4 * c + 1] = h4.y; hi[4 * c + 2] = h4.z; hi[4 * c + 3] = h4.w;
@@ -168,25 +150,29 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
             uint32_t r0[32], r1[32];
             tc_ld32(t_sp, r0);
             tc_ld32(t_sp + 32u, r1);
-            const bool masked = last_win && ((pi < AT_WS / 2) != (i < AT_NC / 2));     // swin_transformer.py:620
+            // swin_transformer.py:620: -100 on the other half of the last (rolled) window.  A whole chunk is on one side, so
+            // the offset is folded into the running-max bookkeeping instead of being added to all 64 scores.
+            const bool masked = last_win && ((pi < AT_WS / 2) != (i < AT_NC / 2));
+            const float moff = masked ? -100.0f * AT_LOG2E : 0.0f;
             const float* bp = s_bias + (pi - i * AT_BK + AT_WS - 1);
-            float mx = m_run;
+            float cmax = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float v0 = __uint_as_float(r0[j]) + bp[-j];
-                float v1 = __uint_as_float(r1[j]) + bp[-j - 32];
-                if (masked) { v0 += -100.0f; v1 += -100.0f; }
+                const float v0 = __uint_as_float(r0[j]) + bp[-j];
+                const float v1 = __uint_as_float(r1[j]) + bp[-j - 32];
                 r0[j] = __float_as_uint(v0); r1[j] = __float_as_uint(v1);
-                mx = fmaxf(mx, fmaxf(v0, v1));
+                cmax = fmaxf(cmax, fmaxf(v0, v1));
             }
-            const float alpha = __expf(m_run - mx);
+            const float mx = fmaxf(m_run, cmax + moff);
+            const float alpha = ex2_approx(m_run - mx);
             m_run = mx;
             const float m_old = b ? m_hist1 : m_hist0;                     // max the in-flight O_c of this buffer refers to
             if (b) m_hist1 = mx; else m_hist0 = mx;
+            const float sub = mx - moff;
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float p0 = __expf(__uint_as_float(r0[j]) - mx), p1 = __expf(__uint_as_float(r1[j]) - mx);
+                const float p0 = ex2_approx(__uint_as_float(r0[j]) - sub), p1 = ex2_approx(__uint_as_float(r1[j]) - sub);
                 sum += p0 + p1;
                 r0[j] = __float_as_uint(p0); r1[j] = __float_as_uint(p1);
             }
@@ -212,7 +198,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[b]);
             if (i >= 2) {                                                  // fold O_c(i-2) into the running output
-                const float sc = __expf(m_acc - m_old);
+                const float sc = ex2_approx(m_acc - m_old);
                 m_acc = m_old;
                 uint32_t q0[32];
                 tc_ld32(trow + AT_T_O + (uint32_t)(b * 64), q0);
@@ -232,7 +218,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
             mbar_wait(&pv_done[b], (j >> 1) & 1);
             tc_fence_after();
             const float m_j = b ? m_hist1 : m_hist0;
-            const float sc = __expf(m_acc - m_j);
+            const float sc = ex2_approx(m_acc - m_j);
             m_acc = m_j;
             uint32_t q0[32];
             tc_ld32(trow + AT_T_O + (uint32_t)(b * 64), q0);

@@ -16,6 +16,7 @@
 // W_hi / W_lo are split once per weight matrix (cached); A tiles are split in shared memory by warps 2-3 between the
 // TMA arrival and the MMA (generic-proxy writes + fence.proxy.async), so activations are still read once from HBM.
 #include <mutex>
+#include <stdlib.h>
 #include <unordered_map>
 #include "tc.cuh"
 
@@ -167,59 +168,293 @@ __global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CU
                             (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0))) &&
                             (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
         const int sub_r = lane >> 3, sub_c = (lane & 7) << 2;
+        constexpr int NCH = BN / 64;                       // 32-column chunks per warp (BN = 64: one chunk, half 1 idle on odd)
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
             const long long row0 = (long long)m_blk * BM + w * 32;
-            // residual rows of the first 32-column chunk: issued before the accumulator wait, later chunks one chunk ahead,
-            // so the (HBM-latency) loads never sit between the shared-memory tile and the stores
-            float4 q[8];
-            auto load_res = [&](int n0, float4 (&dst)[8]) {
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const long long row = row0 + it * 4 + sub_r;
-                    dst[it] = (row < M) ? __ldcs(reinterpret_cast<const float4*>(R + row * ldr + n0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            const bool res_vec = R && vec_ok && row0 < M;
-            if (res_vec && n_blk * BN + half * 32 + 32 <= N) load_res(n_blk * BN + half * 32, q);
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * BN);
+            const bool rows_ok = row0 < M;
+            bool waited = false;
+#pragma unroll
+            for (int p = 0; p < (NCH + 1) / 2; ++p) {      // two chunks per round
+                const int c0 = half * 32 + 128 * p, c1 = c0 + 64;
+                const int n0 = n_blk * BN + c0, n1 = n_blk * BN + c1;
+                const bool have0 = c0 < BN && n0 < N && rows_ok, have1 = c1 < BN && n1 < N && rows_ok;
+                const bool vec0 = have0 && vec_ok && n0 + 32 <= N, vec1 = have1 && vec_ok && n1 + 32 <= N;
+                // residual rows and bias of both chunks first (HBM latency), before the accumulator wait / TMEM loads
+                float4 q0[8], q1[8], b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                if (R) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const long long row = row0 + it * 4 + sub_r;
+                        q0[it] = (vec0 && row < M) ? __ldcs(reinterpret_cast<const float4*>(R + row * ldr + n0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        q1[it] = (vec1 && row < M) ? __ldcs(reinterpret_cast<const float4*>(R + row * ldr + n1 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if (bias) {
+                    if (vec0) b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + sub_c));
+                    if (vec1) b1 = __ldg(reinterpret_cast<const float4*>(bias + n1 + sub_c));
+                }
+                if (!waited) { mbar_wait(&tfull[acc], acc_phase); tc_fence_after(); waited = true; }
+                uint32_t r0[32], r1[32];
+                if (c0 < BN) tc_ld32_nowait(t_row + (uint32_t)c0, r0);
+                if (c1 < BN) tc_ld32_nowait(t_row + (uint32_t)c1, r1);
+                tc_wait_ld();
+                if (p == (NCH + 1) / 2 - 1) {               // accumulator is in registers: hand the TMEM stage back now
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint32_t* r = hh ? r1 : r0;
+                    const float4* q = hh ? q1 : q0;
+                    const float4 b4 = hh ? b1 : b0;
+                    const int nn = hh ? n1 : n0;
+                    if (!(hh ? have1 : have0)) continue;       // warp-uniform
+                    if (hh ? vec1 : vec0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<uint4*>(stg + lane * 32 + ((((j >> 2) ^ lane) & 7) << 2)) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + sub_r;
+                            const long long row = row0 + rr;
+                            if (row < M) {
+                                float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((((sub_c >> 2) ^ rr) & 7) << 2));
+                                v.x = tc_act(v.x + b4.x, act); v.y = tc_act(v.y + b4.y, act);
+                                v.z = tc_act(v.z + b4.z, act); v.w = tc_act(v.w + b4.w, act);
+                                if (R) { v.x += q[it].x; v.y += q[it].y; v.z += q[it].z; v.w += q[it].w; }
+                                __stcs(reinterpret_cast<float4*>(Y + row * ldy + nn + sub_c), v);
+                            }
+                        }
+                        __syncwarp();
+                    } else {
+                        const long long row = row0 + lane;
+                        if (row < M) {
+                            float* yrow = Y + row * ldy + nn;
+                            const float* rrow = R ? R + row * ldr + nn : nullptr;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (nn + j < N) {
+                                    float v = __uint_as_float(r[j]);
+                                    if (bias) v += bias[nn + j];
+                                    v = tc_act(v, act);
+                                    if (rrow) v += rrow[j];
+                                    yrow[j] = v;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (!waited) {                                   // BN = 64 and this warp's half has no chunk: still part of the hand-shake
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3xTF32 kernel with the activation operand in TENSOR MEMORY ("TS" form of tcgen05.mma)
+// ---------------------------------------------------------------------------------------------
+// k_gemm_tf32<.., SPLIT> above keeps A_hi and A_lo in shared memory.  Per 32-wide K block the shared-memory port then
+// carries the TMA writes (48 KB), the in-place split (16 KB read + 32 KB written) and the operand reads of twelve SS-form
+// MMAs (12 x (4 KB A + 4 KB B) = 96 KB): 192 KB at 128 B/clk = 1500 clk against 768 clk of tensor work -- the kernel is
+// shared-memory-bound at ~50 % tensor utilisation (ncu: 45-57 %).  Here four splitter warps (one TMEM lane quarter each,
+// thread = row) read the landed fp32 A tile once and write A_hi / A_lo straight to TMEM with tcgen05.st, and the MMAs
+// take A from TMEM: TMA 48 KB + split read 16 KB + B reads 48 KB = 112 KB = 875 clk per K block.  A_lo no longer
+// occupies shared memory, so the ring is 4 stages deep instead of 3.
+// Warps (512 threads, 128 registers): 0 TMA producer, 1 MMA issuer, 2 TMEM owner, 4-7 splitters, 8-15 epilogue.
+// TMEM (512 columns): accumulators [0, 2 BN) | stage s: A_hi [256 + 64 s, +32), A_lo [+32, +64).
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ CUtensorMap tmA,
+                                                        const __grid_constant__ CUtensorMap tmB,
+                                                        const __grid_constant__ CUtensorMap tmBlo,
+                                                        const float* __restrict__ bias, const float* __restrict__ R,
+                                                        long long ldr, float* __restrict__ Y, long long ldy, long long M, int N,
+                                                        int K, int act) {
+    constexpr int BM = 128, BK = 32;
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;                     // [A fp32 | B_hi | B_lo]
+    constexpr int OFF_B = A_BYTES, OFF_BLO = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 512, T_A = 256;
+    static_assert(2 * BN <= 256 && STAGES * 64 <= 256, "TMEM budget");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* ready = tempty + 2;                        // A_hi / A_lo of the stage are in TMEM (4 splitter warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles_n = (N + BN - 1) / BN;
+    const long long n_tiles = ((M + BM - 1) / BM) * n_tiles_n;
+    const int n_kb = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBlo)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    uint8_t* a = smem + stage * STAGE_BYTES;
+                    tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(a + OFF_B, &tmB, &full[stage], kb * BK, n_blk * BN);
+                    tma_load_2d(a + OFF_BLO, &tmBlo, &full[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&ready[stage], phase);
+                    tc_fence_after();
+                    const uint8_t* a = smem + stage * STAGE_BYTES;
+                    const uint64_t db = make_smem_desc(a + OFF_B), dbl = make_smem_desc(a + OFF_BLO);
+                    const uint32_t ah = tmem_base + T_A + (uint32_t)(stage * 64), al = ah + 32u;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {     // 8 tf32 = 8 TMEM columns of A = 2 descriptor units of B per MMA
+                        const uint64_t o = (uint64_t)(2 * k);
+                        tc_mma_tf32_ts(d_tmem, ah + 8u * k, db + o, idesc, (kb | k) ? 1u : 0u);
+                        tc_mma_tf32_ts(d_tmem, al + 8u * k, db + o, idesc, 1u);
+                        tc_mma_tf32_ts(d_tmem, ah + 8u * k, dbl + o, idesc, 1u);
+                    }
+                    tc_commit(&empty[stage]);              // frees the smem stage and its TMEM A slot when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[acc]);                    // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // splitter: thread = row of the A tile; its 128 bytes sit in 8 swizzled 16-byte chunks of the row's line
+        const int row = (warp - 4) * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + T_A;
+        int stage = 0; uint32_t phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                const uint8_t* a = smem + stage * STAGE_BYTES + row * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(a + ((c ^ (row & 7)) << 4));
+                    hi[4 * c] = v.x & 0xffffe000u; hi[4 * c + 1] = v.y & 0xffffe000u;
+                    hi[4 * c + 2] = v.z & 0xffffe000u; hi[4 * c + 3] = v.w & 0xffffe000u;
+                    lo[4 * c] = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(hi[4 * c]));
+                    lo[4 * c + 1] = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi[4 * c + 1]));
+                    lo[4 * c + 2] = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi[4 * c + 2]));
+                    lo[4 * c + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi[4 * c + 3]));
+                }
+                tc_st32(t_lane + (uint32_t)(stage * 64), hi);
+                tc_st32(t_lane + (uint32_t)(stage * 64) + 32u, lo);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // epilogue: as in k_gemm_tf32, one 32-column chunk at a time (128-register budget)
+        const int w = (warp - 8) & 3;                      // TMEM lane quarter this warp may read (warp id mod 4)
+        const int half = (warp - 8) >> 2;                  // two warps per quarter: even / odd 32-column chunks
+        float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 512) + (warp - 8) * (32 * 32);
+        int acc = 0; uint32_t acc_phase = 0;
+        const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
+                            (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0))) &&
+                            (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
+        const int sub_r = lane >> 3, sub_c = (lane & 7) << 2;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+            const long long row0 = (long long)m_blk * BM + w * 32;
+            const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * BN);
+            bool waited = false;
 #pragma unroll
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 const int n0 = n_blk * BN + c0;
-                if (row0 >= M || n0 >= N) continue;          // warp-uniform
+                const bool have = n0 < N && row0 < M;
+                const bool vec = have && vec_ok && n0 + 32 <= N;
+                float4 q[8], b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (R) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const long long row = row0 + it * 4 + sub_r;
+                        q[it] = (vec && row < M) ? __ldcs(reinterpret_cast<const float4*>(R + row * ldr + n0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if (bias && vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + sub_c));
+                if (!waited) { mbar_wait(&tfull[acc], acc_phase); tc_fence_after(); waited = true; }
                 uint32_t r[32];
                 tc_ld32(t_row + (uint32_t)c0, r);
-                if (vec_ok && n0 + 32 <= N) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v;
-                        v.x = __uint_as_float(r[j]); v.y = __uint_as_float(r[j + 1]);
-                        v.z = __uint_as_float(r[j + 2]); v.w = __uint_as_float(r[j + 3]);
-                        if (bias) { const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + j); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
-                        v.x = tc_act(v.x, act); v.y = tc_act(v.y, act); v.z = tc_act(v.z, act); v.w = tc_act(v.w, act);
-                        *reinterpret_cast<float4*>(stg + lane * 32 + ((((j >> 2) ^ lane) & 7) << 2)) = v;
-                    }
+                if (c0 + 64 >= BN) {                          // last chunk of this warp: the TMEM stage can go back now
+                    tc_fence_before();
                     __syncwarp();
-                    float4 qn[8];
-                    const bool more = res_vec && c0 + 64 < BN && n0 + 96 <= N;
-                    if (more) load_res(n0 + 64, qn);
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                }
+                if (!have) continue;                          // warp-uniform
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(stg + lane * 32 + ((((j >> 2) ^ lane) & 7) << 2)) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    __syncwarp();
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rr = it * 4 + sub_r;
                         const long long row = row0 + rr;
                         if (row < M) {
                             float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((((sub_c >> 2) ^ rr) & 7) << 2));
+                            v.x = tc_act(v.x + b4.x, act); v.y = tc_act(v.y + b4.y, act);
+                            v.z = tc_act(v.z + b4.z, act); v.w = tc_act(v.w + b4.w, act);
                             if (R) { v.x += q[it].x; v.y += q[it].y; v.z += q[it].z; v.w += q[it].w; }
                             __stcs(reinterpret_cast<float4*>(Y + row * ldy + n0 + sub_c), v);
                         }
                     }
                     __syncwarp();
-                    if (more) {
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) q[it] = qn[it];
-                    }
                 } else {
                     const long long row = row0 + lane;
                     if (row < M) {
@@ -238,9 +473,6 @@ __global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CU
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -373,6 +605,24 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     return SCP_OK;
 }
 
+template <int BN, int STAGES>
+static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, const float* res,
+                     long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
+    constexpr int smem = STAGES * (128 * 128 + 2 * BN * 128) + 1024 + 512 + 8 * 32 * 32 * 4;
+    static bool attr = false;
+    if (!attr) {
+        SCP_CUDA(cudaFuncSetAttribute(k_gemm_x3_ts<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    const long long tiles = cdiv(M, 128) * cdiv(N, BN);
+    const int grid = (int)std::min<long long>(tiles, n_sm);
+    k_gemm_x3_ts<BN, STAGES><<<grid, 512, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
 int linear_tf32(const float* x, long long ldx, const float* w, const float* bias, const float* res, long long ldr, float* y,
                 long long ldy, long long M, int N, int K, int act, cudaStream_t st, int split) {
     CUtensorMap ma, mb, mbl;
@@ -383,8 +633,13 @@ int linear_tf32(const float* x, long long ldx, const float* w, const float* bias
         const int BN = N > 64 ? 128 : 64;
         if (int e = get_tensor_map_2d(ws, K, N, K, BN, &mb)) return e;
         if (int e = get_tensor_map_2d(ws + (long long)N * K, K, N, K, BN, &mbl)) return e;
-        if (BN == 128) return launch<128, 3, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
-        return launch<64, 4, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
+        static const bool ss = getenv("SCP_GEMM_X3_SS") != nullptr;       // A/B switch: the older kernel with A_hi/A_lo in smem
+        if (ss) {
+            if (BN == 128) return launch<128, 3, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
+            return launch<64, 4, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
+        }
+        if (BN == 128) return launch_ts<128, 4>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
+        return launch_ts<64, 4>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
     }
     const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
     if (int e = get_tensor_map_2d(w, K, N, K, BN, &mb)) return e;

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
         // list is about to overflow the warp compacts it to the exact top-kc with a radix select and tightens the threshold.
         const int w = warp - 4;
         float* xcs = stage + w * 128;                                     // this warp's copy of the tile's candidate norms
+        float* tr = stage + 4 * 128 + w * (32 * 33);                      // this warp's [32 rows][33] score tile (own row only)
         float* bs = scr_s + ((size_t)blockIdx.x * 128 + w * 32) * KT_CAP;
         int* bi = scr_i + ((size_t)blockIdx.x * 128 + w * 32) * KT_CAP;
         float* my_s = bs + (size_t)lane * KT_CAP;
@@ -288,11 +289,23 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                                 smax = fmaxf(smax, sc);
                             }
                         }
-                        if (smax > th) {
+                        if (__any_sync(0xffffffffu, smax > th)) {
+                            // Hits are per-lane events (lane = row): a loop over the 32 candidates would run its
+                            // compare+branch for every candidate that ANY row accepts.  Instead every lane builds the
+                            // bit mask of its own hits, parks its 32 scores in shared memory ([lane][33], conflict-free)
+                            // and pops only its own bits: the warp iterates max-over-lanes(hits) times, ~2-3.
+                            uint32_t hm = 0u;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                const float sc = __uint_as_float(r[hh][j]);
-                                if (sc > th) { my_s[cnt] = sc; my_i[cnt] = c0 + cb + j; ++cnt; }
+                                hm |= (__uint_as_float(r[hh][j]) > th) ? (1u << j) : 0u;
+                                tr[lane * 33 + j] = __uint_as_float(r[hh][j]);
+                            }
+                            while (hm) {
+                                const int j = __ffs(hm) - 1;
+                                hm &= hm - 1;
+                                my_s[cnt] = tr[lane * 33 + j];
+                                my_i[cnt] = c0 + cb + j;
+                                ++cnt;
                             }
                         }
                         unsigned need = __ballot_sync(0xffffffffu, cnt > KT_CAP - 32);
@@ -392,7 +405,7 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     // when shape and address are identical, which is then also correct)
     if (int e = get_tensor_map_2d(hi, d, total, d, 128, &mh)) return e;
     if (int e = get_tensor_map_2d(lo, d, total, d, 128, &ml)) return e;
-    const int smem = KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + 4 * 32 * 33 * 4;
+    const int smem = KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + 4 * 128 * 4 + 4 * 32 * 33 * 4;
     static int attr = 0;
     if (smem > attr) { SCP_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
     static int n_sm = 0;
