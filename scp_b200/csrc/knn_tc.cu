@@ -5,35 +5,51 @@
 // split (x = x_hi + x_lo, hi.hi + lo.hi + hi.lo: fp32-class accuracy); X is split ONCE per call by an elementwise
 // kernel (the tiles are re-read ~64x from L2, so the extra copy is free) and |x|^2 is fp32.
 //
-// One persistent CTA per (window, 128-query tile): the candidate tiles of the window stream through a TMA -> smem
-// ring -> tcgen05.mma -> TMEM (2 accumulator stages), and the epilogue warps (one thread per query row) read the
-// 128x128 score tile back with tcgen05.ld and keep a sorted top-k list per row in shared memory.  Candidates are
-// visited in index order with a strict ">" insert, so exact ties go to the lowest index (the canonical rule).
+// One persistent CTA per work item = (window, 128-query tile):
+//   * the query rows' X_hi / X_lo are written ONCE to tensor memory (tcgen05.st, lane = row) and serve as the A operand
+//     of every MMA of the work item ("TS" form): only the candidate tiles cross L2 -> shared memory -> tensor core, which
+//     halves the TMA traffic and takes the A reads (2/3 of an SS-form MMA's operand bytes at N = 64) off the
+//     shared-memory port;
+//   * candidate tiles of 64 rows stream through a 6-stage TMA ring; the 128 x 64 score tile accumulates in TMEM (2 stages);
+//   * the epilogue warps (lane = query row) read the scores back with tcgen05.ld and keep, per row, a MIN-HEAP of the
+//     kc = k + 8 best candidates in shared memory ([entry][lane], conflict-free).  The heap root is the row's exact
+//     running threshold, so a row accepts only ~kc (1 + ln(n / kc)) candidates over the whole scan and an accept costs
+//     one sift-down (<= 5 levels).  (Earlier versions appended hits to per-row lists in global memory and compacted
+//     them with a warp-wide radix select: 70 % of the kernel time went into those scattered 4-byte stores.)
+// The kc survivors per row go to an exact float64 re-rank, which defines the final order and the tie rule.
 #include <algorithm>
+#include <stdlib.h>
 #include "tc.cuh"
 
 struct scp_seqs;
 
 namespace scp {
 
-constexpr int KT_BM = 128, KT_BN = 128, KT_BK = 32, KT_STAGES = 3;
+constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 32, KT_STAGES = 6;
 constexpr int KT_EXTRA = 8;                                    // approximate top-(k+8) is re-ranked exactly
-constexpr int KT_TILE_BYTES = 128 * KT_BK * 4;                 // 16 KB
-constexpr int KT_STAGE_BYTES = 4 * KT_TILE_BYTES;              // A_hi | A_lo | B_hi | B_lo
-constexpr int KT_CAP = 256;                                    // per-row scratch list (score, candidate) entries
+constexpr int KT_MAXD = 192;                                   // A_hi + A_lo must fit 384 TMEM columns
+constexpr int KT_TILE_BYTES = KT_BN * KT_BK * 4;               // 8 KB: [64 candidates x 32 floats]
+constexpr int KT_STAGE_BYTES = 2 * KT_TILE_BYTES;              // B_hi | B_lo
+constexpr uint32_t KT_T_AH = 128, KT_T_AL = 128 + KT_MAXD;     // TMEM: acc [0,128) | A_hi [128,320) | A_lo [320,512)
+// shared memory after the ring: barriers 256 B | candidate norms 4 x 64 f | score tiles 4 x [32][33] f | heaps 4 x [32][32] (f, i)
+constexpr int KT_OFF_BAR = KT_STAGES * KT_STAGE_BYTES;
+constexpr int KT_OFF_XC = KT_OFF_BAR + 256;
+constexpr int KT_OFF_TR = KT_OFF_XC + 4 * 64 * 4;
+constexpr int KT_OFF_HS = KT_OFF_TR + 4 * 32 * 33 * 4;
+constexpr int KT_OFF_HI = KT_OFF_HS + 4 * 32 * 32 * 4;
+constexpr int KT_SMEM = KT_OFF_HI + 4 * 32 * 32 * 4 + 1024;
 
-// Candidate-tile visiting order for a query tile t0: its own neighbourhood first (tokens are in Morton order, so the
-// nearest neighbours are mostly index-local and the top-k threshold tightens at once), then the rest ascending.
-// Visiting candidates in plain index order makes the running threshold improve with almost every candidate of the
-// query's own region -- thousands of list insertions per row instead of ~150.
+// Candidate-tile visiting order for the query tile whose first 64-row tile is t0 (a query tile covers t0 and t0+1):
+// its own neighbourhood first (tokens are in Morton order, so the nearest neighbours are mostly index-local and the
+// heap threshold tightens at once), then the rest ascending.
 __host__ __device__ __forceinline__ int knn_tile_order(int i, int t0, int nt) {
-    const int a = t0 > 0 ? t0 - 1 : 0, b = t0 + 1 < nt ? t0 + 1 : nt - 1;      // neighbourhood [a, b]
-    const int first[3] = {t0, t0 - 1, t0 + 1};
+    const int first[4] = {t0, t0 + 1, t0 - 1, t0 + 2};
     int nf = 0;
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
+    for (int u = 0; u < 4; ++u) {
         if (first[u] >= 0 && first[u] < nt) { if (i == nf) return first[u]; ++nf; }
     }
+    const int a = t0 > 0 ? t0 - 1 : 0, b = t0 + 2 < nt ? t0 + 2 : nt - 1;      // neighbourhood [a, b]
     const int j = i - nf;
     return j < a ? j : j + (b - a + 1);
 }
@@ -55,101 +71,24 @@ __global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X,
     if (lane == 0) xx[row] = s;
 }
 
-
-// Warp-cooperative compaction of one row's scratch list (cq entries, kc <= cq <= KT_CAP) to AT MOST 32 entries that
-// contain its top-kc by (score desc, candidate index asc), written back to the front of the list; *kept = how many.
-// Returns a valid new threshold for the row: at least kc kept entries score >= it.
-// Selection = MSB-first radix select on order-preserving keys, 8 entries per lane, stopped as soon as "everything
-// above the current bucket + the bucket" fits in 32 slots (usually after 12-18 of the 32 bits): the exact kc-th value
-// is not needed, the exact re-rank sees every kept candidate.
-__device__ __forceinline__ float knn_compact_row(float* bs, int* bi, int cq, int kc, int lane, int* kept) {
-    __syncwarp();                                                          // the owner lane's appends are visible
-    uint32_t key[KT_CAP / 32];
-    int id[KT_CAP / 32];
-#pragma unroll
-    for (int m = 0; m < KT_CAP / 32; ++m) {
-        const int e = lane + 32 * m;
-        key[m] = 0u; id[m] = 0x7fffffff;
-        if (e < cq) {
-            const uint32_t u = __float_as_uint(__ldcg(bs + e));
-            key[m] = u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);          // ascending uint order == ascending float order
-            id[m] = __ldcg(bi + e);
-        }
-    }
-    uint32_t prefix = 0u;
-    int rem = kc;                                                          // rank of the kc-th best inside the current bucket
-    int bucket = cq;                                                       // entries matching `prefix` on the decided bits
-    int bit = 31;
-#pragma unroll 1
-    for (; bit >= 0 && (kc - rem) + bucket > 32; --bit) {
-        const uint32_t sel = ~((1u << bit) - 1u);                          // this bit and everything above it
-        const uint32_t want = prefix | (1u << bit);
-        int c = 0;
-#pragma unroll
-        for (int m = 0; m < KT_CAP / 32; ++m) c += ((key[m] & sel) == want) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= rem) { prefix = want; bucket = c; } else { rem -= c; bucket -= c; }
-    }
-    // keep every entry >= prefix (the bucket's lower edge): (kc - rem) above the bucket + the bucket itself
-    bool keep[KT_CAP / 32];
-#pragma unroll
-    for (int m = 0; m < KT_CAP / 32; ++m) keep[m] = key[m] >= prefix && key[m] != 0u;
-    int total = (kc - rem) + bucket;
-    if (total > 32) {                                                      // all 32 bits used: > 32 - above exact ties; lowest candidates first
-        const int take = 32 - (kc - rem);
-#pragma unroll
-        for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix) keep[m] = false;
-#pragma unroll 1
-        for (int it = 0; it < take; ++it) {
-            int best = 0x7fffffff;
-#pragma unroll
-            for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix && !keep[m]) best = min(best, id[m]);
-            best = __reduce_min_sync(0xffffffffu, best);
-#pragma unroll
-            for (int m = 0; m < KT_CAP / 32; ++m) if (key[m] == prefix && id[m] == best) keep[m] = true;
-        }
-        total = 32;
-    }
-    __syncwarp();
-    int basep = 0;
-#pragma unroll
-    for (int m = 0; m < KT_CAP / 32; ++m) {
-        const unsigned bal = __ballot_sync(0xffffffffu, keep[m]);
-        if (keep[m]) {
-            const int pos = basep + __popc(bal & ((1u << lane) - 1u));
-            const uint32_t u = key[m] ^ ((key[m] >> 31) ? 0x80000000u : 0xffffffffu);
-            __stcg(bs + pos, __uint_as_float(u));
-            __stcg(bi + pos, id[m]);
-        }
-        basep += __popc(bal);
-    }
-    __syncwarp();
-    *kept = total;
-    if (prefix == 0u) return -INFINITY;                                    // no bit decided: keep accepting everything
-    return __uint_as_float(prefix ^ ((prefix >> 31) ? 0x80000000u : 0xffffffffu));
-}
-
 __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUtensorMap tmHi,
                                                     const __grid_constant__ CUtensorMap tmLo,
+                                                    const float* __restrict__ xhi, const float* __restrict__ xlo,
                                                     const float* __restrict__ xx, const long long* __restrict__ seq_off,
                                                     const int* __restrict__ tile_seq, const int* __restrict__ tile_start,
-                                                    int n_work, long long row0, int d, int k, int* __restrict__ idx_out,
-                                                    float* __restrict__ scr_s, int* __restrict__ scr_i) {
+                                                    int n_work, long long row0, int d, int kc, int* __restrict__ idx_out) {
     extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment by an OFFSET from the shared-space symbol: a pointer rebuilt from an integer would be generic
-    // (LD/ST instead of LDS/STS and no alias information against global memory)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + KT_STAGES * KT_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + KT_OFF_BAR);
     uint64_t* empty = full + KT_STAGES;
     uint64_t* tfull = empty + KT_STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* stage = reinterpret_cast<float*>(tmem_slot + 4);     // 4 warps x [32][33] transpose tiles
-    const int kc = k;                                            // candidates kept per row (k + KT_EXTRA <= 32)
+    uint64_t* a_ready = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (d + KT_BK - 1) / KT_BK;
-    constexpr uint32_t TMEM_COLS = 2 * KT_BN;
+    constexpr uint32_t TMEM_COLS = 512;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmHi)) : "memory");
@@ -158,6 +97,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < KT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        mbar_init(a_ready, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -171,38 +111,39 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // ---------------- TMA producer: candidate tiles only ----------------
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
                 const int s = tile_seq[wk];
                 const long long base = seq_off[s] - row0;               // row of the window inside the split copies
                 const int n = (int)(seq_off[s + 1] - seq_off[s]);
-                const int q0 = tile_start[wk];
                 const int nt = (n + KT_BN - 1) / KT_BN;
                 for (int ci = 0; ci < nt; ++ci) {
-                    const int c0 = knn_tile_order(ci, q0 / KT_BN, nt) * KT_BN;
+                    const int c0 = knn_tile_order(ci, tile_start[wk] / KT_BN, nt) * KT_BN;
                     for (int kb = 0; kb < n_kb; ++kb) {
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_expect_tx(&full[stage], KT_STAGE_BYTES);
-                        uint8_t* a = smem + stage * KT_STAGE_BYTES;
-                        tma_load_2d(a, &tmHi, &full[stage], kb * KT_BK, (int)(base + q0));
-                        tma_load_2d(a + KT_TILE_BYTES, &tmLo, &full[stage], kb * KT_BK, (int)(base + q0));
-                        tma_load_2d(a + 2 * KT_TILE_BYTES, &tmHi, &full[stage], kb * KT_BK, (int)(base + c0));
-                        tma_load_2d(a + 3 * KT_TILE_BYTES, &tmLo, &full[stage], kb * KT_BK, (int)(base + c0));
+                        uint8_t* b = smem + stage * KT_STAGE_BYTES;
+                        tma_load_2d(b, &tmHi, &full[stage], kb * KT_BK, (int)(base + c0));
+                        tma_load_2d(b + KT_TILE_BYTES, &tmLo, &full[stage], kb * KT_BK, (int)(base + c0));
                         if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT_BN >> 3) << 17) | ((uint32_t)(KT_BM >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
+            int acc = 0; uint32_t acc_phase = 0, a_phase = 0;
             for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
                 const int s = tile_seq[wk];
                 const int n = (int)(seq_off[s + 1] - seq_off[s]);
                 const int nt = (n + KT_BN - 1) / KT_BN;
+                mbar_wait(a_ready, a_phase);                            // this work item's query rows are in TMEM
+                a_phase ^= 1;
                 for (int ci = 0; ci < nt; ++ci) {
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
@@ -210,15 +151,15 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                     for (int kb = 0; kb < n_kb; ++kb) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after();
-                        const uint8_t* a = smem + stage * KT_STAGE_BYTES;
-                        const uint64_t dah = make_smem_desc(a), dal = make_smem_desc(a + KT_TILE_BYTES);
-                        const uint64_t dbh = make_smem_desc(a + 2 * KT_TILE_BYTES), dbl = make_smem_desc(a + 3 * KT_TILE_BYTES);
+                        const uint8_t* b = smem + stage * KT_STAGE_BYTES;
+                        const uint64_t dbh = make_smem_desc(b), dbl = make_smem_desc(b + KT_TILE_BYTES);
+                        const uint32_t ah = tmem_base + KT_T_AH + (uint32_t)(kb * KT_BK), al = tmem_base + KT_T_AL + (uint32_t)(kb * KT_BK);
 #pragma unroll
                         for (int kk = 0; kk < KT_BK / 8; ++kk) {
                             const uint64_t o = (uint64_t)(2 * kk);
-                            tc_mma_tf32(d_tmem, dah + o, dbh + o, idesc, (kb | kk) ? 1u : 0u);
-                            tc_mma_tf32(d_tmem, dal + o, dbh + o, idesc, 1u);
-                            tc_mma_tf32(d_tmem, dah + o, dbl + o, idesc, 1u);
+                            tc_mma_tf32_ts(d_tmem, ah + 8u * kk, dbh + o, idesc, (kb | kk) ? 1u : 0u);
+                            tc_mma_tf32_ts(d_tmem, al + 8u * kk, dbh + o, idesc, 1u);
+                            tc_mma_tf32_ts(d_tmem, ah + 8u * kk, dbl + o, idesc, 1u);
                         }
                         tc_commit(&empty[stage]);
                         if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
@@ -229,108 +170,126 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
             }
         }
     } else if (warp >= 4) {
-        // Epilogue: warp w owns query rows 32w..32w+31 of the tile and tcgen05.ld hands lane i the scores of ROW i, so every
-        // lane scans its own row: score, compare with the row's running threshold (the kc-th best seen so far) and, on the
-        // rare hit, append (score, candidate) to the row's scratch list.  No cross-lane traffic in the common case; when a
-        // list is about to overflow the warp compacts it to the exact top-kc with a radix select and tightens the threshold.
+        // ---------------- query loader + epilogue: warp w owns query rows 32w..32w+31, lane = row ----------------
         const int w = warp - 4;
-        float* xcs = stage + w * 128;                                     // this warp's copy of the tile's candidate norms
-        float* tr = stage + 4 * 128 + w * (32 * 33);                      // this warp's [32 rows][33] score tile (own row only)
-        float* bs = scr_s + ((size_t)blockIdx.x * 128 + w * 32) * KT_CAP;
-        int* bi = scr_i + ((size_t)blockIdx.x * 128 + w * 32) * KT_CAP;
-        float* my_s = bs + (size_t)lane * KT_CAP;
-        int* my_i = bi + (size_t)lane * KT_CAP;
+        float* xcs = reinterpret_cast<float*>(smem + KT_OFF_XC) + w * 64;           // candidate norms of the current tile
+        float* tr = reinterpret_cast<float*>(smem + KT_OFF_TR) + w * (32 * 33);     // this warp's parked score tile
+        float* hs = reinterpret_cast<float*>(smem + KT_OFF_HS) + w * (32 * 32) + lane;   // heap scores, entry e at hs[32 e]
+        int* hid = reinterpret_cast<int*>(smem + KT_OFF_HI) + w * (32 * 32) + lane;      // heap candidate indices
+        const uint32_t t_lane = tmem_base + ((uint32_t)(w * 32) << 16);
         int acc = 0; uint32_t acc_phase = 0;
         for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
             const int s = tile_seq[wk];
             const long long gbase = seq_off[s];
             const int n = (int)(seq_off[s + 1] - gbase);
-            const int qw0 = tile_start[wk] + w * 32;                      // first query row of this warp
-            const bool rowv = qw0 + lane < n;
-            const float xq = rowv ? xx[gbase - row0 + qw0 + lane] : 0.f;
+            const int q = tile_start[wk] + w * 32 + lane;                 // this lane's query row inside the window
+            const bool rowv = q < n;
+            // (every MMA of the previous work item has retired: this warp saw its last accumulator)
+            {
+                const float* ph = xhi + (gbase - row0 + q) * (long long)d;
+                const float* pl = xlo + (gbase - row0 + q) * (long long)d;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    uint32_t h[32], l[32];
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const int col = kb * KT_BK + c;
+                        uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+                        if (rowv && col < d) {                            // d % 4 == 0: a float4 never straddles the end
+                            vh = *reinterpret_cast<const uint4*>(ph + col);
+                            vl = *reinterpret_cast<const uint4*>(pl + col);
+                        }
+                        h[c] = vh.x; h[c + 1] = vh.y; h[c + 2] = vh.z; h[c + 3] = vh.w;
+                        l[c] = vl.x; l[c + 1] = vl.y; l[c + 2] = vl.z; l[c + 3] = vl.w;
+                    }
+                    tc_st32(t_lane + KT_T_AH + (uint32_t)(kb * KT_BK), h);
+                    tc_st32(t_lane + KT_T_AL + (uint32_t)(kb * KT_BK), l);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+            }
+            const float xq = rowv ? xx[gbase - row0 + q] : 0.f;
+            for (int e = 0; e < kc; ++e) { hs[32 * e] = -INFINITY; hid[32 * e] = -1; }
             float th = rowv ? -INFINITY : INFINITY;                        // rows past the window never take a candidate
-            int cnt = 0;
             const int nt = (n + KT_BN - 1) / KT_BN;
             for (int ci = 0; ci < nt; ++ci) {
                 const int c0 = knn_tile_order(ci, tile_start[wk] / KT_BN, nt) * KT_BN;
                 __syncwarp();
 #pragma unroll
-                for (int m = 0; m < 4; ++m) {
+                for (int m = 0; m < 2; ++m) {
                     const int c = c0 + lane + 32 * m;
                     xcs[lane + 32 * m] = c < n ? __ldg(xx + (gbase - row0) + c) : INFINITY;   // +inf norm -> score -inf
                 }
                 __syncwarp();
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * KT_BN);
-                // two 32-candidate chunks per round: both tcgen05.ld in flight before the first score is touched
-#pragma unroll 1
-                for (int cc = 0; cc < KT_BN; cc += 64) {
-                    if (c0 + cc >= n) break;                               // warp-uniform
-                    uint32_t r[2][32];
-                    tc_ld32_nowait(t_row + (uint32_t)cc, r[0]);
-                    tc_ld32_nowait(t_row + (uint32_t)cc + 32u, r[1]);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int cb = cc + 32 * hh;
-                        if (c0 + cb >= n) break;                           // warp-uniform
-                        // scores in place; branch-free maximum first: after the first tiles almost no chunk holds a hit
-                        float smax = -INFINITY;
-#pragma unroll
-                        for (int j4 = 0; j4 < 32; j4 += 4) {
-                            const float4 xc = *reinterpret_cast<const float4*>(xcs + cb + j4);
-                            const float xcv[4] = {xc.x, xc.y, xc.z, xc.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                // == (2 g - |c|^2) - |q|^2 with one rounding per subtraction (2 g is exact)
-                                const float sc = __fsub_rn(fmaf(2.0f, __uint_as_float(r[hh][j4 + e]), -xcv[e]), xq);
-                                r[hh][j4 + e] = __float_as_uint(sc);
-                                smax = fmaxf(smax, sc);
-                            }
-                        }
-                        if (__any_sync(0xffffffffu, smax > th)) {
-                            // Hits are per-lane events (lane = row): a loop over the 32 candidates would run its
-                            // compare+branch for every candidate that ANY row accepts.  Instead every lane builds the
-                            // bit mask of its own hits, parks its 32 scores in shared memory ([lane][33], conflict-free)
-                            // and pops only its own bits: the warp iterates max-over-lanes(hits) times, ~2-3.
-                            uint32_t hm = 0u;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                hm |= (__uint_as_float(r[hh][j]) > th) ? (1u << j) : 0u;
-                                tr[lane * 33 + j] = __uint_as_float(r[hh][j]);
-                            }
-                            while (hm) {
-                                const int j = __ffs(hm) - 1;
-                                hm &= hm - 1;
-                                my_s[cnt] = tr[lane * 33 + j];
-                                my_i[cnt] = c0 + cb + j;
-                                ++cnt;
-                            }
-                        }
-                        unsigned need = __ballot_sync(0xffffffffu, cnt > KT_CAP - 32);
-                        while (need) {
-                            const int q = __ffs(need) - 1;
-                            need &= need - 1;
-                            int kept;
-                            const float pv = knn_compact_row(bs + (size_t)q * KT_CAP, bi + (size_t)q * KT_CAP,
-                                                             __shfl_sync(0xffffffffu, cnt, q), kc, lane, &kept);
-                            if (lane == q) { th = pv; cnt = kept; }
-                        }
-                    }
-                }
-                tc_fence_before();
+                uint32_t r[2][32];
+                tc_ld32_nowait(t_lane + (uint32_t)(acc * KT_BN), r[0]);
+                tc_ld32_nowait(t_lane + (uint32_t)(acc * KT_BN) + 32u, r[1]);
+                tc_wait_ld();
+                tc_fence_before();                                         // scores are in registers: the stage can be refilled
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cb = 32 * hh;
+                    if (c0 + cb >= n) break;                               // warp-uniform
+                    float smax = -INFINITY;
+#pragma unroll
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const float4 xc = *reinterpret_cast<const float4*>(xcs + cb + j4);
+                        const float xcv[4] = {xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            // == (2 g - |c|^2) - |q|^2 with one rounding per subtraction (2 g is exact)
+                            const float sc = __fsub_rn(fmaf(2.0f, __uint_as_float(r[hh][j4 + e]), -xcv[e]), xq);
+                            r[hh][j4 + e] = __float_as_uint(sc);
+                            smax = fmaxf(smax, sc);
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, smax > th)) {
+                        // Accepts are per-lane events (lane = row): every lane builds the bit mask of its own candidates
+                        // above the threshold, parks its 32 scores in shared memory ([lane][33], conflict-free) and pops
+                        // only its own bits; the warp iterates max-over-lanes(accepts) times, usually 1-2.
+                        uint32_t hm = 0u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            hm |= (__uint_as_float(r[hh][j]) > th) ? (1u << j) : 0u;
+                            tr[lane * 33 + j] = __uint_as_float(r[hh][j]);
+                        }
+                        while (hm) {
+                            const int j = __ffs(hm) - 1;
+                            hm &= hm - 1;
+                            const float v = tr[lane * 33 + j];
+                            if (!(v > th)) continue;                       // the threshold moved since the mask was built
+                            const int vid = c0 + cb + j;
+                            int i = 0;                                     // replace the root (the row's kc-th best) and sift down
+                            for (;;) {
+                                const int lc = 2 * i + 1;
+                                if (lc >= kc) break;
+                                const float sl = hs[32 * lc];
+                                const float sr = lc + 1 < kc ? hs[32 * (lc + 1)] : INFINITY;
+                                const int cm = sr < sl ? lc + 1 : lc;
+                                const float sm = fminf(sl, sr);
+                                if (!(sm < v)) break;
+                                hs[32 * i] = sm; hid[32 * i] = hid[32 * cm];
+                                i = cm;
+                            }
+                            hs[32 * i] = v; hid[32 * i] = vid;
+                            th = hs[0];
+                        }
+                    }
+                }
             }
-            for (int q = 0; q < 32; ++q) {
-                if (qw0 + q >= n) break;                                   // warp-uniform
-                int cq = __shfl_sync(0xffffffffu, cnt, q);
-                if (cq > 32) knn_compact_row(bs + (size_t)q * KT_CAP, bi + (size_t)q * KT_CAP, cq, kc, lane, &cq);
-                __syncwarp();
-                const long long row = gbase + qw0 + q;                     // up to 32 candidates per row for the exact re-rank
-                idx_out[(row - row0) * 32 + lane] = lane < cq ? (int)(gbase + __ldcg(bi + (size_t)q * KT_CAP + lane)) : -1;
+            if (rowv) {                                                    // kc survivors (unordered) for the exact re-rank
+                int* dst = idx_out + (gbase - row0 + q) * 32;
+#pragma unroll 4
+                for (int e = 0; e < 32; ++e) {
+                    const int id = e < kc ? hid[32 * e] : -1;
+                    dst[e] = id < 0 ? -1 : (int)(gbase + id);
+                }
             }
             __syncwarp();
         }
@@ -386,7 +345,7 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const float* __restrict__ X,
 }
 
 // host ------------------------------------------------------------------------------------------
-bool knn_tc_ok(int d, int k) { return d >= 32 && d % 4 == 0 && k >= 1 && k + KT_EXTRA <= 32; }
+bool knn_tc_ok(int d, int k) { return d >= 32 && d <= KT_MAXD && d % 4 == 0 && k >= 1 && k + KT_EXTRA <= 32; }
 
 int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n_seq, const long long* d_off,
            const int* d_tile_seq, const int* d_tile_start, int n_work, int k, int* d_idx, cudaStream_t st) {
@@ -403,24 +362,17 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     CUtensorMap mh, ml;
     // the split buffers are transient: encode their maps every call (pointer reuse would alias a cached map only
     // when shape and address are identical, which is then also correct)
-    if (int e = get_tensor_map_2d(hi, d, total, d, 128, &mh)) return e;
-    if (int e = get_tensor_map_2d(lo, d, total, d, 128, &ml)) return e;
-    const int smem = KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + 4 * 128 * 4 + 4 * 32 * 33 * 4;
-    static int attr = 0;
-    if (smem > attr) { SCP_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
+    if (int e = get_tensor_map_2d(hi, d, total, d, KT_BN, &mh)) return e;
+    if (int e = get_tensor_map_2d(lo, d, total, d, KT_BN, &ml)) return e;
+    static bool attr = false;
+    if (!attr) { SCP_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM)); attr = true; }
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const int grid = std::min(n_work, n_sm);
-    float* scr_s = nullptr;
-    int* scr_i = nullptr;
-    SCP_CUDA(malloc_async((void**)&scr_s, (size_t)grid * 128 * KT_CAP * 4, st));
-    SCP_CUDA(malloc_async((void**)&scr_i, (size_t)grid * 128 * KT_CAP * 4, st));
-    k_knn_tc<<<grid, 256, smem, st>>>(mh, ml, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, scr_s, scr_i);
+    k_knn_tc<<<grid, 256, KT_SMEM, st>>>(mh, ml, hi, lo, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand);
     SCP_LAUNCHED();
     k_knn_rerank<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x, ldx, d, row0, total, cand, 32, k, d_idx);
     SCP_LAUNCHED();
-    SCP_CUDA(cudaFreeAsync(scr_s, st));
-    SCP_CUDA(cudaFreeAsync(scr_i, st));
     SCP_CUDA(cudaFreeAsync(cand, st));
     SCP_CUDA(cudaFreeAsync(hi, st));
     SCP_CUDA(cudaFreeAsync(lo, st));
