@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
                 for (int d = 0; d < 32; ++d) o_acc[32 + d] = fmaf(o_acc[32 + d], sc, __uint_as_float(q0[d]));
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&o_empty[b]);
+                if (lane == 0) mbar_arrive_relaxed(&o_empty[b]);
             }
         }
 #pragma unroll 1
@@ -237,18 +237,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
                 *reinterpret_cast<float4*>(dst + d) = make_float4(o_acc[d] * inv, o_acc[d + 1] * inv, o_acc[d + 2] * inv, o_acc[d + 3] * inv);
         }
     } else if (warp == 4) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
-            mbar_wait(q_full, 0);
+        // ---------------- MMA issuer: all lanes run the loop, the elected lane issues (tc.cuh elect_one) ----------------
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+        mbar_wait(q_full, 0);
 #pragma unroll 1
-            for (int i = 0; i <= AT_NC; ++i) {
-                if (i < AT_NC) {                                           // S(i) = Q K_i^T  (after PV(i-2) in program order,
-                    const int b = i & 1, n = i >> 1;                       //  which read P_hi from the same columns)
-                    mbar_wait(&k_full[b], n & 1);
-                    tc_fence_after();
-                    const uint8_t* ks_ = sm + AT_OFF_K + b * AT_K_STAGE;
-                    const uint32_t d_tmem = tmem + AT_T_SP + (uint32_t)(b * 128);
+        for (int i = 0; i <= AT_NC; ++i) {
+            if (i < AT_NC) {                                               // S(i) = Q K_i^T  (after PV(i-2) in program order,
+                const int b = i & 1, n = i >> 1;                           //  which read P_hi from the same columns)
+                mbar_wait(&k_full[b], n & 1);
+                tc_fence_after();
+                const uint8_t* ks_ = sm + AT_OFF_K + b * AT_K_STAGE;
+                const uint32_t d_tmem = tmem + AT_T_SP + (uint32_t)(b * 128);
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t ko = (ks >> 2) * AT_K_ATOM;
@@ -260,15 +260,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
                     }
                     tc_commit(&s_full[b]);
                 }
-                if (i >= 1) {                                              // O_c(j) = P_j V_j
-                    const int j = i - 1, b = j & 1, n = j >> 1;
-                    mbar_wait(&v_full[b], n & 1);
-                    mbar_wait(&p_full[b], n & 1);
-                    if (n > 0) mbar_wait(&o_empty[b], (n - 1) & 1);
-                    tc_fence_after();
-                    const uint8_t* vs_ = sm + AT_OFF_V + b * AT_V_STAGE;
-                    const uint32_t p_tmem = tmem + AT_T_SP + (uint32_t)(b * 128);
-                    const uint32_t d_tmem = tmem + AT_T_O + (uint32_t)(b * 64);
+                __syncwarp();
+            }
+            if (i >= 1) {                                                  // O_c(j) = P_j V_j
+                const int j = i - 1, b = j & 1, n = j >> 1;
+                mbar_wait(&v_full[b], n & 1);
+                mbar_wait(&p_full[b], n & 1);
+                if (n > 0) mbar_wait(&o_empty[b], (n - 1) & 1);
+                tc_fence_after();
+                const uint8_t* vs_ = sm + AT_OFF_V + b * AT_V_STAGE;
+                const uint32_t p_tmem = tmem + AT_T_SP + (uint32_t)(b * 128);
+                const uint32_t d_tmem = tmem + AT_T_O + (uint32_t)(b * 64);
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t vo = (ks >> 2) * AT_V_ATOM;
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k_swin_attn_tc(const float* __r
                     }
                     tc_commit(&pv_done[b]);
                 }
+                __syncwarp();
             }
         }
     } else if (warp < 7) {

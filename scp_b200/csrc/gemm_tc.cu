@@ -83,37 +83,38 @@ __global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CU
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
-                for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+        int stage = 0; uint32_t phase = 0;                  // all lanes run the loop, the elected lane issues (uniform operands)
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* a = smem + stage * STAGE_BYTES;
+                if (elect_one()) {
                     mbar_expect_tx(&full[stage], TX_BYTES);
-                    uint8_t* a = smem + stage * STAGE_BYTES;
                     tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
                     tma_load_2d(a + OFF_B, &tmB, &full[stage], kb * BK, n_blk * BN);
                     if (SPLIT) tma_load_2d(a + OFF_BLO, &tmBlo, &full[stage], kb * BK, n_blk * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+        // all lanes run the loop (warp-uniform operands -> uniform registers), the elected lane issues; see tc.cuh elect_one()
+        // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(SPLIT ? &ready[stage] : &full[stage], phase);
-                    tc_fence_after();
-                    const uint8_t* a = smem + stage * STAGE_BYTES;
-                    const uint64_t da = make_smem_desc(a), db = make_smem_desc(a + OFF_B);
-                    const uint64_t dal = make_smem_desc(a + OFF_ALO), dbl = make_smem_desc(a + OFF_BLO);
+                const uint8_t* a = smem + stage * STAGE_BYTES;
+                const uint64_t da = make_smem_desc(a), db = make_smem_desc(a + OFF_B);
+                const uint64_t dal = make_smem_desc(a + OFF_ALO), dbl = make_smem_desc(a + OFF_BLO);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {     // 8 tf32 = 32 bytes = 2 descriptor units per MMA
                         const uint64_t o = (uint64_t)(2 * k);
@@ -124,11 +125,12 @@ __global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CU
                         }
                     }
                     tc_commit(&empty[stage]);              // frees the smem stage when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == n_kb - 1) tc_commit(&tfull[acc]);   // accumulator ready for the epilogue
                 }
-                tc_commit(&tfull[acc]);                    // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (SPLIT && (warp == 2 || warp == 3)) {
         // split the freshly landed A tile in place: A <- A_hi, A_lo tile next to it (same swizzled layout)
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CU
                 if (p == (NCH + 1) / 2 - 1) {               // accumulator is in registers: hand the TMEM stage back now
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);
                 }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CU
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -326,36 +328,37 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
-                for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+        int stage = 0; uint32_t phase = 0;                  // all lanes run the loop, the elected lane issues (uniform operands)
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* a = smem + stage * STAGE_BYTES;
+                if (elect_one()) {
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    uint8_t* a = smem + stage * STAGE_BYTES;
                     tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
                     tma_load_2d(a + OFF_B, &tmB, &full[stage], kb * BK, n_blk * BN);
                     tma_load_2d(a + OFF_BLO, &tmBlo, &full[stage], kb * BK, n_blk * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+        // all lanes run the loop (warp-uniform operands -> uniform registers), the elected lane issues; see tc.cuh elect_one()
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&ready[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(&ready[stage], phase);
-                    tc_fence_after();
-                    const uint8_t* a = smem + stage * STAGE_BYTES;
-                    const uint64_t db = make_smem_desc(a + OFF_B), dbl = make_smem_desc(a + OFF_BLO);
-                    const uint32_t ah = tmem_base + T_A + (uint32_t)(stage * 64), al = ah + 32u;
+                const uint8_t* a = smem + stage * STAGE_BYTES;
+                const uint64_t db = make_smem_desc(a + OFF_B), dbl = make_smem_desc(a + OFF_BLO);
+                const uint32_t ah = tmem_base + T_A + (uint32_t)(stage * 64), al = ah + 32u;
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {     // 8 tf32 = 8 TMEM columns of A = 2 descriptor units of B per MMA
                         const uint64_t o = (uint64_t)(2 * k);
@@ -364,11 +367,12 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                         tc_mma_tf32_ts(d_tmem, ah + 8u * k, dbl + o, idesc, 1u);
                     }
                     tc_commit(&empty[stage]);              // frees the smem stage and its TMEM A slot when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kb == n_kb - 1) tc_commit(&tfull[acc]);   // accumulator ready for the epilogue
                 }
-                tc_commit(&tfull[acc]);                    // accumulator ready for the epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 4 && warp < 8) {
         // splitter: thread = row of the A tile; its 128 bytes sit in 8 swizzled 16-byte chunks of the row's line
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 if (c0 + 64 >= BN) {                          // last chunk of this warp: the TMEM stage can go back now
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);
                 }
                 if (!have) continue;                          // warp-uniform
                 if (vec) {

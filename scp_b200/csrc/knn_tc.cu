@@ -25,7 +25,7 @@ struct scp_seqs;
 
 namespace scp {
 
-constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 32, KT_STAGES = 6;
+constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 32, KT_STAGES = 10;
 constexpr int KT_EXTRA = 8;                                    // approximate top-(k+8) is re-ranked exactly
 constexpr int KT_MAXD = 192;                                   // A_hi + A_lo must fit 384 TMEM columns
 constexpr int KT_TILE_BYTES = KT_BN * KT_BK * 4;               // 8 KB: [64 candidates x 32 floats]
@@ -40,18 +40,18 @@ constexpr int KT_OFF_HI = KT_OFF_HS + 4 * 32 * 32 * 4;
 constexpr int KT_SMEM = KT_OFF_HI + 4 * 32 * 32 * 4 + 1024;
 
 // Candidate-tile visiting order for the query tile whose first 64-row tile is t0 (a query tile covers t0 and t0+1):
-// its own neighbourhood first (tokens are in Morton order, so the nearest neighbours are mostly index-local and the
-// heap threshold tightens at once), then the rest ascending.
+// own tiles first, then outwards by index distance, alternating left / right.  Tokens are in Morton order, so index
+// distance tracks spatial distance: the heap threshold is tight after the first few tiles and the far tiles, visited
+// last, hardly ever produce an accept (ascending order made every row accept ~190 candidates, this order ~60).
 __host__ __device__ __forceinline__ int knn_tile_order(int i, int t0, int nt) {
-    const int first[4] = {t0, t0 + 1, t0 - 1, t0 + 2};
-    int nf = 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        if (first[u] >= 0 && first[u] < nt) { if (i == nf) return first[u]; ++nf; }
-    }
-    const int a = t0 > 0 ? t0 - 1 : 0, b = t0 + 2 < nt ? t0 + 2 : nt - 1;      // neighbourhood [a, b]
-    const int j = i - nf;
-    return j < a ? j : j + (b - a + 1);
+    const int own = (t0 + 1 < nt) ? 2 : 1;
+    if (i < own) return t0 + i;
+    int j = i - own;                                                           // index among the other tiles
+    const int L = t0, R = nt - t0 - own;                                       // tiles left of t0 / right of the own tiles
+    const int m = L < R ? L : R;
+    if (j < 2 * m) { const int k = (j >> 1) + 1; return (j & 1) ? t0 + own - 1 + k : t0 - k; }
+    j -= 2 * m;
+    return L > R ? t0 - m - 1 - j : t0 + own + m + j;
 }
 
 __global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X, long long ldx, int d, long long n,
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                                                     const float* __restrict__ xhi, const float* __restrict__ xlo,
                                                     const float* __restrict__ xx, const long long* __restrict__ seq_off,
                                                     const int* __restrict__ tile_seq, const int* __restrict__ tile_start,
-                                                    int n_work, long long row0, int d, int kc, int* __restrict__ idx_out) {
+                                                    int n_work, long long row0, int d, int kc, int* __restrict__ idx_out, int dbg) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + KT_OFF_BAR);
@@ -111,49 +111,49 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ---------------- TMA producer: candidate tiles only ----------------
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
-                const int s = tile_seq[wk];
-                const long long base = seq_off[s] - row0;               // row of the window inside the split copies
-                const int n = (int)(seq_off[s + 1] - seq_off[s]);
-                const int nt = (n + KT_BN - 1) / KT_BN;
-                for (int ci = 0; ci < nt; ++ci) {
-                    const int c0 = knn_tile_order(ci, tile_start[wk] / KT_BN, nt) * KT_BN;
-                    for (int kb = 0; kb < n_kb; ++kb) {
-                        mbar_wait(&empty[stage], phase ^ 1);
+        // ---------------- TMA producer: candidate tiles only (all lanes loop, the elected lane issues) ----------------
+        int stage = 0; uint32_t phase = 0;
+        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+            const int s = tile_seq[wk];
+            const long long base = seq_off[s] - row0;                   // row of the window inside the split copies
+            const int n = (int)(seq_off[s + 1] - seq_off[s]);
+            const int nt = (n + KT_BN - 1) / KT_BN;
+            for (int ci = 0; ci < nt; ++ci) {
+                const int c0 = knn_tile_order(ci, tile_start[wk] / KT_BN, nt) * KT_BN;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* b = smem + stage * KT_STAGE_BYTES;
+                    if (elect_one()) {
                         mbar_expect_tx(&full[stage], KT_STAGE_BYTES);
-                        uint8_t* b = smem + stage * KT_STAGE_BYTES;
                         tma_load_2d(b, &tmHi, &full[stage], kb * KT_BK, (int)(base + c0));
                         tma_load_2d(b + KT_TILE_BYTES, &tmLo, &full[stage], kb * KT_BK, (int)(base + c0));
-                        if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT_BN >> 3) << 17) | ((uint32_t)(KT_BM >> 4) << 24);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0, a_phase = 0;
-            for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
-                const int s = tile_seq[wk];
-                const int n = (int)(seq_off[s + 1] - seq_off[s]);
-                const int nt = (n + KT_BN - 1) / KT_BN;
-                mbar_wait(a_ready, a_phase);                            // this work item's query rows are in TMEM
-                a_phase ^= 1;
-                for (int ci = 0; ci < nt; ++ci) {
-                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+        // ---------------- MMA issuer: all lanes run the loop, the elected lane issues ----------------
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT_BN >> 3) << 17) | ((uint32_t)(KT_BM >> 4) << 24);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0, a_phase = 0;
+        for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
+            const int s = tile_seq[wk];
+            const int n = (int)(seq_off[s + 1] - seq_off[s]);
+            const int nt = (n + KT_BN - 1) / KT_BN;
+            mbar_wait(a_ready, a_phase);                                // this work item's query rows are in TMEM
+            a_phase ^= 1;
+            for (int ci = 0; ci < nt; ++ci) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * KT_BN);
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * KT_BN);
-                    for (int kb = 0; kb < n_kb; ++kb) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint8_t* b = smem + stage * KT_STAGE_BYTES;
-                        const uint64_t dbh = make_smem_desc(b), dbl = make_smem_desc(b + KT_TILE_BYTES);
-                        const uint32_t ah = tmem_base + KT_T_AH + (uint32_t)(kb * KT_BK), al = tmem_base + KT_T_AL + (uint32_t)(kb * KT_BK);
+                    const uint8_t* b = smem + stage * KT_STAGE_BYTES;
+                    const uint64_t dbh = make_smem_desc(b), dbl = make_smem_desc(b + KT_TILE_BYTES);
+                    const uint32_t ah = tmem_base + KT_T_AH + (uint32_t)(kb * KT_BK), al = tmem_base + KT_T_AL + (uint32_t)(kb * KT_BK);
+                    if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < KT_BK / 8; ++kk) {
                             const uint64_t o = (uint64_t)(2 * kk);
@@ -162,11 +162,12 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                             tc_mma_tf32_ts(d_tmem, ah + 8u * kk, dbl + o, idesc, 1u);
                         }
                         tc_commit(&empty[stage]);
-                        if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
+                        if (kb == n_kb - 1) tc_commit(&tfull[acc]);
                     }
-                    tc_commit(&tfull[acc]);
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    __syncwarp();
+                    if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -174,8 +175,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
         const int w = warp - 4;
         float* xcs = reinterpret_cast<float*>(smem + KT_OFF_XC) + w * 64;           // candidate norms of the current tile
         float* tr = reinterpret_cast<float*>(smem + KT_OFF_TR) + w * (32 * 33);     // this warp's parked score tile
-        float* hs = reinterpret_cast<float*>(smem + KT_OFF_HS) + w * (32 * 32) + lane;   // heap scores, entry e at hs[32 e]
-        int* hid = reinterpret_cast<int*>(smem + KT_OFF_HI) + w * (32 * 32) + lane;      // heap candidate indices
+        float2* hq = reinterpret_cast<float2*>(smem + KT_OFF_HS) + w * (32 * 32) + lane;  // heap (score, candidate), entry e at hq[32 e]
         const uint32_t t_lane = tmem_base + ((uint32_t)(w * 32) << 16);
         int acc = 0; uint32_t acc_phase = 0;
         for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
@@ -210,18 +210,23 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                 if (lane == 0) mbar_arrive(a_ready);
             }
             const float xq = rowv ? xx[gbase - row0 + q] : 0.f;
-            for (int e = 0; e < kc; ++e) { hs[32 * e] = -INFINITY; hid[32 * e] = -1; }
-            float th = rowv ? -INFINITY : INFINITY;                        // rows past the window never take a candidate
+            for (int e = 0; e < kc; ++e) hq[32 * e] = make_float2(-INFINITY, __int_as_float(-1));
+            float th = (rowv && dbg == 0) ? -INFINITY : INFINITY;          // rows past the window never take a candidate
             const int nt = (n + KT_BN - 1) / KT_BN;
+            const float* xw = xx + (gbase - row0);
+            // candidate norms of a tile are fetched one tile ahead, so the global loads are never in flight at a barrier
+            int c0 = knn_tile_order(0, tile_start[wk] / KT_BN, nt) * KT_BN;
+            float nx0 = c0 + lane < n ? __ldg(xw + c0 + lane) : INFINITY;      // +inf norm -> score -inf
+            float nx1 = c0 + lane + 32 < n ? __ldg(xw + c0 + lane + 32) : INFINITY;
             for (int ci = 0; ci < nt; ++ci) {
-                const int c0 = knn_tile_order(ci, tile_start[wk] / KT_BN, nt) * KT_BN;
                 __syncwarp();
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    const int c = c0 + lane + 32 * m;
-                    xcs[lane + 32 * m] = c < n ? __ldg(xx + (gbase - row0) + c) : INFINITY;   // +inf norm -> score -inf
+                xcs[lane] = nx0; xcs[lane + 32] = nx1;
+                __syncwarp();
+                const int c0_next = ci + 1 < nt ? knn_tile_order(ci + 1, tile_start[wk] / KT_BN, nt) * KT_BN : 0;
+                if (ci + 1 < nt) {
+                    nx0 = c0_next + lane < n ? __ldg(xw + c0_next + lane) : INFINITY;
+                    nx1 = c0_next + lane + 32 < n ? __ldg(xw + c0_next + lane + 32) : INFINITY;
                 }
-                __syncwarp();
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 uint32_t r[2][32];
@@ -230,12 +235,12 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                 tc_wait_ld();
                 tc_fence_before();                                         // scores are in registers: the stage can be refilled
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int cb = 32 * hh;
-                    if (c0 + cb >= n) break;                               // warp-uniform
+                    if (c0 + cb >= n || dbg >= 2) break;                   // warp-uniform
                     float smax = -INFINITY;
 #pragma unroll
                     for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -269,25 +274,26 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                             for (;;) {
                                 const int lc = 2 * i + 1;
                                 if (lc >= kc) break;
-                                const float sl = hs[32 * lc];
-                                const float sr = lc + 1 < kc ? hs[32 * (lc + 1)] : INFINITY;
-                                const int cm = sr < sl ? lc + 1 : lc;
-                                const float sm = fminf(sl, sr);
-                                if (!(sm < v)) break;
-                                hs[32 * i] = sm; hid[32 * i] = hid[32 * cm];
-                                i = cm;
+                                const float2 el = hq[32 * lc];
+                                const float2 er = lc + 1 < kc ? hq[32 * (lc + 1)] : make_float2(INFINITY, 0.f);
+                                const bool right = er.x < el.x;
+                                const float2 em = right ? er : el;
+                                if (!(em.x < v)) break;
+                                hq[32 * i] = em;
+                                i = right ? lc + 1 : lc;
                             }
-                            hs[32 * i] = v; hid[32 * i] = vid;
-                            th = hs[0];
+                            hq[32 * i] = make_float2(v, __int_as_float(vid));
+                            th = hq[0].x;
                         }
                     }
                 }
+                c0 = c0_next;
             }
             if (rowv) {                                                    // kc survivors (unordered) for the exact re-rank
                 int* dst = idx_out + (gbase - row0 + q) * 32;
 #pragma unroll 4
                 for (int e = 0; e < 32; ++e) {
-                    const int id = e < kc ? hid[32 * e] : -1;
+                    const int id = e < kc ? __float_as_int(hq[32 * e].y) : -1;
                     dst[e] = id < 0 ? -1 : (int)(gbase + id);
                 }
             }
@@ -369,7 +375,8 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const int grid = std::min(n_work, n_sm);
-    k_knn_tc<<<grid, 256, KT_SMEM, st>>>(mh, ml, hi, lo, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand);
+    const int dbg = getenv("SCP_KNN_DBG") ? atoi(getenv("SCP_KNN_DBG")) : 0;          // timing experiments only
+    k_knn_tc<<<grid, 256, KT_SMEM, st>>>(mh, ml, hi, lo, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, dbg);
     SCP_LAUNCHED();
     k_knn_rerank<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x, ldx, d, row0, total, cand, 32, k, d_idx);
     SCP_LAUNCHED();

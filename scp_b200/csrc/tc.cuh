@@ -19,6 +19,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive without release semantics, for "I have finished READING" hand-overs (a TMEM stage whose tcgen05.ld has been waited
+// for): there is nothing to publish, and the default .release arrive costs a MEMBAR that waits for every memory operation
+// the warp still has in flight (ncu: 14 % of the kNN kernel's samples sat on it behind the next tile's global loads).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // Blocks until the barrier phase with the given parity has completed.  try_wait is given a long suspend-time hint, so a
 // waiting warp SLEEPS in hardware until the phase flips instead of polling: a polling loop (try_wait + clock64 + compare
 // + branch every ~40 cycles) took ~30 % of all issued instructions in the warp-specialised kernels and competed with the
@@ -45,6 +51,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// One leader lane of a fully converged warp (always the same lane for the full mask).  The MMA-issuer warps run their
+// loops with ALL lanes (warp-uniform control flow and operands) and predicate only the tcgen05.mma / tcgen05.commit on the
+// leader: inside an `if (lane == 0)` region the compiler treats descriptors and TMEM addresses as divergent and wraps every
+// UTCHMMA in an R2UR + BRA.U.ANY waterfall loop (~40 issue cycles per MMA -- more than an N = 64 MMA takes to execute).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
