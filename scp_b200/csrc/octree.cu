@@ -237,6 +237,79 @@ __global__ void __launch_bounds__(TPB) k_quantise_keys(const float* __restrict__
     }
 }
 
+// Same as k_quantise_keys for frames that carry several jobs (encode_mullevel: three sub-octrees with different steps
+// over the SAME points): the float32 transform (sqrt, atan2, acos -- most of the instructions) is evaluated once per
+// point, only the divide / round / Morton spread is per job.  One block per frame tile, up to QF_MAXJ jobs per frame.
+constexpr int QF_MAXJ = 4;
+__global__ void __launch_bounds__(TPB) k_quantise_frames(const float* __restrict__ xyz, int stride,
+                                                          const Tile* __restrict__ ftiles, const long long* __restrict__ frame_begin,
+                                                          const int* __restrict__ fj_start, const int* __restrict__ fj,
+                                                          JobDev* jobs, u64* __restrict__ keys, int mode) {
+    __shared__ int s_slow[TILE * QF_MAXJ];            // (job slot << 16) | point
+    __shared__ int s_nslow;
+    __shared__ long long s_kb[QF_MAXJ];
+    const Tile t = ftiles[blockIdx.x];
+    const int f = t.job;
+    const int j0 = fj_start[f], nj = fj_start[f + 1] - j0;
+    const float* p = xyz + (frame_begin[f] + t.begin) * (long long)stride;
+    u32 qmax[QF_MAXJ], ovf[QF_MAXJ];
+#pragma unroll
+    for (int s = 0; s < QF_MAXJ; ++s) { qmax[s] = 0; ovf[s] = 0; }
+    if (threadIdx.x == 0) s_nslow = 0;
+    if (threadIdx.x < nj) {
+        s_kb[threadIdx.x] = jobs[fj[j0 + threadIdx.x]].key_begin;
+    }
+    __syncthreads();
+    auto emit = [&](int slot, int i, long long q0, long long q1, long long q2) {
+        u32 o = 0;
+        if (q0 < 0 || q1 < 0 || q2 < 0 || q0 >= (1 << 21) || q1 >= (1 << 21) || q2 >= (1 << 21)) { o = 1; q0 = q1 = q2 = 0; }
+        const u32 qm = (u32)max(q0, max(q1, q2));
+#pragma unroll
+        for (int s = 0; s < QF_MAXJ; ++s) if (s == slot) { qmax[s] = max(qmax[s], qm); ovf[s] |= o; }
+        keys[s_kb[slot] + t.begin + i] = (spread3((u32)q0) << 2) | (spread3((u32)q1) << 1) | spread3((u32)q2);
+    };
+    for (int i = threadIdx.x; i < t.count; i += TPB) {
+        const float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
+        const float rho = rho_of(x, y, z, mode);
+        const float xe = __fadd_rn(x, 1e-9f);
+        float phi = atan2f(y, xe);
+        if (phi < 0.f) phi = __fadd_rn(phi, 6.2831854820251465f);
+        const float third = (mode == SCP_MODE_SPHER) ? acosf(__fdiv_rn(z, rho)) : z;
+        const bool clear = (phi > 1e-3f) && (phi < 6.28f);                 // keep clear of the 0 / 2*pi fold
+#pragma unroll
+        for (int slot = 0; slot < QF_MAXJ; ++slot) {
+            if (slot >= nj) break;
+            const JobDev& J = jobs[fj[j0 + slot]];                 // (L1-resident; a shared-memory copy cost 40 registers)
+            const double u0 = (double)rho * J.inv_step[0], u1 = (double)phi * J.inv_step[1], u2 = ((double)third - J.off[2]) * J.inv_step[2];
+            const double r0 = rint(u0), r1 = rint(u1), r2 = rint(u2);
+            const bool safe = clear && (0.5 - fabs(u0 - r0) > J.margin[0]) && (0.5 - fabs(u1 - r1) > J.margin[1]) &&
+                              (0.5 - fabs(u2 - r2) > J.margin[2]);
+            if (!safe) { s_slow[atomicAdd(&s_nslow, 1)] = (slot << 16) | i; continue; }
+            emit(slot, i, (long long)r0, (long long)r1, (long long)r2);
+        }
+    }
+    __syncthreads();
+    // exact float64 path for the few (point, job) pairs near a rounding boundary, densely packed over the threads
+    for (int e = threadIdx.x; e < s_nslow; e += TPB) {
+        const int slot = s_slow[e] >> 16, i = s_slow[e] & 0xffff;
+        const JobDev& J = jobs[fj[j0 + slot]];
+        const float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
+        long long q0, q1, q2;
+        quantise_exact(x, y, z, mode, J.step[0], J.step[1], J.step[2], J.off[2], q0, q1, q2);
+        emit(slot, i, q0, q1, q2);
+    }
+#pragma unroll
+    for (int s = 0; s < QF_MAXJ; ++s) {
+        if (s >= nj) break;
+        const u32 qm = __reduce_max_sync(0xffffffffu, qmax[s]), ov = __reduce_max_sync(0xffffffffu, ovf[s]);
+        if ((threadIdx.x & 31) == 0) {
+            JobDev& J = jobs[fj[j0 + s]];
+            if (qm) atomicMax(&J.qmax, qm);
+            if (ov) atomicMax(&J.overflow, 1u);
+        }
+    }
+}
+
 __global__ void k_job_depth(JobDev* jobs, int n_jobs) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
@@ -403,7 +476,9 @@ __global__ void __launch_bounds__(TPB) k_head_hist(const u64* __restrict__ keys,
     __syncthreads();
     const u64* src = keys + J.key_begin;
     const int n = J.depth;
-    for (int i0 = 0; i0 < t.count; i0 += TPB) {
+    // sorted keys: once a tile starts with the sentinel (filtered / padding keys sort last) it holds nothing but sentinels
+    const bool dead = src[t.begin] == SENTINEL;
+    for (int i0 = 0; i0 < (dead ? 0 : t.count); i0 += TPB) {
         int i = i0 + threadIdx.x;
         int h = 0;
         if (i < t.count) {
@@ -476,7 +551,7 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
     __shared__ u32 s_base[MAXL + 2];        // running count of heads per level (index L), [0] = voxels
     __shared__ u32 s_wcnt[8][MAXL + 2];
     __shared__ u32 s_wpre[8][MAXL + 2];
-    __shared__ u32 s_pmin[MAXL + 2], s_pmax[MAXL + 2];
+    __shared__ u32 s_mm[4];                 // min / max coordinate over the tile's voxels: all, and all but the job's last voxel
     const Tile t = tiles[blockIdx.x];
     JobDev& J = jobs[t.job];
     const int n = J.depth;
@@ -489,12 +564,14 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
         if (L == 0) { for (int h = 1; h < NBINS; ++h) s += tb[h]; }
         else if (L <= n) { for (int h = 1; h <= L; ++h) s += tb[h]; }
         s_base[L] = s;
-        s_pmin[L] = 0xffffffffu; s_pmax[L] = 0u;
     }
+    if (threadIdx.x < 4) s_mm[threadIdx.x] = (threadIdx.x & 1) ? 0u : 0xffffffffu;
     __syncthreads();
     const u64* src = keys + J.key_begin;
     const long long node0 = J.node_start;
-    const int last_cnt = J.level_count[n > 0 ? n - 1 : 0];
+    const int n_vox = J.n_voxels;
+    u32 cmin = 0xffffffffu, cmax = 0u, emin = 0xffffffffu, emax = 0u;
+    if (src[t.begin] == SENTINEL) return;                      // block-uniform: a tile of filtered keys opens no node
     for (int i0 = 0; i0 < t.count; i0 += TPB) {
         const int i = i0 + threadIdx.x;
         int h = 0;
@@ -506,6 +583,9 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
             h = head_level(k, prev, g == 0, n);
         }
         const int hh = h == 0 ? 99 : h;
+        // Only levels >= the smallest head level of the warp can open a node here: consecutive sorted keys share long
+        // prefixes, so that is usually n-3 .. n and the 21-level ballot / emit loops shrink to a handful of iterations.
+        const int wmin = __reduce_min_sync(0xffffffffu, hh);
         u32 rank[MAXL + 2];
         {
             u32 b = __ballot_sync(0xffffffffu, h > 0);
@@ -514,6 +594,11 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
         }
 #pragma unroll
         for (int L = 1; L <= MAXL; ++L) {
+            if (L < wmin) {                                     // warp-uniform
+                rank[L] = 0;
+                if (lane == 0) s_wcnt[warp][L] = 0;
+                continue;
+            }
             u32 b = __ballot_sync(0xffffffffu, hh <= L);
             rank[L] = __popc(b & ltmask);
             if (lane == 0) s_wcnt[warp][L] = __popc(b);
@@ -526,12 +611,18 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
         __syncthreads();
         const u32 x = compact3(k >> 2), y = compact3(k >> 1), z = compact3(k);
         const u32 v = s_base[0] + s_wpre[warp][0] + rank[0];
-        if (h > 0 && vox_key) vox_key[J.vox_start + v] = k;
+        if (h > 0) {
+            if (vox_key) vox_key[J.vox_start + v] = k;
+            // x & m is monotone in x, so every level's min / max node coordinate follows from the voxel extremes
+            const u32 lo = min(x, min(y, z)), hi = max(x, max(y, z));
+            cmin = min(cmin, lo); cmax = max(cmax, hi);
+            if ((int)v != n_vox - 1) { emin = min(emin, lo); emax = max(emax, hi); }
+        }
 #pragma unroll
         for (int L = 1; L <= MAXL; ++L) {
             if (L > n) break;                                   // uniform
+            if (L < wmin) continue;                             // warp-uniform: nobody in this warp opens a node on level L
             const bool mine = (h > 0) && (L >= h);
-            u32 vmin = 0xffffffffu, vmax = 0u;
             if (mine) {
                 const u32 kL = s_base[L] + s_wpre[warp][L] + rank[L];
                 const long long r = node0 + J.level_start[L - 1] + kL;
@@ -544,17 +635,8 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
                 }
                 A.parent[r] = par;
                 const u32 m = ~((1u << (n - L + 1)) - 1u);
-                const u32 px = x & m, py = y & m, pz = z & m;
-                A.pos[3 * r] = px; A.pos[3 * r + 1] = py; A.pos[3 * r + 2] = pz;
+                A.pos[3 * r] = x & m; A.pos[3 * r + 1] = y & m; A.pos[3 * r + 2] = z & m;
                 A.fc[r] = (L < n) ? (u32)J.level_start[L] + s_base[L + 1] + s_wpre[warp][L + 1] + rank[L + 1] : v;
-                const bool dropped = J.drop_last && L == n && (int)kL == last_cnt - 1;
-                if (!dropped) { vmin = min(px, min(py, pz)); vmax = max(px, max(py, pz)); }
-            }
-            const u32 any = __ballot_sync(0xffffffffu, mine);
-            if (any) {                                          // warp-uniform
-                vmin = __reduce_min_sync(0xffffffffu, vmin);
-                vmax = __reduce_max_sync(0xffffffffu, vmax);
-                if (lane == 0 && vmin != 0xffffffffu) { atomicMin(&s_pmin[L], vmin); atomicMax(&s_pmax[L], vmax); }
             }
         }
         __syncthreads();
@@ -565,9 +647,23 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
         }
         __syncthreads();
     }
-    if (threadIdx.x >= 1 && threadIdx.x <= n && s_pmin[threadIdx.x] != 0xffffffffu) {
-        atomicMin(&J.pos_min[threadIdx.x - 1], s_pmin[threadIdx.x]);
-        atomicMax(&J.pos_max[threadIdx.x - 1], s_pmax[threadIdx.x]);
+    cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
+    emin = __reduce_min_sync(0xffffffffu, emin); emax = __reduce_max_sync(0xffffffffu, emax);
+    if (lane == 0) {
+        atomicMin(&s_mm[0], cmin); atomicMax(&s_mm[1], cmax); atomicMin(&s_mm[2], emin); atomicMax(&s_mm[3], emax);
+    }
+    __syncthreads();
+    // level L (1-based): nodes are the voxels masked to the level's cell size.  The dropped last row (Octree.py:259-262)
+    // is the last node of the LAST level only, i.e. the job's last voxel; every other level keeps all its nodes.
+    if (threadIdx.x >= 1 && threadIdx.x <= n) {
+        const int L = threadIdx.x;
+        const u32 m = ~((1u << (n - L + 1)) - 1u);
+        const bool excl = J.drop_last && L == n;
+        const u32 mn = excl ? s_mm[2] : s_mm[0], mx = excl ? s_mm[3] : s_mm[1];
+        if (mn != 0xffffffffu) {
+            atomicMin(&J.pos_min[L - 1], mn & m);
+            atomicMax(&J.pos_max[L - 1], mx & m);
+        }
     }
 }
 
@@ -615,15 +711,24 @@ __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles,
         const bool last_block = (L == n);
         int lv[4], oc[4], occ[4];
         u32 px[4], py[4], pz[4];
-        long long a = r;
-        bool have = true;
+        // Own record; the ancestors' level, octant and cell origin follow from it (an ancestor's cell is the own cell with
+        // more low bits cleared, its octant is the coordinate bit triple of its level), so only the occupancy bytes are
+        // fetched through the parent chain: 3 dependent (parent, occ) gathers instead of 3 full 23-byte records.
+        lv[3] = L; oc[3] = A.octant[r]; occ[3] = A.occ[r];
+        px[3] = A.pos[3 * r]; py[3] = A.pos[3 * r + 1]; pz[3] = A.pos[3 * r + 2];
+        u32 a = A.parent[r];
 #pragma unroll
-        for (int k = 3; k >= 0; --k) {
-            if (have) {
-                lv[k] = A.level[a]; oc[k] = A.octant[a]; occ[k] = A.occ[a];
-                px[k] = A.pos[3 * a]; py[k] = A.pos[3 * a + 1]; pz[k] = A.pos[3 * a + 2];
-                have = lv[k] > 1;
-                a = J.node_start + A.parent[a];
+        for (int k = 2; k >= 0; --k) {
+            const int Lk = L - (3 - k);
+            if (Lk >= 1) {
+                const long long ar = J.node_start + a;
+                const int sh = n - Lk + 1;                      // lowest coordinate bit that survives on level Lk
+                const u32 m = sh >= 32 ? 0u : ~((1u << sh) - 1u);
+                lv[k] = Lk;
+                occ[k] = A.occ[ar];
+                a = A.parent[ar];
+                px[k] = px[3] & m; py[k] = py[3] & m; pz[k] = pz[3] & m;
+                oc[k] = (Lk == 1) ? 1 : (int)((((px[3] >> sh) & 1u) << 2) | (((py[3] >> sh) & 1u) << 1) | ((pz[3] >> sh) & 1u)) + 1;
             } else {
                 lv[k] = 0; oc[k] = 0; occ[k] = 256; px[k] = py[k] = pz[k] = 0;
             }
@@ -813,8 +918,28 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     }
     k_job_setup<<<(int)cdiv(n_jobs, 128), 128, 0, st>>>(d_jobs, n_jobs, t->frames.as<FrameDev>(), mode);
     SCP_LAUNCHED();
-    k_quantise_keys<<<nt_p, TPB, 0, st>>>(d_xyz, point_stride, d_ptiles, d_jobs, t->keys_a.as<u64>(), mode);
-    SCP_LAUNCHED();
+    // frames with several jobs over the same points (mullevel) share the transform: one pass over the FRAME's points
+    std::vector<int> fj_start(n_frames + 1, 0), fj(n_jobs);
+    for (int j = 0; j < n_jobs; ++j) fj_start[h_jobs[j].frame + 1]++;
+    int max_per_frame = 0;
+    for (int f = 0; f < n_frames; ++f) { max_per_frame = std::max(max_per_frame, fj_start[f + 1]); fj_start[f + 1] += fj_start[f]; }
+    {
+        std::vector<int> fill(fj_start.begin(), fj_start.end() - 1);
+        for (int j = 0; j < n_jobs; ++j) fj[fill[h_jobs[j].frame]++] = j;
+    }
+    if (mode != SCP_MODE_CART && max_per_frame >= 2 && max_per_frame <= QF_MAXJ) {
+        int *d_fjs = nullptr, *d_fj = nullptr;
+        SCP_CUDA(upload_async((void**)&d_fjs, fj_start.data(), (size_t)(n_frames + 1) * 4, st));
+        SCP_CUDA(upload_async((void**)&d_fj, fj.data(), (size_t)n_jobs * 4, st));
+        k_quantise_frames<<<nt_f, TPB, 0, st>>>(d_xyz, point_stride, d_ftiles, t->frame_begin.as<long long>(), d_fjs, d_fj, d_jobs,
+                                                t->keys_a.as<u64>(), mode);
+        SCP_LAUNCHED();
+        SCP_CUDA(cudaFreeAsync(d_fjs, st));
+        SCP_CUDA(cudaFreeAsync(d_fj, st));
+    } else {
+        k_quantise_keys<<<nt_p, TPB, 0, st>>>(d_xyz, point_stride, d_ptiles, d_jobs, t->keys_a.as<u64>(), mode);
+        SCP_LAUNCHED();
+    }
     k_job_depth<<<(int)cdiv(n_jobs, 128), 128, 0, st>>>(d_jobs, n_jobs);
     SCP_LAUNCHED();
     SCP_CUDA(cudaEventRecord(t->ev[1], st));
