@@ -378,12 +378,17 @@ __host__ __device__ __forceinline__ int knn_tile_order(int i, int t0, int nt) { 
     const int j = i - nf;
     return j < a ? j : j + (b - a + 1);
 }
+// d <= 4 (positions): the neighbour list is DEFINED by the exact float64 squared distance ((dx^2 + dy^2) + dz^2 + dw^2,
+// one rounding per operation, no FMA), ties -> lowest index.  Evaluating that for all n^2 pairs is bound by the FP64
+// pipe (8 FP64 instructions per pair).  So every pair is first screened in float32 (the float32 value is within 4e-7
+// relative of the exact one) against the row's current k-th distance inflated by 4e-6; only survivors -- a few hundred
+// of 8192 per row -- take the exact path.  The screen can only pass extra candidates, never drop one.
 __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X, long long ldx, int d,
                                                      const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
                                                      const int* __restrict__ tile_start, int k, int* __restrict__ idx_out) {
     extern __shared__ __align__(16) double smd[];
-    double* cs = smd;                                   // [KS_C][4]
-    double* ls = smd + KS_C * 4;                        // [k][KS_Q]
+    float4* cs = reinterpret_cast<float4*>(smd);        // [KS_C] candidate coordinates (unused dims = 0)
+    double* ls = smd + KS_C * 2;                        // [k][KS_Q]
     int* li = reinterpret_cast<int*>(ls + k * KS_Q);    // [k][KS_Q]
     const int t = threadIdx.x;
     const int s = tile_seq[blockIdx.x];
@@ -391,28 +396,43 @@ __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X,
     const int n = (int)(seq_off[s + 1] - base);
     const int q = tile_start[blockIdx.x] + t;
     const bool active = q < n;
-    double xq[4] = {0, 0, 0, 0};
-    if (active) for (int c = 0; c < d; ++c) xq[c] = (double)X[(base + q) * ldx + c];
+    float xf[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) for (int c = 0; c < d; ++c) xf[c] = X[(base + q) * ldx + c];
+    const double xq[4] = {(double)xf[0], (double)xf[1], (double)xf[2], (double)xf[3]};
     for (int j = 0; j < k; ++j) { ls[j * KS_Q + t] = INFINITY; li[j * KS_Q + t] = -1; }
     double worst = INFINITY;
+    float wf = INFINITY;                                // float32 screen: >= worst * (1 + 4e-6)
     const int nchunk = (n + KS_C - 1) / KS_C;
     for (int ci = 0; ci < nchunk; ++ci) {
         // own neighbourhood first, then ascending (see knn_tile_order): ties are still resolved by (distance, index)
         const int c0 = knn_tile_order(ci, tile_start[blockIdx.x] / KS_C, nchunk) * KS_C;
         __syncthreads();
-        for (int e = t; e < KS_C * 4; e += KS_Q) {
-            int r = e >> 2, c = e & 3;
-            cs[e] = (c0 + r < n && c < d) ? (double)X[(base + c0 + r) * ldx + c] : 0.0;
+        for (int r = t; r < KS_C; r += KS_Q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + r < n) {
+                const float* px = X + (base + c0 + r) * ldx;
+                v.x = px[0];
+                if (d > 1) v.y = px[1];
+                if (d > 2) v.z = px[2];
+                if (d > 3) v.w = px[3];
+            }
+            cs[r] = v;
         }
         __syncthreads();
         if (!active) continue;
         const int cmax = min(KS_C, n - c0);
+#pragma unroll 4
         for (int r = 0; r < cmax; ++r) {
+            const float4 c = cs[r];
+            const float fx = xf[0] - c.x, fy = xf[1] - c.y, fz = xf[2] - c.z, fw = xf[3] - c.w;
+            const float d32 = fmaf(fw, fw, fmaf(fz, fz, fmaf(fy, fy, fx * fx)));
+            if (!(d32 <= wf)) continue;
             double dist = 0.0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double df = __dsub_rn(xq[c], cs[r * 4 + c]);
-                dist = __dadd_rn(dist, __dmul_rn(df, df));
+            {
+                double df = __dsub_rn(xq[0], (double)c.x); dist = __dadd_rn(dist, __dmul_rn(df, df));
+                df = __dsub_rn(xq[1], (double)c.y); dist = __dadd_rn(dist, __dmul_rn(df, df));
+                df = __dsub_rn(xq[2], (double)c.z); dist = __dadd_rn(dist, __dmul_rn(df, df));
+                df = __dsub_rn(xq[3], (double)c.w); dist = __dadd_rn(dist, __dmul_rn(df, df));
             }
             const int cidx = c0 + r;
             if (dist < worst || (dist == worst && cidx < li[(k - 1) * KS_Q + t])) {
@@ -425,6 +445,7 @@ __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X,
                 ls[j * KS_Q + t] = dist;
                 li[j * KS_Q + t] = cidx;
                 worst = ls[(k - 1) * KS_Q + t];
+                wf = worst == INFINITY ? INFINITY : __double2float_ru(worst * (1.0 + 4e-6));
             }
         }
     }
@@ -938,7 +959,7 @@ int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, i
     if (seqs->total == 0) return SCP_OK;
     cudaStream_t st = as_stream(stream);
     if (d <= 4) {
-        const int smem_s = KS_C * 4 * 8 + k * KS_Q * 12;
+        const int smem_s = KS_C * 16 + k * KS_Q * 12;
         static int attr_s = 0;
         if (smem_s > attr_s) {
             SCP_CUDA(cudaFuncSetAttribute(k_knn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
