@@ -259,6 +259,14 @@ def run_ours(args):
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof.update({"kernel": tag, "launches": cnt, "avg_ms": tms / cnt, "share_of_step": tms / prof_ms, "peak_source": src,
                  "traffic": None, "timed_in": "instrumented repeat of the timed steps (events around every launch)"})
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/r01_ncu_traffic.json):
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches of that kernel
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp):
+        tr = json.load(open(tp)).get(tag)
+        if tr:
+            roof["traffic"] = tr["dram_bytes_per_launch_mean"]
+            roof["traffic_note"] = tr["note"]
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[3] // args.steps,
                    "TFLOPs": v[1] / v[0] / 1e9 if v[0] else None, "GBps": v[2] / v[0] / 1e6 if v[0] else None}
                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
