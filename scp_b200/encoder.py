@@ -58,6 +58,7 @@ class Encoder:
         self.lib = _lib.require_device()
         self.pool = ThreadPoolExecutor(coder_threads or min(32, os.cpu_count() or 1))
         self.timings = {}
+        self._pin, self._pin_i = {}, {}
 
     # -- stage 1: octrees ---------------------------------------------------------------------
     def _jobs(self, n_frames):
@@ -159,14 +160,10 @@ class Encoder:
         return interval
 
     # -- public API ---------------------------------------------------------------------------
-    @torch.no_grad()
-    def encode_device(self, xyz, frame_offsets):
-        """xyz: CUDA float32 (n,3|4); returns (interval tensor int32 [N,2] in coding order on the device,
-        per-frame (row_start, n_rows), job infos)."""
-        b, t, per_frame = self.build_context(xyz, frame_offsets)
+    def _encode_from_context(self, b, t, per_frame, dev):
         infos = b.infos
         N = b.total_rows
-        interval_row = torch.empty((N, 2), dtype=torch.int32, device=xyz.device)
+        interval_row = torch.empty((N, 2), dtype=torch.int32, device=dev)
         if self.is_ehem:
             self._ehem_logits_to_intervals(t, infos, interval_row)
             sizes, restart = [], []
@@ -182,33 +179,94 @@ class Encoder:
             self._octattn_logits_to_intervals(t, infos, per_frame, interval_row)
             interval = interval_row                              # OctAttention codes in BFS order (encode.py:67-69)
         frames = []
-        for f in range(len(frame_offsets) - 1):
+        for f in range(len(infos) // per_frame):
             fi = infos[f * per_frame:(f + 1) * per_frame]
             frames.append((fi[0].row_start, sum(i.n_rows for i in fi)))
-        return interval, frames, infos, per_frame
+        return interval, frames
 
     @torch.no_grad()
-    def encode(self, frames_xyz: List[np.ndarray]) -> List[FrameResult]:
-        """frames_xyz: list of host float32 (n,3|4) arrays (KITTI .bin rows).  Returns one FrameResult per frame."""
+    def encode_device(self, xyz, frame_offsets):
+        """xyz: CUDA float32 (n,3|4); returns (interval tensor int32 [N,2] in coding order on the device,
+        per-frame (row_start, n_rows), job infos)."""
+        b, t, per_frame = self.build_context(xyz, frame_offsets)
+        interval, frames = self._encode_from_context(b, t, per_frame, xyz.device)
+        return interval, frames, b.infos, per_frame
+
+    # -- host-side pipeline -----------------------------------------------------------------
+    def _pinned(self, kind, shape, dtype):
+        """Rotating pinned host buffers (three per kind): pinning a fresh 4-8 MB array per batch costs milliseconds."""
+        ring = self._pin.setdefault(kind, [])
+        n = int(np.prod(shape))
+        slot = self._pin_i.get(kind, 0)
+        self._pin_i[kind] = (slot + 1) % 3
+        if len(ring) <= slot:
+            ring.append(None)
+        if ring[slot] is None or ring[slot].numel() < n or ring[slot].dtype != dtype:
+            ring[slot] = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+        return ring[slot][:n].view(shape)
+
+    def _gpu_stage(self, frames_xyz):
+        """Enqueues everything a batch needs on the GPU (H2D, octree, entropy model, intervals, D2H) and returns a handle;
+        only the octree planning synchronises (the window layout is needed on the host)."""
         offs = np.concatenate([[0], np.cumsum([len(f) for f in frames_xyz])]).astype(np.int64)
-        host = torch.from_numpy(np.ascontiguousarray(np.concatenate(frames_xyz, 0), dtype=np.float32))
-        if not host.is_pinned():
-            host = host.pin_memory()
+        cols = frames_xyz[0].shape[1]
+        host = self._pinned("xyz", (int(offs[-1]), cols), torch.float32)
+        hn = host.numpy()
+        for f, a, b in zip(frames_xyz, offs[:-1], offs[1:]):
+            hn[a:b] = f
         xyz = host.cuda(non_blocking=True)
-        interval, frames, infos, per_frame = self.encode_device(xyz, offs)
-        iv = torch.empty(interval.shape, dtype=torch.int32).pin_memory()
-        iv.copy_(interval, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        _lib.check(self.lib.scp_octree_finish(self.builder.h, _lib.stream_ptr()), "scp_octree_finish")
+        b, t, per_frame = self.build_context(xyz, offs)
+        _lib.check(self.lib.scp_octree_finish(self.builder.h, _lib.stream_ptr()), "scp_octree_finish")   # level min/max: final after emit
         self.builder._read_infos()
-        infos = self.builder.infos
-        ivn = iv.numpy().view(np.uint32)
-        streams = list(self.pool.map(lambda fr: coder.range_encode(ivn[fr[0]:fr[0] + fr[1]]), frames))
+        infos = list(self.builder.infos)
+        interval, frames = self._encode_from_context(b, t, per_frame, xyz.device)
+        iv = self._pinned("iv", tuple(interval.shape), torch.int32)
+        iv.copy_(interval, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        return {"offs": offs, "infos": infos, "per_frame": per_frame, "frames": frames, "iv": iv, "done": done,
+                "keep": (xyz, interval, t)}
+
+    def _launch_coder(self, st):
+        st["done"].synchronize()
+        ivn = st["iv"].numpy().view(np.uint32)
+        st["futures"] = [self.pool.submit(coder.range_encode, ivn[r0:r0 + n]) for r0, n in st["frames"]]
+        st["keep"] = None
+        return st
+
+    def _collect(self, st):
         out = []
-        for f, ((r0, n), bs) in enumerate(zip(frames, streams)):
+        offs, infos, per_frame = st["offs"], st["infos"], st["per_frame"]
+        for f, ((r0, n), fut) in enumerate(zip(st["frames"], st["futures"])):
+            bs = fut.result()
             fi = infos[f * per_frame:(f + 1) * per_frame]
             npts = int(offs[f + 1] - offs[f])
             out.append(FrameResult(npts, n, sum(len(i.level_rows) for i in fi), int(fi[0].bin_num),
                                    float(fi[0].offset[2]), bs, 8.0 * len(bs) / npts,
                                    [p for i in fi for p in i.pos_mm]))
         return out
+
+    @torch.no_grad()
+    def encode(self, frames_xyz: List[np.ndarray]) -> List[FrameResult]:
+        """frames_xyz: list of host float32 (n,3|4) arrays (KITTI .bin rows).  Returns one FrameResult per frame."""
+        return self._collect(self._launch_coder(self._gpu_stage(frames_xyz)))
+
+    @torch.no_grad()
+    def encode_stream(self, batches):
+        """Generator: ``batches`` yields lists of host frames; yields the list of FrameResult of each batch, in order.
+        Pipelined over batches: while the GPU encodes batch i+1, the host range coder (one thread per frame, the GIL is
+        released inside the C call) writes the bitstreams of batch i, so throughput is bound by the GPU alone."""
+        staged, coding = None, None
+        for frames_xyz in batches:
+            cur = self._gpu_stage(frames_xyz)          # its octree sync also waits for the previous batch's GPU work
+            if staged is not None:
+                if coding is not None:
+                    yield self._collect(coding)
+                coding = self._launch_coder(staged)
+            staged = cur
+        if staged is not None:
+            if coding is not None:
+                yield self._collect(coding)
+            coding = self._launch_coder(staged)
+        if coding is not None:
+            yield self._collect(coding)

@@ -62,3 +62,21 @@ def test_octattention_encode_runs_and_codes_all_nodes():
     pts = synth.make_frame("kitti", 5, 12, "spher", guard=True, n_points=3000)[0]
     r = enc.encode([pts])[0]
     assert r.n_nodes > 1000 and len(r.bitstream) > 100
+
+
+def test_encode_stream_equals_encode():
+    """The pipelined generator returns, batch by batch, exactly what encode() returns."""
+    from scp_b200.encoder import Encoder
+    from scp_b200.models import EHEM
+    from scp_b200 import synth
+    model = EHEM(cfg_ehem()).cuda()
+    enc = Encoder(model, 12, "spher", mullevel=False)
+    batches = [[synth.make_frame("kitti", seed=s, level=12, mode="spher", guard=True, n_points=2500)[0] for s in (b, b + 10)]
+               for b in range(4)]
+    ref = [enc.encode(b) for b in batches]
+    got = list(enc.encode_stream(iter(batches)))
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        assert [x.bitstream for x in g] == [x.bitstream for x in r]
+        assert [x.n_nodes for x in g] == [x.n_nodes for x in r]
+        assert [x.pos_mm for x in g] == [x.pos_mm for x in r]
