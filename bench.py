@@ -204,8 +204,9 @@ def run_ours(args):
     prof_ms = p0.elapsed_time(p1)
     prof, model.ops.prof = model.ops.prof, None
 
-    # octree / gather kernels alone on a batch large enough to fill the GPU (64 frames = 192 jobs, > L2)
-    OB = 64
+    # octree / gather kernels alone on a batch large enough to fill the GPU (256 frames = 768 jobs, >> L2; SURVEY 8d:
+    # "measure on batches of >= 100 frames per launch" -- one frame is 1.4 MB of points)
+    OB = 256
     big = torch.cat([xyz] * (OB // F + 1))[: 0 + sum(len(f) for f in frames) * (OB // F)] if F <= OB else xyz
     reps = OB // F if F <= OB else 1
     boffs = np.concatenate([[0], np.cumsum([len(f) for f in frames] * reps)]).astype(np.int64)

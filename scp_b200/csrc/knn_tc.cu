@@ -12,7 +12,7 @@
 //     shared-memory port;
 //   * candidate tiles of 64 rows stream through a 6-stage TMA ring; the 128 x 64 score tile accumulates in TMEM (2 stages);
 //   * the epilogue warps (lane = query row) read the scores back with tcgen05.ld and keep, per row, a MIN-HEAP of the
-//     kc = k + 8 best candidates in shared memory ([entry][lane], conflict-free).  The heap root is the row's exact
+//     kc = k + 8 best candidates in shared memory (4-ary, [entry][lane], conflict-free).  The heap root is the row's exact
 //     running threshold, so a row accepts only ~kc (1 + ln(n / kc)) candidates over the whole scan and an accept costs
 //     one sift-down (<= 5 levels).  (Earlier versions appended hits to per-row lists in global memory and compacted
 //     them with a warp-wide radix select: 70 % of the kernel time went into those scattered 4-byte stores.)
@@ -271,16 +271,21 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                             if (!(v > th)) continue;                       // the threshold moved since the mask was built
                             const int vid = c0 + cb + j;
                             int i = 0;                                     // replace the root (the row's kc-th best) and sift down
-                            for (;;) {
-                                const int lc = 2 * i + 1;
-                                if (lc >= kc) break;
-                                const float2 el = hq[32 * lc];
-                                const float2 er = lc + 1 < kc ? hq[32 * (lc + 1)] : make_float2(INFINITY, 0.f);
-                                const bool right = er.x < el.x;
-                                const float2 em = right ? er : el;
+                            for (;;) {                                     // 4-ary heap: 3 levels for kc <= 32, the four child
+                                const int c0 = 4 * i + 1;                  // loads of a level are independent (one smem latency)
+                                if (c0 >= kc) break;
+                                const float2 inf2 = make_float2(INFINITY, 0.f);
+                                const float2 e0 = hq[32 * c0];
+                                const float2 e1 = c0 + 1 < kc ? hq[32 * (c0 + 1)] : inf2;
+                                const float2 e2 = c0 + 2 < kc ? hq[32 * (c0 + 2)] : inf2;
+                                const float2 e3 = c0 + 3 < kc ? hq[32 * (c0 + 3)] : inf2;
+                                const bool b01 = e1.x < e0.x, b23 = e3.x < e2.x;
+                                const float2 m01 = b01 ? e1 : e0, m23 = b23 ? e3 : e2;
+                                const bool bm = m23.x < m01.x;
+                                const float2 em = bm ? m23 : m01;
                                 if (!(em.x < v)) break;
                                 hq[32 * i] = em;
-                                i = right ? lc + 1 : lc;
+                                i = c0 + (bm ? (b23 ? 3 : 2) : (b01 ? 1 : 0));
                             }
                             hq[32 * i] = make_float2(v, __int_as_float(vid));
                             th = hq[0].x;

@@ -51,6 +51,7 @@ struct JobDev {
     u32 qmax;
     u32 overflow;
     int depth;
+    int n_kept;                  // keys that take part in the sort (after the morton_path filter); = n_points without a filter
     int n_voxels, n_nodes, n_rows;
     int level_count[MAXL + 1];   // nodes on level L at [L-1]
     int level_start[MAXL + 2];   // node offset of level L inside the job at [L-1]
@@ -126,7 +127,7 @@ __global__ void k_job_setup(JobDev* jobs, int n_jobs, const FrameDev* fr, int mo
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     JobDev& J = jobs[j];
-    J.qmax = 0; J.overflow = 0; J.depth = 0;
+    J.qmax = 0; J.overflow = 0; J.depth = 0; J.n_kept = J.n_points;
     for (int l = 0; l <= MAXL; ++l) { J.pos_min[l] = 0xffffffffu; J.pos_max[l] = 0u; }
     if (mode == SCP_MODE_CART) {
         J.bin_num = 0.f;
@@ -353,6 +354,79 @@ __global__ void __launch_bounds__(TPB) k_sort_hist(u64* __restrict__ keys, const
         if (sh[i]) atomicAdd(&h[i], sh[i]);
 }
 
+// morton_path filter of Octree.py:188 as a stream compaction in front of the sort (mullevel: each of the three jobs of a
+// frame keeps a third of the points on average, so sorting the rejected keys as sentinels tripled the sort's traffic):
+//   k_filter_count  kept keys per sort tile            k_kept_scan   per-job exclusive scan, n_kept
+//   k_compact_hist  kept keys -> dense prefix of `out` (order inside a tile preserved) + the digit histograms of the sort
+__device__ __forceinline__ bool path_keep(u64 k, int n, int plen, int pbits) {
+    bool keep = true;
+    for (int j = 0; j < plen; ++j) {
+        const int b = n - 1 - j;
+        const int bit = b >= 0 ? (int)((k >> (3 * b + 2)) & 1) : 0;
+        keep &= (bit == ((pbits >> j) & 1));
+    }
+    return keep;
+}
+
+__global__ void __launch_bounds__(TPB) k_filter_count(const u64* __restrict__ keys, const Tile* __restrict__ tiles,
+                                                       const JobDev* __restrict__ jobs, u32* __restrict__ tile_kept) {
+    __shared__ u32 s_cnt;
+    const Tile t = tiles[blockIdx.x];
+    const JobDev& J = jobs[t.job];
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const u64* src = keys + J.key_begin + t.begin;
+    u32 c = 0;
+    for (int i = threadIdx.x; i < t.count; i += TPB) c += path_keep(src[i], J.depth, J.path_len, J.path_bits) ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_kept[blockIdx.x] = s_cnt;
+}
+
+__global__ void k_kept_scan(JobDev* jobs, const int* __restrict__ job_tile_begin, u32* tile_kept /* in: counts, out: offsets */) {
+    if (threadIdx.x) return;
+    JobDev& J = jobs[blockIdx.x];
+    u32 run = 0;
+    for (int t = job_tile_begin[blockIdx.x]; t < job_tile_begin[blockIdx.x + 1]; ++t) { const u32 c = tile_kept[t]; tile_kept[t] = run; run += c; }
+    J.n_kept = (int)run;
+}
+
+__global__ void __launch_bounds__(TPB) k_compact_hist(const u64* __restrict__ in, u64* __restrict__ out,
+                                                       const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+                                                       const u32* __restrict__ tile_off, u32* __restrict__ hist, int P) {
+    __shared__ u32 sh[8 * 256];
+    __shared__ u32 s_wbase[8];
+    const Tile t = tiles[blockIdx.x];
+    const JobDev& J = jobs[t.job];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < P * 256; i += TPB) sh[i] = 0;
+    const u64* src = in + J.key_begin + t.begin;
+    u64* dst = out + J.key_begin + tile_off[blockIdx.x];
+    u32 base = 0;                                        // kept keys of the tile written so far
+    for (int i0 = 0; i0 < t.count; i0 += TPB) {
+        __syncthreads();
+        const int i = i0 + threadIdx.x;
+        u64 k = 0;
+        bool keep = false;
+        if (i < t.count) { k = src[i]; keep = path_keep(k, J.depth, J.path_len, J.path_bits); }
+        const u32 bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_wbase[warp] = __popc(bal);
+        __syncthreads();
+        u32 wb = 0, tot = 0;
+        for (int w = 0; w < 8; ++w) { const u32 c = s_wbase[w]; if (w < warp) wb += c; tot += c; }
+        if (keep) {
+            dst[base + wb + __popc(bal & ((1u << lane) - 1u))] = k;
+            for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + (u32)((k >> (8 * p)) & 0xff)], 1u);
+        }
+        base += tot;
+    }
+    __syncthreads();
+    u32* h = hist + (size_t)t.job * P * 256;
+    for (int i = threadIdx.x; i < P * 256; i += TPB)
+        if (sh[i]) atomicAdd(&h[i], sh[i]);
+}
+
 __global__ void __launch_bounds__(256) k_scan_hist(u32* hist) {   // one block per (job, pass): exclusive scan of 256 bins
     __shared__ u32 ws[8];
     u32* h = hist + (size_t)blockIdx.x * 256;
@@ -383,8 +457,10 @@ __global__ void __launch_bounds__(TPB) k_onesweep(const u64* __restrict__ in, u6
     __syncthreads();
     const int t = s_tile;
     if (t >= n_tiles) return;
-    const Tile tl = tiles[t];
+    Tile tl = tiles[t];
     const JobDev& J = jobs[tl.job];
+    tl.count = min(tl.count, J.n_kept - tl.begin);       // compacted jobs: the tail tiles are empty and nobody looks back at them
+    if (tl.count <= 0) return;
     const u64* src = in + J.key_begin + tl.begin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int shift = pass * 8;
@@ -476,12 +552,12 @@ __global__ void __launch_bounds__(TPB) k_head_hist(const u64* __restrict__ keys,
     __syncthreads();
     const u64* src = keys + J.key_begin;
     const int n = J.depth;
-    // sorted keys: once a tile starts with the sentinel (filtered / padding keys sort last) it holds nothing but sentinels
-    const bool dead = src[t.begin] == SENTINEL;
-    for (int i0 = 0; i0 < (dead ? 0 : t.count); i0 += TPB) {
+    // keys past n_kept were filtered out before the sort (tail tiles are empty)
+    const int cnt = min(t.count, J.n_kept - t.begin);
+    for (int i0 = 0; i0 < cnt; i0 += TPB) {
         int i = i0 + threadIdx.x;
         int h = 0;
-        if (i < t.count) {
+        if (i < cnt) {
             int g = t.begin + i;
             u64 k = src[g];
             u64 prev = g > 0 ? src[g - 1] : 0ull;
@@ -571,12 +647,13 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
     const long long node0 = J.node_start;
     const int n_vox = J.n_voxels;
     u32 cmin = 0xffffffffu, cmax = 0u, emin = 0xffffffffu, emax = 0u;
-    if (src[t.begin] == SENTINEL) return;                      // block-uniform: a tile of filtered keys opens no node
-    for (int i0 = 0; i0 < t.count; i0 += TPB) {
+    const int cnt = min(t.count, J.n_kept - t.begin);          // keys past n_kept were filtered out before the sort
+    if (cnt <= 0) return;                                      // block-uniform
+    for (int i0 = 0; i0 < cnt; i0 += TPB) {
         const int i = i0 + threadIdx.x;
         int h = 0;
         u64 k = 0;
-        if (i < t.count) {
+        if (i < cnt) {
             int g = t.begin + i;
             k = src[g];
             u64 prev = g > 0 ? src[g - 1] : 0ull;
@@ -809,17 +886,20 @@ static void build_tiles(const std::vector<long long>& counts, int tile, std::vec
     if (job_begin) job_begin->push_back((int)out.size());
 }
 
+// keys -> sorted (ping-pong with tmp).  hist_ready: the digit histograms were already produced (k_compact_hist).
 static int run_sort(u64* keys, u64* tmp, const Tile* d_tiles, int n_tiles, const JobDev* d_jobs, int n_jobs, int P,
-                    int apply_filter, DevBuf& hist, DevBuf& desc, DevBuf& misc, cudaStream_t st, u64** result) {
+                    bool hist_ready, DevBuf& hist, DevBuf& desc, DevBuf& misc, cudaStream_t st, u64** result) {
     if (P <= 0 || n_tiles == 0) { *result = keys; return SCP_OK; }
-    if (int e = hist.reserve((size_t)n_jobs * P * 256 * 4)) return e;
     if (int e = desc.reserve((size_t)P * n_tiles * 256 * 4)) return e;
     if (int e = misc.reserve(64 * 4)) return e;
-    SCP_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)n_jobs * P * 256 * 4, st));
     SCP_CUDA(cudaMemsetAsync(desc.p, 0, (size_t)P * n_tiles * 256 * 4, st));
     SCP_CUDA(cudaMemsetAsync(misc.p, 0, 64 * 4, st));
-    k_sort_hist<<<n_tiles, TPB, 0, st>>>(keys, d_tiles, d_jobs, hist.as<u32>(), P, apply_filter);
-    SCP_LAUNCHED();
+    if (!hist_ready) {
+        if (int e = hist.reserve((size_t)n_jobs * P * 256 * 4)) return e;
+        SCP_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)n_jobs * P * 256 * 4, st));
+        k_sort_hist<<<n_tiles, TPB, 0, st>>>(keys, d_tiles, d_jobs, hist.as<u32>(), P, 0);
+        SCP_LAUNCHED();
+    }
     k_scan_hist<<<n_jobs * P, 256, 0, st>>>(hist.as<u32>());
     SCP_LAUNCHED();
     u64* a = keys; u64* b = tmp;
@@ -953,8 +1033,31 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     }
     SCP_REQUIRE(max_depth >= 1 && max_depth <= MAXL, "octree depth %d outside [1,%d]", max_depth, MAXL);
     t->P = (3 * max_depth + 1 + 7) / 8;
-    if (int e = run_sort(t->keys_a.as<u64>(), t->keys_b.as<u64>(), t->tiles_sort.as<Tile>(), nt_s, d_jobs, n_jobs, t->P,
-                         any_filter, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
+    if (any_filter) {
+        // jobs with a morton_path (mullevel): drop the rejected keys before sorting
+        std::vector<int> stb;
+        { std::vector<Tile> tmp_tiles; build_tiles(jcount, SORT_TILE, tmp_tiles, &stb); }
+        int* d_stb = nullptr;
+        u32* d_kept = nullptr;
+        SCP_CUDA(upload_async((void**)&d_stb, stb.data(), stb.size() * 4, st));
+        SCP_CUDA(malloc_async((void**)&d_kept, (size_t)(nt_s + 1) * 4, st));
+        if (int e = t->hist.reserve((size_t)n_jobs * t->P * 256 * 4)) return e;
+        SCP_CUDA(cudaMemsetAsync(t->hist.p, 0, (size_t)n_jobs * t->P * 256 * 4, st));
+        k_filter_count<<<nt_s, TPB, 0, st>>>(t->keys_a.as<u64>(), t->tiles_sort.as<Tile>(), d_jobs, d_kept);
+        SCP_LAUNCHED();
+        k_kept_scan<<<n_jobs, 32, 0, st>>>(d_jobs, d_stb, d_kept);
+        SCP_LAUNCHED();
+        k_compact_hist<<<nt_s, TPB, 0, st>>>(t->keys_a.as<u64>(), t->keys_b.as<u64>(), t->tiles_sort.as<Tile>(), d_jobs, d_kept,
+                                             t->hist.as<u32>(), t->P);
+        SCP_LAUNCHED();
+        SCP_CUDA(cudaFreeAsync(d_stb, st));
+        SCP_CUDA(cudaFreeAsync(d_kept, st));
+        if (int e = run_sort(t->keys_b.as<u64>(), t->keys_a.as<u64>(), t->tiles_sort.as<Tile>(), nt_s, d_jobs, n_jobs, t->P,
+                             true, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
+    } else {
+        if (int e = run_sort(t->keys_a.as<u64>(), t->keys_b.as<u64>(), t->tiles_sort.as<Tile>(), nt_s, d_jobs, n_jobs, t->P,
+                             false, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
+    }
     SCP_CUDA(cudaEventRecord(t->ev[2], st));
     k_head_hist<<<nt_p, TPB, 0, st>>>(t->sorted, d_ptiles, d_jobs, t->tile_hist.as<u32>());
     SCP_LAUNCHED();
@@ -1065,6 +1168,7 @@ int scp_segmented_sort_u64(uint64_t* d_keys, uint64_t* d_tmp, const int64_t* h_s
         jobs[j].key_begin = h_seg_offsets[j];
         cnt[j] = h_seg_offsets[j + 1] - h_seg_offsets[j];
         jobs[j].n_points = (int)cnt[j];
+        jobs[j].n_kept = (int)cnt[j];
     }
     std::vector<Tile> tiles;
     build_tiles(cnt, SORT_TILE, tiles, nullptr);
@@ -1079,7 +1183,7 @@ int scp_segmented_sort_u64(uint64_t* d_keys, uint64_t* d_tmp, const int64_t* h_s
             cudaMemcpyAsync(dt.p, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st) != cudaSuccess) {
             set_error("scp_segmented_sort_u64: upload failed"); rc = SCP_ERR_CUDA; break;
         }
-        rc = run_sort((u64*)d_keys, (u64*)d_tmp, dt.as<Tile>(), (int)tiles.size(), dj.as<JobDev>(), n_seg, P, 0, hist, desc,
+        rc = run_sort((u64*)d_keys, (u64*)d_tmp, dt.as<Tile>(), (int)tiles.size(), dj.as<JobDev>(), n_seg, P, false, hist, desc,
                       misc, st, &res);
         if (rc) break;
         long long total = h_seg_offsets[n_seg] - h_seg_offsets[0];

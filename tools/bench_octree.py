@@ -42,5 +42,6 @@ def main(n_frames=64, level=16, mul=False, mode="spher"):
 if __name__ == "__main__":
     main(64, 16, False)
     main(64, 16, True)
-    main(64, 12, False)
-    main(8, 16, False)
+    main(256, 16, True)
+    main(256, 16, False)
+    main(256, 14, False, "cylin")
