@@ -217,6 +217,8 @@ def run_ours(args):
         m = enc.builder.stage_ms()
         octree_ms = m if octree_ms is None else {k: min(octree_ms[k], v) for k, v in m.items()}
     o_pts = int(boffs[-1]) * 3
+    o_kept = bb.total_kept
+    o_bytes = bb.stage_bytes()
     o_nodes = bb.total_rows
     o_depth = max(i.depth for i in bb.infos)
     del big, tt_
@@ -274,9 +276,7 @@ def run_ours(args):
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[3] // args.steps,
                    "TFLOPs": v[1] / v[0] / 1e9 if v[0] else None, "GBps": v[2] / v[0] / 1e6 if v[0] else None}
                for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
-    P = (3 * o_depth + 1 + 7) // 8
-    bm = {"quantise": 20 * o_pts, "sort": (1 + 2 * P) * 8 * o_pts, "heads": 8 * o_pts, "emit": 28 * o_nodes,
-          "occupancy": 6 * o_nodes, "context": 60 * o_nodes}
+    bm = o_bytes          # OctreeBuilder.stage_bytes(): SURVEY 8d figures x the units each stage really processes
     oct_rep = {k: {"ms": round(v, 4), "GBps": round(bm[k] / v / 1e6, 1) if v > 0 else None,
                    "frac_of_hbm_peak": round(bm[k] / v / 1e6 / hbm_peak, 3) if v > 0 else None} for k, v in octree_ms.items()}
 
@@ -297,7 +297,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
         "kernels": kernels,
-        "octree_stages": {"batch_frames": reps * F, "points": o_pts, "nodes": o_nodes, "stages": oct_rep},
+        "octree_stages": {"batch_frames": reps * F, "point_job_pairs": o_pts, "sorted_keys": o_kept, "nodes": o_nodes,
+                          "algorithmic_bytes": o_bytes, "stages": oct_rep},
         "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
                          "sample": cpu_desc},
     }

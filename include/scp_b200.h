@@ -101,6 +101,8 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride,
 int     scp_octree_job_info(const scp_octree* t, int job, scp_job_info* out);
 int64_t scp_octree_total_rows(const scp_octree* t);
 int64_t scp_octree_total_voxels(const scp_octree* t);
+/* keys that took part in the sort (points that passed the morton_path filter, summed over the jobs) */
+int64_t scp_octree_total_kept(const scp_octree* t);
 /* Phase 2: node records, occupancy, K=4 ancestor context, level-wise normalised positions. Asynchronous. */
 int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream);
 /* After emit + stream sync: fills pos_min/pos_max of every job_info. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "scp_octree_job_info": (_i, [_vp, _i, C.POINTER(JobInfo)]),
     "scp_octree_total_rows": (_i64, [_vp]),
     "scp_octree_total_voxels": (_i64, [_vp]),
+    "scp_octree_total_kept": (_i64, [_vp]),
     "scp_octree_emit": (_i, [_vp, C.POINTER(OctreeOut), _vp]),
     "scp_octree_finish": (_i, [_vp, _vp]),
     "scp_octree_stage_ms": (_i, [_vp, C.POINTER(_f * 6)]),

@@ -20,12 +20,15 @@
 #include <vector>
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace scp {
 
 constexpr int TPB = 256;
 constexpr int TILE = 2048;            // elements per tile for the streaming kernels
+constexpr int NODE_TILE = 8192;       // nodes per tile of k_occupancy / k_context: the per-tile prologue (tile -> job -> level
+                                      // tables, a dependent chain of global loads) is amortised over 8 rounds per thread
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = TPB * SORT_ITEMS;   // 4096 keys
 constexpr int NBINS = 24;             // head-level histogram bins (0 = not a new voxel, 1..22)
@@ -81,6 +84,7 @@ __host__ __device__ __forceinline__ u32 compact3(u64 x) {
     x = (x ^ (x >> 32)) & 0x1fffffull;
     return (u32)x;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ u32 enc_ordered(float f) {
     u32 b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -543,28 +547,48 @@ __device__ __forceinline__ int head_level(u64 k, u64 prev, bool first, int n) {
     return n - hb / 3 + 1;      // d = n-1-hb/3
 }
 
+// A warp owns WKEYS consecutive sorted keys of the tile, 32 at a time: lane l holds key 32*it + l of the warp's run, its
+// predecessor comes from lane l-1 by shuffle (one extra global load per warp, for the key in front of the run).
+constexpr int WITER = TILE / TPB;            // 8 rounds of 32 keys per warp
+constexpr int WKEYS = 32 * WITER;            // 256
+__device__ __forceinline__ void load_heads(const u64* __restrict__ src, int tbegin, int cnt, int warp, int lane, int n,
+                                           u64 (&k)[WITER], int (&h)[WITER]) {
+    const int wbeg = warp * WKEYS;
+#pragma unroll
+    for (int it = 0; it < WITER; ++it) {
+        const int idx = wbeg + it * 32 + lane;
+        k[it] = idx < cnt ? __ldg(src + tbegin + idx) : SENTINEL;
+    }
+    const int g0 = tbegin + wbeg;
+    u64 carry = (lane == 0 && g0 > 0 && wbeg < cnt) ? __ldg(src + g0 - 1) : 0ull;
+#pragma unroll
+    for (int it = 0; it < WITER; ++it) {
+        u64 prev = __shfl_up_sync(0xffffffffu, k[it], 1);
+        if (lane == 0) prev = carry;
+        h[it] = head_level(k[it], prev, g0 + it * 32 + lane == 0, n);
+        carry = __shfl_sync(0xffffffffu, k[it], 31);
+    }
+}
+
 __global__ void __launch_bounds__(TPB) k_head_hist(const u64* __restrict__ keys, const Tile* __restrict__ tiles,
                                                     const JobDev* __restrict__ jobs, u32* __restrict__ tile_hist) {
     __shared__ u32 sh[NBINS];
-    Tile t = tiles[blockIdx.x];
+    const Tile t = tiles[blockIdx.x];
     const JobDev& J = jobs[t.job];
     if (threadIdx.x < NBINS) sh[threadIdx.x] = 0;
     __syncthreads();
-    const u64* src = keys + J.key_begin;
-    const int n = J.depth;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // keys past n_kept were filtered out before the sort (tail tiles are empty)
     const int cnt = min(t.count, J.n_kept - t.begin);
-    for (int i0 = 0; i0 < cnt; i0 += TPB) {
-        int i = i0 + threadIdx.x;
-        int h = 0;
-        if (i < cnt) {
-            int g = t.begin + i;
-            u64 k = src[g];
-            u64 prev = g > 0 ? src[g - 1] : 0ull;
-            h = head_level(k, prev, g == 0, n);
+    if (cnt > 0) {
+        u64 k[WITER];
+        int h[WITER];
+        load_heads(keys + J.key_begin, t.begin, cnt, warp, lane, J.depth, k, h);
+#pragma unroll
+        for (int it = 0; it < WITER; ++it) {
+            const u32 peers = __match_any_sync(0xffffffffu, h[it]);
+            if (h[it] > 0 && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sh[h[it]], (u32)__popc(peers));
         }
-        u32 peers = __match_any_sync(0xffffffffu, h);
-        if (h > 0 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&sh[h], (u32)__popc(peers));
     }
     __syncthreads();
     if (threadIdx.x < NBINS) tile_hist[(size_t)blockIdx.x * NBINS + threadIdx.x] = sh[threadIdx.x];
@@ -579,7 +603,16 @@ __global__ void k_level_scan(JobDev* jobs, int n_jobs, const int* __restrict__ j
     int b = threadIdx.x;
     u32 run = 0;
     if (b < NBINS) {
-        for (int t = job_tile_begin[j]; t < job_tile_begin[j + 1]; ++t) {
+        const int t0 = job_tile_begin[j], t1 = job_tile_begin[j + 1];
+        int t = t0;
+        for (; t + 4 <= t1; t += 4) {                   // four independent loads in flight
+            u32 c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = tile_hist[(size_t)(t + q) * NBINS + b];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { tile_hist[(size_t)(t + q) * NBINS + b] = run; run += c[q]; }
+        }
+        for (; t < t1; ++t) {
             u32 c = tile_hist[(size_t)t * NBINS + b];
             tile_hist[(size_t)t * NBINS + b] = run;
             run += c;
@@ -605,10 +638,26 @@ __global__ void k_level_scan(JobDev* jobs, int n_jobs, const int* __restrict__ j
     }
 }
 
-__global__ void k_job_offsets(JobDev* jobs, int n_jobs) {
-    if (threadIdx.x || blockIdx.x) return;
-    long long node = 0, row = 0, vox = 0;
-    for (int j = 0; j < n_jobs; ++j) {
+// exclusive scan of (n_nodes, n_rows, n_voxels) over the jobs: one block, each thread a contiguous run of jobs
+__global__ void __launch_bounds__(1024) k_job_offsets(JobDev* jobs, int n_jobs) {
+    __shared__ long long s[3][1024];
+    const int per = (n_jobs + 1023) / 1024;
+    const int j0 = min(n_jobs, (int)threadIdx.x * per), j1 = min(n_jobs, j0 + per);
+    long long a[3] = {0, 0, 0};
+    for (int j = j0; j < j1; ++j) { a[0] += jobs[j].n_nodes; a[1] += jobs[j].n_rows; a[2] += jobs[j].n_voxels; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s[c][threadIdx.x] = a[c];
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        long long v[3] = {0, 0, 0};
+        if ((int)threadIdx.x >= o)
+            for (int c = 0; c < 3; ++c) v[c] = s[c][threadIdx.x - o];
+        __syncthreads();
+        for (int c = 0; c < 3; ++c) s[c][threadIdx.x] += v[c];
+        __syncthreads();
+    }
+    long long node = s[0][threadIdx.x] - a[0], row = s[1][threadIdx.x] - a[1], vox = s[2][threadIdx.x] - a[2];
+    for (int j = j0; j < j1; ++j) {
         jobs[j].node_start = node; jobs[j].row_start = row; jobs[j].vox_start = vox;
         node += jobs[j].n_nodes; row += jobs[j].n_rows; vox += jobs[j].n_voxels;
     }
@@ -617,10 +666,15 @@ __global__ void k_job_offsets(JobDev* jobs, int n_jobs) {
 // ------------------------------------------------------------------------------------------
 // K6: node records for all levels in one pass
 // ------------------------------------------------------------------------------------------
+// Internal node records, structure of arrays (BFS order inside a job): 23 B/node + 1 B/voxel
 struct NodeArrays {
-    uint8_t* level; uint8_t* octant; uint8_t* occ; u32* parent; u32* pos; u32* fc;
+    uint8_t* level; uint8_t* octant; uint8_t* occ; u32* parent; u32* px; u32* py; u32* pz; u32* fc;
+    uint8_t* vdig;              // per voxel: child digit + 1 inside its level-n node (the "octant" of the voxel)
 };
 
+// One block iteration handles 256 consecutive sorted keys: per level one ballot per warp gives the rank of every head inside
+// the warp, a 22-entry scan over the 8 warps gives the rank inside the block.  Only levels >= the smallest head level of
+// the warp are visited (consecutive sorted keys share long prefixes: 3-4 levels out of up to 21).
 __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys, const Tile* __restrict__ tiles,
                                                      JobDev* jobs, const u32* __restrict__ tile_base,
                                                      NodeArrays A, u64* __restrict__ vox_key) {
@@ -636,7 +690,7 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
     if (threadIdx.x <= MAXL) {
         int L = threadIdx.x;       // L = 0: voxel counter
         u32 s = 0;
-        const u32* tb = tile_base + (size_t)blockIdx.x * NBINS;
+        const u32* tb = tile_base + (size_t)(t.first + t.begin / TILE) * NBINS;   // tiles may be a compacted list
         if (L == 0) { for (int h = 1; h < NBINS; ++h) s += tb[h]; }
         else if (L <= n) { for (int h = 1; h <= L; ++h) s += tb[h]; }
         s_base[L] = s;
@@ -658,6 +712,7 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
             k = src[g];
             u64 prev = g > 0 ? src[g - 1] : 0ull;
             h = head_level(k, prev, g == 0, n);
+            if (i + 2 * TPB < cnt) prefetch_l2(src + g + 2 * TPB);
         }
         const int hh = h == 0 ? 99 : h;
         // Only levels >= the smallest head level of the warp can open a node here: consecutive sorted keys share long
@@ -690,6 +745,7 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
         const u32 v = s_base[0] + s_wpre[warp][0] + rank[0];
         if (h > 0) {
             if (vox_key) vox_key[J.vox_start + v] = k;
+            A.vdig[J.vox_start + v] = (uint8_t)((k & 7) + 1);
             // x & m is monotone in x, so every level's min / max node coordinate follows from the voxel extremes
             const u32 lo = min(x, min(y, z)), hi = max(x, max(y, z));
             cmin = min(cmin, lo); cmax = max(cmax, hi);
@@ -712,7 +768,7 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
                 }
                 A.parent[r] = par;
                 const u32 m = ~((1u << (n - L + 1)) - 1u);
-                A.pos[3 * r] = x & m; A.pos[3 * r + 1] = y & m; A.pos[3 * r + 2] = z & m;
+                A.px[r] = x & m; A.py[r] = y & m; A.pz[r] = z & m;
                 A.fc[r] = (L < n) ? (u32)J.level_start[L] + s_base[L + 1] + s_wpre[warp][L + 1] + rank[L + 1] : v;
             }
         }
@@ -747,26 +803,47 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
 // ------------------------------------------------------------------------------------------
 // K7a: occupancy byte = OR over the node's children run           Octree.py:175-176
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
-                                                    NodeArrays A, const u64* __restrict__ vox_key) {
+// The <= 8 children of a node are consecutive bytes of `octant` (of `vdig` for the deepest level, whose children are the
+// voxels); two nodes per thread are in flight.
+constexpr int NPT = 4;
+__global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs, NodeArrays A) {
+    __shared__ int s_ls[MAXL + 2];
     const Tile t = tiles[blockIdx.x];
     const JobDev& J = jobs[t.job];
     const int n = J.depth;
-    for (int i = threadIdx.x; i < t.count; i += TPB) {
-        const int loc = t.begin + i;
-        const long long r = J.node_start + loc;
-        const int L = A.level[r];
-        const u32 c0 = A.fc[r];
-        const bool last_of_level = (loc + 1 == J.level_start[L]);    // level_start[L] = start of level L+1
-        u32 occ = 0;
-        if (L < n) {
-            const u32 c1 = last_of_level ? (u32)J.level_start[L + 1] : A.fc[r + 1];
-            for (u32 c = c0; c < c1; ++c) occ |= 1u << (A.octant[J.node_start + c] - 1);
-        } else {
-            const u32 c1 = last_of_level ? (u32)J.n_voxels : A.fc[r + 1];
-            for (u32 c = c0; c < c1; ++c) occ |= 1u << (u32)(vox_key[J.vox_start + c] & 7);
+    if (threadIdx.x <= MAXL + 1) s_ls[threadIdx.x] = J.level_start[threadIdx.x];
+    __syncthreads();
+    const uint8_t* __restrict__ lvl = A.level + J.node_start;
+    const u32* __restrict__ fc = A.fc + J.node_start;
+    const uint8_t* __restrict__ oct = A.octant + J.node_start;
+    const uint8_t* __restrict__ vd = A.vdig + J.vox_start;
+    uint8_t* __restrict__ out = A.occ + J.node_start;
+    const u32 n_vox = (u32)J.n_voxels;
+    for (int i0 = threadIdx.x; i0 < t.count; i0 += 2 * TPB) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {                           // next round's records into L2 (see k_context_lean)
+            const int i = i0 + (4 + u) * TPB;
+            if (i < t.count) { prefetch_l2(fc + t.begin + i); if ((threadIdx.x & 7) == 0) prefetch_l2(lvl + t.begin + i); }
         }
-        A.occ[r] = (uint8_t)occ;
+        int L[2];
+        u32 c0[2], c1[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * TPB;
+            L[u] = 0; c0[u] = c1[u] = 0;
+            if (i < t.count) { const int loc = t.begin + i; L[u] = lvl[loc]; c0[u] = fc[loc]; c1[u] = fc[loc + 1]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (L[u] == 0) continue;
+            const int loc = t.begin + i0 + u * TPB;
+            const bool leaf = (L[u] == n);
+            if (loc + 1 == s_ls[L[u]]) c1[u] = leaf ? n_vox : (u32)s_ls[L[u] + 1];       // level_start[L] = start of level L+1
+            const uint8_t* __restrict__ arr = leaf ? vd : oct;
+            u32 occ = 0;
+            for (u32 c = c0[u]; c < c1[u]; ++c) occ |= 1u << (arr[c] - 1);
+            out[loc] = (uint8_t)occ;
+        }
     }
 }
 
@@ -774,6 +851,163 @@ __global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tile
 // K7b: K=4 ancestor context + level-normalised positions (+ optional reference-layout expansion)
 //   Octree.py:102-137 gen_K_parent_seq ; encode_dataset_ehem.py:54,66-72,85-93
 // ------------------------------------------------------------------------------------------
+// float32((x - mn) / den) exactly as numpy computes it (float64 divide, then one rounding to float32) without the divide:
+// q' = (x - mn) * (1/den) is within 2 ulp(float64) of the correctly rounded quotient, so both round to the same float32
+// unless q' lies within a few ulp of the midpoint of two float32 values (low 29 mantissa bits = 0x10000000); only then
+// (probability 2^-25) the divide is executed -- out of line, so that its ~25 instructions are not if-converted into the
+// common path.  `thr` = 16, or 0xffffffff to force the divide (den == 0: single-cell level without the 1e-9).
+__device__ __noinline__ float norm_pos_exact(double d, double den) { return (float)(d / den); }
+__device__ __forceinline__ float norm_pos(u32 x, double mn, double den, double inv, u32 thr) {
+    const double d = (double)x - mn;
+    const double q = d * inv;
+    const u32 m = ((u32)__double2loint(q) + 0x10000008u) & 0x1fffffffu;     // <= 16  <=>  |low29 - 0x10000000| <= 8
+    if (m <= thr) return norm_pos_exact(d, den);
+    return (float)q;
+}
+
+// Lean variant for the encoder's outputs (occ, sym, ctx, pos_norm): own record + 3 dependent (parent, occupancy) gathers;
+// the ancestors' level, octant and cell origin are derived from the own record (an ancestor's cell is the own cell with
+// more low bits cleared, its octant is the coordinate bit triple of its level).  The kernel is instruction-issue bound
+// (ncu: ~300 instructions per node before this version), hence the bit tricks: all four octants from one 12-bit word,
+// byte permutes for the 12 context bytes, the divide out of line.  Four nodes per thread keep four gather chains in flight.
+__global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+                                                          NodeArrays A, scp_octree_out O) {
+    __shared__ double s_mn[MAXL + 1], s_den[MAXL + 1], s_inv[MAXL + 1];
+    __shared__ u32 s_thr[MAXL + 1];
+    __shared__ u32 s_stage[TPB / 32][2][96];
+    const Tile t = tiles[blockIdx.x];
+    const JobDev& J = jobs[t.job];
+    const int n = J.depth;
+    if (threadIdx.x >= 1 && threadIdx.x <= n) {
+        const int L = threadIdx.x;
+        const double den = (double)(J.pos_max[L - 1] - J.pos_min[L - 1]) + ((L == n && !J.pos_eps_last) ? 0.0 : 1e-9);
+        s_mn[L] = (double)J.pos_min[L - 1]; s_den[L] = den; s_inv[L] = 1.0 / den;
+        s_thr[L] = den > 0.0 ? 16u : 0xffffffffu;
+    }
+    __syncthreads();
+    const long long node0 = J.node_start, row0 = J.row_start;
+    const uint8_t* __restrict__ a_lvl = A.level + node0;
+    const uint8_t* __restrict__ a_occ = A.occ + node0;
+    const u32* __restrict__ a_par = A.parent + node0;
+    const u32* __restrict__ a_px = A.px + node0;
+    const u32* __restrict__ a_py = A.py + node0;
+    const u32* __restrict__ a_pz = A.pz + node0;
+    const int cnt = min(t.count, J.n_rows - t.begin);             // the dropped last row (Octree.py:259-262)
+    const int lidar_level = J.lidar_level;
+    const bool clip = n > lidar_level;                            // encode_dataset_ehem.py:86 can only bite then
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) {                                        // warm-up: round 1 (round 0 is loaded right away)
+        const int i = (int)threadIdx.x + (NPT + u) * TPB;
+        if (i < cnt) {
+            const int loc = t.begin + i;
+            prefetch_l2(a_par + loc); prefetch_l2(a_px + loc); prefetch_l2(a_py + loc); prefetch_l2(a_pz + loc);
+            if ((lane & 7) == 0) { prefetch_l2(a_lvl + loc); prefetch_l2(a_occ + loc); }
+        }
+    }
+    for (int i0 = threadIdx.x; i0 - lane < cnt; i0 += NPT * TPB) {        // warp-uniform trip count
+        int L[NPT];
+        u32 occp[NPT], a[NPT], px[NPT], py[NPT], pz[NPT];          // occp: (occ-1) of ggp | gp << 8 | parent << 16 | self << 24
+        // the own records of the NEXT round are pulled into L2 now: the three dependent gather rounds below would otherwise
+        // leave the DRAM pipe idle for three quarters of every round
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            const int i = i0 + (2 * NPT + u) * TPB;                 // two rounds ahead
+            if (i < cnt) {
+                const int loc = t.begin + i;
+                prefetch_l2(a_par + loc); prefetch_l2(a_px + loc); prefetch_l2(a_py + loc); prefetch_l2(a_pz + loc);
+                if ((lane & 7) == 0) { prefetch_l2(a_lvl + loc); prefetch_l2(a_occ + loc); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            const int i = i0 + u * TPB;
+            L[u] = 0; occp[u] = 0; a[u] = 0; px[u] = py[u] = pz[u] = 0;
+            if (i < cnt) {
+                const int loc = t.begin + i;
+                L[u] = a_lvl[loc]; a[u] = a_par[loc];
+                occp[u] = (u32)a_occ[loc];
+                px[u] = a_px[loc]; py[u] = a_py[loc]; pz[u] = a_pz[loc];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) occp[u] = ((occp[u] - 1u) & 0xffu) << 24;
+#pragma unroll
+        for (int k = 2; k >= 0; --k) {
+#pragma unroll
+            for (int u = 0; u < NPT; ++u) {
+                u32 oc = 0x100u;                                    // missing ancestor: occ 256 -> byte 255
+                if (L[u] - (3 - k) >= 1) {
+                    oc = a_occ[a[u]];
+                    if (k > 0) a[u] = a_par[a[u]];
+                }
+                occp[u] |= ((oc - 1u) & 0xffu) << (8 * k);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NPT; ++u) {
+            // a warp's 32 nodes are 32 consecutive output rows: ctx (12 B) and pos_norm (12 B) go through a per-warp staging
+            // tile and leave as three fully coalesced 128-byte stores each instead of 4-byte stores 12 bytes apart
+            const int wbase = i0 - lane + u * TPB;                 // tile-relative index of the warp's first node
+            const int nvw = 3 * max(0, min(32, cnt - wbase));       // valid words of the staging tile
+            if (nvw == 0) continue;                                 // warp-uniform
+            const long long o0 = row0 + t.begin + wbase;
+            const int Lu = L[u];
+            u32 w0 = 0, w1 = 0, w2 = 0;
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+            if (Lu > 0) {
+                const u32 self = occp[u] >> 24;
+                if (O.occ) O.occ[o0 + lane] = (uint8_t)(self + 1);
+                if (O.sym) O.sym[o0 + lane] = (int16_t)self;
+                // bit j of (coordinate >> sh3) is the octant bit of the ancestor j levels up (sh3 = lowest bit of the own cell)
+                const int sh3 = n - Lu + 1;
+                const u32 W = (((px[u] >> sh3) & 0xfu) << 8) | (((py[u] >> sh3) & 0xfu) << 4) | ((pz[u] >> sh3) & 0xfu);
+                u32 OC = 0, LV = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = 3 - k, Lk = Lu - j;
+                    u32 o = ((((W >> j) & 0x111u) * 0x124u) >> 8 & 7u) + 1u;       // 4*xbit + 2*ybit + zbit + 1
+                    if (Lk <= 1) o = (Lk == 1) ? 1u : 0u;                           // root: octant 1; missing: 0
+                    OC |= o << (8 * k);
+                    LV |= (u32)max(Lk, 0) << (8 * k);
+                }
+                if (clip && Lu == n) {                                              // encode_dataset_ehem.py:86
+                    u32 c = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) c |= min((LV >> (8 * k)) & 0xffu, (u32)lidar_level) << (8 * k);
+                    LV = c;
+                }
+                // 12 context bytes (level, octant, occ-1) x 4 from the three byte-planes
+                w0 = __byte_perm(__byte_perm(LV, OC, 0x1040), occp[u], 0x3410);
+                w1 = __byte_perm(__byte_perm(LV, OC, 0x6205), occp[u], 0x3250);
+                w2 = __byte_perm(__byte_perm(LV, OC, 0x0730), occp[u], 0x7216);
+                if (O.pos_norm) {
+                    const double mn = s_mn[Lu], den = s_den[Lu], inv = s_inv[Lu];
+                    const u32 thr = s_thr[Lu];
+                    f0 = norm_pos(px[u], mn, den, inv, thr); f1 = norm_pos(py[u], mn, den, inv, thr); f2 = norm_pos(pz[u], mn, den, inv, thr);
+                }
+            }
+            u32* sc = s_stage[warp][0];
+            float* sp = reinterpret_cast<float*>(s_stage[warp][1]);
+            sc[3 * lane] = w0; sc[3 * lane + 1] = w1; sc[3 * lane + 2] = w2;      // stride 3 words: conflict-free
+            sp[3 * lane] = f0; sp[3 * lane + 1] = f1; sp[3 * lane + 2] = f2;
+            __syncwarp();
+            if (O.ctx) {
+                u32* dst = reinterpret_cast<u32*>(O.ctx + 12 * o0);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) if (32 * j + lane < nvw) dst[32 * j + lane] = sc[32 * j + lane];
+            }
+            if (O.pos_norm) {
+                float* dst = O.pos_norm + 3 * o0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) if (32 * j + lane < nvw) dst[32 * j + lane] = sp[32 * j + lane];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// General variant: every optional output of scp_octree_out
 __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
                                                   NodeArrays A, scp_octree_out O) {
     const Tile t = tiles[blockIdx.x];
@@ -788,11 +1022,8 @@ __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles,
         const bool last_block = (L == n);
         int lv[4], oc[4], occ[4];
         u32 px[4], py[4], pz[4];
-        // Own record; the ancestors' level, octant and cell origin follow from it (an ancestor's cell is the own cell with
-        // more low bits cleared, its octant is the coordinate bit triple of its level), so only the occupancy bytes are
-        // fetched through the parent chain: 3 dependent (parent, occ) gathers instead of 3 full 23-byte records.
         lv[3] = L; oc[3] = A.octant[r]; occ[3] = A.occ[r];
-        px[3] = A.pos[3 * r]; py[3] = A.pos[3 * r + 1]; pz[3] = A.pos[3 * r + 2];
+        px[3] = A.px[r]; py[3] = A.py[r]; pz[3] = A.pz[r];
         u32 a = A.parent[r];
 #pragma unroll
         for (int k = 2; k >= 0; --k) {
@@ -862,10 +1093,10 @@ __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles,
 using namespace scp;
 
 struct scp_octree {
-    DevBuf keys_a, keys_b, tiles_pts, tiles_sort, tiles_node, frames, jobs, frame_begin, hist, desc, misc,
-        tile_hist, job_tile_begin, n_level, n_octant, n_occ, n_parent, n_pos, n_fc, vox;
+    DevBuf keys_a, keys_b, tiles_pts, tiles_sort, tiles_node, tiles_emit, frames, jobs, frame_begin, hist, desc, misc,
+        tile_hist, job_tile_begin, n_level, n_octant, n_occ, n_parent, n_pos, n_fc, n_vdig;
     std::vector<JobDev> hjobs;
-    std::vector<Tile> h_tiles_pts, h_tiles_sort, h_tiles_node;
+    std::vector<Tile> h_tiles_pts, h_tiles_sort, h_tiles_node, h_tiles_emit;
     int n_jobs = 0, mode = 0, P = 0, nt_frame = 0;
     long long total_keys = 0, total_nodes = 0, total_rows = 0, total_vox = 0;
     bool planned = false, emitted = false;
@@ -919,9 +1150,9 @@ scp_octree* scp_octree_create(void) { return new scp_octree(); }
 
 void scp_octree_destroy(scp_octree* t) {
     if (!t) return;
-    DevBuf* bufs[] = {&t->keys_a, &t->keys_b, &t->tiles_pts, &t->tiles_sort, &t->tiles_node, &t->frames, &t->jobs,
+    DevBuf* bufs[] = {&t->keys_a, &t->keys_b, &t->tiles_pts, &t->tiles_sort, &t->tiles_node, &t->tiles_emit, &t->frames, &t->jobs,
                       &t->frame_begin, &t->hist, &t->desc, &t->misc, &t->tile_hist, &t->job_tile_begin, &t->n_level,
-                      &t->n_octant, &t->n_occ, &t->n_parent, &t->n_pos, &t->n_fc, &t->vox};
+                      &t->n_octant, &t->n_occ, &t->n_parent, &t->n_pos, &t->n_fc, &t->n_vdig};
     for (DevBuf* b : bufs) b->release();
     if (t->ev_ok) for (auto& e : t->ev) cudaEventDestroy(e);
     delete t;
@@ -1063,7 +1294,7 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     SCP_LAUNCHED();
     k_level_scan<<<n_jobs, 32, 0, st>>>(d_jobs, n_jobs, t->job_tile_begin.as<int>(), t->tile_hist.as<u32>());
     SCP_LAUNCHED();
-    k_job_offsets<<<1, 32, 0, st>>>(d_jobs, n_jobs);
+    k_job_offsets<<<1, 1024, 0, st>>>(d_jobs, n_jobs);
     SCP_LAUNCHED();
     SCP_CUDA(cudaEventRecord(t->ev[3], st));
     u32 err = 0;
@@ -1077,7 +1308,13 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
         t->total_nodes += t->hjobs[j].n_nodes; t->total_rows += t->hjobs[j].n_rows; t->total_vox += t->hjobs[j].n_voxels;
         ncount[j] = t->hjobs[j].n_nodes;
     }
-    build_tiles(ncount, TILE, t->h_tiles_node, nullptr);
+    build_tiles(ncount, NODE_TILE, t->h_tiles_node, nullptr);
+    // key tiles for k_emit_nodes: only the tiles that hold sorted keys (compacted jobs keep a third of them); `first` stays
+    // the job's first tile in the point-tile numbering, which is how the per-tile level prefixes are indexed
+    t->h_tiles_emit.clear();
+    for (int j = 0; j < n_jobs; ++j)
+        for (int b = 0; b < t->hjobs[j].n_kept; b += TILE)
+            t->h_tiles_emit.push_back(Tile{j, b, std::min(TILE, t->hjobs[j].n_kept - b), jtb[j]});
     t->planned = true;
     return SCP_OK;
 }
@@ -1103,6 +1340,12 @@ int scp_octree_job_info(const scp_octree* t, int job, scp_job_info* out) {
 
 int64_t scp_octree_total_rows(const scp_octree* t) { return t && t->planned ? t->total_rows : -1; }
 int64_t scp_octree_total_voxels(const scp_octree* t) { return t && t->planned ? t->total_vox : -1; }
+int64_t scp_octree_total_kept(const scp_octree* t) {
+    if (!t || !t->planned) return -1;
+    long long s = 0;
+    for (const JobDev& J : t->hjobs) s += J.n_kept;
+    return s;
+}
 
 int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     SCP_REQUIRE(t && d_out && t->planned, "scp_octree_emit: plan first");
@@ -1114,26 +1357,32 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     if (int e = t->n_parent.reserve(N * 4)) return e;
     if (int e = t->n_pos.reserve(N * 12)) return e;
     if (int e = t->n_fc.reserve(N * 4)) return e;
-    u64* vox = reinterpret_cast<u64*>(d_out->voxel_key);
-    if (!vox) { if (int e = t->vox.reserve((t->total_vox + 1) * 8)) return e; vox = t->vox.as<u64>(); }
-    const int nt_n = (int)t->h_tiles_node.size(), nt_p = (int)t->h_tiles_pts.size();
+    u64* vox = reinterpret_cast<u64*>(d_out->voxel_key);          // optional output; the pipeline itself needs only `vdig`
+    if (int e = t->n_vdig.reserve(t->total_vox + 1)) return e;
+    const int nt_n = (int)t->h_tiles_node.size(), nt_e = (int)t->h_tiles_emit.size();
     if (int e = t->tiles_node.reserve((size_t)(nt_n + 1) * sizeof(Tile))) return e;
+    if (int e = t->tiles_emit.reserve((size_t)(nt_e + 1) * sizeof(Tile))) return e;
     SCP_CUDA(cudaMemcpyAsync(t->tiles_node.p, t->h_tiles_node.data(), nt_n * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    SCP_CUDA(cudaMemcpyAsync(t->tiles_emit.p, t->h_tiles_emit.data(), nt_e * sizeof(Tile), cudaMemcpyHostToDevice, st));
     NodeArrays A{t->n_level.as<uint8_t>(), t->n_octant.as<uint8_t>(), t->n_occ.as<uint8_t>(), t->n_parent.as<u32>(),
-                 t->n_pos.as<u32>(), t->n_fc.as<u32>()};
+                 t->n_pos.as<u32>(), t->n_pos.as<u32>() + N, t->n_pos.as<u32>() + 2 * N, t->n_fc.as<u32>(),
+                 t->n_vdig.as<uint8_t>()};
     JobDev* d_jobs = t->jobs.as<JobDev>();
-    Tile* d_ptiles = t->tiles_pts.as<Tile>() + t->nt_frame;   // point tiles live behind the frame tiles
     SCP_CUDA(cudaEventRecord(t->ev[4], st));
-    k_emit_nodes<<<nt_p, TPB, 0, st>>>(t->sorted, d_ptiles, d_jobs, t->tile_hist.as<u32>(), A, vox);
-    SCP_LAUNCHED();
+    if (nt_e) {
+        k_emit_nodes<<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), d_jobs, t->tile_hist.as<u32>(), A, vox);
+        SCP_LAUNCHED();
+    }
     SCP_CUDA(cudaEventRecord(t->ev[5], st));
     if (nt_n) {
-        k_occupancy<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, vox);
+        k_occupancy<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A);
         SCP_LAUNCHED();
     }
     SCP_CUDA(cudaEventRecord(t->ev[6], st));
     if (nt_n) {
-        k_context<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
+        const bool lean = !d_out->level && !d_out->octant && !d_out->parent && !d_out->pos && !d_out->ctx_pos && !d_out->rows_i64;
+        if (lean) k_context_lean<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
+        else k_context<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
         SCP_LAUNCHED();
     }
     SCP_CUDA(cudaEventRecord(t->ev[7], st));

@@ -97,6 +97,7 @@ class OctreeBuilder:
         self.n_jobs = len(jobs)
         self.total_rows = int(self.lib.scp_octree_total_rows(self.h))
         self.total_voxels = int(self.lib.scp_octree_total_voxels(self.h))
+        self.total_kept = int(self.lib.scp_octree_total_kept(self.h))
         self._read_infos()
         return self
 
@@ -130,6 +131,20 @@ class OctreeBuilder:
             _lib.check(self.lib.scp_octree_finish(self.h, _lib.stream_ptr()), "scp_octree_finish")
             self._read_infos()
         return out
+
+    def stage_bytes(self):
+        """Algorithmic bytes of each stage of the last plan+emit (SURVEY.md section 8d figures x the units the stage really
+        processes): quantise reads 12 B per frame point once and writes 8 B per (point, job) key; the sort moves
+        (1 + 2P) * 8 B per key that takes part in it, plus, for jobs with a morton_path, two reads of all keys and one
+        write of the kept ones for the compaction in front of it; heads 8 B per sorted key; emit 28 B, occupancy 6 B and
+        context 60 B per node."""
+        n_frame_pts = int(self._keep.shape[0])
+        n_keys = sum(i.n_points for i in self.infos)
+        kept, N = self.total_kept, self.total_rows
+        P = (3 * max(i.depth for i in self.infos) + 1 + 7) // 8
+        filt = (16 * n_keys + 8 * kept) if kept != n_keys else 0
+        return {"quantise": 12 * n_frame_pts + 8 * n_keys, "sort": filt + (1 + 2 * P) * 8 * kept, "heads": 8 * kept,
+                "emit": 28 * N, "occupancy": 6 * N, "context": 60 * N}
 
     def stage_ms(self):
         arr = (C.c_float * 6)()

@@ -31,10 +31,10 @@ def main(n_frames=64, level=16, mul=False, mode="spher"):
     npts = int(offs[-1]) * (3 if mul else 1)
     N = b.total_rows
     P = (3 * max(i.depth for i in b.infos) + 1 + 7) // 8
-    bytes_model = {"quantise": 20 * npts, "sort": (1 + 2 * P) * 8 * npts, "heads": 8 * npts, "emit": 28 * N,
-                   "occupancy": 6 * N, "context": 60 * N}
-    rep = {k: {"ms": round(v, 4), "GBps": round(bytes_model[k] / v / 1e6, 1) if v > 0 else None} for k, v in ms.items()}
-    print(json.dumps({"frames": n_frames, "level": level, "mullevel": mul, "points": npts, "rows": N, "P": P,
+    bytes_model = b.stage_bytes()
+    rep = {k: {"ms": round(v, 4), "GBps": round(bytes_model[k] / v / 1e6, 1) if v > 0 else None,
+                "frac": round(bytes_model[k] / v / 1e6 / 6547.2, 3) if v > 0 else None} for k, v in ms.items()}
+    print(json.dumps({"frames": n_frames, "level": level, "mullevel": mul, "points": npts, "kept": b.total_kept, "rows": N, "P": P,
                       "depths": sorted(set(i.depth for i in b.infos)), "wall_ms": round(wall * 1e3, 3),
                       "device_ms": round(sum(ms.values()), 3), "stages": rep}))
 

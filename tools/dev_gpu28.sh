@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_octree_gpu.py tests/test_dropin_gpu.py -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_28.log
+timeout 300 python tools/exp_ctx.py 2>&1 | tail -2 | tee gpurun_out/exp_ctx.log
+timeout 300 python tools/bench_octree.py 2>&1 | tee gpurun_out/bench_octree_28.log
