@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) k_scan_hist(u32* hist) {   // one block p
     h[threadIdx.x] = base + inc - v;
 }
 
-__global__ void __launch_bounds__(TPB) k_onesweep(const u64* __restrict__ in, u64* __restrict__ out,
+__global__ void __launch_bounds__(TPB, 4) k_onesweep(const u64* __restrict__ in, u64* __restrict__ out,
                                                    const Tile* __restrict__ tiles, int n_tiles,
                                                    const JobDev* __restrict__ jobs, const u32* __restrict__ hist,
                                                    int P, int pass, u32* desc, u32* ticket, u32* err) {
@@ -666,11 +666,19 @@ __global__ void __launch_bounds__(1024) k_job_offsets(JobDev* jobs, int n_jobs) 
 // ------------------------------------------------------------------------------------------
 // K6: node records for all levels in one pass
 // ------------------------------------------------------------------------------------------
-// Internal node records, structure of arrays (BFS order inside a job): 23 B/node + 1 B/voxel
+// Internal node records, structure of arrays (BFS order inside a job): 19 B/node + 1 B/voxel
 struct NodeArrays {
-    uint8_t* level; uint8_t* octant; uint8_t* occ; u32* parent; u32* px; u32* py; u32* pz; u32* fc;
+    uint16_t* lo;               // level | octant << 8
+    uint8_t* occ;
+    u32* parent;
+    u64* pos;                   // cell origin, 21 bits per axis: x | y << 21 | z << 42
+    u32* fc;                    // first child (BFS index inside the job; voxel index for the deepest level)
     uint8_t* vdig;              // per voxel: child digit + 1 inside its level-n node (the "octant" of the voxel)
 };
+__device__ __forceinline__ u64 pack_pos(u32 x, u32 y, u32 z) { return (u64)x | ((u64)y << 21) | ((u64)z << 42); }
+__device__ __forceinline__ void unpack_pos(u64 p, u32& x, u32& y, u32& z) {
+    x = (u32)p & 0x1fffffu; y = (u32)(p >> 21) & 0x1fffffu; z = (u32)(p >> 42);
+}
 
 // One block iteration handles 256 consecutive sorted keys: per level one ballot per warp gives the rank of every head inside
 // the warp, a 22-entry scan over the 8 warps gives the rank inside the block.  Only levels >= the smallest head level of
@@ -682,11 +690,17 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
     __shared__ u32 s_wcnt[8][MAXL + 2];
     __shared__ u32 s_wpre[8][MAXL + 2];
     __shared__ u32 s_mm[4];                 // min / max coordinate over the tile's voxels: all, and all but the job's last voxel
+    __shared__ u64 s_keep[MAXL + 2];        // packed-position bits that survive on level L (cell size 2^(n-L+1))
     const Tile t = tiles[blockIdx.x];
     JobDev& J = jobs[t.job];
     const int n = J.depth;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 ltmask = (1u << lane) - 1u;
+    if (threadIdx.x >= 32 && threadIdx.x <= 32 + MAXL) {
+        const int L = threadIdx.x - 32;
+        const u32 m = (L >= 1 && L <= n) ? (~((1u << (n - L + 1)) - 1u)) & 0x1fffffu : 0u;
+        s_keep[L] = pack_pos(m, m, m);
+    }
     if (threadIdx.x <= MAXL) {
         int L = threadIdx.x;       // L = 0: voxel counter
         u32 s = 0;
@@ -742,6 +756,7 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
         }
         __syncthreads();
         const u32 x = compact3(k >> 2), y = compact3(k >> 1), z = compact3(k);
+        const u64 P = pack_pos(x, y, z);
         const u32 v = s_base[0] + s_wpre[warp][0] + rank[0];
         if (h > 0) {
             if (vox_key) vox_key[J.vox_start + v] = k;
@@ -759,16 +774,14 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
             if (mine) {
                 const u32 kL = s_base[L] + s_wpre[warp][L] + rank[L];
                 const long long r = node0 + J.level_start[L - 1] + kL;
-                A.level[r] = (uint8_t)L;
-                A.octant[r] = (L == 1) ? 1 : (uint8_t)(((k >> (3 * (n - L + 1))) & 7) + 1);
+                A.lo[r] = (uint16_t)(L | (((L == 1) ? 1u : (u32)((k >> (3 * (n - L + 1))) & 7) + 1u) << 8));
                 u32 par = 0;
                 if (L > 1) {
                     u32 kp = s_base[L - 1] + s_wpre[warp][L - 1] + rank[L - 1] + ((hh <= L - 1) ? 1u : 0u) - 1u;
                     par = (u32)J.level_start[L - 2] + kp;
                 }
                 A.parent[r] = par;
-                const u32 m = ~((1u << (n - L + 1)) - 1u);
-                A.px[r] = x & m; A.py[r] = y & m; A.pz[r] = z & m;
+                A.pos[r] = P & s_keep[L];
                 A.fc[r] = (L < n) ? (u32)J.level_start[L] + s_base[L + 1] + s_wpre[warp][L + 1] + rank[L + 1] : v;
             }
         }
@@ -813,9 +826,8 @@ __global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tile
     const int n = J.depth;
     if (threadIdx.x <= MAXL + 1) s_ls[threadIdx.x] = J.level_start[threadIdx.x];
     __syncthreads();
-    const uint8_t* __restrict__ lvl = A.level + J.node_start;
+    const uint16_t* __restrict__ lvl = A.lo + J.node_start;
     const u32* __restrict__ fc = A.fc + J.node_start;
-    const uint8_t* __restrict__ oct = A.octant + J.node_start;
     const uint8_t* __restrict__ vd = A.vdig + J.vox_start;
     uint8_t* __restrict__ out = A.occ + J.node_start;
     const u32 n_vox = (u32)J.n_voxels;
@@ -823,7 +835,7 @@ __global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tile
 #pragma unroll
         for (int u = 0; u < 2; ++u) {                           // next round's records into L2 (see k_context_lean)
             const int i = i0 + (4 + u) * TPB;
-            if (i < t.count) { prefetch_l2(fc + t.begin + i); if ((threadIdx.x & 7) == 0) prefetch_l2(lvl + t.begin + i); }
+            if (i < t.count) { prefetch_l2(fc + t.begin + i); if ((threadIdx.x & 15) == 0) prefetch_l2(lvl + t.begin + i); }
         }
         int L[2];
         u32 c0[2], c1[2];
@@ -831,7 +843,7 @@ __global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tile
         for (int u = 0; u < 2; ++u) {
             const int i = i0 + u * TPB;
             L[u] = 0; c0[u] = c1[u] = 0;
-            if (i < t.count) { const int loc = t.begin + i; L[u] = lvl[loc]; c0[u] = fc[loc]; c1[u] = fc[loc + 1]; }
+            if (i < t.count) { const int loc = t.begin + i; L[u] = lvl[loc] & 0xff; c0[u] = fc[loc]; c1[u] = fc[loc + 1]; }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -839,9 +851,9 @@ __global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tile
             const int loc = t.begin + i0 + u * TPB;
             const bool leaf = (L[u] == n);
             if (loc + 1 == s_ls[L[u]]) c1[u] = leaf ? n_vox : (u32)s_ls[L[u] + 1];       // level_start[L] = start of level L+1
-            const uint8_t* __restrict__ arr = leaf ? vd : oct;
             u32 occ = 0;
-            for (u32 c = c0[u]; c < c1[u]; ++c) occ |= 1u << (arr[c] - 1);
+            if (leaf) { for (u32 c = c0[u]; c < c1[u]; ++c) occ |= 1u << (vd[c] - 1); }
+            else { for (u32 c = c0[u]; c < c1[u]; ++c) occ |= 1u << ((lvl[c] >> 8) - 1); }
             out[loc] = (uint8_t)occ;
         }
     }
@@ -886,12 +898,10 @@ __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict_
     }
     __syncthreads();
     const long long node0 = J.node_start, row0 = J.row_start;
-    const uint8_t* __restrict__ a_lvl = A.level + node0;
+    const uint16_t* __restrict__ a_lvl = A.lo + node0;
     const uint8_t* __restrict__ a_occ = A.occ + node0;
     const u32* __restrict__ a_par = A.parent + node0;
-    const u32* __restrict__ a_px = A.px + node0;
-    const u32* __restrict__ a_py = A.py + node0;
-    const u32* __restrict__ a_pz = A.pz + node0;
+    const u64* __restrict__ a_pos = A.pos + node0;
     const int cnt = min(t.count, J.n_rows - t.begin);             // the dropped last row (Octree.py:259-262)
     const int lidar_level = J.lidar_level;
     const bool clip = n > lidar_level;                            // encode_dataset_ehem.py:86 can only bite then
@@ -901,13 +911,14 @@ __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict_
         const int i = (int)threadIdx.x + (NPT + u) * TPB;
         if (i < cnt) {
             const int loc = t.begin + i;
-            prefetch_l2(a_par + loc); prefetch_l2(a_px + loc); prefetch_l2(a_py + loc); prefetch_l2(a_pz + loc);
+            prefetch_l2(a_par + loc); prefetch_l2(a_pos + loc);
             if ((lane & 7) == 0) { prefetch_l2(a_lvl + loc); prefetch_l2(a_occ + loc); }
         }
     }
     for (int i0 = threadIdx.x; i0 - lane < cnt; i0 += NPT * TPB) {        // warp-uniform trip count
         int L[NPT];
-        u32 occp[NPT], a[NPT], px[NPT], py[NPT], pz[NPT];          // occp: (occ-1) of ggp | gp << 8 | parent << 16 | self << 24
+        u64 pp[NPT];
+        u32 occp[NPT], a[NPT];                                     // occp: (occ-1) of ggp | gp << 8 | parent << 16 | self << 24
         // the own records of the NEXT round are pulled into L2 now: the three dependent gather rounds below would otherwise
         // leave the DRAM pipe idle for three quarters of every round
 #pragma unroll
@@ -915,19 +926,19 @@ __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict_
             const int i = i0 + (2 * NPT + u) * TPB;                 // two rounds ahead
             if (i < cnt) {
                 const int loc = t.begin + i;
-                prefetch_l2(a_par + loc); prefetch_l2(a_px + loc); prefetch_l2(a_py + loc); prefetch_l2(a_pz + loc);
+                prefetch_l2(a_par + loc); prefetch_l2(a_pos + loc);
                 if ((lane & 7) == 0) { prefetch_l2(a_lvl + loc); prefetch_l2(a_occ + loc); }
             }
         }
 #pragma unroll
         for (int u = 0; u < NPT; ++u) {
             const int i = i0 + u * TPB;
-            L[u] = 0; occp[u] = 0; a[u] = 0; px[u] = py[u] = pz[u] = 0;
+            L[u] = 0; occp[u] = 0; a[u] = 0; pp[u] = 0;
             if (i < cnt) {
                 const int loc = t.begin + i;
-                L[u] = a_lvl[loc]; a[u] = a_par[loc];
+                L[u] = a_lvl[loc] & 0xff; a[u] = a_par[loc];
                 occp[u] = (u32)a_occ[loc];
-                px[u] = a_px[loc]; py[u] = a_py[loc]; pz[u] = a_pz[loc];
+                pp[u] = a_pos[loc];
             }
         }
 #pragma unroll
@@ -961,7 +972,9 @@ __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict_
                 if (O.sym) O.sym[o0 + lane] = (int16_t)self;
                 // bit j of (coordinate >> sh3) is the octant bit of the ancestor j levels up (sh3 = lowest bit of the own cell)
                 const int sh3 = n - Lu + 1;
-                const u32 W = (((px[u] >> sh3) & 0xfu) << 8) | (((py[u] >> sh3) & 0xfu) << 4) | ((pz[u] >> sh3) & 0xfu);
+                u32 px, py, pz;
+                unpack_pos(pp[u], px, py, pz);
+                const u32 W = (((px >> sh3) & 0xfu) << 8) | (((py >> sh3) & 0xfu) << 4) | ((pz >> sh3) & 0xfu);
                 u32 OC = 0, LV = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -984,7 +997,7 @@ __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict_
                 if (O.pos_norm) {
                     const double mn = s_mn[Lu], den = s_den[Lu], inv = s_inv[Lu];
                     const u32 thr = s_thr[Lu];
-                    f0 = norm_pos(px[u], mn, den, inv, thr); f1 = norm_pos(py[u], mn, den, inv, thr); f2 = norm_pos(pz[u], mn, den, inv, thr);
+                    f0 = norm_pos(px, mn, den, inv, thr); f1 = norm_pos(py, mn, den, inv, thr); f2 = norm_pos(pz, mn, den, inv, thr);
                 }
             }
             u32* sc = s_stage[warp][0];
@@ -1018,12 +1031,13 @@ __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles,
         if (loc >= J.n_rows) continue;                    // the dropped last row (Octree.py:259-262)
         const long long r = J.node_start + loc;
         const long long o = J.row_start + loc;
-        const int L = A.level[r];
+        const u32 lo16 = A.lo[r];
+        const int L = lo16 & 0xff;
         const bool last_block = (L == n);
         int lv[4], oc[4], occ[4];
         u32 px[4], py[4], pz[4];
-        lv[3] = L; oc[3] = A.octant[r]; occ[3] = A.occ[r];
-        px[3] = A.px[r]; py[3] = A.py[r]; pz[3] = A.pz[r];
+        lv[3] = L; oc[3] = lo16 >> 8; occ[3] = A.occ[r];
+        unpack_pos(A.pos[r], px[3], py[3], pz[3]);
         u32 a = A.parent[r];
 #pragma unroll
         for (int k = 2; k >= 0; --k) {
@@ -1094,7 +1108,7 @@ using namespace scp;
 
 struct scp_octree {
     DevBuf keys_a, keys_b, tiles_pts, tiles_sort, tiles_node, tiles_emit, frames, jobs, frame_begin, hist, desc, misc,
-        tile_hist, job_tile_begin, n_level, n_octant, n_occ, n_parent, n_pos, n_fc, n_vdig;
+        tile_hist, job_tile_begin, n_lo, n_occ, n_parent, n_pos, n_fc, n_vdig;
     std::vector<JobDev> hjobs;
     std::vector<Tile> h_tiles_pts, h_tiles_sort, h_tiles_node, h_tiles_emit;
     int n_jobs = 0, mode = 0, P = 0, nt_frame = 0;
@@ -1151,8 +1165,8 @@ scp_octree* scp_octree_create(void) { return new scp_octree(); }
 void scp_octree_destroy(scp_octree* t) {
     if (!t) return;
     DevBuf* bufs[] = {&t->keys_a, &t->keys_b, &t->tiles_pts, &t->tiles_sort, &t->tiles_node, &t->tiles_emit, &t->frames, &t->jobs,
-                      &t->frame_begin, &t->hist, &t->desc, &t->misc, &t->tile_hist, &t->job_tile_begin, &t->n_level,
-                      &t->n_octant, &t->n_occ, &t->n_parent, &t->n_pos, &t->n_fc, &t->n_vdig};
+                      &t->frame_begin, &t->hist, &t->desc, &t->misc, &t->tile_hist, &t->job_tile_begin, &t->n_lo,
+                      &t->n_occ, &t->n_parent, &t->n_pos, &t->n_fc, &t->n_vdig};
     for (DevBuf* b : bufs) b->release();
     if (t->ev_ok) for (auto& e : t->ev) cudaEventDestroy(e);
     delete t;
@@ -1351,11 +1365,10 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     SCP_REQUIRE(t && d_out && t->planned, "scp_octree_emit: plan first");
     cudaStream_t st = as_stream(stream);
     const long long N = t->total_nodes + 1;
-    if (int e = t->n_level.reserve(N)) return e;
-    if (int e = t->n_octant.reserve(N)) return e;
+    if (int e = t->n_lo.reserve(N * 2)) return e;
     if (int e = t->n_occ.reserve(N)) return e;
     if (int e = t->n_parent.reserve(N * 4)) return e;
-    if (int e = t->n_pos.reserve(N * 12)) return e;
+    if (int e = t->n_pos.reserve(N * 8)) return e;
     if (int e = t->n_fc.reserve(N * 4)) return e;
     u64* vox = reinterpret_cast<u64*>(d_out->voxel_key);          // optional output; the pipeline itself needs only `vdig`
     if (int e = t->n_vdig.reserve(t->total_vox + 1)) return e;
@@ -1364,8 +1377,7 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     if (int e = t->tiles_emit.reserve((size_t)(nt_e + 1) * sizeof(Tile))) return e;
     SCP_CUDA(cudaMemcpyAsync(t->tiles_node.p, t->h_tiles_node.data(), nt_n * sizeof(Tile), cudaMemcpyHostToDevice, st));
     SCP_CUDA(cudaMemcpyAsync(t->tiles_emit.p, t->h_tiles_emit.data(), nt_e * sizeof(Tile), cudaMemcpyHostToDevice, st));
-    NodeArrays A{t->n_level.as<uint8_t>(), t->n_octant.as<uint8_t>(), t->n_occ.as<uint8_t>(), t->n_parent.as<u32>(),
-                 t->n_pos.as<u32>(), t->n_pos.as<u32>() + N, t->n_pos.as<u32>() + 2 * N, t->n_fc.as<u32>(),
+    NodeArrays A{t->n_lo.as<uint16_t>(), t->n_occ.as<uint8_t>(), t->n_parent.as<u32>(), t->n_pos.as<u64>(), t->n_fc.as<u32>(),
                  t->n_vdig.as<uint8_t>()};
     JobDev* d_jobs = t->jobs.as<JobDev>();
     SCP_CUDA(cudaEventRecord(t->ev[4], st));
