@@ -175,6 +175,17 @@ int64_t scp_range_encode_cdf(const uint16_t* h_cdf, const int16_t* h_sym, int64_
                              uint8_t* h_out, int64_t out_cap);
 
 /* ------------------------------------------------------------------------------------------
+ * Range decoder (row f-2 of SURVEY.md section 8, host): numpyAc_backend.cpp:134-229 `decode` / numpyAc.py:139-170
+ * `arithmeticDeCoding`.  Stateful: the caller hands over the CDF rows (uint16 [n,Lp], the table scp_pmf_to_cdf
+ * writes) in coding order, any number at a time, and gets the symbols back.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct scp_range_decoder scp_range_decoder;
+scp_range_decoder* scp_range_decoder_create(const uint8_t* h_bytes, int64_t n_bytes);
+void    scp_range_decoder_destroy(scp_range_decoder* d);
+int     scp_range_decode(scp_range_decoder* d, const uint16_t* h_cdf, int64_t n, int Lp, int16_t* h_sym);
+int64_t scp_range_decoder_count(const scp_range_decoder* d);
+
+/* ------------------------------------------------------------------------------------------
  * Entropy-model operators (A8-A12).  Device pointers, float32 activations, row-major [tokens, channels].
  * Windows of ANY length are processed together as one ragged batch: a `scp_seqs` describes how the token
  * stream is cut into sequences (one per context window of encode.py:112-115).

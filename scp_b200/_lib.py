@@ -54,6 +54,10 @@ SIGNATURES = {
     "scp_octree_total_rows": (_i64, [_vp]),
     "scp_octree_total_voxels": (_i64, [_vp]),
     "scp_octree_total_kept": (_i64, [_vp]),
+    "scp_range_decoder_create": (_vp, [_vp, _i64]),
+    "scp_range_decoder_destroy": (None, [_vp]),
+    "scp_range_decode": (_i, [_vp, _vp, _i64, _i, _vp]),
+    "scp_range_decoder_count": (_i64, [_vp]),
     "scp_octree_emit": (_i, [_vp, C.POINTER(OctreeOut), _vp]),
     "scp_octree_finish": (_i, [_vp, _vp]),
     "scp_octree_stage_ms": (_i, [_vp, C.POINTER(_f * 6)]),

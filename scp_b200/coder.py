@@ -72,3 +72,36 @@ def range_encode_cdf(cdf, sym):
     got = lib.scp_range_encode_cdf(_lib.ptr(cdf), _lib.ptr(sym), n, Lp, _lib.ptr(buf), need)
     _lib.check(got, "scp_range_encode_cdf")
     return buf[:got].tobytes()
+
+
+class RangeDecoder:
+    """numpyAc.arithmeticDeCoding (numpyAc.py:139-170) on the library's host decoder: ``decode(cdf)`` takes the uint16
+    CDF rows [n,256] of the next n symbols in coding order and returns them (int16 [n])."""
+
+    def __init__(self, bitstream: bytes):
+        self.lib = _lib.load()
+        buf = np.frombuffer(bytes(bitstream), np.uint8)
+        self.h = self.lib.scp_range_decoder_create(_lib.ptr(np.ascontiguousarray(buf)), len(buf))
+        if not self.h:
+            raise RuntimeError(self.lib.scp_last_error().decode())
+
+    def decode(self, cdf) -> np.ndarray:
+        cdf = np.ascontiguousarray(np.asarray(cdf).view(np.uint16))
+        if cdf.ndim != 2:
+            raise ValueError("cdf must be [n, Lp]")
+        n, Lp = cdf.shape
+        sym = np.empty(n, np.int16)
+        _lib.check(self.lib.scp_range_decode(self.h, _lib.ptr(cdf), n, Lp, _lib.ptr(sym)), "scp_range_decode")
+        return sym
+
+    @property
+    def count(self):
+        return int(self.lib.scp_range_decoder_count(self.h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.scp_range_decoder_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

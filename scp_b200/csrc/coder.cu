@@ -210,6 +210,61 @@ static long long range_encode_impl(long long n, uint8_t* out, long long cap, Get
     return sink.n;
 }
 
+
+// Decoder mirror of range_encode_impl (numpyAc_backend.cpp:134-229 `decode`): same low/high/value registers, same E1/E2/E3
+// renormalisation, symbol by binary search for the last CDF entry <= count.  Stateful, so that the caller can hand over the
+// CDF rows in the order the symbols were coded, a window at a time (the entropy model needs decoded symbols to go on).
+struct RangeDecoder {
+    std::vector<uint8_t> in;
+    size_t in_ptr = 0;
+    uint8_t cache = 0;
+    int cached_bits = 0;
+    uint32_t low = 0, high = 0xFFFFFFFFu, value = 0;
+    long long decoded = 0;
+    inline void get() {
+        if (cached_bits == 0) {
+            if (in_ptr == in.size()) { value <<= 1; return; }      // past the end: zeros (numpyAc_backend.cpp:83-86)
+            cache = in[in_ptr++];
+            cached_bits = 8;
+        }
+        value = (value << 1) | (uint32_t)((cache >> (cached_bits - 1)) & 1);
+        --cached_bits;
+    }
+    inline int decode_one(const uint16_t* cdf, int Lp) {
+        const int max_symbol = Lp - 2;
+        const uint64_t span = (uint64_t)high - (uint64_t)low + 1;
+        const uint32_t count = (uint32_t)((((uint64_t)value - (uint64_t)low + 1) * 0x10000ull - 1) / span);
+        // last s in [0, max_symbol] with cdf[s] <= count (cdf[0] = 0; entry Lp-1 wraps to 0 and is never read: the
+        // upper bound of the last symbol is the constant 0x10000, numpyAc_backend.cpp:277)
+        int lo = 0, hi = max_symbol + 1;
+        while (lo + 1 < hi) {
+            const int m = (lo + hi) >> 1;
+            if ((uint32_t)cdf[m] <= count) lo = m; else hi = m;
+        }
+        const int s = lo;
+        const uint32_t c_low = cdf[s];
+        const uint32_t c_high = s == max_symbol ? 0x10000u : cdf[s + 1];
+        high = (low - 1) + (uint32_t)((span * (uint64_t)c_high) >> 16);
+        low = low + (uint32_t)((span * (uint64_t)c_low) >> 16);
+        for (;;) {
+            if (low >= 0x80000000u || high < 0x80000000u) {
+                low <<= 1;
+                high = (high << 1) | 1u;
+                get();
+            } else if (low >= 0x40000000u && high < 0xC0000000u) {
+                low = (low << 1) & 0x7FFFFFFFu;
+                high = (high << 1) | 0x80000001u;
+                value -= 0x40000000u;
+                get();
+            } else {
+                break;
+            }
+        }
+        ++decoded;
+        return s;
+    }
+};
+
 }  // namespace scp
 
 using namespace scp;
@@ -309,5 +364,24 @@ int64_t scp_range_encode_cdf(const uint16_t* h_cdf, const int16_t* h_sym, int64_
         hi = s == max_symbol ? 0x10000u : h_cdf[i * Lp + s + 1];
     });
 }
+
+scp_range_decoder* scp_range_decoder_create(const uint8_t* h_bytes, int64_t n_bytes) {
+    if ((!h_bytes && n_bytes > 0) || n_bytes < 0) { set_error("scp_range_decoder_create: bad argument"); return nullptr; }
+    RangeDecoder* d = new RangeDecoder();
+    d->in.assign(h_bytes, h_bytes + n_bytes);
+    for (int i = 0; i < 32; ++i) d->get();
+    return reinterpret_cast<scp_range_decoder*>(d);
+}
+
+void scp_range_decoder_destroy(scp_range_decoder* d) { delete reinterpret_cast<RangeDecoder*>(d); }
+
+int scp_range_decode(scp_range_decoder* dh, const uint16_t* h_cdf, int64_t n, int Lp, int16_t* h_sym) {
+    RangeDecoder* d = reinterpret_cast<RangeDecoder*>(dh);
+    if (!d || !h_cdf || !h_sym || n < 0 || Lp < 2) { set_error("scp_range_decode: bad argument"); return SCP_ERR_ARG; }
+    for (int64_t i = 0; i < n; ++i) h_sym[i] = (int16_t)d->decode_one(h_cdf + i * Lp, Lp);
+    return SCP_OK;
+}
+
+int64_t scp_range_decoder_count(const scp_range_decoder* d) { return d ? reinterpret_cast<const RangeDecoder*>(d)->decoded : -1; }
 
 }  // extern "C"

@@ -67,3 +67,40 @@ def test_range_coder_edge_cases():
     sym = np.array([300], np.int16)
     cdf = np.zeros((1, 256), np.uint16)
     assert lib.scp_range_encode_cdf(_lib.ptr(cdf), _lib.ptr(sym), 1, 256, _lib.ptr(out), 16) < 0
+
+
+def test_range_decoder_inverts_numpyac_bitstream():
+    """The reference's own bitstream (numpyAc.encode on the golden case) decodes back to the golden symbols, in one call
+    and in ragged pieces (the decoder is stateful: the entropy model hands over CDF rows a window at a time)."""
+    from oracle.make_golden import coder_case
+    from oracle import octree_np as onp
+    from scp_b200 import coder
+    g = golden("coder.npz")
+    pmf, sym = coder_case()
+    cdf = onp.pmf_to_cdf_u16(pmf)
+    d = coder.RangeDecoder(g["bitstream"].tobytes())
+    assert np.array_equal(d.decode(cdf), sym)
+    d = coder.RangeDecoder(g["bitstream"].tobytes())
+    got, i = [], 0
+    for step in (1, 7, 500, 3, 10 ** 6):
+        got.append(d.decode(cdf[i:i + step]))
+        i += step
+    assert np.array_equal(np.concatenate(got), sym) and d.count == len(sym)
+
+
+def test_range_coder_round_trip_skewed_and_wrapped_cdfs():
+    """Peaked PMFs (CDF entries above 0x7fff wrap negative as int16, numpyAc.py:104), symbol 254 (c_high = 0x10000) and
+    long runs of near-certain symbols (E3 pending bits)."""
+    from oracle import octree_np as onp
+    from scp_b200 import coder
+    rng = np.random.default_rng(5)
+    n = 20000
+    pmf = rng.random((n, 255)).astype(np.float32) ** 8 + 1e-6
+    hot = rng.integers(0, 255, n)
+    hot[:200] = 254
+    pmf[np.arange(n), hot] += rng.choice([0.5, 50.0, 5000.0], n).astype(np.float32)
+    pmf /= pmf.sum(1, keepdims=True)
+    sym = np.where(rng.random(n) < 0.9, hot, rng.integers(0, 255, n)).astype(np.int16)
+    cdf = onp.pmf_to_cdf_u16(pmf)
+    bs = coder.range_encode_cdf(cdf, sym)
+    assert np.array_equal(coder.RangeDecoder(bs).decode(cdf), sym)
