@@ -35,7 +35,8 @@ class FrameResult:
     z_offset: float
     bitstream: bytes
     bpp: float
-    pos_mm: list = field(default_factory=list)
+    pos_mm: list = field(default_factory=list)      # (min, max) of every level's pos block: the .dat side file (encode.py:150)
+    depths: list = field(default_factory=list)      # levels per sub-octree (one entry, or three for encode_mullevel)
 
 
 class Encoder:
@@ -243,7 +244,7 @@ class Encoder:
             npts = int(offs[f + 1] - offs[f])
             out.append(FrameResult(npts, n, sum(len(i.level_rows) for i in fi), int(fi[0].bin_num),
                                    float(fi[0].offset[2]), bs, 8.0 * len(bs) / npts,
-                                   [p for i in fi for p in i.pos_mm]))
+                                   [p for i in fi for p in i.pos_mm], [len(i.level_rows) for i in fi]))
         return out
 
     @torch.no_grad()

@@ -186,6 +186,13 @@ class EHEM(nn.Module):
         """ctx uint8 [T,4,3] (level, octant, occ; self occupancy is ignored), pos float32 [T,3]; ``offsets``
         cut the token stream into context windows, every window of EVEN length (the caller appends the pad token
         of ehem.py:92-99 to odd windows).  Returns (logits1 [T/2,255] for even tokens, logits2 [T/2,255] for odd)."""
+        feat_a, logits1 = self.phase1(ctx, pos, offsets)
+        return logits1, self.phase2(ctx, feat_a, offsets)
+
+    @torch.no_grad()
+    def phase1(self, ctx, pos, offsets):
+        """Everything that depends on the ancestors only (ehem.py:100-113; the first call of EHEM.decode, :138-160):
+        returns (feat_a [T,256], logits1 [T/2,255]).  The self occupancy column of ``ctx`` is not read."""
         ops = self.ops
         P = self._prepare()
         sd = P["sd"]
@@ -230,9 +237,23 @@ class EHEM(nn.Module):
         self._mlp("ancient_mlp", V(SELF), V(feat_a))
         del SELF, FEAT
         H = T // 2
-        half = ops.seqs([o // 2 for o in offsets])
         logits1 = ops.empty(H, 255, pos)
         self._mlp("prob_pred_mlp1", V(feat_a), V(logits1), row_step=2, row_off=0, rows=H)
+        return feat_a, logits1
+
+    @torch.no_grad()
+    def phase2(self, ctx, feat_a, offsets):
+        """Group 2 (ehem.py:117-125; the second call of EHEM.decode, :162-180): logits of the odd tokens given the
+        occupancy of the even tokens (read from the self column of ``ctx`` at even positions) -> logits2 [T/2,255]."""
+        ops = self.ops
+        P = self._prepare()
+        sd = P["sd"]
+        g = "geo_feat_generator"
+        T = ctx.shape[0]
+        ctx = ctx.reshape(T, 12).contiguous()
+        pos = feat_a
+        H = T // 2
+        half = ops.seqs([o // 2 for o in offsets])
         # group 2: cross Swin with the even tokens' true occupancy ---------------------------
         PRE = ops.empty(H, 256, pos)
         occ16 = ops.empty(H, 16, pos)
@@ -246,7 +267,7 @@ class EHEM(nn.Module):
         self._swin_encoder("swin_cross_transformer", W.EHEM_CROSS_DEPTHS, PRE, half, CROSS, query=fa2)
         logits2 = ops.empty(H, 255, pos)
         self._mlp("prob_pred_mlp2", V(CROSS), V(logits2))
-        return logits1, logits2
+        return logits2
 
     @torch.no_grad()
     def forward(self, data, pos, enc=True):
@@ -269,3 +290,28 @@ class EHEM(nn.Module):
         if padded:
             l2 = l2[:, :-1]
         return l1, l2
+
+    @torch.no_grad()
+    def decode(self, data, pos, pre_occ=None):
+        """Reference interface (models/ehem.py:138-180): first call (``pre_occ`` None) -> logits of the even tokens
+        [B,ceil(csz/2),255] and caches the ancestor features; second call with the decoded occupancy symbols of the even
+        tokens (int [B,ceil(csz/2)], 0..254) -> logits of the odd tokens [B,floor(csz/2),255]."""
+        B, csz = data.shape[0], data.shape[1]
+        if pre_occ is None:
+            ctx = data.to(torch.uint8)
+            p = pos.transpose(1, 2).to(torch.float32)
+            if csz % 2 == 1:                                         # ehem.py:142-149
+                pad = torch.zeros_like(ctx[:, :1])
+                pad[:, :, :, 2] = 255
+                ctx = torch.cat((ctx, pad), 1)
+                p = torch.cat((p, torch.zeros_like(p[:, :1])), 1)
+            c2 = ctx.shape[1]
+            ctx = ctx.reshape(B * c2, 4, 3).contiguous()
+            offsets = [i * c2 for i in range(B + 1)]
+            feat_a, l1 = self.phase1(ctx, p.reshape(B * c2, 3).contiguous(), offsets)
+            self._dec = (ctx, feat_a, offsets, c2)
+            return l1.reshape(B, c2 // 2, 255)
+        ctx, feat_a, offsets, c2 = self._dec
+        ctx[0::2, 3, 2] = pre_occ.reshape(-1).to(torch.uint8)
+        l2 = self.phase2(ctx, feat_a, offsets).reshape(B, c2 // 2, 255)
+        return l2[:, :-1] if csz % 2 == 1 else l2
