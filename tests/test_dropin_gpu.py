@@ -122,3 +122,12 @@ def test_compress_ehem_dropin_writes_reference_sized_stream(tmp_path, name, mul)
     assert os.path.exists(fn) and os.path.exists(fn + ".dat")
     assert abs(os.path.getsize(fn) - len(e["bitstream"])) / len(e["bitstream"]) < 0.005
     assert abs(bpp - float(e["bpp"])) / float(e["bpp"]) < 0.005
+    # ... and the decode drop-in reads the files back to the reference's own occupancy sequence (decode_ehem.py:184)
+    from scp_b200 import decode_ehem, decode_ehem_mullevel
+    label = g["ds_oct_seq"][:, -1, 0] + 1          # the dataset already subtracted 1 (encode_dataset_ehem.py:54); the .npy holds 1..255
+    if mul:
+        cuts = np.cumsum(np.concatenate([[0], g["sub_rows"]]))
+        code, bn, zo, _, spher, cylin = decode_ehem_mullevel.decodeOct(fn, [label[a:b] for a, b in zip(cuts[:-1], cuts[1:])], model)
+    else:
+        code, bn, zo, _, spher, cylin = decode_ehem.decodeOct(fn, label[:, None], model)
+    assert np.array_equal(np.asarray(code) + 1, label) and bn == int(g["bin_num"]) and spher and not cylin
