@@ -254,12 +254,15 @@ def run_ours(args):
     top = max(agg.items(), key=lambda kv: kv[1][0])
     hbm_peak, tf_peak, src = peaks()
     tag, (tms, tfl, tby, cnt) = top
-    # Dense contractions run as error-compensated 3xTF32 (three tcgen05.mma per product, fp32-class result), so the
-    # tensor-pipe work is 3x the nominal 2MNK and the pipe's TF32 rate is half the measured bf16 rate.
+    # Dense contractions run error-compensated (x = x_hi + x_lo, three tcgen05.mma per fp32-class product), so the tensor-pipe
+    # work is 3x the nominal 2MNK.  nn.Linear runs the split on the FP16 pipe (kind::f16: peak = measured sustained bf16
+    # rate; SCP_AUTO_ENGINE=1 selects the 3xTF32 form, half that rate); attention and kNN use the 3xTF32 form.
     tensor_kernel = tag in ("linear", "swin_attention") or tag.startswith("knn_d1")
+    f16 = tag == "linear" and os.environ.get("SCP_AUTO_ENGINE", "2") == "2" and os.environ.get("SCP_GEMM", "auto") == "auto"
     if tensor_kernel:
-        roof = {"bound": "tensor", "achieved": 3.0 * tfl / tms / 1e9, "peak": tf_peak / 2.0, "unit": "TFLOP/s",
-                "note": "TF32 MMA flops issued (3 per fp32-class product) vs TF32 peak = measured sustained bf16 / 2"}
+        roof = {"bound": "tensor", "achieved": 3.0 * tfl / tms / 1e9, "peak": tf_peak if f16 else tf_peak / 2.0, "unit": "TFLOP/s",
+                "note": ("FP16 MMA flops issued (3 per fp32-class product, 3xFP16 split) vs measured sustained bf16 peak" if f16 else
+                         "TF32 MMA flops issued (3 per fp32-class product) vs TF32 peak = measured sustained bf16 / 2")}
     else:
         roof = {"bound": "hbm", "achieved": tby / tms / 1e6, "peak": hbm_peak, "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
@@ -280,6 +283,21 @@ def run_ours(args):
     oct_rep = {k: {"ms": round(v, 4), "GBps": round(bm[k] / v / 1e6, 1) if v > 0 else None,
                    "frac_of_hbm_peak": round(bm[k] / v / 1e6 / hbm_peak, 3) if v > 0 else None} for k, v in octree_ms.items()}
 
+    # decode path: one frame of the last e2e batch back through Decoder, checked against the encoder's
+    # own octree (lossless round trip) -- reported next to the encode numbers, not part of `value`
+    from scp_b200.decoder import Decoder
+    dcd = Decoder(model, LEVEL, "spher", mullevel=True, kind="kitti")
+    torch.cuda.synchronize()
+    t0 = time.time()
+    dres = dcd.decode(res[0])
+    torch.cuda.synchronize()
+    dec_s = time.time() - t0
+    chk_b, _t, _pf = enc.build_context(xyz[: int(offs[1])], offs[:2])
+    chk_occ = chk_b.emit(("occ",), finish=False)["occ"].cpu().numpy()
+    dec_ok = bool(np.array_equal(np.concatenate(dres.occ), chk_occ))
+    decode_rep = {"frames_per_s": 1.0 / dec_s, "s_per_frame": dec_s, "symbols": int(dres.n_symbols), "round_trip_exact": dec_ok,
+                  "api": "Decoder.decode (phase 1 per level batched, phase 2 + host range decoder per window)"}
+
     cpu_s, cpu_desc = cpu_reference_frame_time(2)
     fps = world * F * args.steps / (ms / 1e3)
     e2e_fps = world * F / (e2e_ms / 1e3)
@@ -289,11 +307,12 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "nodes_per_step": n_nodes,
                    "l2": "inputs/activations per step >> 126 MB L2 (no explicit flush needed)",
-                   "weights": "random-init+ (seeded)", "gemm_engine": os.environ.get("SCP_GEMM", "auto")},
+                   "weights": "random-init+ (seeded)", "gemm_engine": os.environ.get("SCP_GEMM", "auto"), "auto_engine": {"0": "fp32 simt", "1": "3xTF32 tcgen05", "2": "3xFP16 tcgen05"}[os.environ.get("SCP_AUTO_ENGINE", "2")]},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(host.numel() * 4),
                 "d2h_bytes_per_step": int(n_nodes * 8), "bpp_mean": float(np.mean([r.bpp for r in res])),
                 "api": "Encoder.encode_stream (pipelined batches)", "batches_timed": e2e_steps},
         "gpu_launches": int(launches),
+        "decode": decode_rep,
         "clocks": clocks,
         "roofline": roof,
         "kernels": kernels,

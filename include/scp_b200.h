@@ -207,6 +207,7 @@ int64_t   scp_seqs_total(const scp_seqs* s);
 #define SCP_GEMM_SIMT 1      /* fp32 FFMA tiles */
 #define SCP_GEMM_TF32 2      /* tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators (10-bit mantissa operands) */
 #define SCP_GEMM_TF32X3 3    /* same engine, error-compensated split (x_hi + x_lo): fp32-class accuracy */
+#define SCP_GEMM_F16X3 4     /* the same split on the fp16 pipe (kind::f16, twice the tf32 rate), weights scaled per matrix */
 
 /* y[M,N] = act( x[M,K] @ W[N,K]^T + bias[N] ) (+ residual[M,N])   -- nn.Linear with fused epilogue.
  * bias, residual may be NULL.  ldx/ldy/ldr = row strides in floats (W is dense [N,K]). */

@@ -18,6 +18,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <unordered_map>
+#include <cuda_fp16.h>
 #include "tc.cuh"
 
 namespace scp {
@@ -268,6 +269,21 @@ __global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CU
     }
 }
 
+// x0, x1 -> packed fp16 pairs (x0 in the low half): hi = fp16(x) with saturation, lo = fp16(x - hi)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    float h0, h1;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // 3xTF32 kernel with the activation operand in TENSOR MEMORY ("TS" form of tcgen05.mma)
 // ---------------------------------------------------------------------------------------------
@@ -280,15 +296,23 @@ __global__ void __launch_bounds__(384, 1) k_gemm_tf32(const __grid_constant__ CU
 // occupies shared memory, so the ring is 4 stages deep instead of 3.
 // Warps (512 threads, 128 registers): 0 TMA producer, 1 MMA issuer, 2 TMEM owner, 4-7 splitters, 8-15 epilogue.
 // TMEM (512 columns): accumulators [0, 2 BN) | stage s: A_hi [256 + 64 s, +32), A_lo [+32, +64).
-template <int BN, int STAGES>
+//
+// H = true is the same kernel on the FP16 pipe ("3xFP16"): x = x_hi + x_lo with two fp16 numbers (11 + 11 mantissa bits like
+// the tf32 split), kind::f16 MMAs at twice the tf32 rate, K blocks of 64 (two fp32 TMA boxes of A; W_hi/W_lo are stored as
+// fp16, 64 per 128-byte row), A_hi/A_lo packed two per TMEM column (even k in the low half).  fp16 has 5 exponent bits:
+// the weights are scaled by a power of two per matrix so that max|W| sits at 2^13..2^14 (the epilogue multiplies by the
+// exact inverse, read from `oscale`), the activations are taken as they are -- |x| < 65504 converts with saturation,
+// and what falls below the fp16 subnormal step (2^-24) is an ABSOLUTE error of 3e-8 per product term, far below the
+// 2^-22 relative error of the split itself for the O(1) activations of this model.
+template <int BN, int STAGES, bool H>
 __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ CUtensorMap tmBlo,
                                                         const float* __restrict__ bias, const float* __restrict__ R,
                                                         long long ldr, float* __restrict__ Y, long long ldy, long long M, int N,
-                                                        int K, int act) {
-    constexpr int BM = 128, BK = 32;
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+                                                        int K, int act, const float* __restrict__ oscale) {
+    constexpr int BM = 128, BK = H ? 64 : 32;
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * 128;               // B rows: 32 tf32 or 64 fp16 = 128 bytes
     constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;                     // [A fp32 | B_hi | B_lo]
     constexpr int OFF_B = A_BYTES, OFF_BLO = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 512, T_A = 256;
@@ -337,6 +361,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 if (elect_one()) {
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
+                    if (H) tma_load_2d(a + BM * 128, &tmA, &full[stage], kb * BK + 32, m_blk * BM);   // second 32-wide fp32 box
                     tma_load_2d(a + OFF_B, &tmB, &full[stage], kb * BK, n_blk * BN);
                     tma_load_2d(a + OFF_BLO, &tmBlo, &full[stage], kb * BK, n_blk * BN);
                 }
@@ -346,7 +371,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
         }
     } else if (warp == 1) {
         // all lanes run the loop (warp-uniform operands -> uniform registers), the elected lane issues; see tc.cuh elect_one()
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint32_t idesc = H ? ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24))                  // f16 x f16 -> f32
+                                 : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24));
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -360,11 +386,17 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 const uint32_t ah = tmem_base + T_A + (uint32_t)(stage * 64), al = ah + 32u;
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {     // 8 tf32 = 8 TMEM columns of A = 2 descriptor units of B per MMA
+                    for (int k = 0; k < 4; ++k) {          // 8 tf32 / 16 fp16 = 8 TMEM columns of A = 2 descriptor units of B per MMA
                         const uint64_t o = (uint64_t)(2 * k);
-                        tc_mma_tf32_ts(d_tmem, ah + 8u * k, db + o, idesc, (kb | k) ? 1u : 0u);
-                        tc_mma_tf32_ts(d_tmem, al + 8u * k, db + o, idesc, 1u);
-                        tc_mma_tf32_ts(d_tmem, ah + 8u * k, dbl + o, idesc, 1u);
+                        if (H) {
+                            tc_mma_f16_ts(d_tmem, ah + 8u * k, db + o, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_f16_ts(d_tmem, al + 8u * k, db + o, idesc, 1u);
+                            tc_mma_f16_ts(d_tmem, ah + 8u * k, dbl + o, idesc, 1u);
+                        } else {
+                            tc_mma_tf32_ts(d_tmem, ah + 8u * k, db + o, idesc, (kb | k) ? 1u : 0u);
+                            tc_mma_tf32_ts(d_tmem, al + 8u * k, db + o, idesc, 1u);
+                            tc_mma_tf32_ts(d_tmem, ah + 8u * k, dbl + o, idesc, 1u);
+                        }
                     }
                     tc_commit(&empty[stage]);              // frees the smem stage and its TMEM A slot when these MMAs retire
                     if (kb == n_kb - 1) tc_commit(&tfull[acc]);   // accumulator ready for the epilogue
@@ -384,6 +416,15 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 mbar_wait(&full[stage], phase);
                 const uint8_t* a = smem + stage * STAGE_BYTES + row * 128;
                 uint32_t hi[32], lo[32];
+                if (H) {
+                    // 64 fp32 of the row (two boxes) -> 32 + 32 packed fp16 pairs, even k in the low half
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(a + (c >> 3) * (BM * 128) + (((c & 7) ^ (row & 7)) << 4));
+                        split_f16x2(v.x, v.y, hi[2 * c], lo[2 * c]);
+                        split_f16x2(v.z, v.w, hi[2 * c + 1], lo[2 * c + 1]);
+                    }
+                } else {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint4 v = *reinterpret_cast<const uint4*>(a + ((c ^ (row & 7)) << 4));
@@ -393,6 +434,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                     lo[4 * c + 1] = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(hi[4 * c + 1]));
                     lo[4 * c + 2] = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(hi[4 * c + 2]));
                     lo[4 * c + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi[4 * c + 3]));
+                }
                 }
                 tc_st32(t_lane + (uint32_t)(stage * 64), hi);
                 tc_st32(t_lane + (uint32_t)(stage * 64) + 32u, lo);
@@ -412,6 +454,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
         const bool vec_ok = (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
                             (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0))) &&
                             (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
+        const float osc = H ? __ldg(oscale) : 1.0f;
         const int sub_r = lane >> 3, sub_c = (lane & 7) << 2;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
@@ -435,6 +478,10 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 if (!waited) { mbar_wait(&tfull[acc], acc_phase); tc_fence_after(); waited = true; }
                 uint32_t r[32];
                 tc_ld32(t_row + (uint32_t)c0, r);
+                if (H) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * osc);      // exact: power of two
+                }
                 if (c0 + 64 >= BN) {                          // last chunk of this warp: the TMEM stage can go back now
                     tc_fence_before();
                     __syncwarp();
@@ -509,22 +556,27 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-    const void* p; long long ld; long long rows; int cols; int box_rows;
-    bool operator==(const MapKey& o) const { return p == o.p && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows; }
+    const void* p; long long ld; long long rows; int cols; int box_rows; int f16;
+    bool operator==(const MapKey& o) const { return p == o.p && ld == o.ld && rows == o.rows && cols == o.cols && box_rows == o.box_rows && f16 == o.f16; }
 };
 struct MapHash {
     size_t operator()(const MapKey& k) const {
         size_t h = reinterpret_cast<size_t>(k.p);
         h ^= (size_t)k.ld * 0x9e3779b97f4a7c15ull; h ^= (size_t)k.rows * 0xc2b2ae3d27d4eb4full;
-        h ^= ((size_t)k.cols << 20) ^ (size_t)k.box_rows;
+        h ^= ((size_t)k.cols << 20) ^ (size_t)k.box_rows ^ ((size_t)k.f16 << 50);
         return h;
     }
 };
 
+static int get_tensor_map_2d_t(const void* p, long long ld, long long rows, int cols, int box_rows, int f16, CUtensorMap* out);
 int get_tensor_map_2d(const float* p, long long ld, long long rows, int cols, int box_rows, CUtensorMap* out) {
+    return get_tensor_map_2d_t(p, ld, rows, cols, box_rows, 0, out);
+}
+// f16 = 0: float32 elements, boxes of 32 columns; f16 = 1: fp16 elements, boxes of 64 columns (128-byte rows either way)
+static int get_tensor_map_2d_t(const void* p, long long ld, long long rows, int cols, int box_rows, int f16, CUtensorMap* out) {
     static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
     static std::mutex mu;
-    MapKey key{p, ld, rows, cols, box_rows};
+    MapKey key{p, ld, rows, cols, box_rows, f16};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -533,10 +585,10 @@ int get_tensor_map_2d(const float* p, long long ld, long long rows, int cols, in
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return SCP_ERR_CUDA; }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {f16 ? 64u : 32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), gdim, gstr, box, estr,
+    CUresult r = enc(out, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(p), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d ld=%lld", (int)r, rows, cols, ld); return SCP_ERR_CUDA; }
@@ -556,15 +608,71 @@ __global__ void __launch_bounds__(256) k_split_weights(const float* __restrict__
     }
 }
 
+// W -> scale 2^e with max|W| 2^e in [2^13, 2^14), then [W_hi ; W_lo] as fp16 ([N,K] each) + the inverse scale (float) behind
+// them; one block computes the maximum (weights are small and this runs once per matrix)
+__global__ void __launch_bounds__(1024) k_weight_scale(const float* __restrict__ w, long long n, float* __restrict__ scales) {
+    __shared__ float sm[32];
+    float m = 0.f;
+    for (long long i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(w[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = warp_max(sm[threadIdx.x]);
+        if (threadIdx.x == 0) {
+            int e = 0;
+            if (m > 0.f && m < 3e38f) { frexpf(m, &e); e = 14 - e; }          // m = f * 2^(14-e), f in [0.5, 1)
+            e = max(-100, min(100, e));
+            scales[0] = ldexpf(1.0f, e);                                       // applied to W
+            scales[1] = ldexpf(1.0f, -e);                                      // applied to the accumulators
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_split_weights_f16(const float* __restrict__ w, long long n, const float* __restrict__ scales,
+                                                            __half* __restrict__ hi, __half* __restrict__ lo) {
+    const float s = scales[0];
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float v = w[i] * s;
+        const __half h = __float2half_rn(v);
+        hi[i] = h; lo[i] = __float2half_rn(v - __half2float(h));
+    }
+}
+
 struct WKey { const void* p; int n, k; bool operator==(const WKey& o) const { return p == o.p && n == o.n && k == o.k; } };
 struct WHash { size_t operator()(const WKey& k) const { return reinterpret_cast<size_t>(k.p) ^ ((size_t)k.n << 40) ^ ((size_t)k.k << 20); } };
 static std::unordered_map<WKey, float*, WHash> g_wsplit;
 static std::mutex g_wmu;
 
+static std::unordered_map<WKey, __half*, WHash> g_wsplit_h;
+
 void gemm_cache_clear() {
     std::lock_guard<std::mutex> g(g_wmu);
     for (auto& kv : g_wsplit) cudaFree(kv.second);
     g_wsplit.clear();
+    for (auto& kv : g_wsplit_h) cudaFree(kv.second);
+    g_wsplit_h.clear();
+}
+
+// fp16 split: [hi N*K halfs | lo N*K halfs | pad to 16 bytes | scale, 1/scale (floats)]
+static int get_weight_split_f16(const float* w, int N, int K, cudaStream_t st, __half** out, const float** oscale) {
+    std::lock_guard<std::mutex> g(g_wmu);
+    WKey key{w, N, K};
+    const long long n = (long long)N * K;
+    const size_t off_scale = (size_t)((2 * n * 2 + 15) / 16) * 16;
+    auto it = g_wsplit_h.find(key);
+    if (it == g_wsplit_h.end()) {
+        __half* buf = nullptr;
+        SCP_CUDA(cudaMalloc((void**)&buf, off_scale + 16));
+        float* sc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(buf) + off_scale);
+        k_weight_scale<<<1, 1024, 0, st>>>(w, n, sc);
+        SCP_LAUNCHED();
+        k_split_weights_f16<<<(unsigned)std::min<long long>(cdiv(n, 256), 1184), 256, 0, st>>>(w, n, sc, buf, buf + n);
+        SCP_LAUNCHED();
+        it = g_wsplit_h.emplace(key, buf).first;
+    }
+    *out = it->second;
+    *oscale = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(it->second) + off_scale) + 1;
+    return SCP_OK;
 }
 
 static int get_weight_split(const float* w, int N, int K, cudaStream_t st, float** out) {
@@ -609,20 +717,22 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     return SCP_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool H>
 static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, const float* res,
-                     long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st) {
-    constexpr int smem = STAGES * (128 * 128 + 2 * BN * 128) + 1024 + 512 + 8 * 32 * 32 * 4;
+                     long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st,
+                     const float* oscale = nullptr) {
+    constexpr int smem = STAGES * (128 * (H ? 256 : 128) + 2 * BN * 128) + 1024 + 512 + 8 * 32 * 32 * 4;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool attr = false;
     if (!attr) {
-        SCP_CUDA(cudaFuncSetAttribute(k_gemm_x3_ts<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SCP_CUDA(cudaFuncSetAttribute(k_gemm_x3_ts<BN, STAGES, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const long long tiles = cdiv(M, 128) * cdiv(N, BN);
     const int grid = (int)std::min<long long>(tiles, n_sm);
-    k_gemm_x3_ts<BN, STAGES><<<grid, 512, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act);
+    k_gemm_x3_ts<BN, STAGES, H><<<grid, 512, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, oscale);
     SCP_LAUNCHED();
     return SCP_OK;
 }
@@ -631,6 +741,16 @@ int linear_tf32(const float* x, long long ldx, const float* w, const float* bias
                 long long ldy, long long M, int N, int K, int act, cudaStream_t st, int split) {
     CUtensorMap ma, mb, mbl;
     if (int e = get_tensor_map_2d(x, ldx, M, K, 128, &ma)) return e;
+    if (split == 2 && K % 8 == 0) {                                       // 3xFP16 (fp16 rows need 16-byte strides)
+        __half* wh = nullptr;
+        const float* osc = nullptr;
+        if (int e = get_weight_split_f16(w, N, K, st, &wh, &osc)) return e;
+        const int BN = N > 64 ? 128 : 64;
+        if (int e = get_tensor_map_2d_t(wh, K, N, K, BN, 1, &mb)) return e;
+        if (int e = get_tensor_map_2d_t(wh + (long long)N * K, K, N, K, BN, 1, &mbl)) return e;
+        if (BN == 128) return launch_ts<128, 3, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st, osc);
+        return launch_ts<64, 3, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st, osc);
+    }
     if (split) {
         float* ws = nullptr;
         if (int e = get_weight_split(w, N, K, st, &ws)) return e;
@@ -642,8 +762,8 @@ int linear_tf32(const float* x, long long ldx, const float* w, const float* bias
             if (BN == 128) return launch<128, 3, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
             return launch<64, 4, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
         }
-        if (BN == 128) return launch_ts<128, 4>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
-        return launch_ts<64, 4>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
+        if (BN == 128) return launch_ts<128, 4, false>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
+        return launch_ts<64, 4, false>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st);
     }
     const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
     if (int e = get_tensor_map_2d(w, K, N, K, BN, &mb)) return e;

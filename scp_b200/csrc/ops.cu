@@ -9,6 +9,7 @@
 #include <math.h>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 struct scp_seqs {
@@ -805,7 +806,9 @@ __global__ void __launch_bounds__(128) k_octattn_attn(const float* __restrict__ 
 
 static int g_knn_tc = 1;         // learned-feature kNN on the tensor cores (3xTF32 Gram + fused top-k); 0 = fp32 SIMT tiles
 static int g_attn_tc = 1;        // window attention on the tensor cores (3xTF32 QK^T and PV, fused online softmax); 0 = fp32 SIMT
-static int g_auto_tf32 = 1;      // SCP_GEMM_AUTO = 3xTF32 tcgen05 engine for the large layers (validated: PMF err 7e-5)
+// SCP_GEMM_AUTO: 0 = fp32 SIMT, 1 = 3xTF32, 2 = 3xFP16 tcgen05 engine for the large layers (env SCP_AUTO_ENGINE overrides)
+static int auto_engine_default() { const char* e = getenv("SCP_AUTO_ENGINE"); return e ? (atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e))) : 2; }
+static int g_auto_tf32 = auto_engine_default();
 
 static inline int grid_for(long long work, int per_block, int cap = 148 * 16) {
     return (int)std::max<long long>(1, std::min<long long>(cdiv(work, per_block), cap));
@@ -881,7 +884,7 @@ int scp_set_knn_engine(int use_tensor_cores) { int old = g_knn_tc; g_knn_tc = us
 
 int scp_set_attn_engine(int use_tensor_cores) { int old = g_attn_tc; g_attn_tc = use_tensor_cores ? 1 : 0; return old; }
 
-int scp_set_auto_engine(int use_tf32) { int old = g_auto_tf32; g_auto_tf32 = use_tf32 ? 1 : 0; return old; }
+int scp_set_auto_engine(int mode) { int old = g_auto_tf32; g_auto_tf32 = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return old; }
 
 int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K) {
     return linear_tf32_ok(ldx, ldy, M, N, K, nullptr, nullptr, nullptr) ? 1 : 0;
@@ -898,6 +901,8 @@ int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b
     // tiles); SCP_GEMM_AUTO: error-compensated tensor cores for every layer with N >= 64.  The choice must not depend on
     // M: a window has to produce bit-identical logits whatever batch it is encoded in (frame partition = multi-GPU)
     if (tc_ok && engine == SCP_GEMM_TF32) return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st, 0);
+    if (tc_ok && (engine == SCP_GEMM_F16X3 || (engine == SCP_GEMM_AUTO && g_auto_tf32 == 2 && N >= 64)))
+        return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st, 2);
     if (tc_ok && (engine == SCP_GEMM_TF32X3 || (engine == SCP_GEMM_AUTO && g_auto_tf32 && N >= 64)))
         return linear_tf32(d_x, ldx, d_w, d_bias, d_res, ldr, d_y, ldy, M, N, K, act, st, 1);
     const int vec4 = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) &&

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 
 ACT = {"none": 0, "leaky": 1, "gelu": 2, "relu": 3}
-ENGINE = {"auto": 0, "simt": 1, "tf32": 2, "tf32x3": 3}
+ENGINE = {"auto": 0, "simt": 1, "tf32": 2, "tf32x3": 3, "f16x3": 4}
 
 
 class Seqs:

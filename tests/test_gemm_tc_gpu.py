@@ -15,10 +15,11 @@ def V(t, col=0, ncol=None):
     (4096, 1024, 1280, "leaky", False, 1), (2500, 255, 512, "none", False, 1), (640, 240, 256, "relu", False, 2),
     (300, 64, 80, "leaky", False, 1), (3000, 256, 1024, "none", True, 1), (2500, 1024, 256, "gelu", False, 1),
     (70000, 256, 256, "none", True, 1), (33, 128, 448, "none", False, 1)])
-@pytest.mark.parametrize("engine,tol", [("tf32", 4e-3), ("tf32x3", 1e-5)])
+@pytest.mark.parametrize("engine,tol", [("tf32", 4e-3), ("tf32x3", 1e-5), ("f16x3", 1e-5)])
 def test_linear_tensor_core_engines(M, N, K, act, res, step, engine, tol):
     from scp_b200.ops import CudaOps
     cu = CudaOps(engine=engine)
+    cu.lib.scp_gemm_cache_clear()          # split weights are cached per device pointer (the models clear it in _prepare)
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M * step, K + 8, generator=g)
     w = torch.randn(N, K, generator=g) * 0.1
@@ -41,3 +42,30 @@ def test_linear_tensor_core_engines(M, N, K, act, res, step, engine, tol):
     scale = ref.abs().max().item()
     print(M, N, K, engine, "max err", err, "scale", scale)
     assert err < tol * scale * max(1.0, (K / 256) ** 0.5)
+
+
+@pytest.mark.parametrize("xs,ws,tol", [(1.0, 1.0, 2e-6), (300.0, 1e-3, 2e-6), (1e-3, 30.0, 2e-5), (20.0, 1e-5, 2e-6)])
+def test_f16x3_dynamic_range(xs, ws, tol):
+    """3xFP16 engine: fp16 has 5 exponent bits, so the weights are rescaled per matrix and the activations are taken as they
+    are.  Rows mixing large and tiny activations, tiny / large weights: the error stays at the 3xTF32 level relative to the
+    size of the result (what falls under the fp16 subnormal step is an absolute error of 2^-25 per term)."""
+    from scp_b200.ops import CudaOps
+    cu = CudaOps(engine="f16x3")
+    cu.lib.scp_gemm_cache_clear()          # split weights are cached per device pointer (the models clear it in _prepare)
+    g = torch.Generator().manual_seed(7)
+    M, N, K = 3000, 256, 1024
+    x = torch.randn(M, K, generator=g) * xs
+    x[:, ::7] *= 1e-4                                          # tiny entries next to large ones
+    x[::5] *= 50.0
+    w = torch.randn(N, K, generator=g) * ws
+    w[:, ::11] *= 1e-3
+    b = torch.randn(N, generator=g) * xs * ws
+    ref = x.double() @ w.double().T + b.double()
+    y = torch.empty((M, N), device="cuda")
+    cu.linear(V(x.cuda()), w.cuda(), b.cuda(), V(y))
+    got = y.cpu().double()
+    assert torch.isfinite(got).all()
+    row_scale = (x.double().abs() @ w.double().abs().T)        # size of the terms that were summed
+    rel = ((got - ref).abs() / row_scale).max().item()
+    print("xs", xs, "ws", ws, "max err / sum|terms|", rel)
+    assert rel < tol          # activations of 1e-3 and below sit on the fp16 subnormal step: absolute 3e-8 per term
