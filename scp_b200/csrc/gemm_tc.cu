@@ -276,13 +276,6 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
     asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
-__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------
 // 3xTF32 kernel with the activation operand in TENSOR MEMORY ("TS" form of tcgen05.mma)
@@ -441,7 +434,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ready[stage]);
+                if (lane == 0) mbar_arrive_relaxed(&ready[stage]);    // TMEM writes are ordered by wait::st + the tcgen05 fence; nothing in
+                                                                         // generic memory to publish, and a release arrive costs a MEMBAR
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -571,6 +565,9 @@ struct MapHash {
 static int get_tensor_map_2d_t(const void* p, long long ld, long long rows, int cols, int box_rows, int f16, CUtensorMap* out);
 int get_tensor_map_2d(const float* p, long long ld, long long rows, int cols, int box_rows, CUtensorMap* out) {
     return get_tensor_map_2d_t(p, ld, rows, cols, box_rows, 0, out);
+}
+int get_tensor_map_2d_f16(const void* p, long long ld, long long rows, int cols, int box_rows, CUtensorMap* out) {
+    return get_tensor_map_2d_t(p, ld, rows, cols, box_rows, 1, out);
 }
 // f16 = 0: float32 elements, boxes of 32 columns; f16 = 1: fp16 elements, boxes of 64 columns (128-byte rows either way)
 static int get_tensor_map_2d_t(const void* p, long long ld, long long rows, int cols, int box_rows, int f16, CUtensorMap* out) {

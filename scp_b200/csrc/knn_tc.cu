@@ -1,9 +1,12 @@
 // kNN in learned feature space (dgcnn.py:10-28 on 144-/192-d activations) on the 5th-gen tensor cores.
 //
 // score(i,j) = 2 x_i.x_j - |x_j|^2 - |x_i|^2; the Gram tile x_i.x_j is a K-major x K-major tcgen05 GEMM of the
-// token matrix with itself.  Neighbour sets must not move, so the dot products use the error-compensated 3xTF32
-// split (x = x_hi + x_lo, hi.hi + lo.hi + hi.lo: fp32-class accuracy); X is split ONCE per call by an elementwise
-// kernel (the tiles are re-read ~64x from L2, so the extra copy is free) and |x|^2 is fp32.
+// token matrix with itself.  Neighbour sets must not move, so the dot products use the error-compensated split
+// x = x_hi + x_lo (hi.hi + lo.hi + hi.lo: fp32-class accuracy) -- on the FP16 pipe: x_hi, x_lo are fp16 (11 + 11 mantissa
+// bits, like the tf32 split) of X scaled by one power of two per call (max|X| -> [2^7, 2^8); the score undoes it exactly).
+// kind::f16 runs at twice the tf32 rate and, more important here, the candidate tiles are HALF the bytes: every work item
+// streams its whole window through L2 -> shared memory (ncu on the tf32 form: ~5 TB/s of L2 reads, the actual limiter).
+// X is split ONCE per call by an elementwise kernel (the tiles are re-read ~64x from L2) and |x|^2 is fp32.
 //
 // One persistent CTA per work item = (window, 128-query tile):
 //   * the query rows' X_hi / X_lo are written ONCE to tensor memory (tcgen05.st, lane = row) and serve as the A operand
@@ -19,18 +22,19 @@
 // The kc survivors per row go to an exact float64 re-rank, which defines the final order and the tie rule.
 #include <algorithm>
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "tc.cuh"
 
 struct scp_seqs;
 
 namespace scp {
 
-constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 32, KT_STAGES = 10;
+constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 64, KT_STAGES = 10;      // K blocks of 64 fp16 = 128-byte rows
 constexpr int KT_EXTRA = 8;                                    // approximate top-(k+8) is re-ranked exactly
-constexpr int KT_MAXD = 192;                                   // A_hi + A_lo must fit 384 TMEM columns
-constexpr int KT_TILE_BYTES = KT_BN * KT_BK * 4;               // 8 KB: [64 candidates x 32 floats]
+constexpr int KT_MAXD = 192;                                   // A_hi + A_lo: 2 x 96 TMEM columns (two fp16 per column)
+constexpr int KT_TILE_BYTES = KT_BN * KT_BK * 2;               // 8 KB: [64 candidates x 64 halfs]
 constexpr int KT_STAGE_BYTES = 2 * KT_TILE_BYTES;              // B_hi | B_lo
-constexpr uint32_t KT_T_AH = 128, KT_T_AL = 128 + KT_MAXD;     // TMEM: acc [0,128) | A_hi [128,320) | A_lo [320,512)
+constexpr uint32_t KT_T_AH = 128, KT_T_AL = 128 + KT_MAXD / 2; // TMEM: acc [0,128) | A_hi [128,224) | A_lo [224,320)
 // shared memory after the ring: barriers 256 B | candidate norms 4 x 64 f | score tiles 4 x [32][33] f | heaps 4 x [32][32] (f, i)
 constexpr int KT_OFF_BAR = KT_STAGES * KT_STAGE_BYTES;
 constexpr int KT_OFF_XC = KT_OFF_BAR + 256;
@@ -54,17 +58,37 @@ __host__ __device__ __forceinline__ int knn_tile_order(int i, int t0, int nt) {
     return L > R ? t0 - m - 1 - j : t0 + own + m + j;
 }
 
+// max|X| of the call -> scales[0] = 2^e with max * 2^e in [2^7, 2^8), scales[1] = 2 * 2^(-2e) (the factor of the Gram term)
+__global__ void __launch_bounds__(256) k_knn_absmax(const float* __restrict__ X, long long ldx, int d, long long n, unsigned* __restrict__ mx) {
+    float m = 0.f;
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (long long)gridDim.x * 8)
+        for (int c = threadIdx.x & 31; c < d; c += 32) m = fmaxf(m, fabsf(X[r * ldx + c]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(mx, __float_as_uint(m));       // non-negative floats order like their bits
+}
+__global__ void k_knn_scale(const unsigned* __restrict__ mx, float* __restrict__ scales) {
+    const float m = __uint_as_float(*mx);
+    int e = 0;
+    if (m > 0.f && m < 3e38f) { frexpf(m, &e); e = 8 - e; }
+    e = max(-60, min(60, e));
+    scales[0] = ldexpf(1.0f, e);
+    scales[1] = ldexpf(2.0f, -2 * e);
+}
+
 __global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X, long long ldx, int d, long long n,
-                                                     float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ xx) {
+                                                     const float* __restrict__ scales, __half* __restrict__ hi,
+                                                     __half* __restrict__ lo, float* __restrict__ xx) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= n) return;
+    const float sc = scales[0];
     float s = 0.f;
     for (int c = lane; c < d; c += 32) {
         const float v = X[row * ldx + c];
-        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float vs = v * sc;
+        const __half h = __float2half_rn(vs);
         hi[row * d + c] = h;
-        lo[row * d + c] = v - h;
+        lo[row * d + c] = __float2half_rn(vs - __half2float(h));
         s = fmaf(v, v, s);
     }
     s = warp_sum(s);
@@ -73,8 +97,8 @@ __global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X,
 
 __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUtensorMap tmHi,
                                                     const __grid_constant__ CUtensorMap tmLo,
-                                                    const float* __restrict__ xhi, const float* __restrict__ xlo,
-                                                    const float* __restrict__ xx, const long long* __restrict__ seq_off,
+                                                    const __half* __restrict__ xhi, const __half* __restrict__ xlo,
+                                                    const float* __restrict__ scales, const float* __restrict__ xx, const long long* __restrict__ seq_off,
                                                     const int* __restrict__ tile_seq, const int* __restrict__ tile_start,
                                                     int n_work, long long row0, int d, int kc, int* __restrict__ idx_out, int dbg) {
     extern __shared__ uint8_t smem_raw[];
@@ -135,7 +159,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer: all lanes run the loop, the elected lane issues ----------------
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT_BN >> 3) << 17) | ((uint32_t)(KT_BM >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(KT_BN >> 3) << 17) | ((uint32_t)(KT_BM >> 4) << 24);     // f16 x f16 -> f32
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0, a_phase = 0;
         for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
@@ -152,14 +176,14 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                     tc_fence_after();
                     const uint8_t* b = smem + stage * KT_STAGE_BYTES;
                     const uint64_t dbh = make_smem_desc(b), dbl = make_smem_desc(b + KT_TILE_BYTES);
-                    const uint32_t ah = tmem_base + KT_T_AH + (uint32_t)(kb * KT_BK), al = tmem_base + KT_T_AL + (uint32_t)(kb * KT_BK);
+                    const uint32_t ah = tmem_base + KT_T_AH + (uint32_t)(kb * 32), al = tmem_base + KT_T_AL + (uint32_t)(kb * 32);
                     if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < KT_BK / 8; ++kk) {
+                        for (int kk = 0; kk < 4; ++kk) {                     // 16 fp16 = 8 TMEM columns of A = 2 descriptor units of B
                             const uint64_t o = (uint64_t)(2 * kk);
-                            tc_mma_tf32_ts(d_tmem, ah + 8u * kk, dbh + o, idesc, (kb | kk) ? 1u : 0u);
-                            tc_mma_tf32_ts(d_tmem, al + 8u * kk, dbh + o, idesc, 1u);
-                            tc_mma_tf32_ts(d_tmem, ah + 8u * kk, dbl + o, idesc, 1u);
+                            tc_mma_f16_ts(d_tmem, ah + 8u * kk, dbh + o, idesc, (kb | kk) ? 1u : 0u);
+                            tc_mma_f16_ts(d_tmem, al + 8u * kk, dbh + o, idesc, 1u);
+                            tc_mma_f16_ts(d_tmem, ah + 8u * kk, dbl + o, idesc, 1u);
                         }
                         tc_commit(&empty[stage]);
                         if (kb == n_kb - 1) tc_commit(&tfull[acc]);
@@ -186,23 +210,23 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
             const bool rowv = q < n;
             // (every MMA of the previous work item has retired: this warp saw its last accumulator)
             {
-                const float* ph = xhi + (gbase - row0 + q) * (long long)d;
-                const float* pl = xlo + (gbase - row0 + q) * (long long)d;
+                const __half* ph = xhi + (gbase - row0 + q) * (long long)d;
+                const __half* pl = xlo + (gbase - row0 + q) * (long long)d;
                 for (int kb = 0; kb < n_kb; ++kb) {
-                    uint32_t h[32], l[32];
+                    uint32_t h[32], l[32];                                // 64 halfs of the K block, two per word (even k low)
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
-                        const int col = kb * KT_BK + c;
+                        const int col = kb * KT_BK + 2 * c;
                         uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
-                        if (rowv && col < d) {                            // d % 4 == 0: a float4 never straddles the end
+                        if (rowv && col < d) {                            // d % 8 == 0: eight halfs never straddle the end
                             vh = *reinterpret_cast<const uint4*>(ph + col);
                             vl = *reinterpret_cast<const uint4*>(pl + col);
                         }
                         h[c] = vh.x; h[c + 1] = vh.y; h[c + 2] = vh.z; h[c + 3] = vh.w;
                         l[c] = vl.x; l[c + 1] = vl.y; l[c + 2] = vl.z; l[c + 3] = vl.w;
                     }
-                    tc_st32(t_lane + KT_T_AH + (uint32_t)(kb * KT_BK), h);
-                    tc_st32(t_lane + KT_T_AL + (uint32_t)(kb * KT_BK), l);
+                    tc_st32(t_lane + KT_T_AH + (uint32_t)(kb * 32), h);
+                    tc_st32(t_lane + KT_T_AL + (uint32_t)(kb * 32), l);
                 }
                 tc_wait_st();
                 tc_fence_before();
@@ -210,6 +234,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                 if (lane == 0) mbar_arrive(a_ready);
             }
             const float xq = rowv ? xx[gbase - row0 + q] : 0.f;
+            const float two_g = __ldg(scales + 1);                       // 2 / scale^2: the Gram tile is of the scaled rows
             for (int e = 0; e < kc; ++e) hq[32 * e] = make_float2(-INFINITY, __int_as_float(-1));
             float th = (rowv && dbg == 0) ? -INFINITY : INFINITY;          // rows past the window never take a candidate
             const int nt = (n + KT_BN - 1) / KT_BN;
@@ -248,8 +273,8 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                         const float xcv[4] = {xc.x, xc.y, xc.z, xc.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            // == (2 g - |c|^2) - |q|^2 with one rounding per subtraction (2 g is exact)
-                            const float sc = __fsub_rn(fmaf(2.0f, __uint_as_float(r[hh][j4 + e]), -xcv[e]), xq);
+                            // == (2 g - |c|^2) - |q|^2 with one rounding per subtraction (2 g / scale^2 is exact)
+                            const float sc = __fsub_rn(fmaf(two_g, __uint_as_float(r[hh][j4 + e]), -xcv[e]), xq);
                             r[hh][j4 + e] = __float_as_uint(sc);
                             smax = fmaxf(smax, sc);
                         }
@@ -356,32 +381,40 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const float* __restrict__ X,
 }
 
 // host ------------------------------------------------------------------------------------------
-bool knn_tc_ok(int d, int k) { return d >= 32 && d <= KT_MAXD && d % 4 == 0 && k >= 1 && k + KT_EXTRA <= 32; }
+bool knn_tc_ok(int d, int k) { return d >= 32 && d <= KT_MAXD && d % 8 == 0 && k >= 1 && k + KT_EXTRA <= 32; }
 
 int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n_seq, const long long* d_off,
            const int* d_tile_seq, const int* d_tile_start, int n_work, int k, int* d_idx, cudaStream_t st) {
     const long long row0 = h_off[0], total = h_off[n_seq] - h_off[0];
-    float *hi = nullptr, *lo = nullptr, *xx = nullptr;
+    __half *hi = nullptr, *lo = nullptr;
+    float *xx = nullptr, *scales = nullptr;
     int* cand = nullptr;
     const int kc = k + KT_EXTRA;
     SCP_CUDA(malloc_async((void**)&cand, (size_t)total * 32 * 4 + 1024, st));
-    SCP_CUDA(malloc_async((void**)&hi, (size_t)total * d * 4 + 1024, st));
-    SCP_CUDA(malloc_async((void**)&lo, (size_t)total * d * 4 + 1024, st));
+    SCP_CUDA(malloc_async((void**)&hi, (size_t)total * d * 2 + 1024, st));
+    SCP_CUDA(malloc_async((void**)&lo, (size_t)total * d * 2 + 1024, st));
     SCP_CUDA(malloc_async((void**)&xx, (size_t)total * 4 + 1024, st));
-    k_split_rows<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x + row0 * ldx, ldx, d, total, hi, lo, xx);
+    SCP_CUDA(malloc_async((void**)&scales, 64, st));
+    SCP_CUDA(cudaMemsetAsync(scales, 0, 64, st));
+    k_knn_absmax<<<(unsigned)std::min<long long>(cdiv(total, 8), 2368), 256, 0, st>>>(d_x + row0 * ldx, ldx, d, total,
+                                                                                     reinterpret_cast<unsigned*>(scales) + 4);
+    SCP_LAUNCHED();
+    k_knn_scale<<<1, 1, 0, st>>>(reinterpret_cast<unsigned*>(scales) + 4, scales);
+    SCP_LAUNCHED();
+    k_split_rows<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x + row0 * ldx, ldx, d, total, scales, hi, lo, xx);
     SCP_LAUNCHED();
     CUtensorMap mh, ml;
     // the split buffers are transient: encode their maps every call (pointer reuse would alias a cached map only
     // when shape and address are identical, which is then also correct)
-    if (int e = get_tensor_map_2d(hi, d, total, d, KT_BN, &mh)) return e;
-    if (int e = get_tensor_map_2d(lo, d, total, d, KT_BN, &ml)) return e;
+    if (int e = get_tensor_map_2d_f16(hi, d, total, d, KT_BN, &mh)) return e;
+    if (int e = get_tensor_map_2d_f16(lo, d, total, d, KT_BN, &ml)) return e;
     static bool attr = false;
     if (!attr) { SCP_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM)); attr = true; }
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const int grid = std::min(n_work, n_sm);
     const int dbg = getenv("SCP_KNN_DBG") ? atoi(getenv("SCP_KNN_DBG")) : 0;          // timing experiments only
-    k_knn_tc<<<grid, 256, KT_SMEM, st>>>(mh, ml, hi, lo, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, dbg);
+    k_knn_tc<<<grid, 256, KT_SMEM, st>>>(mh, ml, hi, lo, scales, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, dbg);
     SCP_LAUNCHED();
     k_knn_rerank<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x, ldx, d, row0, total, cand, 32, k, d_idx);
     SCP_LAUNCHED();
@@ -389,6 +422,7 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     SCP_CUDA(cudaFreeAsync(hi, st));
     SCP_CUDA(cudaFreeAsync(lo, st));
     SCP_CUDA(cudaFreeAsync(xx, st));
+    SCP_CUDA(cudaFreeAsync(scales, st));
     return SCP_OK;
 }
 

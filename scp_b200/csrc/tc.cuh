@@ -108,6 +108,13 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -141,5 +148,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(const void* tile) {
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency); cached.
 int get_tensor_map_2d(const float* p, long long ld, long long rows, int cols, int box_rows, CUtensorMap* out);
+// same for fp16 elements (boxes of 64 columns = 128-byte rows)
+int get_tensor_map_2d_f16(const void* p, long long ld, long long rows, int cols, int box_rows, CUtensorMap* out);
 
 }  // namespace scp
