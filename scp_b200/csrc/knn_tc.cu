@@ -29,12 +29,20 @@ struct scp_seqs;
 
 namespace scp {
 
-constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 64, KT_STAGES = 10;      // K blocks of 64 fp16 = 128-byte rows
+constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 64;                      // K blocks of 64 fp16 = 128-byte rows
+// TWO CTAs per SM: the kernel is bound by its four epilogue warps (lane = query row is forced by the TMEM lane mapping, so
+// a CTA cannot have more of them), each alone on its scheduler with nothing to hide its dependent-issue latency behind
+// (ncu: 0.8 IPC per SM).  Half the TMEM (256 columns: one accumulator stage) and a 3-stage ring (one candidate tile) per
+// CTA let a second CTA share the SM: two epilogue warps per scheduler, and each CTA's MMAs / TMA run under the other's
+// epilogue.
+constexpr int KT_STAGES = 3, KT_ACC = 1;
 constexpr int KT_EXTRA = 8;                                    // approximate top-(k+8) is re-ranked exactly
 constexpr int KT_MAXD = 192;                                   // A_hi + A_lo: 2 x 96 TMEM columns (two fp16 per column)
 constexpr int KT_TILE_BYTES = KT_BN * KT_BK * 2;               // 8 KB: [64 candidates x 64 halfs]
 constexpr int KT_STAGE_BYTES = 2 * KT_TILE_BYTES;              // B_hi | B_lo
-constexpr uint32_t KT_T_AH = 128, KT_T_AL = 128 + KT_MAXD / 2; // TMEM: acc [0,128) | A_hi [128,224) | A_lo [224,320)
+constexpr uint32_t KT_TMEM_COLS = 256;
+constexpr uint32_t KT_T_AH = KT_ACC * KT_BN, KT_T_AL = KT_T_AH + KT_MAXD / 2;   // TMEM: acc [0,64) | A_hi [64,160) | A_lo [160,256)
+static_assert(KT_T_AL + KT_MAXD / 2 <= KT_TMEM_COLS, "TMEM budget");
 // shared memory after the ring: barriers 256 B | candidate norms 4 x 64 f | score tiles 4 x [32][33] f | heaps 4 x [32][32] (f, i)
 constexpr int KT_OFF_BAR = KT_STAGES * KT_STAGE_BYTES;
 constexpr int KT_OFF_XC = KT_OFF_BAR + 256;
@@ -95,7 +103,7 @@ __global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X,
     if (lane == 0) xx[row] = s;
 }
 
-__global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUtensorMap tmHi,
+__global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUtensorMap tmHi,
                                                     const __grid_constant__ CUtensorMap tmLo,
                                                     const __half* __restrict__ xhi, const __half* __restrict__ xlo,
                                                     const float* __restrict__ scales, const float* __restrict__ xx, const long long* __restrict__ seq_off,
@@ -112,7 +120,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kb = (d + KT_BK - 1) / KT_BK;
-    constexpr uint32_t TMEM_COLS = 512;
+    constexpr uint32_t TMEM_COLS = KT_TMEM_COLS;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmHi)) : "memory");
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < KT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < KT_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         mbar_init(a_ready, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                     __syncwarp();
                     if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == KT_ACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(256, 1) k_knn_tc(const __grid_constant__ CUten
                 tc_fence_before();                                         // scores are in registers: the stage can be refilled
                 __syncwarp();
                 if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == KT_ACC) { acc = 0; acc_phase ^= 1; }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int cb = 32 * hh;
@@ -412,7 +420,7 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     if (!attr) { SCP_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM)); attr = true; }
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-    const int grid = std::min(n_work, n_sm);
+    const int grid = std::min(n_work, 2 * n_sm);                      // two resident CTAs per SM
     const int dbg = getenv("SCP_KNN_DBG") ? atoi(getenv("SCP_KNN_DBG")) : 0;          // timing experiments only
     k_knn_tc<<<grid, 256, KT_SMEM, st>>>(mh, ml, hi, lo, scales, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, dbg);
     SCP_LAUNCHED();
