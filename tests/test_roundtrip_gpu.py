@@ -100,6 +100,23 @@ def test_round_trip_full_size_k16_mullevel():
     print("k16m full: nodes", res.n_nodes, "bytes", len(res.bitstream), "bpp", res.bpp)
 
 
+def test_round_trip_full_size_ford_l17():
+    """BASELINE.json configs[2]: Ford-shaped ~80 k points (integer millimetres), spherical level 17, qs = 2 -- the deepest
+    octree (depth 16) and the largest context tensors."""
+    from scp_b200 import synth
+    pts = synth.make_frame("ford", 0, 17, "spher", guard=True)[0]
+    res, dec, trees = _round_trip(17, "spher", False, pts, kind="ford")
+    print("f17 full: points", len(pts), "nodes", res.n_nodes, "depth", dec.depths, "bytes", len(res.bitstream))
+
+
+def test_round_trip_full_size_k14_cylin():
+    """BASELINE.json configs[4] (one frame of the batch): KITTI-shaped 120 k points, cylindrical level 14."""
+    from scp_b200 import synth
+    pts = synth.make_frame("kitti", 1, 14, "cylin", guard=True, n_points=120000)[0]
+    res, dec, trees = _round_trip(14, "cylin", False, pts)
+    print("k14c full: nodes", res.n_nodes, "depth", dec.depths, "bytes", len(res.bitstream))
+
+
 def test_dequantise_matches_reference_formula():
     from scp_b200.decoder import dequantise
     rng = np.random.default_rng(0)
