@@ -54,6 +54,7 @@ SIGNATURES = {
     "scp_octree_total_rows": (_i64, [_vp]),
     "scp_octree_total_voxels": (_i64, [_vp]),
     "scp_octree_total_kept": (_i64, [_vp]),
+    "scp_set_tree_builder": (_i, [_i]),
     "scp_range_decoder_create": (_vp, [_vp, _i64]),
     "scp_range_decoder_destroy": (None, [_vp]),
     "scp_range_decode": (_i, [_vp, _vp, _i64, _i, _vp]),

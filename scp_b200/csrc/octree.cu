@@ -672,12 +672,14 @@ struct NodeArrays {
     uint8_t* occ;
     u32* parent;
     u64* pos;                   // cell origin, 21 bits per axis: x | y << 21 | z << 42
-    u32* fc;                    // first child (BFS index inside the job; voxel index for the deepest level)
-    uint8_t* vdig;              // per voxel: child digit + 1 inside its level-n node (the "octant" of the voxel)
+    u32* fc;                    // first child (BFS index inside the job; voxel index for the deepest level)   [k_emit_nodes path]
+    uint8_t* vdig;              // per voxel: child digit + 1 inside its level-n node (the "octant" of the voxel) [k_emit_nodes path]
+    int morton;                 // 1: `pos` holds the node's Morton key masked to its level (k_level_pass path)
 };
 __device__ __forceinline__ u64 pack_pos(u32 x, u32 y, u32 z) { return (u64)x | ((u64)y << 21) | ((u64)z << 42); }
-__device__ __forceinline__ void unpack_pos(u64 p, u32& x, u32& y, u32& z) {
-    x = (u32)p & 0x1fffffu; y = (u32)(p >> 21) & 0x1fffffu; z = (u32)(p >> 42);
+__device__ __forceinline__ void unpack_pos(u64 p, int morton, u32& x, u32& y, u32& z) {
+    if (morton) { x = compact3(p >> 2); y = compact3(p >> 1); z = compact3(p); }
+    else { x = (u32)p & 0x1fffffu; y = (u32)(p >> 21) & 0x1fffffu; z = (u32)(p >> 42); }
 }
 
 // One block iteration handles 256 consecutive sorted keys: per level one ballot per warp gives the rank of every head inside
@@ -805,6 +807,209 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
         const int L = threadIdx.x;
         const u32 m = ~((1u << (n - L + 1)) - 1u);
         const bool excl = J.drop_last && L == n;
+        const u32 mn = excl ? s_mm[2] : s_mm[0], mx = excl ? s_mm[3] : s_mm[1];
+        if (mn != 0xffffffffu) {
+            atomicMin(&J.pos_min[L - 1], mn & m);
+            atomicMax(&J.pos_max[L - 1], mx & m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6': bottom-up tree build, one pass per level ("per-level occupancy-byte emission")
+// ------------------------------------------------------------------------------------------
+// Pass p handles, for every job, the children on level Lc = depth + 1 - p (p = 0: the sorted voxel keys) and creates their
+// parents on level Lc - 1: consecutive children with the same key prefix share a parent, so a parent's BFS index inside its
+// level is the number of prefix changes in front of it (warp ballots + an 8-entry block scan + a decoupled look-back over
+// one word per tile), and its occupancy byte is the OR of its children's digit bits -- a segmented OR over <= 8 adjacent
+// lanes (three shuffle rounds).  Every child is read once (its masked Morton key, 8 B) and written once (parent index +
+// level|octant, 6 B); every parent gets its key (8 B) and occupancy (1 B).  ~50 instructions per node, all accesses
+// coalesced; the all-levels-in-one-pass kernel above spends ~200 per node because on the sparse upper levels most lanes of
+// a level iteration idle, and needs k_occupancy (another ~110) behind it.  Level sizes come from k_head_hist / k_level_scan,
+// so nodes land directly in BFS order.
+// Segments cut by a 32-key boundary add their part with atomicOr on the aligned word of the (zeroed) occupancy array; the
+// byte stores of complete segments next to them are safe (an L2 atomic ORs zeros into foreign bytes).
+constexpr u32 PF_AGG = 1u << 30, PF_INC = 1u << 31, PF_MASK = (1u << 30) - 1;
+// Everything a block of k_level_pass needs, prepared on the host (which has the level sizes after scp_octree_plan): one
+// 64-byte load instead of the tile -> job -> level-table chain of dependent global loads, and exact per-pass tile lists
+// (no empty blocks on the sparse upper levels).
+struct PassTile {
+    int job, begin, count, first;       // children [begin, begin+count) of the level; first = first tile of the job's level in the list
+    int n_child, sh, Lc, depth;
+    u32 lsp, lsc;                       // level starts (inside the job) of the parents' / children's level
+    long long node0, src_off;           // job's first node; children keys: sorted + src_off (voxel pass) or pos + node0 + lsc
+    long long vox_start;
+    u32 drop_last, pad;
+};
+
+// MODE 0: inner level (children are nodes), 1: voxel pass (children are the sorted keys), 2: voxel pass + voxel_key output
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_level_pass(const u64* __restrict__ sorted, const PassTile* __restrict__ tiles, int n_tiles,
+                                                     JobDev* jobs, NodeArrays A, u64* __restrict__ vox_key,
+                                                     u32* desc /* [2][n_tiles] of this pass */, u32* ticket, u32* err) {
+    __shared__ u32 s_wcnt[8], s_wvox[8], s_base[2];
+    __shared__ u32 s_mm[4];
+    __shared__ int s_tile;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    if (threadIdx.x < 4) s_mm[threadIdx.x] = (threadIdx.x & 1) ? 0u : 0xffffffffu;
+    __syncthreads();
+    const int tix = s_tile;
+    if (tix >= n_tiles) return;
+    const PassTile t = tiles[tix];
+    const int n = t.depth;
+    const int Lc = t.Lc, Lp = Lc - 1;                               // children / parents level (1-based; n+1 = voxels)
+    constexpr bool vox = MODE != 0;
+    const int Nc = t.n_child;
+    const int cnt = t.count;
+    const int sb = n - Lc + 1;                                      // coordinate bit that selects the child inside its parent
+    const long long node0 = t.node0;
+    const u32 lsp = t.lsp;
+    // nodes carry their cell origin packed as x | y << 21 | z << 42: a parent's origin is its child's with one more bit
+    // per axis cleared, two children share a parent iff their origins agree on the parent's bits
+    const u32 km = (~((2u << sb) - 1u)) & 0x1fffffu;
+    const u64 keep = pack_pos(km, km, km);
+    constexpr bool want_vk = MODE == 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 lemask = (2u << lane) - 1u;                           // lanes <= me
+    const int wbeg = warp * WKEYS;
+
+    u64 c[WITER];                                                   // packed origin of the child (voxel pass: full-resolution position)
+    u64 kraw[want_vk ? WITER : 1];                                  // voxel pass with voxel_key output only: the Morton keys
+    u32 hflag = 0, dflag = 0;                                       // bit it: this lane's child opens a parent / is a new distinct voxel
+    if (vox) {
+        const u64* src = sorted + t.src_off + t.begin;
+#pragma unroll
+        for (int it = 0; it < WITER; ++it) {
+            const int idx = wbeg + it * 32 + lane;
+            const u64 k = idx < cnt ? __ldg(src + idx) : 0ull;
+            if (want_vk) kraw[it] = k;
+            c[it] = pack_pos(compact3(k >> 2), compact3(k >> 1), compact3(k));
+        }
+    } else {
+        const u64* src = A.pos + node0 + t.lsc + t.begin;
+#pragma unroll
+        for (int it = 0; it < WITER; ++it) {
+            const int idx = wbeg + it * 32 + lane;
+            c[it] = idx < cnt ? __ldg(src + idx) : 0ull;
+        }
+    }
+    {
+        const int g0 = t.begin + wbeg;
+        u64 carry = 0ull;
+        if (lane == 0 && g0 > 0 && wbeg < cnt) {
+            if (vox) { const u64 k = __ldg(sorted + t.src_off + g0 - 1); carry = pack_pos(compact3(k >> 2), compact3(k >> 1), compact3(k)); }
+            else carry = __ldg(A.pos + node0 + t.lsc + g0 - 1);
+        }
+        u32 wc = 0, wv = 0;
+#pragma unroll
+        for (int it = 0; it < WITER; ++it) {
+            u64 prev = __shfl_up_sync(0xffffffffu, c[it], 1);
+            if (lane == 0) prev = carry;
+            const int idx = wbeg + it * 32 + lane;
+            const bool valid = idx < cnt, first = (g0 + it * 32 + lane == 0);
+            const u64 df = c[it] ^ prev;
+            const bool h = valid && (first || (df & keep) != 0ull);
+            const bool d = valid && (first || df != 0ull);
+            hflag |= h ? (1u << it) : 0u; dflag |= d ? (1u << it) : 0u;
+            wc += __popc(__ballot_sync(0xffffffffu, h));
+            if (want_vk) wv += __popc(__ballot_sync(0xffffffffu, d));
+            carry = __shfl_sync(0xffffffffu, c[it], 31);
+        }
+        if (lane == 0) { s_wcnt[warp] = wc; s_wvox[warp] = wv; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {                                          // thread 0: parents, thread 1: distinct voxels (only if wanted)
+        const int q = threadIdx.x;
+        u32 base = 0;
+        if (q == 0 || want_vk) {
+            u32 total = 0;
+            for (int w = 0; w < 8; ++w) total += q ? s_wvox[w] : s_wcnt[w];
+            volatile u32* vd = desc + (size_t)q * n_tiles;
+            vd[tix] = total | PF_AGG;
+            // tiles of the job's level in front of this one (tickets are handed out in launch order: they run or are done)
+            for (int pt = tix - 1; pt >= t.first; --pt) {
+                u32 v;
+                int spins = 0;
+                do { v = vd[pt]; } while ((v & (PF_AGG | PF_INC)) == 0 && ++spins < (1 << 22));
+                if ((v & (PF_AGG | PF_INC)) == 0) { atomicExch(err, 1u); break; }      // never hang the GPU
+                base += v & PF_MASK;
+                if (v & PF_INC) break;
+            }
+            vd[tix] = ((base + total) & PF_MASK) | PF_INC;
+        }
+        s_base[q] = base;
+    }
+    __syncthreads();
+    u32 r0 = s_base[0], v0 = s_base[1];
+    for (int w = 0; w < warp; ++w) { r0 += s_wcnt[w]; v0 += s_wvox[w]; }
+    u32 cmin = 0xffffffffu, cmax = 0u, emin = 0xffffffffu, emax = 0u;
+    u32* occ32 = reinterpret_cast<u32*>(A.occ);
+    uint8_t* occ_p = A.occ + node0 + lsp;
+    u64* pos_p = A.pos + node0 + lsp;
+    u32* par_c = A.parent + node0 + t.lsc + t.begin + wbeg + lane;
+    uint16_t* lo_c = A.lo + node0 + t.lsc + t.begin + wbeg + lane;
+    u64 clast = 0ull;
+    if (vox && t.drop_last) { const u64 k = __ldg(sorted + t.src_off + Nc - 1); clast = pack_pos(compact3(k >> 2), compact3(k >> 1), compact3(k)); }
+#pragma unroll
+    for (int it = 0; it < WITER; ++it) {
+        const int idx = wbeg + it * 32 + lane;
+        const bool valid = idx < cnt;
+        const bool h = (hflag >> it) & 1u;
+        const u32 b = __ballot_sync(0xffffffffu, h), vm = __ballot_sync(0xffffffffu, valid);
+        if (vm == 0) break;                                         // warp-uniform: past the end of the tile
+        const u64 cc = c[it];
+        const u32 r = r0 + __popc(b & lemask) - 1u;                 // parent of this child, index inside level Lp
+        const u32 dig = ((u32)(cc >> sb) & 1u) << 2 | ((u32)(cc >> (21 + sb)) & 1u) << 1 | ((u32)(cc >> (42 + sb)) & 1u);
+        u32 v = valid ? (1u << dig) : 0u;
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {                           // segmented OR scan: a parent has <= 8 children
+            const u32 uv = __shfl_up_sync(0xffffffffu, v, o), ur = __shfl_up_sync(0xffffffffu, r, o);
+            if (lane >= o && ur == r) v |= uv;
+        }
+        const bool next_valid = lane < 31 && ((vm >> (lane + 1)) & 1u), next_head = lane < 31 && ((b >> (lane + 1)) & 1u);
+        if (valid && (!next_valid || next_head)) {                  // last child of its parent among these 32
+            const bool headed = (b & lemask) != 0;                  // the parent was opened inside these 32 children
+            const bool closed = next_head || (t.begin + idx == Nc - 1);
+            if (headed && closed) occ_p[r] = (uint8_t)v;
+            else { const long long g = node0 + lsp + r; atomicOr(occ32 + (g >> 2), v << (8 * (int)(g & 3))); }
+        }
+        if (h) {
+            pos_p[r] = cc & keep;
+            if (Lp == 1) { A.parent[node0] = 0u; A.lo[node0] = (uint16_t)(1u | (1u << 8)); }      // root: level 1, octant 1
+        }
+        if (!vox) {
+            if (valid) { par_c[it * 32] = lsp + r; lo_c[it * 32] = (uint16_t)((u32)Lc | ((dig + 1u) << 8)); }
+        } else {
+            const bool d = (dflag >> it) & 1u;
+            if (d) {
+                // x & m is monotone in x, so every level's min / max node coordinate follows from the voxel extremes
+                const u32 x = (u32)cc & 0x1fffffu, y = (u32)(cc >> 21) & 0x1fffffu, z = (u32)(cc >> 42);
+                const u32 lo = min(x, min(y, z)), hi = max(x, max(y, z));
+                cmin = min(cmin, lo); cmax = max(cmax, hi);
+                if (cc != clast) { emin = min(emin, lo); emax = max(emax, hi); }
+            }
+            if (want_vk) {
+                const u32 bd = __ballot_sync(0xffffffffu, d);
+                if (d) vox_key[t.vox_start + v0 + __popc(bd & lemask) - 1u] = kraw[want_vk ? it : 0];
+                v0 += __popc(bd);
+            }
+        }
+        r0 += __popc(b);
+    }
+    if (!vox) return;                                               // block-uniform
+    cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
+    emin = __reduce_min_sync(0xffffffffu, emin); emax = __reduce_max_sync(0xffffffffu, emax);
+    if (lane == 0) {
+        atomicMin(&s_mm[0], cmin); atomicMax(&s_mm[1], cmax); atomicMin(&s_mm[2], emin); atomicMax(&s_mm[3], emax);
+    }
+    __syncthreads();
+    // level L (1-based): nodes are the voxels masked to the level's cell size.  The dropped last row (Octree.py:259-262)
+    // is the last node of the LAST level only, i.e. the job's last voxel; every other level keeps all its nodes.
+    if (threadIdx.x >= 1 && threadIdx.x <= n) {
+        JobDev& J = jobs[t.job];
+        const int L = threadIdx.x;
+        const u32 m = ~((1u << (n - L + 1)) - 1u);
+        const bool excl = t.drop_last && L == n;
         const u32 mn = excl ? s_mm[2] : s_mm[0], mx = excl ? s_mm[3] : s_mm[1];
         if (mn != 0xffffffffu) {
             atomicMin(&J.pos_min[L - 1], mn & m);
@@ -973,7 +1178,7 @@ __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict_
                 // bit j of (coordinate >> sh3) is the octant bit of the ancestor j levels up (sh3 = lowest bit of the own cell)
                 const int sh3 = n - Lu + 1;
                 u32 px, py, pz;
-                unpack_pos(pp[u], px, py, pz);
+                unpack_pos(pp[u], A.morton, px, py, pz);
                 const u32 W = (((px >> sh3) & 0xfu) << 8) | (((py >> sh3) & 0xfu) << 4) | ((pz >> sh3) & 0xfu);
                 u32 OC = 0, LV = 0;
 #pragma unroll
@@ -1037,7 +1242,7 @@ __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles,
         int lv[4], oc[4], occ[4];
         u32 px[4], py[4], pz[4];
         lv[3] = L; oc[3] = lo16 >> 8; occ[3] = A.occ[r];
-        unpack_pos(A.pos[r], px[3], py[3], pz[3]);
+        unpack_pos(A.pos[r], A.morton, px[3], py[3], pz[3]);
         u32 a = A.parent[r];
 #pragma unroll
         for (int k = 2; k >= 0; --k) {
@@ -1111,6 +1316,10 @@ struct scp_octree {
         tile_hist, job_tile_begin, n_lo, n_occ, n_parent, n_pos, n_fc, n_vdig;
     std::vector<JobDev> hjobs;
     std::vector<Tile> h_tiles_pts, h_tiles_sort, h_tiles_node, h_tiles_emit;
+    std::vector<PassTile> h_tiles_pass;
+    std::vector<int> pass_begin;          // tiles of pass p: h_tiles_pass[pass_begin[p] .. pass_begin[p+1])
+    int max_depth = 0;
+    DevBuf pass_desc, tiles_pass;
     int n_jobs = 0, mode = 0, P = 0, nt_frame = 0;
     long long total_keys = 0, total_nodes = 0, total_rows = 0, total_vox = 0;
     bool planned = false, emitted = false;
@@ -1158,7 +1367,12 @@ static int run_sort(u64* keys, u64* tmp, const Tile* d_tiles, int n_tiles, const
     return SCP_OK;
 }
 
+static int tree_builder_default() { const char* e = getenv("SCP_TREE"); return (e && !strcmp(e, "level")) ? 1 : 0; }
+static int g_tree_builder = tree_builder_default();
+
 extern "C" {
+
+int scp_set_tree_builder(int by_level) { int old = g_tree_builder; g_tree_builder = by_level ? 1 : 0; return old; }
 
 scp_octree* scp_octree_create(void) { return new scp_octree(); }
 
@@ -1166,7 +1380,7 @@ void scp_octree_destroy(scp_octree* t) {
     if (!t) return;
     DevBuf* bufs[] = {&t->keys_a, &t->keys_b, &t->tiles_pts, &t->tiles_sort, &t->tiles_node, &t->tiles_emit, &t->frames, &t->jobs,
                       &t->frame_begin, &t->hist, &t->desc, &t->misc, &t->tile_hist, &t->job_tile_begin, &t->n_lo,
-                      &t->n_occ, &t->n_parent, &t->n_pos, &t->n_fc, &t->n_vdig};
+                      &t->n_occ, &t->n_parent, &t->n_pos, &t->n_fc, &t->n_vdig, &t->pass_desc, &t->tiles_pass};
     for (DevBuf* b : bufs) b->release();
     if (t->ev_ok) for (auto& e : t->ev) cudaEventDestroy(e);
     delete t;
@@ -1278,6 +1492,7 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     }
     SCP_REQUIRE(max_depth >= 1 && max_depth <= MAXL, "octree depth %d outside [1,%d]", max_depth, MAXL);
     t->P = (3 * max_depth + 1 + 7) / 8;
+    t->max_depth = max_depth;
     if (any_filter) {
         // jobs with a morton_path (mullevel): drop the rejected keys before sorting
         std::vector<int> stb;
@@ -1329,6 +1544,28 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     for (int j = 0; j < n_jobs; ++j)
         for (int b = 0; b < t->hjobs[j].n_kept; b += TILE)
             t->h_tiles_emit.push_back(Tile{j, b, std::min(TILE, t->hjobs[j].n_kept - b), jtb[j]});
+    // exact tile lists of the level passes: pass p handles the children on level depth + 1 - p of every job
+    t->h_tiles_pass.clear();
+    t->pass_begin.assign(1, 0);
+    for (int p = 0; p < max_depth; ++p) {
+        for (int j = 0; j < n_jobs; ++j) {
+            const JobDev& J = t->hjobs[j];
+            const int n = J.depth, Lc = n + 1 - p;
+            if (Lc < 2) continue;
+            const bool vx = Lc == n + 1;
+            const int Nc = vx ? J.n_kept : J.level_count[Lc - 1];
+            const int first = (int)t->h_tiles_pass.size() - t->pass_begin[p];
+            for (int b = 0; b < Nc; b += TILE) {
+                PassTile pt{};
+                pt.job = j; pt.begin = b; pt.count = std::min(TILE, Nc - b); pt.first = first;
+                pt.n_child = Nc; pt.sh = 3 * (n - Lc + 1); pt.Lc = Lc; pt.depth = n;
+                pt.lsp = (u32)J.level_start[Lc - 2]; pt.lsc = vx ? 0u : (u32)J.level_start[Lc - 1];
+                pt.node0 = J.node_start; pt.src_off = J.key_begin; pt.vox_start = J.vox_start; pt.drop_last = (u32)J.drop_last;
+                t->h_tiles_pass.push_back(pt);
+            }
+        }
+        t->pass_begin.push_back((int)t->h_tiles_pass.size());
+    }
     t->planned = true;
     return SCP_OK;
 }
@@ -1369,24 +1606,55 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     if (int e = t->n_occ.reserve(N)) return e;
     if (int e = t->n_parent.reserve(N * 4)) return e;
     if (int e = t->n_pos.reserve(N * 8)) return e;
-    if (int e = t->n_fc.reserve(N * 4)) return e;
-    u64* vox = reinterpret_cast<u64*>(d_out->voxel_key);          // optional output; the pipeline itself needs only `vdig`
-    if (int e = t->n_vdig.reserve(t->total_vox + 1)) return e;
-    const int nt_n = (int)t->h_tiles_node.size(), nt_e = (int)t->h_tiles_emit.size();
+    // tree builder: 0 = all levels in one pass over the sorted keys (k_emit_nodes + k_occupancy, default: faster), 1 = one
+    // pass per level, bottom-up (k_level_pass); scp_set_tree_builder() / env SCP_TREE=level
+    const bool by_level = g_tree_builder == 1;
+    u64* vox = reinterpret_cast<u64*>(d_out->voxel_key);          // optional output
+    if (!by_level) {
+        if (int e = t->n_fc.reserve(N * 4)) return e;
+        if (int e = t->n_vdig.reserve(t->total_vox + 1)) return e;
+    }
+    const int nt_n = (int)t->h_tiles_node.size(), nt_e = (int)t->h_tiles_emit.size(), nt_p = (int)t->h_tiles_pass.size();
     if (int e = t->tiles_node.reserve((size_t)(nt_n + 1) * sizeof(Tile))) return e;
-    if (int e = t->tiles_emit.reserve((size_t)(nt_e + 1) * sizeof(Tile))) return e;
     SCP_CUDA(cudaMemcpyAsync(t->tiles_node.p, t->h_tiles_node.data(), nt_n * sizeof(Tile), cudaMemcpyHostToDevice, st));
-    SCP_CUDA(cudaMemcpyAsync(t->tiles_emit.p, t->h_tiles_emit.data(), nt_e * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    if (by_level) {
+        if (int e = t->tiles_pass.reserve((size_t)(nt_p + 1) * sizeof(PassTile))) return e;
+        SCP_CUDA(cudaMemcpyAsync(t->tiles_pass.p, t->h_tiles_pass.data(), (size_t)nt_p * sizeof(PassTile), cudaMemcpyHostToDevice, st));
+    } else {
+        if (int e = t->tiles_emit.reserve((size_t)(nt_e + 1) * sizeof(Tile))) return e;
+        SCP_CUDA(cudaMemcpyAsync(t->tiles_emit.p, t->h_tiles_emit.data(), nt_e * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    }
     NodeArrays A{t->n_lo.as<uint16_t>(), t->n_occ.as<uint8_t>(), t->n_parent.as<u32>(), t->n_pos.as<u64>(), t->n_fc.as<u32>(),
-                 t->n_vdig.as<uint8_t>()};
+                 t->n_vdig.as<uint8_t>(), 0};
     JobDev* d_jobs = t->jobs.as<JobDev>();
+    const int n_pass = t->max_depth;                              // children levels depth+1 (voxels) ... 2
+    if (by_level && nt_p) {
+        const size_t words = (size_t)2 * nt_p + n_pass + 64;
+        if (int e = t->pass_desc.reserve(words * 4)) return e;
+        SCP_CUDA(cudaMemsetAsync(t->pass_desc.p, 0, words * 4, st));
+        SCP_CUDA(cudaMemsetAsync(t->n_occ.p, 0, (size_t)N, st));
+    }
     SCP_CUDA(cudaEventRecord(t->ev[4], st));
-    if (nt_e) {
+    if (by_level && nt_p) {
+        u32* desc = t->pass_desc.as<u32>();
+        u32* ticket = desc + (size_t)2 * nt_p;
+        for (int p = 0; p < n_pass; ++p) {
+            const int b0 = t->pass_begin[p], ntp = t->pass_begin[p + 1] - b0;
+            if (ntp == 0) continue;
+            if (p > 0) k_level_pass<0><<<ntp, TPB, 0, st>>>(t->sorted, t->tiles_pass.as<PassTile>() + b0, ntp, d_jobs, A, vox,
+                                                            desc + (size_t)2 * b0, ticket + p, t->misc.as<u32>());
+            else if (!vox) k_level_pass<1><<<ntp, TPB, 0, st>>>(t->sorted, t->tiles_pass.as<PassTile>() + b0, ntp, d_jobs, A, vox,
+                                                                desc + (size_t)2 * b0, ticket + p, t->misc.as<u32>());
+            else k_level_pass<2><<<ntp, TPB, 0, st>>>(t->sorted, t->tiles_pass.as<PassTile>() + b0, ntp, d_jobs, A, vox,
+                                                      desc + (size_t)2 * b0, ticket + p, t->misc.as<u32>());
+            SCP_LAUNCHED();
+        }
+    } else if (!by_level && nt_e) {
         k_emit_nodes<<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), d_jobs, t->tile_hist.as<u32>(), A, vox);
         SCP_LAUNCHED();
     }
     SCP_CUDA(cudaEventRecord(t->ev[5], st));
-    if (nt_n) {
+    if (!by_level && nt_n) {
         k_occupancy<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A);
         SCP_LAUNCHED();
     }

@@ -173,3 +173,36 @@ def test_plan_errors_are_reported():
         octree.OctreeBuilder().plan(pts, [0, 10], [octree.JobSpec(0, 1e-3, None)], "cart")
     with pytest.raises(_lib.ScpError):
         octree.OctreeBuilder().plan(pts, [0, 0], [octree.JobSpec(0, 1.0, None)], "cart")
+
+
+@pytest.mark.parametrize("mul,level,mode", [(False, 12, "spher"), (True, 16, "spher"), (False, 14, "cylin")])
+def test_level_pass_tree_builder_is_bit_identical(mul, level, mode):
+    """The bottom-up builder (one pass per level: k_level_pass, scp_set_tree_builder(1)) and the default one (all levels in
+    one pass over the sorted keys: k_emit_nodes + k_occupancy) produce identical outputs, ragged batch included
+    (a 1-point frame, frames that end inside a 32-key group, full-size frames)."""
+    from scp_b200 import _lib, octree, synth
+    lib = _lib.require_device()
+    frames = [synth.make_frame("kitti", s, level, mode, guard=True, n_points=n)[0]
+              for s, n in ((20, 120000), (21, 1), (22, 4097), (23, 33), (24, 60000))]
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    allp = torch.from_numpy(np.concatenate(frames, 0)).cuda()
+    if mul:
+        jobs = [j for i in range(len(frames)) for j in octree.mullevel_jobs(i, level)]
+    else:
+        jobs = [octree.JobSpec(i, synth.KITTI_QS(level), None, lidar_level=level) for i in range(len(frames))]
+    names = ("occ", "level", "octant", "parent", "pos", "ctx", "pos_norm", "ctx_pos", "voxel_key", "sym")
+    res = []
+    for by_level in (0, 1):
+        old = lib.scp_set_tree_builder(by_level)
+        try:
+            b = octree.OctreeBuilder().plan(allp, offs, jobs, mode)
+            out = b.emit(names)
+            lean = b.emit(("occ", "sym", "ctx", "pos_norm"))
+            res.append(({k: v.cpu().numpy() for k, v in out.items()}, {k: v.cpu().numpy() for k, v in lean.items()},
+                        [(i.depth, i.n_rows, i.n_voxels, tuple(i.level_rows), tuple(i.pos_mm)) for i in b.infos]))
+        finally:
+            lib.scp_set_tree_builder(old)
+    assert res[0][2] == res[1][2]
+    for a, c in ((res[0][0], res[1][0]), (res[0][1], res[1][1])):
+        for k in a:
+            assert np.array_equal(a[k], c[k], equal_nan=True), k
