@@ -476,15 +476,23 @@ __global__ void __launch_bounds__(TPB, 4) k_onesweep(const u64* __restrict__ in,
         int idx = wbase + i * 32 + lane;
         key[i] = idx < tl.count ? src[idx] : SENTINEL;
     }
+    // the 16 match operations are independent of the histogram chain below: issue them back to back (each has ~40 cycles
+    // of latency; inside the read-modify-write loop they were the largest stall of the kernel)
+    u32 peers[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         int idx = wbase + i * 32 + lane;
         u32 d = idx < tl.count ? (u32)((key[i] >> shift) & 0xff) : 256u;
-        u32 peers = __match_any_sync(0xffffffffu, d);
-        u32 lt = peers & ((1u << lane) - 1u);
+        peers[i] = __match_any_sync(0xffffffffu, d);
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        int idx = wbase + i * 32 + lane;
+        u32 d = idx < tl.count ? (u32)((key[i] >> shift) & 0xff) : 256u;
+        u32 lt = peers[i] & ((1u << lane) - 1u);
         u32 prev = s_whist[warp][d];
         __syncwarp();
-        if (lt == 0) s_whist[warp][d] = prev + __popc(peers);
+        if (lt == 0) s_whist[warp][d] = prev + __popc(peers[i]);
         __syncwarp();
         rank[i] = prev + __popc(lt);
     }
