@@ -261,8 +261,9 @@ int scp_swin_attention(const float* d_q, int64_t ldq, const float* d_k, int64_t 
                        const float* d_qb, const float* d_kb, const float* d_vb, const float* d_relpos, int heads,
                        const scp_seqs* seqs, int shift, float* d_out, int64_t ldo, void* stream);
 
-/* 1 (default) = tcgen05 3xTF32 window attention (attn_tc.cu), 0 = fp32 SIMT tiles.  Returns the old value. */
-int scp_set_attn_engine(int use_tensor_cores);
+/* 2 (default) = tcgen05 3xFP16 window attention, two CTAs per SM (attn_h.cu); 1 = tcgen05 3xTF32 (attn_tc.cu); 0 = fp32 SIMT
+ * tiles.  Returns the old value. */
+int scp_set_attn_engine(int mode);
 
 /* Patch merging input (swin_transformer.py:350-362): per sequence, out[j] = [x[2j], x[2j+1]] (zeros if 2j+1 >= S),
  * j < ceil(S/2).  `dst` describes the halved sequences. */

@@ -47,6 +47,9 @@ bool swin_attn_tc_ok(long long ldq, long long ldk, long long ldv, long long ldo,
 int swin_attn_tc(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, const float* qb,
                  const float* kb, const float* vb, const float* relpos, int heads, const long long* d_off, const int* d_win_seq,
                  const int* d_win_idx, int n_win, int shift, float* out, long long ldo, cudaStream_t st);
+int swin_attn_h(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, const float* qb,
+                const float* kb, const float* vb, const float* relpos, int heads, const long long* d_off, const int* d_win_seq,
+                const int* d_win_idx, int n_win, int shift, float* out, long long ldo, cudaStream_t st);          // attn_h.cu
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
@@ -805,7 +808,10 @@ __global__ void __launch_bounds__(128) k_octattn_attn(const float* __restrict__ 
 }
 
 static int g_knn_tc = 1;         // learned-feature kNN on the tensor cores (3xTF32 Gram + fused top-k); 0 = fp32 SIMT tiles
-static int g_attn_tc = 1;        // window attention on the tensor cores (3xTF32 QK^T and PV, fused online softmax); 0 = fp32 SIMT
+// window attention: 0 = fp32 SIMT, 1 = tensor cores 3xTF32 (attn_tc.cu), 2 = tensor cores 3xFP16, two CTAs per SM (attn_h.cu);
+// env SCP_ATTN_ENGINE overrides the default
+static int attn_engine_default() { const char* e = getenv("SCP_ATTN_ENGINE"); return e ? (atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e))) : 2; }
+static int g_attn_tc = attn_engine_default();
 // SCP_GEMM_AUTO: 0 = fp32 SIMT, 1 = 3xTF32, 2 = 3xFP16 tcgen05 engine for the large layers (env SCP_AUTO_ENGINE overrides)
 static int auto_engine_default() { const char* e = getenv("SCP_AUTO_ENGINE"); return e ? (atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e))) : 2; }
 static int g_auto_tf32 = auto_engine_default();
@@ -882,7 +888,7 @@ void scp_gemm_cache_clear(void) { gemm_cache_clear(); }
 
 int scp_set_knn_engine(int use_tensor_cores) { int old = g_knn_tc; g_knn_tc = use_tensor_cores ? 1 : 0; return old; }
 
-int scp_set_attn_engine(int use_tensor_cores) { int old = g_attn_tc; g_attn_tc = use_tensor_cores ? 1 : 0; return old; }
+int scp_set_attn_engine(int mode) { int old = g_attn_tc; g_attn_tc = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return old; }
 
 int scp_set_auto_engine(int mode) { int old = g_auto_tf32; g_auto_tf32 = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return old; }
 
@@ -1014,6 +1020,9 @@ int scp_swin_attention(const float* d_q, int64_t ldq, const float* d_k, int64_t 
     SCP_REQUIRE(heads > 0 && heads <= 16 && (shift == 0 || shift == 256), "scp_swin_attention: heads/shift");
     SCP_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "scp_swin_attention: out must be 16B aligned");
     if (seqs->n_win == 0) return SCP_OK;
+    if (g_attn_tc == 2 && heads * 64 <= 1024 && swin_attn_tc_ok(ldq, ldk, ldv, ldo, d_q, d_k, d_v, d_out, d_qb, d_kb, d_vb))
+        return swin_attn_h(d_q, ldq, d_k, ldk, d_v, ldv, d_qb, d_kb, d_vb, d_relpos, heads, seqs->d_off, seqs->d_win_seq,
+                           seqs->d_win_idx, seqs->n_win, shift, d_out, ldo, as_stream(stream));
     if (g_attn_tc && heads * 64 <= 1024 && swin_attn_tc_ok(ldq, ldk, ldv, ldo, d_q, d_k, d_v, d_out, d_qb, d_kb, d_vb))
         return swin_attn_tc(d_q, ldq, d_k, ldk, d_v, ldv, d_qb, d_kb, d_vb, d_relpos, heads, seqs->d_off, seqs->d_win_seq,
                             seqs->d_win_idx, seqs->n_win, shift, d_out, ldo, as_stream(stream));

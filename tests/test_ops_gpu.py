@@ -136,7 +136,7 @@ def test_edge_gather(ops):
         close(yc, y, 1e-6)
 
 
-@pytest.mark.parametrize("tensor_cores", [1, 0])
+@pytest.mark.parametrize("tensor_cores", [2, 1, 0])          # 2 = 3xFP16 two CTAs/SM (default), 1 = 3xTF32, 0 = fp32 SIMT
 @pytest.mark.parametrize("lens,shift", [([37], 0), ([37], 256), ([600, 2, 512], 256), ([1100], 0), ([1100, 300], 256),
                                         ([2048], 256), ([8192, 130], 0)])
 def test_swin_attention(ops, lens, shift, tensor_cores):
