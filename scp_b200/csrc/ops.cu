@@ -387,9 +387,31 @@ __host__ __device__ __forceinline__ int knn_tile_order(int i, int t0, int nt) { 
 // pipe (8 FP64 instructions per pair).  So every pair is first screened in float32 (the float32 value is within 4e-7
 // relative of the exact one) against the row's current k-th distance inflated by 4e-6; only survivors -- a few hundred
 // of 8192 per row -- take the exact path.  The screen can only pass extra candidates, never drop one.
+// Bounding box of every 128-token tile (min x,y,z,w | max x,y,z,w): tokens are in Morton order, so a tile is a compact
+// region and whole candidate chunks can be rejected against a query tile by their box distance.
+__global__ void __launch_bounds__(256) k_tile_aabb(const float* __restrict__ X, long long ldx, int d,
+                                                    const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
+                                                    const int* __restrict__ tile_start, int n_tile, float* __restrict__ aabb) {
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile >= n_tile) return;
+    const int s = tile_seq[tile];
+    const long long base = seq_off[s];
+    const int n = (int)(seq_off[s + 1] - base), t0 = tile_start[tile];
+    float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int r = t0 + lane; r < min(n, t0 + 128); r += 32)
+        for (int c = 0; c < 4; ++c) { const float v = c < d ? X[(base + r) * ldx + c] : 0.f; mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v); }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+    }
+    if (lane < 4) { aabb[tile * 8 + lane] = mn[lane]; aabb[tile * 8 + 4 + lane] = mx[lane]; }
+}
+
 __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X, long long ldx, int d,
                                                      const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
-                                                     const int* __restrict__ tile_start, int k, int* __restrict__ idx_out) {
+                                                     const int* __restrict__ tile_start, int k, int* __restrict__ idx_out,
+                                                     const float* __restrict__ aabb) {
     extern __shared__ __align__(16) double smd[];
     float4* cs = reinterpret_cast<float4*>(smd);        // [KS_C] candidate coordinates (unused dims = 0)
     double* ls = smd + KS_C * 2;                        // [k][KS_Q]
@@ -407,10 +429,39 @@ __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X,
     double worst = INFINITY;
     float wf = INFINITY;                                // float32 screen: >= worst * (1 + 4e-6)
     const int nchunk = (n + KS_C - 1) / KS_C;
+    const int tile0 = (int)blockIdx.x - tile_start[blockIdx.x] / KS_Q;    // first 128-token tile of this sequence
+    const float4 qmn = *reinterpret_cast<const float4*>(aabb + (size_t)blockIdx.x * 8);
+    const float4 qmx = *reinterpret_cast<const float4*>(aabb + (size_t)blockIdx.x * 8 + 4);
+    // the same test per warp (32 consecutive queries: a tighter box) decides whether the warp scans a chunk that was loaded
+    float wmn[4], wmx[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        wmn[c] = active ? xf[c] : INFINITY; wmx[c] = active ? xf[c] : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { wmn[c] = fminf(wmn[c], __shfl_xor_sync(0xffffffffu, wmn[c], o)); wmx[c] = fmaxf(wmx[c], __shfl_xor_sync(0xffffffffu, wmx[c], o)); }
+    }
     for (int ci = 0; ci < nchunk; ++ci) {
         // own neighbourhood first, then ascending (see knn_tile_order): ties are still resolved by (distance, index)
         const int c0 = knn_tile_order(ci, tile_start[blockIdx.x] / KS_C, nchunk) * KS_C;
-        __syncthreads();
+        // box-to-box distance between this block's queries and the chunk (two 128-token tiles): if it exceeds every row's
+        // screen threshold, no candidate of the chunk can pass the float32 screen below -- skip it unread
+        float dmin2, wmin2;
+        {
+            const int ta = tile0 + c0 / KS_Q;
+            float4 cmn = *reinterpret_cast<const float4*>(aabb + (size_t)ta * 8), cmx = *reinterpret_cast<const float4*>(aabb + (size_t)ta * 8 + 4);
+            if (c0 + KS_Q < n) {
+                const float4 m2 = *reinterpret_cast<const float4*>(aabb + (size_t)(ta + 1) * 8), x2 = *reinterpret_cast<const float4*>(aabb + (size_t)(ta + 1) * 8 + 4);
+                cmn = make_float4(fminf(cmn.x, m2.x), fminf(cmn.y, m2.y), fminf(cmn.z, m2.z), fminf(cmn.w, m2.w));
+                cmx = make_float4(fmaxf(cmx.x, x2.x), fmaxf(cmx.y, x2.y), fmaxf(cmx.z, x2.z), fmaxf(cmx.w, x2.w));
+            }
+            const float gx = fmaxf(0.f, fmaxf(qmn.x - cmx.x, cmn.x - qmx.x)), gy = fmaxf(0.f, fmaxf(qmn.y - cmx.y, cmn.y - qmx.y));
+            const float gz = fmaxf(0.f, fmaxf(qmn.z - cmx.z, cmn.z - qmx.z)), gw = fmaxf(0.f, fmaxf(qmn.w - cmx.w, cmn.w - qmx.w));
+            dmin2 = (gx * gx + gy * gy + gz * gz + gw * gw) * (1.0f - 2e-6f);
+            const float hx = fmaxf(0.f, fmaxf(wmn[0] - cmx.x, cmn.x - wmx[0])), hy = fmaxf(0.f, fmaxf(wmn[1] - cmx.y, cmn.y - wmx[1]));
+            const float hz = fmaxf(0.f, fmaxf(wmn[2] - cmx.z, cmn.z - wmx[2])), hw = fmaxf(0.f, fmaxf(wmn[3] - cmx.w, cmn.w - wmx[3]));
+            wmin2 = (hx * hx + hy * hy + hz * hz + hw * hw) * (1.0f - 2e-6f);
+        }
+        if (__syncthreads_and(!active || dmin2 > wf)) continue;          // (also the barrier in front of rewriting `cs`)
         for (int r = t; r < KS_C; r += KS_Q) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c0 + r < n) {
@@ -424,6 +475,7 @@ __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X,
         }
         __syncthreads();
         if (!active) continue;
+        if (__all_sync(__activemask(), wmin2 > wf)) continue;            // no row of this warp can take a candidate of the chunk
         const int cmax = min(KS_C, n - c0);
 #pragma unroll 4
         for (int r = 0; r < cmax; ++r) {
@@ -976,8 +1028,14 @@ int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, i
             SCP_CUDA(cudaFuncSetAttribute(k_knn_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
             attr_s = smem_s;
         }
-        k_knn_small<<<seqs->n_tile128, KS_Q, smem_s, st>>>(d_x, ldx, d, seqs->d_off, seqs->d_tile128_seq, seqs->d_tile128_start, k, d_idx);
+        float* aabb = nullptr;
+        SCP_CUDA(malloc_async((void**)&aabb, (size_t)seqs->n_tile128 * 32 + 64, st));
+        k_tile_aabb<<<(unsigned)cdiv(seqs->n_tile128, 8), 256, 0, st>>>(d_x, ldx, d, seqs->d_off, seqs->d_tile128_seq, seqs->d_tile128_start,
+                                                                       seqs->n_tile128, aabb);
         SCP_LAUNCHED();
+        k_knn_small<<<seqs->n_tile128, KS_Q, smem_s, st>>>(d_x, ldx, d, seqs->d_off, seqs->d_tile128_seq, seqs->d_tile128_start, k, d_idx, aabb);
+        SCP_LAUNCHED();
+        SCP_CUDA(cudaFreeAsync(aabb, st));
         return SCP_OK;
     }
     if (g_knn_tc && knn_tc_ok(d, k))
