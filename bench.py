@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 LEVEL = 16
 N_POINTS = 120000
-FRAMES_PER_STEP = 2
+FRAMES_PER_STEP = 4
 WORKLOAD = "kitti-shaped 120k-pt sweep, spherical, lidar_level 16, SCP-EHEM encode_mullevel (3 sub-octrees/frame)"
 
 
