@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                                                         const __grid_constant__ CUtensorMap tmBlo,
                                                         const float* __restrict__ bias, const float* __restrict__ R,
                                                         long long ldr, float* __restrict__ Y, long long ldy, long long M, int N,
-                                                        int K, int act, const float* __restrict__ oscale) {
+                                                        int K, int act, const float* __restrict__ oscale, int a_stationary) {
     constexpr int BM = 128, BK = H ? 64 : 32;
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * 128;               // B rows: 32 tf32 or 64 fp16 = 128 bytes
     constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;                     // [A fp32 | B_hi | B_lo]
@@ -338,6 +338,22 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
     const int n_tiles_n = (N + BN - 1) / BN;
     const long long n_tiles = ((M + BM - 1) / BM) * n_tiles_n;
     const int n_kb = (K + BK - 1) / BK;
+    // Tile order.  Default: tiles round-robin over the CTAs.  A-stationary (K <= 4 K blocks, many M blocks): a CTA takes
+    // whole M blocks and walks their N tiles back to back; A is loaded and split ONCE per M block and stays in TMEM
+    // (columns [T_A + 64 kb, +64)) while only the weight tiles stream -- a 128x128 tile otherwise refetches and re-splits
+    // its fp32 A block (128 KB at K = 256) for each of the 6-8 N tiles of the layer, which made the K = 256 layers
+    // L2 -> shared-memory bound (8.4 TB/s of L2 reads) and kept the splitter warps as busy as the tensor pipe.
+    const long long n_mblk = (M + BM - 1) / BM;
+    auto tile_of = [&](long long it, int& m_blk, int& n_blk) -> bool {
+        if (a_stationary) {
+            const long long m = (long long)blockIdx.x + (it / n_tiles_n) * gridDim.x;
+            m_blk = (int)m; n_blk = (int)(it % n_tiles_n);
+            return m < n_mblk;
+        }
+        const long long tile = (long long)blockIdx.x + it * gridDim.x;
+        m_blk = (int)(tile / n_tiles_n); n_blk = (int)(tile % n_tiles_n);
+        return tile < n_tiles;
+    };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -361,15 +377,16 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
 
     if (warp == 0) {
         int stage = 0; uint32_t phase = 0;                  // all lanes run the loop, the elected lane issues (uniform operands)
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+        int m_blk, n_blk;
+        for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
+            const bool load_a = !a_stationary || n_blk == 0;
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* a = smem + stage * STAGE_BYTES;
                 if (elect_one()) {
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
-                    if (H) tma_load_2d(a + BM * 128, &tmA, &full[stage], kb * BK + 32, m_blk * BM);   // second 32-wide fp32 box
+                    mbar_expect_tx(&full[stage], load_a ? STAGE_BYTES : 2 * B_BYTES);
+                    if (load_a) tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
+                    if (H && load_a) tma_load_2d(a + BM * 128, &tmA, &full[stage], kb * BK + 32, m_blk * BM);   // second 32-wide fp32 box
                     tma_load_2d(a + OFF_B, &tmB, &full[stage], kb * BK, n_blk * BN);
                     tma_load_2d(a + OFF_BLO, &tmBlo, &full[stage], kb * BK, n_blk * BN);
                 }
@@ -383,7 +400,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                                  : ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24));
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
             mbar_wait(&tempty[acc], acc_phase ^ 1);
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
             for (int kb = 0; kb < n_kb; ++kb) {
@@ -391,7 +409,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 tc_fence_after();
                 const uint8_t* a = smem + stage * STAGE_BYTES;
                 const uint64_t db = make_smem_desc(a + OFF_B), dbl = make_smem_desc(a + OFF_BLO);
-                const uint32_t ah = tmem_base + T_A + (uint32_t)(stage * 64), al = ah + 32u;
+                const uint32_t ah = tmem_base + T_A + (uint32_t)((a_stationary ? kb : stage) * 64), al = ah + 32u;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {          // 8 tf32 / 16 fp16 = 8 TMEM columns of A = 2 descriptor units of B per MMA
@@ -419,9 +437,23 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
         const int row = (warp - 4) * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + T_A;
         int stage = 0; uint32_t phase = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int acc = 0, prev_acc = 0; uint32_t acc_phase = 0, prev_phase = 0;
+        int m_blk, n_blk;
+        for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
+            const bool split_a = !a_stationary || n_blk == 0;
+            if (a_stationary && n_blk == 0 && it > 0) {
+                // the resident A of the previous M block is still read by the MMAs of its last tile: wait for that accumulator
+                mbar_wait(&tfull[prev_acc], prev_phase);
+                tc_fence_after();
+            }
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(&full[stage], phase);
+                if (!split_a) {                            // weights only: nothing to split, keep the barrier phases in step
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_relaxed(&ready[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 const uint8_t* a = smem + stage * STAGE_BYTES + row * 128;
                 uint32_t hi[32], lo[32];
                 if (H) {
@@ -444,8 +476,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                     lo[4 * c + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi[4 * c + 3]));
                 }
                 }
-                tc_st32(t_lane + (uint32_t)(stage * 64), hi);
-                tc_st32(t_lane + (uint32_t)(stage * 64) + 32u, lo);
+                tc_st32(t_lane + (uint32_t)((a_stationary ? kb : stage) * 64), hi);
+                tc_st32(t_lane + (uint32_t)((a_stationary ? kb : stage) * 64) + 32u, lo);
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
@@ -453,6 +485,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                                                                          // generic memory to publish, and a release arrive costs a MEMBAR
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            prev_acc = acc; prev_phase = acc_phase;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 8) {
         // epilogue: as in k_gemm_tf32, one 32-column chunk at a time (128-register budget)
@@ -465,8 +499,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                             (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
         const float osc = H ? __ldg(oscale) : 1.0f;
         const int sub_r = lane >> 3, sub_c = (lane & 7) << 2;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int m_blk = (int)(tile / n_tiles_n), n_blk = (int)(tile % n_tiles_n);
+        int m_blk, n_blk;
+        for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
             const long long row0 = (long long)m_blk * BM + w * 32;
             const uint32_t t_row = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * BN);
             bool waited = false;
@@ -742,9 +776,14 @@ static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
     }
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-    const long long tiles = cdiv(M, 128) * cdiv(N, BN);
-    const int grid = (int)std::min<long long>(tiles, n_sm);
-    k_gemm_x3_ts<BN, STAGES, H><<<grid, 512, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, oscale);
+    const long long tiles = cdiv(M, 128) * cdiv(N, BN), n_mblk = cdiv(M, 128);
+    // A-stationary tile order (see the kernel) when A fits the 256 spare TMEM columns and there are M blocks to spare
+    // (opt-in, SCP_GEMM_AS=1: measured on the K = 256 layers of a K16 frame it cuts the L2 reads by a quarter but not the
+    // time -- 0.72 / 1.21 ms either way -- so the default stays the round-robin order)
+    static const bool as_on = getenv("SCP_GEMM_AS") && atoi(getenv("SCP_GEMM_AS")) != 0;
+    const int a_stationary = (H && as_on && K <= 256 && cdiv(N, BN) >= 2 && n_mblk >= 2 * n_sm) ? 1 : 0;
+    const int grid = (int)std::min<long long>(a_stationary ? n_mblk : tiles, n_sm);
+    k_gemm_x3_ts<BN, STAGES, H><<<grid, 512, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, oscale, a_stationary);
     SCP_LAUNCHED();
     return SCP_OK;
 }
