@@ -18,6 +18,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <unordered_map>
+#include <stdio.h>
 #include <cuda_fp16.h>
 #include "tc.cuh"
 
@@ -318,7 +319,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                                                         const __grid_constant__ CUtensorMap tmBlo,
                                                         const float* __restrict__ bias, const float* __restrict__ R,
                                                         long long ldr, float* __restrict__ Y, long long ldy, long long M, int N,
-                                                        int K, int act, const float* __restrict__ oscale, int a_stationary) {
+                                                        int K, int act, const float* __restrict__ oscale, int a_stationary,
+                                                        long long* __restrict__ trace) {
     constexpr int BM = 128, BK = H ? 64 : 32;
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * 128;               // B rows: 32 tf32 or 64 fp16 = 128 bytes
     constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;                     // [A fp32 | B_hi | B_lo]
@@ -401,11 +403,16 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         int m_blk, n_blk;
+        int tr_n = 0;                                      // development aid (SCP_GEMM_TRACE=1): clock stamps of CTA 0's MMA warp
+        const bool TR = trace && blockIdx.x == 0;
         for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
+            if (TR && lane == 0 && tr_n < 480) trace[tr_n++] = clock64();            // tile: before the accumulator wait
             mbar_wait(&tempty[acc], acc_phase ^ 1);
+            if (TR && lane == 0 && tr_n < 480) trace[tr_n++] = clock64();            // tile: accumulator free
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(&ready[stage], phase);
+                if (TR && lane == 0 && tr_n < 480) trace[tr_n++] = clock64();        // K block: operands ready
                 tc_fence_after();
                 const uint8_t* a = smem + stage * STAGE_BYTES;
                 const uint64_t db = make_smem_desc(a + OFF_B), dbl = make_smem_desc(a + OFF_BLO);
@@ -499,6 +506,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                             (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
         const float osc = H ? __ldg(oscale) : 1.0f;
         const int sub_r = lane >> 3, sub_c = (lane & 7) << 2;
+        const bool ETR = trace && blockIdx.x == 0 && warp == 8 && lane == 0;
+        int e_n = 0;
         int m_blk, n_blk;
         for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
             const long long row0 = (long long)m_blk * BM + w * 32;
@@ -518,9 +527,12 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                     }
                 }
                 if (bias && vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + sub_c));
+                if (ETR && e_n < 960) trace[1024 + e_n++] = clock64();                  // chunk: before the accumulator wait
                 if (!waited) { mbar_wait(&tfull[acc], acc_phase); tc_fence_after(); waited = true; }
+                if (ETR && e_n < 960) trace[1024 + e_n++] = clock64();                  // chunk: accumulator ready
                 uint32_t r[32];
                 tc_ld32(t_row + (uint32_t)c0, r);
+                if (ETR && e_n < 960) trace[1024 + e_n++] = clock64();                  // chunk: scores in registers
                 if (H) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * osc);      // exact: power of two
@@ -536,19 +548,30 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                     for (int j = 0; j < 32; j += 4)
                         *reinterpret_cast<uint4*>(stg + lane * 32 + ((((j >> 2) ^ lane) & 7) << 2)) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
                     __syncwarp();
+                    // the activation is chosen ONCE per chunk: a `switch (act)` per element was a third of the epilogue's
+                    // instructions, and the eight epilogue warps set the pace of the K = 256 layers (MMA-warp trace: ~4500 of
+                    // 9000 cycles per tile spent waiting for an accumulator to come back)
+                    auto store_rows = [&](auto actf) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rr = it * 4 + sub_r;
-                        const long long row = row0 + rr;
-                        if (row < M) {
-                            float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((((sub_c >> 2) ^ rr) & 7) << 2));
-                            v.x = tc_act(v.x + b4.x, act); v.y = tc_act(v.y + b4.y, act);
-                            v.z = tc_act(v.z + b4.z, act); v.w = tc_act(v.w + b4.w, act);
-                            if (R) { v.x += q[it].x; v.y += q[it].y; v.z += q[it].z; v.w += q[it].w; }
-                            __stcs(reinterpret_cast<float4*>(Y + row * ldy + n0 + sub_c), v);
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + sub_r;
+                            const long long row = row0 + rr;
+                            if (row < M) {
+                                float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((((sub_c >> 2) ^ rr) & 7) << 2));
+                                v.x = actf(v.x + b4.x); v.y = actf(v.y + b4.y); v.z = actf(v.z + b4.z); v.w = actf(v.w + b4.w);
+                                if (R) { v.x += q[it].x; v.y += q[it].y; v.z += q[it].z; v.w += q[it].w; }
+                                __stcs(reinterpret_cast<float4*>(Y + row * ldy + n0 + sub_c), v);
+                            }
                         }
+                    };
+                    switch (act) {                          // warp-uniform
+                        case SCP_ACT_GELU: store_rows([](float v) { return 0.5f * v * (1.0f + tc_erf(v * 0.70710678118654752440f)); }); break;
+                        case SCP_ACT_LEAKY001: store_rows([](float v) { return v > 0.f ? v : 0.01f * v; }); break;
+                        case SCP_ACT_RELU: store_rows([](float v) { return fmaxf(v, 0.f); }); break;
+                        default: store_rows([](float v) { return v; }); break;
                     }
                     __syncwarp();
+                    if (ETR && e_n < 960) trace[1024 + e_n++] = clock64();              // chunk: stored
                 } else {
                     const long long row = row0 + lane;
                     if (row < M) {
@@ -783,7 +806,30 @@ static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
     static const bool as_on = getenv("SCP_GEMM_AS") && atoi(getenv("SCP_GEMM_AS")) != 0;
     const int a_stationary = (H && as_on && K <= 256 && cdiv(N, BN) >= 2 && n_mblk >= 2 * n_sm) ? 1 : 0;
     const int grid = (int)std::min<long long>(a_stationary ? n_mblk : tiles, n_sm);
-    k_gemm_x3_ts<BN, STAGES, H><<<grid, 512, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, oscale, a_stationary);
+    static long long* d_trace = nullptr;
+    static const bool want_trace = getenv("SCP_GEMM_TRACE") != nullptr;
+    if (want_trace && !d_trace) { cudaMalloc(&d_trace, 2048 * 8); }
+    if (want_trace) cudaMemsetAsync(d_trace, 0, 2048 * 8, st);
+    k_gemm_x3_ts<BN, STAGES, H><<<grid, 512, smem, st>>>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, oscale, a_stationary,
+                                                         want_trace ? d_trace : nullptr);
+    if (want_trace && M > 100000) {                      // development aid: MMA-warp timeline of CTA 0, first tiles
+        long long hh[2048];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hh, d_trace, sizeof(hh), cudaMemcpyDeviceToHost);
+        const int n_kb = (K + (H ? 64 : 32) - 1) / (H ? 64 : 32), per = 2 + n_kb;
+        printf("GEMM TRACE M=%lld N=%d K=%d act=%d as=%d: per tile [wait_acc | kb waits... | tile total]\n", M, N, K, act, a_stationary);
+        for (int t = 2; t < 14 && hh[(t + 1) * per]; ++t) {
+            const long long* q = hh + t * per;
+            printf("  tile %2d: acc_wait %5lld |", t, q[1] - q[0]);
+            for (int kb = 0; kb < n_kb; ++kb) printf(" %5lld", q[2 + kb] - q[1 + kb]);
+            printf(" | total %6lld\n", q[per] - q[0]);
+        }
+        printf("  epilogue warp 8, per chunk [wait_acc | tcgen05.ld | stage+store | gap to next chunk]\n");
+        for (int c = 8; c < 20 && hh[1024 + 4 * (c + 1)]; ++c) {
+            const long long* q = hh + 1024 + 4 * c;
+            printf("  chunk %2d: %6lld %6lld %6lld %6lld\n", c, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3]);
+        }
+    }
     SCP_LAUNCHED();
     return SCP_OK;
 }
