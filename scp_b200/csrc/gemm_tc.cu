@@ -801,10 +801,10 @@ static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtenso
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const long long tiles = cdiv(M, 128) * cdiv(N, BN), n_mblk = cdiv(M, 128);
     // A-stationary tile order (see the kernel) when A fits the 256 spare TMEM columns and there are M blocks to spare
-    // (opt-in, SCP_GEMM_AS=1: measured on the K = 256 layers of a K16 frame it cuts the L2 reads by a quarter but not the
-    // time -- 0.72 / 1.21 ms either way -- so the default stays the round-robin order)
-    static const bool as_on = getenv("SCP_GEMM_AS") && atoi(getenv("SCP_GEMM_AS")) != 0;
-    const int a_stationary = (H && as_on && K <= 256 && cdiv(N, BN) >= 2 && n_mblk >= 2 * n_sm) ? 1 : 0;
+    // (SCP_GEMM_AS=0 restores the round-robin order.  While the epilogue set the pace it made no difference; with the
+    // epilogue fixed it takes another 3 ms per step off nn.Linear)
+    static const bool as_off = getenv("SCP_GEMM_AS") && atoi(getenv("SCP_GEMM_AS")) == 0;
+    const int a_stationary = (H && !as_off && K <= 256 && cdiv(N, BN) >= 2 && n_mblk >= 2 * n_sm) ? 1 : 0;
     const int grid = (int)std::min<long long>(a_stationary ? n_mblk : tiles, n_sm);
     static long long* d_trace = nullptr;
     static const bool want_trace = getenv("SCP_GEMM_TRACE") != nullptr;
