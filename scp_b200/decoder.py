@@ -23,6 +23,8 @@ The child expansion and the window bookkeeping are torch index operations on the
 model, the CDF table and the range decoder are the library's.
 """
 import ctypes as C
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import List
 
@@ -56,6 +58,7 @@ class Decoder:
         self.max_tokens = max_tokens
         self.lib = _lib.require_device()
         self.dev = torch.device("cuda")
+        self.pool = ThreadPoolExecutor(min(16, os.cpu_count() or 1))
 
     # ------------------------------------------------------------------------------------------------------------
     def _windows(self, n):
@@ -64,18 +67,36 @@ class Decoder:
         toks = np.concatenate([[0], np.cumsum(lens + (lens & 1))]).astype(np.int64)
         return starts, lens, toks
 
-    def _decode_level(self, dec, ctx, pos_norm, n_code):
-        """ctx uint8 [N,4,3] (self occupancy column = 255), pos_norm float32 [N,3]; decodes the first n_code nodes
-        (the windows of encode.py:112-115) and returns their occupancy symbols 0..254 (host int16 [n_code])."""
+    def _decode_level_batch(self, items):
+        """items: list of (decoder, ctx uint8 [N,4,3] (self occupancy column = 255), pos_norm float32 [N,3], n_code), one per
+        frame.  Decodes, for every frame, its first n_code nodes (the windows of encode.py:112-115) and returns the list of
+        occupancy symbol arrays (host int16 [n_code]).  Phase 1 runs over the windows of ALL frames at once; the per-window
+        part (even symbols -> phase 2 -> odd symbols, the order the stream was written in) runs in lock-step over the
+        frames: window w of every frame that has one forms one phase-2 batch, and the host decoders of the frames run
+        in parallel threads (the C call releases the GIL)."""
         dev, st = self.dev, _lib.stream_ptr()
-        starts, lens, toks = self._windows(n_code)
-        out = np.empty(n_code, np.int16)
-        ctx = ctx.contiguous()
-        pos_norm = pos_norm.contiguous()
+        outs = [np.empty(n, np.int16) for (_, _, _, n) in items]
+        # global window table: (frame, start row inside the frame's level, length)
+        wins = []
+        row0 = [0]
+        for f, (_, ctx, _, n) in enumerate(items):
+            starts, lens, _ = self._windows(n)
+            wins += [(f, int(s0), int(l)) for s0, l in zip(starts, lens)]
+            row0.append(row0[-1] + ctx.shape[0])
+        if not wins:
+            return outs
+        ctx_all = torch.cat([it[1] for it in items]).contiguous()
+        pos_all = torch.cat([it[2] for it in items]).contiguous()
+        lens = np.asarray([w[2] for w in wins], np.int32)
+        rows = np.asarray([row0[w[0]] + w[1] for w in wins], np.int64)
+        toks = np.concatenate([[0], np.cumsum(lens + (lens & 1))]).astype(np.int64)
+        # phase 1, chunks of windows bounded by max_tokens (like the encoder)
+        where = [None] * len(wins)                                 # window -> (chunk, token offset inside the chunk)
+        chunks = []
         w0 = 0
-        while w0 < len(starts):                                   # chunks of windows bounded by max_tokens, like the encoder
+        while w0 < len(wins):
             w1 = w0 + 1
-            while w1 < len(starts) and toks[w1 + 1] - toks[w0] <= self.max_tokens:
+            while w1 < len(wins) and toks[w1 + 1] - toks[w0] <= self.max_tokens:
                 w1 += 1
             T = int(toks[w1] - toks[w0])
             ctxp = torch.empty((T, 4, 3), dtype=torch.uint8, device=dev)
@@ -83,83 +104,142 @@ class Decoder:
             re = torch.empty(T // 2, dtype=torch.int64, device=dev)
             ro = torch.empty(T // 2, dtype=torch.int64, device=dev)
             tk = np.ascontiguousarray(toks[w0:w1] - toks[w0])
-            _lib.check(self.lib.scp_gather_windows(_lib.ptr(ctx), _lib.ptr(pos_norm), _lib.ptr(np.ascontiguousarray(starts[w0:w1])),
+            _lib.check(self.lib.scp_gather_windows(_lib.ptr(ctx_all), _lib.ptr(pos_all), _lib.ptr(np.ascontiguousarray(rows[w0:w1])),
                                                    _lib.ptr(np.ascontiguousarray(lens[w0:w1])), _lib.ptr(tk), w1 - w0,
                                                    _lib.ptr(ctxp), _lib.ptr(posp), _lib.ptr(re), _lib.ptr(ro), st),
                        "scp_gather_windows")
-            offs = [int(x) for x in np.append(tk, T)]
-            feat_a, l1 = self.model.phase1(ctxp, posp, offs)
+            feat_a, l1 = self.model.phase1(ctxp, posp, [int(x) for x in np.append(tk, T)])
             cdf1 = coder.pmf_to_cdf(l1, is_logits=True, want_cdf=True)["cdf"].cpu().numpy()
             for w in range(w0, w1):
-                t0, ln, s = int(tk[w - w0]), int(lens[w]), int(starts[w])
-                ne, no, Tw = (ln + 1) // 2, ln // 2, ln + (ln & 1)
-                sym_e = dec.decode(cdf1[t0 // 2: t0 // 2 + ne])
-                out[s: s + ln: 2] = sym_e
-                if no == 0:
-                    continue
-                cw = ctxp[t0: t0 + Tw]
-                cw[0: 2 * ne: 2, 3, 2] = torch.from_numpy(sym_e.astype(np.uint8)).to(dev)
-                l2 = self.model.phase2(cw, feat_a[t0: t0 + Tw], [0, Tw])
-                cdf2 = coder.pmf_to_cdf(l2[:no].contiguous(), is_logits=True, want_cdf=True)["cdf"].cpu().numpy()
-                out[s + 1: s + ln: 2] = dec.decode(cdf2)
+                where[w] = (len(chunks), int(tk[w - w0]))
+            chunks.append((ctxp, feat_a, cdf1))
             w0 = w1
-        return out
+        # per-frame window lists, then lock-step over the window index
+        per_frame = [[] for _ in items]
+        for w, (f, _, _) in enumerate(wins):
+            per_frame[f].append(w)
+        for k in range(max(len(p) for p in per_frame)):
+            group = [p[k] for p in per_frame if k < len(p)]
 
-    def _decode_tree(self, dec, depth, pos_mm, drop_last, pos_eps_last):
+            def even(w):
+                f, s0, ln = wins[w]
+                c, t0 = where[w]
+                ne = (ln + 1) // 2
+                sym = items[f][0].decode(chunks[c][2][t0 // 2: t0 // 2 + ne])
+                outs[f][s0: s0 + ln: 2] = sym
+                return sym
+            syms_e = list(self.pool.map(even, group)) if len(group) > 1 else [even(group[0])]
+            g2 = [(w, se) for w, se in zip(group, syms_e) if wins[w][2] > 1]
+            if not g2:
+                continue
+            cws, fas, offs = [], [], [0]
+            for w, se in g2:
+                f, s0, ln = wins[w]
+                c, t0 = where[w]
+                Tw = ln + (ln & 1)
+                cw = chunks[c][0][t0: t0 + Tw]
+                cw[0: 2 * len(se): 2, 3, 2] = torch.from_numpy(se.astype(np.uint8)).to(dev)
+                cws.append(cw)
+                fas.append(chunks[c][1][t0: t0 + Tw])
+                offs.append(offs[-1] + Tw)
+            if len(g2) == 1:
+                cw_all, fa_all = cws[0], fas[0]
+            else:
+                cw_all, fa_all = torch.cat(cws), torch.cat(fas)
+            l2 = self.model.phase2(cw_all, fa_all, offs)
+            # rows of logits2 that belong to real odd nodes (the pad token of an odd-length window is dropped)
+            keep = np.concatenate([np.arange(o // 2, o // 2 + wins[w][2] // 2) for (w, _), o in zip(g2, offs[:-1])])
+            l2k = l2 if len(keep) == l2.shape[0] else l2[torch.from_numpy(keep).to(dev)]
+            cdf2 = coder.pmf_to_cdf(l2k.contiguous(), is_logits=True, want_cdf=True)["cdf"].cpu().numpy()
+            cuts = np.concatenate([[0], np.cumsum([wins[w][2] // 2 for w, _ in g2])])
+
+            def odd(i):
+                w = g2[i][0]
+                f, s0, ln = wins[w]
+                outs[f][s0 + 1: s0 + ln: 2] = items[f][0].decode(cdf2[cuts[i]: cuts[i + 1]])
+            if len(g2) > 1:
+                list(self.pool.map(odd, range(len(g2))))
+            else:
+                odd(0)
+        return outs
+
+    def _tree_level_inputs(self, st_, L, n, pos_mm, pos_eps_last):
+        """Model inputs of level L from the per-tree state (pos, anc, octant): (ctx unclipped, ctx for the model, pos_norm)."""
         dev = self.dev
-        n = depth
-        # level 1: the root (decode_ehem.py:79-82: ancestors (0,0,255), self (level 1, octant 1))
-        pos = torch.zeros((1, 3), dtype=torch.int64, device=dev)
-        anc = torch.zeros((1, 3, 3), dtype=torch.uint8, device=dev)
-        anc[:, :, 2] = 255
-        octant = torch.ones(1, dtype=torch.uint8, device=dev)
-        bits = torch.tensor([[(d >> 2) & 1, (d >> 1) & 1, d & 1] for d in range(8)], dtype=torch.int64, device=dev)
-        occ_all = []
-        for L in range(1, n + 1):
-            N = pos.shape[0]
-            own = torch.stack([torch.full((N,), L, dtype=torch.uint8, device=dev), octant,
-                               torch.full((N,), 255, dtype=torch.uint8, device=dev)], 1)
-            ctx = torch.cat([anc, own[:, None, :]], 1)                      # [N,4,3], unclipped levels
-            ctx_model = ctx
-            if L == n and n > self.level:                                   # encode_dataset_ehem.py:86
-                ctx_model = ctx.clone()
-                ctx_model[:, :, 0] = torch.clamp(ctx_model[:, :, 0], max=self.level)
-            mn, mx = pos_mm[L - 1]
-            den = float(mx - mn) + (0.0 if (L == n and not pos_eps_last) else 1e-9)
-            pos_norm = ((pos.to(torch.float64) - float(mn)) / den).to(torch.float32)     # encode_dataset_ehem.py:70-72
-            n_code = N - 1 if (drop_last and L == n) else N
-            if n_code == 1 and L > 1 and not self.mullevel:
-                raise NotImplementedError("single-node level below the root: encode.py:123 codes the root again instead "
-                                          "of this node (reference defect), the stream is not decodable")
-            sym = self._decode_level(dec, ctx_model, pos_norm, n_code) if n_code > 0 else np.empty(0, np.int16)
-            occ_all.append((sym + 1).astype(np.uint8))
-            occ = torch.zeros(N, dtype=torch.int64, device=dev)              # a dropped last node contributes no children
-            occ[:n_code] = torch.from_numpy(sym.astype(np.int64) + 1).to(dev)
-            # children in BFS order: parents in order, child digit ascending (bit d of the byte <-> digit d, Octree.py:175)
-            child = ((occ[:, None] >> torch.arange(8, device=dev)[None, :]) & 1).nonzero()
-            par, dig = child[:, 0], child[:, 1]
-            cell = 1 << (n - L)                                              # cell size one level down
-            pos = pos[par] + bits[dig] * cell
-            if L < n:
-                ctx[:, 3, 2] = (occ - 1).clamp(min=0).to(torch.uint8)
-                anc = ctx[par][:, 1:4].contiguous()
-                octant = (dig + 1).to(torch.uint8)
-        return np.concatenate(occ_all), pos.cpu().numpy()
+        pos, anc, octant = st_
+        N = pos.shape[0]
+        own = torch.stack([torch.full((N,), L, dtype=torch.uint8, device=dev), octant,
+                           torch.full((N,), 255, dtype=torch.uint8, device=dev)], 1)
+        ctx = torch.cat([anc, own[:, None, :]], 1)                      # [N,4,3], unclipped levels
+        ctx_model = ctx
+        if L == n and n > self.level:                                   # encode_dataset_ehem.py:86
+            ctx_model = ctx.clone()
+            ctx_model[:, :, 0] = torch.clamp(ctx_model[:, :, 0], max=self.level)
+        mn, mx = pos_mm[L - 1]
+        den = float(mx - mn) + (0.0 if (L == n and not pos_eps_last) else 1e-9)
+        pos_norm = ((pos.to(torch.float64) - float(mn)) / den).to(torch.float32)     # encode_dataset_ehem.py:70-72
+        return ctx, ctx_model, pos_norm
 
     @torch.no_grad()
+    def decode_batch(self, frs) -> List[DecodedFrame]:
+        """frs: list of FrameResult (bitstream, depths, pos_mm).  Frames are decoded in lock-step (tree by tree, level by
+        level, window by window), so that every model call covers all frames."""
+        dev = self.dev
+        decs = [coder.RangeDecoder(fr.bitstream) for fr in frs]
+        outs = [DecodedFrame(depths=list(fr.depths)) for fr in frs]
+        bits = torch.tensor([[(d >> 2) & 1, (d >> 1) & 1, d & 1] for d in range(8)], dtype=torch.int64, device=dev)
+        drop_last, pos_eps_last = self.mullevel, not self.mullevel
+        lv0 = [0] * len(frs)
+        for j in range(max(len(fr.depths) for fr in frs)):
+            act = [f for f, fr in enumerate(frs) if j < len(fr.depths)]
+            state, occs = {}, {f: [] for f in act}
+            for f in act:
+                # level 1: the root (decode_ehem.py:79-82: ancestors (0,0,255), self (level 1, octant 1))
+                anc = torch.zeros((1, 3, 3), dtype=torch.uint8, device=dev)
+                anc[:, :, 2] = 255
+                state[f] = (torch.zeros((1, 3), dtype=torch.int64, device=dev), anc, torch.ones(1, dtype=torch.uint8, device=dev))
+            for L in range(1, max(frs[f].depths[j] for f in act) + 1):
+                cur = [f for f in act if L <= frs[f].depths[j]]
+                items, ctxs = [], {}
+                for f in cur:
+                    n = frs[f].depths[j]
+                    ctx, ctx_model, pos_norm = self._tree_level_inputs(state[f], L, n, frs[f].pos_mm[lv0[f]: lv0[f] + n], pos_eps_last)
+                    N = ctx.shape[0]
+                    n_code = N - 1 if (drop_last and L == n) else N
+                    if n_code == 1 and L > 1 and not self.mullevel:
+                        raise NotImplementedError("single-node level below the root: encode.py:123 codes the root again instead "
+                                                  "of this node (reference defect), the stream is not decodable")
+                    ctxs[f] = ctx
+                    items.append((decs[f], ctx_model, pos_norm, n_code))
+                syms = self._decode_level_batch(items)
+                for f, sym, (_, _, _, n_code) in zip(cur, syms, items):
+                    n = frs[f].depths[j]
+                    pos = state[f][0]
+                    N = pos.shape[0]
+                    occs[f].append((sym + 1).astype(np.uint8))
+                    occ = torch.zeros(N, dtype=torch.int64, device=dev)          # a dropped last node contributes no children
+                    occ[:n_code] = torch.from_numpy(sym.astype(np.int64) + 1).to(dev)
+                    # children in BFS order: parents in order, child digit ascending (bit d of the byte <-> digit d, Octree.py:175)
+                    child = ((occ[:, None] >> torch.arange(8, device=dev)[None, :]) & 1).nonzero()
+                    par, dig = child[:, 0], child[:, 1]
+                    npos = pos[par] + bits[dig] * (1 << (n - L))                  # cell size one level down
+                    if L < n:
+                        ctx = ctxs[f]
+                        ctx[:, 3, 2] = (occ - 1).clamp(min=0).to(torch.uint8)
+                        state[f] = (npos, ctx[par][:, 1:4].contiguous(), (dig + 1).to(torch.uint8))
+                    else:
+                        state[f] = (npos, None, None)
+            for f in act:
+                outs[f].occ.append(np.concatenate(occs[f]))
+                outs[f].voxels.append(state[f][0].cpu().numpy())
+                lv0[f] += frs[f].depths[j]
+        for f in range(len(frs)):
+            outs[f].n_symbols = decs[f].count
+        return outs
+
     def decode(self, fr) -> DecodedFrame:
         """fr: FrameResult (bitstream, depths, pos_mm)."""
-        dec = coder.RangeDecoder(fr.bitstream)
-        out = DecodedFrame(depths=list(fr.depths))
-        lv = 0
-        for depth in fr.depths:
-            occ, vox = self._decode_tree(dec, depth, fr.pos_mm[lv: lv + depth], drop_last=self.mullevel,
-                                         pos_eps_last=not self.mullevel)
-            out.occ.append(occ)
-            out.voxels.append(vox)
-            lv += depth
-        out.n_symbols = dec.count
-        return out
+        return self.decode_batch([fr])[0]
 
 
 def dequantise(voxels, steps, offset, mode):

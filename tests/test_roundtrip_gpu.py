@@ -117,6 +117,31 @@ def test_round_trip_full_size_k14_cylin():
     print("k14c full: nodes", res.n_nodes, "depth", dec.depths, "bytes", len(res.bitstream))
 
 
+@pytest.mark.parametrize("mul,level", [(False, 12), (True, 16)])
+def test_decode_batch_lock_step_over_ragged_frames(mul, level):
+    """Decoder.decode_batch runs the frames in lock-step (one phase-1 call per level, one phase-2 call per window index over
+    all frames).  Frames of very different sizes (different numbers of windows per level, a 3-point frame whose trees are
+    a single path): every frame decodes to its encoder tree."""
+    from scp_b200 import synth
+    from scp_b200.decoder import Decoder
+    from scp_b200.encoder import Encoder
+    from scp_b200.models import EHEM
+    model = EHEM(cfg_ehem()).cuda()
+    enc = Encoder(model, level, "spher", mullevel=mul)
+    frames = [synth.make_frame("kitti", s, level, "spher", guard=True, n_points=n)[0] for s, n in ((31, 40000), (32, 3), (33, 9000), (34, 120000))]
+    res = enc.encode(frames)
+    dec = Decoder(model, level, "spher", mullevel=mul).decode_batch(res)
+    for fr, r, d in zip(frames, res, dec):
+        trees = _encoder_tree(enc, fr)
+        assert d.n_symbols == r.n_nodes
+        for (occ, vox), d_occ, d_vox in zip(trees, d.occ, d.voxels):
+            assert np.array_equal(d_occ, occ)
+            if mul:
+                assert len(vox) - len(d_vox) <= 8 and np.array_equal(d_vox, vox[:len(d_vox)])
+            else:
+                assert np.array_equal(d_vox, vox)
+
+
 def test_dequantise_matches_reference_formula():
     from scp_b200.decoder import dequantise
     rng = np.random.default_rng(0)
