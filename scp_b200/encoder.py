@@ -97,9 +97,13 @@ class Encoder:
         dev = ctx.device
         w0 = 0
         st = _lib.stream_ptr()
-        while w0 < len(rows):                               # chunks of windows bounded by max_tokens
+        # chunks of windows bounded by max_tokens, of EQUAL size: a greedy split leaves a tail chunk of a few thousand tokens
+        # (a K16 frame is 529 k tokens against 2^19) whose ~850 launches run latency-bound
+        n_chunks = max(1, -(-int(toks[-1]) // self.max_tokens))
+        target = -(-int(toks[-1]) // n_chunks)
+        while w0 < len(rows):
             w1 = w0 + 1
-            while w1 < len(rows) and toks[w1 + 1] - toks[w0] <= self.max_tokens:
+            while w1 < len(rows) and toks[w1 + 1] - toks[w0] <= min(self.max_tokens, target + self.context):
                 w1 += 1
             T = int(toks[w1] - toks[w0])
             ctxp = torch.empty((T, 4, 3), dtype=torch.uint8, device=dev)
