@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const float* __restrict__ X,
     // chunks of the candidate rows into shared memory with coalesced loads (eight lanes per row) and each lane then reads
     // its row from there -- same values, same channel order, same float64 arithmetic.
     __shared__ float s_c[8][32][33];
-    __shared__ float s_q[8][32];
+    __shared__ double s_q[8][32];                                         // query chunk, converted to float64 ONCE per warp
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const long long r = (long long)blockIdx.x * 8 + wid;
     if (r >= n) return;                                                   // warp-uniform; no block-wide barrier below
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const float* __restrict__ X,
         for (int c0 = 0; c0 < d; c0 += 32) {
             const int jn = min(32, d - c0);                               // (d = 144: the last chunk is 16 wide)
             __syncwarp();
-            s_q[wid][lane] = lane < jn ? a[c0 + lane] : 0.f;
+            s_q[wid][lane] = lane < jn ? (double)a[c0 + lane] : 0.0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int cj = __shfl_sync(0xffffffffu, c, 4 * j + sub);
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256) k_knn_rerank(const float* __restrict__ X,
             if (c >= 0) {
 #pragma unroll 8
                 for (int j = 0; j < jn; ++j) {
-                    const double df = (double)s_q[wid][j] - (double)sc[lane][j];
+                    const double df = s_q[wid][j] - (double)sc[lane][j];
                     acc = __dadd_rn(acc, __dmul_rn(df, df));
                 }
             }
