@@ -188,6 +188,21 @@ void    scp_range_decoder_destroy(scp_range_decoder* d);
 int     scp_range_decode(scp_range_decoder* d, const uint16_t* h_cdf, int64_t n, int Lp, int16_t* h_sym);
 int64_t scp_range_decoder_count(const scp_range_decoder* d);
 
+/* Decode side, device: the decoder rebuilds every level from the occupancy bytes decoded so far (decode_ehem.py:100-140).
+ * Node state of a level: d_pos int32 [n,3] cell origins, d_anc uint8 [n,3,3] (level, octant, occ-1) of the three ancestors
+ * (missing = (0,0,255)), d_octant uint8 [n].
+ * scp_decode_level_inputs: the context rows the entropy model is fed, as on the encode side -- d_ctx [n,4,3] with the self
+ *   row (level, octant, 255), d_ctx_model = the same with the level column clipped to clip_level (encode_dataset_ehem.py:86;
+ *   255 = no clip), d_pos_norm float32 [n,3] = float32((pos - pos_min) / pos_den) (encode_dataset_ehem.py:70-72).
+ * scp_expand_children: d_occ uint8 [n] decoded occupancy bytes (0 = no children), d_ctx [n,4,3] of scp_decode_level_inputs;
+ *   writes the next level's state in BFS order (parents in order, child digit ascending), sum(popcount(occ)) nodes;
+ *   `level` = the parents' level, `cell` = the children's cell size. */
+int scp_decode_level_inputs(const int32_t* d_pos, const uint8_t* d_anc, const uint8_t* d_octant, int64_t n, int level,
+                            int clip_level, double pos_min, double pos_den, uint8_t* d_ctx, uint8_t* d_ctx_model,
+                            float* d_pos_norm, void* stream);
+int scp_expand_children(const uint8_t* d_occ, const int32_t* d_pos, const uint8_t* d_ctx, int64_t n, int level, int cell,
+                        int32_t* d_child_pos, uint8_t* d_child_anc, uint8_t* d_child_octant, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Entropy-model operators (A8-A12).  Device pointers, float32 activations, row-major [tokens, channels].
  * Windows of ANY length are processed together as one ragged batch: a `scp_seqs` describes how the token

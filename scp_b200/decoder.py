@@ -19,8 +19,8 @@ tests/test_roundtrip_gpu.py checks at full size.  Differences to the reference's
   them from the parent's normalised float and only uses the max;
 * termination comes from the number of levels in the header, not from the length of the original sequence
   (decode_ehem.py:66 reads it from the uncompressed .npy "for checking").
-The child expansion and the window bookkeeping are torch index operations on the device (plumbing); the entropy
-model, the CDF table and the range decoder are the library's.
+The level inputs (scp_decode_level_inputs), the child expansion (scp_expand_children), the entropy model, the CDF table
+and the range decoder are the library's; torch only owns the device buffers.
 """
 import ctypes as C
 import os
@@ -164,21 +164,42 @@ class Decoder:
         return outs
 
     def _tree_level_inputs(self, st_, L, n, pos_mm, pos_eps_last):
-        """Model inputs of level L from the per-tree state (pos, anc, octant): (ctx unclipped, ctx for the model, pos_norm)."""
+        """Model inputs of level L from the per-tree state (pos int32 [N,3], anc uint8 [N,3,3], octant uint8 [N]):
+        (ctx with unclipped levels, ctx for the model, pos_norm) -- scp_decode_level_inputs."""
         dev = self.dev
         pos, anc, octant = st_
         N = pos.shape[0]
-        own = torch.stack([torch.full((N,), L, dtype=torch.uint8, device=dev), octant,
-                           torch.full((N,), 255, dtype=torch.uint8, device=dev)], 1)
-        ctx = torch.cat([anc, own[:, None, :]], 1)                      # [N,4,3], unclipped levels
-        ctx_model = ctx
-        if L == n and n > self.level:                                   # encode_dataset_ehem.py:86
-            ctx_model = ctx.clone()
-            ctx_model[:, :, 0] = torch.clamp(ctx_model[:, :, 0], max=self.level)
+        ctx = torch.empty((N, 4, 3), dtype=torch.uint8, device=dev)
+        ctx_model = torch.empty((N, 4, 3), dtype=torch.uint8, device=dev)
+        pos_norm = torch.empty((N, 3), dtype=torch.float32, device=dev)
         mn, mx = pos_mm[L - 1]
-        den = float(mx - mn) + (0.0 if (L == n and not pos_eps_last) else 1e-9)
-        pos_norm = ((pos.to(torch.float64) - float(mn)) / den).to(torch.float32)     # encode_dataset_ehem.py:70-72
+        den = float(mx - mn) + (0.0 if (L == n and not pos_eps_last) else 1e-9)      # encode_dataset_ehem.py:70-72 / mullevel :80
+        clip = self.level if (L == n and n > self.level) else 255                    # encode_dataset_ehem.py:86
+        _lib.check(self.lib.scp_decode_level_inputs(_lib.ptr(pos), _lib.ptr(anc), _lib.ptr(octant), N, L, clip, float(mn), den,
+                                                    _lib.ptr(ctx), _lib.ptr(ctx_model), _lib.ptr(pos_norm), _lib.stream_ptr()),
+                   "scp_decode_level_inputs")
         return ctx, ctx_model, pos_norm
+
+    _POPC = np.array([bin(i).count("1") for i in range(256)], np.int64)
+
+    def _expand(self, st_, ctx, sym, n_code, L, n):
+        """Next level's node state from the decoded symbols of level L (scp_expand_children).  A dropped last node
+        (encode_mullevel, Octree.py:259-262) has no decoded occupancy and contributes no children."""
+        dev = self.dev
+        pos = st_[0]
+        N = pos.shape[0]
+        occ_h = np.zeros(N, np.uint8)
+        occ_h[:n_code] = (sym + 1).astype(np.uint8)
+        M = int(self._POPC[occ_h].sum())
+        occ = torch.from_numpy(occ_h).to(dev)
+        cpos = torch.empty((M, 3), dtype=torch.int32, device=dev)
+        canc = torch.empty((M, 3, 3), dtype=torch.uint8, device=dev)
+        coct = torch.empty((M,), dtype=torch.uint8, device=dev)
+        if M == 0:                                              # (a tree whose only node on this level was dropped)
+            return (cpos, canc, coct)
+        _lib.check(self.lib.scp_expand_children(_lib.ptr(occ), _lib.ptr(pos), _lib.ptr(ctx), N, L, 1 << (n - L), _lib.ptr(cpos),
+                                                _lib.ptr(canc), _lib.ptr(coct), _lib.stream_ptr()), "scp_expand_children")
+        return (cpos, canc, coct)
 
     @torch.no_grad()
     def decode_batch(self, frs) -> List[DecodedFrame]:
@@ -187,7 +208,6 @@ class Decoder:
         dev = self.dev
         decs = [coder.RangeDecoder(fr.bitstream) for fr in frs]
         outs = [DecodedFrame(depths=list(fr.depths)) for fr in frs]
-        bits = torch.tensor([[(d >> 2) & 1, (d >> 1) & 1, d & 1] for d in range(8)], dtype=torch.int64, device=dev)
         drop_last, pos_eps_last = self.mullevel, not self.mullevel
         lv0 = [0] * len(frs)
         for j in range(max(len(fr.depths) for fr in frs)):
@@ -197,7 +217,7 @@ class Decoder:
                 # level 1: the root (decode_ehem.py:79-82: ancestors (0,0,255), self (level 1, octant 1))
                 anc = torch.zeros((1, 3, 3), dtype=torch.uint8, device=dev)
                 anc[:, :, 2] = 255
-                state[f] = (torch.zeros((1, 3), dtype=torch.int64, device=dev), anc, torch.ones(1, dtype=torch.uint8, device=dev))
+                state[f] = (torch.zeros((1, 3), dtype=torch.int32, device=dev), anc, torch.ones(1, dtype=torch.uint8, device=dev))
             for L in range(1, max(frs[f].depths[j] for f in act) + 1):
                 cur = [f for f in act if L <= frs[f].depths[j]]
                 items, ctxs = [], {}
@@ -213,25 +233,11 @@ class Decoder:
                     items.append((decs[f], ctx_model, pos_norm, n_code))
                 syms = self._decode_level_batch(items)
                 for f, sym, (_, _, _, n_code) in zip(cur, syms, items):
-                    n = frs[f].depths[j]
-                    pos = state[f][0]
-                    N = pos.shape[0]
                     occs[f].append((sym + 1).astype(np.uint8))
-                    occ = torch.zeros(N, dtype=torch.int64, device=dev)          # a dropped last node contributes no children
-                    occ[:n_code] = torch.from_numpy(sym.astype(np.int64) + 1).to(dev)
-                    # children in BFS order: parents in order, child digit ascending (bit d of the byte <-> digit d, Octree.py:175)
-                    child = ((occ[:, None] >> torch.arange(8, device=dev)[None, :]) & 1).nonzero()
-                    par, dig = child[:, 0], child[:, 1]
-                    npos = pos[par] + bits[dig] * (1 << (n - L))                  # cell size one level down
-                    if L < n:
-                        ctx = ctxs[f]
-                        ctx[:, 3, 2] = (occ - 1).clamp(min=0).to(torch.uint8)
-                        state[f] = (npos, ctx[par][:, 1:4].contiguous(), (dig + 1).to(torch.uint8))
-                    else:
-                        state[f] = (npos, None, None)
+                    state[f] = self._expand(state[f], ctxs[f], sym, n_code, L, frs[f].depths[j])
             for f in act:
                 outs[f].occ.append(np.concatenate(occs[f]))
-                outs[f].voxels.append(state[f][0].cpu().numpy())
+                outs[f].voxels.append(state[f][0].cpu().numpy().astype(np.int64))
                 lv0[f] += frs[f].depths[j]
         for f in range(len(frs)):
             outs[f].n_symbols = decs[f].count
