@@ -203,6 +203,17 @@ int scp_decode_level_inputs(const int32_t* d_pos, const uint8_t* d_anc, const ui
 int scp_expand_children(const uint8_t* d_occ, const int32_t* d_pos, const uint8_t* d_ctx, int64_t n, int level, int cell,
                         int32_t* d_child_pos, uint8_t* d_child_anc, uint8_t* d_child_octant, void* stream);
 
+/* Distortion report.
+ * scp_dequantise_keys: voxel Morton keys of a job (scp_octree_out.voxel_key; bit triple b = (x,y,z) at bits 3b+2,3b+1,3b)
+ *   -> float64 [n,3] points `v * steps + offset` mapped back to Cartesian (spher2cart / cylin2cart,
+ *   data_preprocess.py:179-229; what proc_pc :68-92 / mul_proc_pc :160-167 return as the quantised cloud).
+ *   h_steps / h_offset: 3 host doubles each (scp_job_info.steps / .offset; offset zero for SCP_MODE_SPHER).
+ * scp_nn_dist2: d_dist2[i] = min_j |query_i - cand_j|^2 in float64, exact (brute force) -- the two KDTree queries of
+ *   pt.py:88-95 (distChamfer) and the nearest-neighbour pass of pc_error's D1 metric.  Points float64 [n,3]. */
+int scp_dequantise_keys(const int64_t* d_keys, int64_t n, const double* h_steps, const double* h_offset, int mode,
+                        double* d_xyz, void* stream);
+int scp_nn_dist2(const double* d_query, int64_t n_query, const double* d_cand, int64_t n_cand, double* d_dist2, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Entropy-model operators (A8-A12).  Device pointers, float32 activations, row-major [tokens, channels].
  * Windows of ANY length are processed together as one ragged batch: a `scp_seqs` describes how the token

@@ -283,10 +283,29 @@ def gen_coder(ns, tmp):
         nac.arithmeticCoding.encode = real_encode
         np.savez_compressed(os.path.join(GOLD, f"e2e_{name}.npz"), bpp=bpp, n_points=len(g["points"]), **captured)
         print("e2e", name, "bpp", bpp, "bytes", len(captured["bitstream"]))
+def gen_metrics(ns, tmp):
+    """pt.distChamfer of the reference on (original cloud, quantised cloud of proc_pc / mul_proc_pc) of the octree cases."""
+    dp = ns.data_preprocess
+    out = {}
+    for name, (kind, seed, level, mode, n_points, mullevel) in OCTREE_CASES.items():
+        pts, qs = case_points(kind, seed, level, mode, n_points, mullevel)
+        binf = os.path.join(tmp, name + ".bin")
+        pts.astype(np.float32).tofile(binf)
+        kw = dict(spher=(mode == "spher"), cylin=(mode == "cylin"))
+        if mullevel:
+            q = np.vstack([dp.mul_proc_pc(binf, tmp, name, qs=s, test=True, normalize=False, morton_path=mp, **kw)[1]
+                           for s, mp in zip(qs, [[0, 0], [0, 1], [1]])])
+        else:
+            q = dp.proc_pc(binf, tmp, name, qs=qs[0], test=True, normalize=False, **kw)[1]
+        pc = dp.pointCloud.ptread(binf)
+        out[name + "_q"] = np.asarray(q)
+        out[name + "_chamfer"] = float(dp.pointCloud.distChamfer(pc.copy(), np.array(q, copy=True)))
+        print(name, "quantised cloud", out[name + "_q"].shape, out[name + "_q"].dtype, "chamfer", out[name + "_chamfer"])
+    np.savez_compressed(os.path.join(GOLD, "metrics.npz"), **out)
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["octree", "ehem", "octattn", "coder"]
+    what = sys.argv[1:] or ["octree", "ehem", "octattn", "coder", "metrics"]
     os.makedirs(GOLD, exist_ok=True)
     ns = ref_shims.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
@@ -298,3 +317,5 @@ if __name__ == "__main__":
             gen_octattn_logits(ns)
         if "coder" in what:
             gen_coder(ns, tmp)
+        if "metrics" in what:
+            gen_metrics(ns, tmp)

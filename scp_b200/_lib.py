@@ -61,6 +61,8 @@ SIGNATURES = {
     "scp_range_decoder_count": (_i64, [_vp]),
     "scp_decode_level_inputs": (_i, [_vp, _vp, _vp, _i64, _i, _i, C.c_double, C.c_double, _vp, _vp, _vp, _vp]),
     "scp_expand_children": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp]),
+    "scp_dequantise_keys": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _vp]),
+    "scp_nn_dist2": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "scp_octree_emit": (_i, [_vp, C.POINTER(OctreeOut), _vp]),
     "scp_octree_finish": (_i, [_vp, _vp]),
     "scp_octree_stage_ms": (_i, [_vp, C.POINTER(_f * 6)]),

@@ -39,3 +39,9 @@ def pcread(path, color_format="rgb"):
 def ptread(path):
     """pt.py:162-168"""
     return pcread(path, "geometry")[0]
+
+
+def distChamfer(f1, f2, scale=1.0):
+    """pt.py:88-95 on the GPU (exact brute-force nearest neighbours, ``scp_b200.metrics``)."""
+    from .. import metrics
+    return metrics.distChamfer(f1, f2, scale)

@@ -3,6 +3,7 @@ import numpy as np
 import torch
 import torch.utils.data as data
 
+from .. import metrics as _metrics
 from .. import octree as _oct
 from ..data_preproc import pt as pointCloud
 from ..synth import FORD_QS, KITTI_QS
@@ -23,7 +24,11 @@ class EncodeDataset(data.Dataset):
         qf = KITTI_QS if self.data_type == 'kitti' else FORD_QS
         xyz = torch.from_numpy(np.ascontiguousarray(pt, dtype=np.float32)).cuda()
         b = self.builder.plan(xyz, [0, len(pt)], [_oct.JobSpec(0, qf(self.lidar_level), None)], "spher")
-        rows = b.emit(("rows_i64",))["rows_i64"].cpu().numpy()
+        out = b.emit(("rows_i64", "voxel_key"))
+        rows = out["rows_i64"].cpu().numpy()
+        # distChamfer(pc, quantized_pc) and the D1 PSNR of pc_error (encode_dataset.py:98-99)
+        chamfer, psnr = _metrics.distortion(pt, _metrics.dequantised_cloud(b, out["voxel_key"], "spher"),
+                                            _metrics.KITTI_PEAK if self.data_type == 'kitti' else _metrics.FORD_PEAK)
         cs = self.context_size
         padding = np.zeros([cs - 1, 4, 6], np.int64)
         padding[:, :, 0] = 255
@@ -40,7 +45,7 @@ class EncodeDataset(data.Dataset):
             dat.append(np.vstack((padding[:, :, :3], oct_seq[a:e, :, :3])))
             pos.append(np.vstack((padding[:, :, 3:].astype(np.float32), (oct_seq[a:e, :, 3:] / (2 ** max_level)).astype(np.float32))))
             ids.append(np.hstack((ids_pad, np.arange(e - a, dtype=np.int64))))
-        return ids, pos, dat, oct_seq, len(pt), int(b.infos[0].bin_num), 0.0, 0.0
+        return ids, pos, dat, oct_seq, len(pt), int(b.infos[0].bin_num), chamfer, psnr
 
     def __len__(self):
         return len(self.test_files)

@@ -5,6 +5,7 @@ import numpy as np
 import torch
 import torch.utils.data as data
 
+from .. import metrics as _metrics
 from .. import octree as _oct
 from ..data_preproc import pt as pointCloud
 from ..synth import FORD_QS, KITTI_QS
@@ -39,6 +40,7 @@ class EncodeEHEMDataset(data.Dataset):
         self.cylin = cylin
         self.spher = spher
         self.builder = None
+        self._mullevel = False
 
     def _jobs(self):
         qf = KITTI_QS if self.data_type == 'kitti' else FORD_QS
@@ -54,6 +56,15 @@ class EncodeEHEMDataset(data.Dataset):
             seq[e - n_last:e, :, 1] = np.minimum(seq[e - n_last:e, :, 1], self.lidar_level)
         return seq
 
+    def _distortion(self, pc, b, voxel_key):
+        """``distChamfer(pc, quantized_pc)`` and pc_error's D1 PSNR (:147, :170-171; mullevel :141-144): original cloud
+        against the dequantised voxels of all jobs.  The single-level cylindrical branch reports PSNR 0 (:146-147)."""
+        mode = "cylin" if self.cylin else "spher"
+        q_pc = _metrics.dequantised_cloud(b, voxel_key, mode)
+        peak = _metrics.KITTI_PEAK if self.data_type == 'kitti' else _metrics.FORD_PEAK
+        chamfer, psnr = _metrics.distortion(pc, q_pc, peak)
+        return chamfer, (0 if self.cylin and not self._mullevel else psnr)
+
     def __getitem__(self, index):
         pc = pointCloud.ptread(self.test_files[index])
         if self.builder is None:
@@ -61,12 +72,12 @@ class EncodeEHEMDataset(data.Dataset):
         jobs, _ = self._jobs()
         xyz = torch.from_numpy(np.ascontiguousarray(pc, dtype=np.float32)).cuda()
         b = self.builder.plan(xyz, [0, len(pc)], jobs, "cylin" if self.cylin else "spher")
-        out = b.emit(("rows_i64", "ctx", "pos_norm"))
+        out = b.emit(("rows_i64", "ctx", "pos_norm", "voxel_key"))
         rows, ctx, posn = (out[k].cpu().numpy() for k in ("rows_i64", "ctx", "pos_norm"))
         ids, poss, pos_mm, dat = _split_levels(rows, ctx, posn, b.infos)
         bin_num = int(b.infos[0].bin_num)
         z_offset = float(b.infos[0].offset[2]) if self.cylin else 0
-        chamfer = psnr = 0.0     # distortion metrics are outside the encode hot path
+        chamfer, psnr = self._distortion(pc, b, out["voxel_key"])
         return ids, poss, pos_mm, dat, self._oct_seq(rows, b.infos), len(pc), pc, bin_num, z_offset, chamfer, psnr
 
     def __len__(self):

@@ -8,6 +8,7 @@ class EncodeEHEMDataset(_Base):
     def __init__(self, test_files, context_size, data_type, level_wise=True, lidar_level=12, cylin=False, spher=False,
                  preproc_path=''):
         super().__init__(test_files, context_size, data_type, level_wise, lidar_level, cylin, spher, False, False, preproc_path)
+        self._mullevel = True
 
     def _jobs(self):
         return _oct.mullevel_jobs(0, self.lidar_level, self.data_type), True

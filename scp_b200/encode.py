@@ -139,7 +139,7 @@ def main(args, mullevel=MULLEVEL):
                                         args.spher or args.spher_circle, args.spher_circle, False, args.preproc_path)
     else:
         testset = EncodeDataset(test_files, 1024, args.type, args.level_wise, args.lidar_level, args.spher, args.preproc_path)
-    bpps, times = [], []
+    bpps, times, psnr, chamfer = [], [], [], []
     print("Encoding with", args.model)
     for i, cur_file in enumerate(test_files):
         print("Encoding ", cur_file, i, '/', len(test_files))
@@ -151,12 +151,19 @@ def main(args, mullevel=MULLEVEL):
             bpp, t = compress(batch[:-2], test_output_path + Path(cur_file).stem, model, args)
         bpps.append(bpp)
         times.append(t)
+        psnr.append(float(batch[-1]))            # encode.py:288-291: per-frame and running means
+        chamfer.append(float(batch[-2]))
+        print(psnr[-1], bpps[-1], chamfer[-1], times[-1])
+        print(sum(psnr) / (i + 1), sum(bpps) / (i + 1), sum(chamfer) / (i + 1), sum(times) / (i + 1))
     print('bpps:', bpps)
     print('sample number:', len(bpps))
     print('times:', float(np.array(times).mean()))
+    print('chamfer_dist:', float(np.array(chamfer).mean()))
+    print('PSNR:', sum(psnr) / len(psnr))
     with open(f"test_results_{'mul' if mullevel else 'same'}_{args.type}_{args.lidar_level}.txt", 'a') as f:
-        f.write(f"{'mul' if mullevel else 'same'} {args.lidar_level} {args.test_files} {args.ckpt_path}\\nsample number: {len(bpps)}\\n"
-                f"times: {float(np.array(times).mean())}\\nbpp: {float(np.array(bpps).mean())}\\n\\n")
+        f.write(f"{'mul' if mullevel else 'same'} {args.lidar_level} {args.test_files} {args.ckpt_path}\nsample number: {len(bpps)}\n"
+                f"times: {float(np.array(times).mean())}\nbpp: {float(np.array(bpps).mean())}\n"
+                f"chamfer_dist: {float(np.array(chamfer).mean())}\nPSNR: {sum(psnr) / len(psnr)}\n\n")
     return bpps
 
 
