@@ -41,6 +41,27 @@ def ptread(path):
     return pcread(path, "geometry")[0]
 
 
+def write_ply_data(filename, points, attributeName=[], attriType=[]):
+    """pt.py:114-151: ASCII PLY, ``%f`` coordinates, optional integer / float attribute columns."""
+    points = np.asarray(points)
+    assert points.shape[1] >= len(attributeName) + 3
+    filename = str(filename)
+    d = os.path.dirname(filename)
+    if d != "" and not os.path.exists(d):
+        os.makedirs(d)
+    head = ["ply", "format ascii 1.0", "element vertex " + str(points.shape[0]),
+            "property float x", "property float y", "property float z"]
+    head += ["property " + t + " " + n for n, t in zip(attributeName, attriType)]
+    kinds = {"uint16": "%d", "float": "%f", "uchar": "%d"}
+    fmt = " ".join(["%f", "%f", "%f"] + [kinds[t] for t in attriType])
+    with open(filename, "w") as f:
+        f.write("\n".join(head + ["end_header"]) + "\n")
+        rows = points[:, :3 + len(attriType)]
+        for a in range(0, len(rows), 65536):              # one C-level format call per block instead of one per row
+            blk = rows[a:a + 65536]
+            f.write((fmt + "\n") * len(blk) % tuple(blk.ravel().tolist()))
+
+
 def distChamfer(f1, f2, scale=1.0):
     """pt.py:88-95 on the GPU (exact brute-force nearest neighbours, ``scp_b200.metrics``)."""
     from .. import metrics
