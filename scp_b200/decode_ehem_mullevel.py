@@ -9,3 +9,14 @@ def decodeOct(binfile, oct_data_seqs, model, context_size=8192, anc_k=4):
     import numpy as np
     seq = None if oct_data_seqs is None else np.concatenate([np.asarray(s).reshape(-1) for s in oct_data_seqs])
     return _dec.decodeOct(binfile, seq, model, context_size, anc_k, mullevel=True)
+
+
+def main(args):
+    """decode_ehem_mullevel.py:209-274"""
+    return _dec.main(args, mullevel=True)
+
+
+get_args = _dec.get_args
+
+if __name__ == "__main__":
+    main(get_args())

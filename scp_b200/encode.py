@@ -13,6 +13,7 @@ from pathlib import Path
 
 import numpy as np
 import torch
+from torch.utils.data import default_collate
 
 from .dataloaders.encode_dataset import EncodeDataset
 from .dataloaders.encode_dataset_ehem import EncodeEHEMDataset
@@ -143,7 +144,7 @@ def main(args, mullevel=MULLEVEL):
     print("Encoding with", args.model)
     for i, cur_file in enumerate(test_files):
         print("Encoding ", cur_file, i, '/', len(test_files))
-        batch = testset[i]
+        batch = default_collate([testset[i]])       # DataLoader(batch_size=1) of encode.py:266: leading batch axis of 1
         name = (cur_file.split('/')[-2] + Path(cur_file).stem) if args.type == 'kitti' and cur_file.count('/') >= 2 else Path(cur_file).stem
         if args.model == "EHEM":
             bpp, t = compress_ehem(batch[:-2], test_output_path + name, model, args, mullevel)

@@ -131,3 +131,34 @@ def test_compress_ehem_dropin_writes_reference_sized_stream(tmp_path, name, mul)
     else:
         code, bn, zo, _, spher, cylin = decode_ehem.decodeOct(fn, label[:, None], model)
     assert np.array_equal(np.asarray(code) + 1, label) and bn == int(g["bin_num"]) and spher and not cylin
+
+
+@pytest.mark.parametrize("name,mul", [("k12s", False), ("k16m", True)])
+def test_encode_and_decode_command_lines(tmp_path, monkeypatch, name, mul):
+    """``python -m scp_b200.encode[_mullevel]`` then ``python -m scp_b200.decode_ehem[_mullevel]`` on a sweep file: the
+    decoder finds the stream by name, checks it against the pre-generated rows and writes the reconstructed cloud."""
+    from scp_b200 import decode_ehem, decode_ehem_mullevel, encode, encode_mullevel
+    from scp_b200.data_preproc import pt, test_gene
+    from oracle import metrics_np as om
+    monkeypatch.chdir(tmp_path)                               # encode.main appends test_results_*.txt to the cwd
+    g, f = write_bin(tmp_path, name)
+    m = golden("metrics.npz")
+    level = str(int(g["level"]))
+    pre, out = str(tmp_path / "pre"), str(tmp_path / "out")
+    test_gene.main(test_gene.get_args(["--ori_dir", f, "--out_dir", pre, "--lidar_level", level, "--spher"] + (["--mullevel"] if mul else [])))
+    torch.manual_seed(0)
+    bpps = (encode_mullevel if mul else encode).main(encode.get_args(["--test_files", f, "--out_dir", out, "--lidar_level", level, "--spher"]))
+    assert len(bpps) == 1 and bpps[0] > 0
+    report = open(tmp_path / f"test_results_{'mul' if mul else 'same'}_kitti_{level}.txt").read().splitlines()
+    assert any(l.startswith("chamfer_dist: ") for l in report) and any(l.startswith("PSNR: ") for l in report)
+    torch.manual_seed(0)                                      # same random-init weights as the encoder
+    dec = decode_ehem_mullevel if mul else decode_ehem
+    written = dec.main(dec.get_args(["--test_files", f, "--out_dir", out, "--lidar_level", level, "--preproc_path", pre]))
+    assert written == [out + f"/{name}.ply"]
+    rec, want = pt.loadply(written[0])[0].astype(np.float64), m[name + "_q"].astype(np.float64)
+    tol = 1e-2 if mul else 2e-4                               # mullevel: bin_num of the finer sub-octrees is re-derived
+    assert om.nn_dist(rec, want).max() < tol                  # every reconstructed point is a voxel of the encoder
+    # the mullevel stream does not code the last node of each sub-octree (Octree.py:259-262 drops that row), so its
+    # children (here one voxel per sub-octree) cannot be rebuilt; the single-level stream is complete
+    lost = int((om.nn_dist(want, rec) >= tol).sum())
+    assert len(want) - len(rec) == lost and lost <= (3 if mul else 0)
