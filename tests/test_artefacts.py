@@ -119,3 +119,30 @@ def test_gene_artefacts_feed_the_datasets(tmp_path, name, mode, mul):
     if mode == "spher" and not mul:
         d, p = EncodeDataset([f], 1024, "kitti", False, level, True, "")[0], EncodeDataset([f], 1024, "kitti", False, level, True, out + "/")[0]
         assert all(_same(d[i], p[i]) for i in range(6)) and p[6] == meta[1] and p[7] == 0
+
+
+@pytest.mark.parametrize("name,mul", [("k12s", False), ("k16m", True)])
+def test_reconstruct_from_header_fields(name, mul):
+    """decode side (host logic, no GPU): voxels + the header fields of the file name -> the reference's quantised cloud.
+    The mullevel sub-octrees re-derive their own bin_num from the first one (see ``reconstruct``), hence the looser bound."""
+    import types
+    from oracle import metrics_np as om
+    from oracle import octree_np as onp
+    from scp_b200.decode_ehem import reconstruct
+    g, m = golden(f"octree_{name}.npz"), golden("metrics.npz")
+    pts, level = g["points"][:, :3], int(g["level"])
+    vox = []
+    for qs, mp in zip(g["qs"], ([0, 0], [0, 1], [1]) if mul else (None,)):
+        q = np.asarray(onp.quantize(pts, float(qs), "spher")["q"], np.int64)
+        if mp is not None:
+            n = onp.depth_of(q)
+            keep = np.ones(len(q), bool)
+            for j, bit in enumerate(mp):
+                keep &= ((q[:, 0] >> (n - 1 - j)) & 1) == bit
+            q = q[keep]
+        vox.append(onp.voxels_unique(q))
+    rec = reconstruct(types.SimpleNamespace(voxels=vox), int(g["bin_num"]), 0, True, False, level, "kitti")
+    want = m[name + "_q"].astype(np.float64)
+    assert rec.shape == want.shape and rec.dtype == np.float64
+    tol = 1e-2 if mul else 2e-4
+    assert om.nn_dist(rec, want).max() < tol and om.nn_dist(want, rec).max() < tol
