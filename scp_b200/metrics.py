@@ -58,13 +58,23 @@ def d1_psnr(ref, deg, peak):
     return mse, (math.inf if mse == 0.0 else 10.0 * math.log10(3.0 * peak * peak / mse))
 
 
-def distortion(ref, deg, peak):
-    """Chamfer distance and D1 PSNR from ONE pair of nearest-neighbour passes.  Returns (chamfer, psnr)."""
+def distortion_terms(ref, deg):
+    """CUDA float64 [2] = (Chamfer distance, symmetric mean squared nearest-neighbour distance) from ONE pair of
+    nearest-neighbour passes, without synchronising the stream (``Encoder(distortion=True)`` reads it back with the
+    intervals)."""
     a, b = _dev64(ref), _dev64(deg)
     ab, ba = nn_dist2(a, b), nn_dist2(b, a)
-    chamfer = float(torch.maximum(ba.sqrt().mean(), ab.sqrt().mean()))
-    mse = float(torch.maximum(ab.mean(), ba.mean()))
-    return chamfer, (math.inf if mse == 0.0 else 10.0 * math.log10(3.0 * peak * peak / mse))
+    return torch.stack((torch.maximum(ba.sqrt().mean(), ab.sqrt().mean()), torch.maximum(ab.mean(), ba.mean())))
+
+
+def psnr_of(mse, peak):
+    return math.inf if mse == 0.0 else 10.0 * math.log10(3.0 * peak * peak / mse)
+
+
+def distortion(ref, deg, peak):
+    """Chamfer distance and D1 PSNR of a frame.  Returns (chamfer, psnr)."""
+    chamfer, mse = distortion_terms(ref, deg).tolist()
+    return chamfer, psnr_of(mse, peak)
 
 
 def dequantise_keys(keys, steps, offset, mode):
@@ -84,10 +94,11 @@ def dequantise_keys(keys, steps, offset, mode):
 
 
 def dequantised_cloud(builder, voxel_key, mode):
-    """The quantised cloud of every job of ``builder`` back to back (the ``np.vstack`` of
-    encode_dataset_ehem_mullevel.py:141,188): spherical jobs carry no offset, cylindrical ones their z offset."""
+    """The quantised cloud of every job of ``builder`` (an ``OctreeBuilder``, or a list of its ``JobResult``s) back to back
+    (the ``np.vstack`` of encode_dataset_ehem_mullevel.py:141,188): spherical jobs carry no offset, cylindrical ones their
+    z offset."""
     parts = []
-    for i in builder.infos:
+    for i in getattr(builder, "infos", builder):
         off = np.zeros(3) if mode == "spher" else i.offset
         parts.append(dequantise_keys(voxel_key[i.voxel_start:i.voxel_start + i.n_voxels], i.steps, off, mode))
     return torch.cat(parts, 0)

@@ -180,3 +180,24 @@ def test_full_size_frame_distortion():
     assert ps == pytest.approx(om.d1_psnr(pc, q, metrics.KITTI_PEAK)[1], rel=1e-12)
     assert 18 < psnrs[1] - psnrs[0] < 30                               # 4 levels, ~6 dB each
     assert metrics.distChamfer(pc, pc) == 0.0 and metrics.d1_psnr(pc, pc, 1.0)[1] == math.inf
+
+
+@gpu
+def test_encoder_reports_distortion_per_frame():
+    """``Encoder(distortion=True)``: every FrameResult of a ragged batch carries the Chamfer distance / D1 PSNR of ITS
+    frame (original points against the dequantised voxels of its three sub-octrees), equal to the KD-tree oracle."""
+    from test_models_cpu import cfg_ehem
+    from scp_b200 import metrics, octree as oc, synth
+    from scp_b200.encoder import Encoder
+    from scp_b200.models import EHEM
+    frames = [synth.kitti_sweep(7, 6000).astype(np.float32), synth.kitti_sweep(8, 2500).astype(np.float32)]
+    model = EHEM(cfg_ehem()).cuda()
+    res = Encoder(model, 16, "spher", mullevel=True, distortion=True).encode(frames)
+    plain = Encoder(model, 16, "spher", mullevel=True).encode(frames)
+    for fr, r, p in zip(frames, res, plain):
+        assert r.bitstream == p.bitstream and p.chamfer is None and p.psnr is None
+        pc = fr[:, :3]
+        b = oc.OctreeBuilder().plan(torch.from_numpy(fr).cuda(), [0, len(fr)], oc.mullevel_jobs(0, 16, "kitti"), "spher")
+        q = metrics.dequantised_cloud(b, b.emit(("voxel_key",))["voxel_key"], "spher").cpu().numpy()
+        assert r.chamfer == pytest.approx(om.dist_chamfer(pc, q), rel=1e-12)
+        assert r.psnr == pytest.approx(om.d1_psnr(pc, q, metrics.KITTI_PEAK)[1], rel=1e-12)
