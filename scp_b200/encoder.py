@@ -59,7 +59,7 @@ class Encoder:
         self.distortion = distortion
         self.is_ehem = model.__class__.__name__ == "EHEM"
         self.context = model.cfg.model.context_size
-        self.max_tokens = max_tokens
+        self.max_tokens = int(os.environ.get("SCP_MAX_TOKENS", max_tokens))    # tokens per ragged model call
         self.builder = octree.OctreeBuilder()
         self.lib = _lib.require_device()
         self.pool = ThreadPoolExecutor(coder_threads or min(32, os.cpu_count() or 1))
