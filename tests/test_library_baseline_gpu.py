@@ -37,7 +37,7 @@ def test_kernels_beat_plain_pytorch_fp32_on_a_full_window():
     pos = torch.from_numpy(j["pos"]).cuda()
     model = EHEM(cfg_ehem()).cuda()
     sd = {k: v.cuda() for k, v in W.synth_state_dict(W.ehem_spec(19), 0, True).items()}
-    assert not torch.backends.cuda.matmul.allow_tf32                               # true fp32 library GEMMs
+    torch.backends.cuda.matmul.allow_tf32 = False                                  # true fp32 library GEMMs (the default)
     with torch.device("cuda"):
         ref = O.ehem_forward(sd, data, pos)
         ms_torch = _time(lambda: O.ehem_forward(sd, data, pos))
