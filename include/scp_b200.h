@@ -153,6 +153,14 @@ int scp_coding_order(const int64_t* h_level_sizes, const uint8_t* h_level_restar
 int scp_gather_windows(const uint8_t* d_ctx, const float* d_pos, const int64_t* h_win_row, const int32_t* h_win_len,
                        const int64_t* h_win_tok, int n_win, uint8_t* d_ctx_out, float* d_pos_out,
                        int64_t* d_row_even, int64_t* d_row_odd, void* stream);
+/* OctAttention sequences (encode.py:23-82 with encode_dataset.py:31-55 / encode_dataset_mullevel.py:45-69): sequence i of the
+ * output = `pad` pad rows ((level 0, octant 0, occupancy 255), zero positions, row_of -1) followed by h_len[i]-pad rows
+ * of d_ctx [N,4,3] / d_ctx_pos [N,4,3] starting at row h_src_start[i], written at output row h_dst_start[i]; positions are
+ * shifted left by h_shift[i] (= 21 - deepest level of the row file, so that pos / 2^max_level == out * 2^-21).
+ * d_row_of (optional) [total] = source row of every output row. */
+int scp_pad_gather_seqs(const uint8_t* d_ctx, const uint32_t* d_ctx_pos, const int64_t* h_dst_start, const int64_t* h_src_start,
+                        const int32_t* h_len, const int32_t* h_shift, int n_seq, int pad, uint8_t* d_ctx_out,
+                        uint32_t* d_pos_out, int64_t* d_row_of, void* stream);
 /* out[i, :] = in[idx[i], :] for 8-byte rows (coding-order gather of the (c_low,c_high) intervals). */
 int scp_gather_rows8(const void* d_in, const int64_t* d_idx, int64_t n, void* d_out, void* stream);
 

@@ -33,6 +33,7 @@ OCTREE_CASES = {
     "k16m": ("kitti", 3, 16, "spher", 2500, True),
     "f17s": ("ford", 4, 17, "spher", 1200, False),
     "k10c": ("kitti", 5, 10, "cylin", 3000, False),     # many duplicate voxels
+    "k14s": ("kitti", 6, 14, "spher", 1500, False),     # OctAttention config 4 (levels above 12: oct_attention.py:57-61)
 }
 
 
@@ -56,9 +57,11 @@ def pack_levels(lst):
                            for a in lst], 0)
 
 
-def gen_octree(ns, tmp):
+def gen_octree(ns, tmp, only=None):
     dp = ns.data_preprocess
     for name, (kind, seed, level, mode, n_points, mullevel) in OCTREE_CASES.items():
+        if only and name not in only:
+            continue
         pts, qs = case_points(kind, seed, level, mode, n_points, mullevel)
         binf = os.path.join(tmp, name + ".bin")
         pts.astype(np.float32).tofile(binf)
@@ -283,6 +286,78 @@ def gen_coder(ns, tmp):
         nac.arithmeticCoding.encode = real_encode
         np.savez_compressed(os.path.join(GOLD, f"e2e_{name}.npz"), bpp=bpp, n_points=len(g["points"]), **captured)
         print("e2e", name, "bpp", bpp, "bytes", len(captured["bitstream"]))
+def _spy_encode(nac, captured):
+    """Wraps numpyAc.arithmeticCoding.encode so that what the reference hands to its coder is recorded."""
+    real_encode = nac.arithmeticCoding.encode
+
+    def spy(self, pdf, sym, binfile=None):
+        captured["pdf_s16"] = np.asarray(pdf)[::16].copy()
+        captured["sym"] = np.asarray(sym).copy()
+        bsx, bitsx = real_encode(self, pdf, sym, binfile)
+        captured["bitstream"] = np.frombuffer(bsx, np.uint8).copy()
+        return bsx, bitsx
+
+    nac.arithmeticCoding.encode = spy
+    return real_encode
+
+
+def gen_octattn_e2e(ns, tmp):
+    """The reference's own OctAttention end-to-end runs (SURVEY config 4): ``encode.compress`` (encode.py:23-82, one
+    sequence [1023 pads ; nodes], windows of 1024) on the k12s and k14s frames, and ``encode_mullevel.compress``
+    (encode_mullevel.py:23-85) on the three sub-octrees of k16m, whole-sequence and level-wise, fed by the reference's
+    ``dataloaders/encode_dataset_mullevel.EncodeDataset`` (whose ``__getitem__`` output is stored for the mirror test)."""
+    from torch.utils.data import default_collate
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    enc, encm, nac = import_encode(ns)
+    dp = ns.data_preprocess
+    model = load_octattn(ns, sharpen=True)
+    model.cfg = ref_shims.make_cfg("oct", train_type="kitti")
+    args = types.SimpleNamespace(spher=True, cylin=False, sequential=False)
+    for name in ("k12s", "k14s"):
+        kind, seed, level, mode, n_points, mullevel = OCTREE_CASES[name]
+        pts, qs = case_points(kind, seed, level, mode, n_points, mullevel)
+        binf = os.path.join(tmp, name + ".bin")
+        pts.astype(np.float32).tofile(binf)
+        res = dp.proc_pc(binf, tmp, name, qs=qs[0], test=True, normalize=False, spher=True)
+        ds = ns.ds_oct.EncodeDataset([binf], 1024, kind, False, level, True, "")
+        ds.preproc = lambda f, r=res: (r[0], r[2], 0.0, r[3], 0.0)
+        batch = default_collate([ds[0]])[:-2]
+        captured = {}
+        real = _spy_encode(nac, captured)
+        bpp, _ = enc.compress(batch, os.path.join(tmp, "out", name + "_oa"), model, args)
+        nac.arithmeticCoding.encode = real
+        np.savez_compressed(os.path.join(GOLD, f"e2e_octattn_{name}.npz"), bpp=bpp, n_points=len(pts), **captured)
+        print("e2e octattn", name, "bpp", bpp, "bytes", len(captured["bitstream"]), "nodes", len(captured["sym"]))
+    # mullevel: encode_mullevel.compress on the k16m sub-octrees
+    name = "k16m"
+    kind, seed, level, mode, n_points, mullevel = OCTREE_CASES[name]
+    pts, qs = case_points(kind, seed, level, mode, n_points, mullevel)
+    binf = os.path.join(tmp, name + ".bin")
+    pts.astype(np.float32).tofile(binf)
+    files, bn = [], None
+    for q, mp in zip(qs, [[0, 0], [0, 1], [1]]):
+        res = dp.mul_proc_pc(binf, tmp, name, qs=q, test=True, normalize=False, morton_path=mp, spher=True)
+        files.append(res[0])
+        bn = res[3] if bn is None else bn
+    for lw in (False, True):
+        ds = ns.ds_oct_mul.EncodeDataset([binf], 1024, kind, lw, level, True, "unused/")
+        ds.preproc = lambda f: (files, pts[:, :3], 0.0, int(bn), 0.0)
+        item = ds[0]
+        batch = default_collate([item])[:-2]
+        captured = {}
+        real = _spy_encode(nac, captured)
+        bpp, _ = encm.compress(batch, os.path.join(tmp, "out", name + "_oa"), model, args)
+        nac.arithmeticCoding.encode = real
+        tag = "lw" if lw else "seq"
+        ids, pos, data, oct_seq = item[:4]
+        np.savez_compressed(os.path.join(GOLD, f"e2e_octattn_{name}_{tag}.npz"), bpp=bpp, n_points=len(pts),
+                            ds_sizes=np.array([len(i) for i in ids]), ds_ids=np.concatenate(ids).astype(np.int32),
+                            ds_pos=np.concatenate(pos, 0), ds_data=np.concatenate(data, 0).astype(np.int16),
+                            ds_oct_seq=oct_seq.astype(np.int32), **captured)
+        print("e2e octattn", name, tag, "bpp", bpp, "bytes", len(captured["bitstream"]), "blocks", len(ids))
+
+
 def gen_metrics(ns, tmp):
     """pt.distChamfer of the reference on (original cloud, quantised cloud of proc_pc / mul_proc_pc) of the octree cases."""
     dp = ns.data_preprocess
@@ -300,22 +375,49 @@ def gen_metrics(ns, tmp):
         pc = dp.pointCloud.ptread(binf)
         out[name + "_q"] = np.asarray(q)
         out[name + "_chamfer"] = float(dp.pointCloud.distChamfer(pc.copy(), np.array(q, copy=True)))
+        # D1 PSNR exactly as the datasets obtain it (encode_dataset_ehem.py:170-171): pt.pcerror shells out to the
+        # reference's utils/pc_error (an executable copy under oracle/_ref/, the tree itself is read-only without +x),
+        # utils.get_psnr parses section 3 of its report.  The tool prints 6 significant digits.
+        import importlib
+        import shutil
+        ref_utils = importlib.import_module("utils")
+        exe = os.path.join(HERE, "_ref", "pc_error")
+        if not os.path.exists(exe):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            shutil.copyfile(os.path.join(ref_shims.REF_ROOT, "utils", "pc_error"), exe)
+            os.chmod(exe, 0o755)
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            os.makedirs("temp/data", exist_ok=True)
+            rep = os.path.join(tmp, name + "_pcerror.txt")
+            peak = "59.70" if kind == "kitti" else "30000"
+            dp.pointCloud.pcerror(pc, np.asarray(q), None, "-r " + peak, rep, pcerror_path=exe)
+            txt = open(rep).read()
+            out[name + "_mseF"] = float([l for l in txt.splitlines() if "mseF      (p2point)" in l][0].split()[-1])
+            out[name + "_psnr"] = float(ref_utils.get_psnr(rep)[0])
+        finally:
+            os.chdir(cwd)
+        print(name, "pc_error D1 PSNR", out[name + "_psnr"], "mseF", out[name + "_mseF"])
         print(name, "quantised cloud", out[name + "_q"].shape, out[name + "_q"].dtype, "chamfer", out[name + "_chamfer"])
     np.savez_compressed(os.path.join(GOLD, "metrics.npz"), **out)
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["octree", "ehem", "octattn", "coder", "metrics"]
+    what = [a for a in sys.argv[1:] if "=" not in a] or ["octree", "ehem", "octattn", "coder", "octattn_e2e", "metrics"]
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv[1:] if a.startswith("only=")]
     os.makedirs(GOLD, exist_ok=True)
     ns = ref_shims.import_reference()
     with tempfile.TemporaryDirectory() as tmp:
         if "octree" in what:
-            gen_octree(ns, tmp)
+            gen_octree(ns, tmp, only[0] if only else None)
         if "ehem" in what:
             gen_ehem_logits(ns)
         if "octattn" in what:
             gen_octattn_logits(ns)
         if "coder" in what:
             gen_coder(ns, tmp)
+        if "octattn_e2e" in what:
+            gen_octattn_e2e(ns, tmp)
         if "metrics" in what:
             gen_metrics(ns, tmp)

@@ -89,6 +89,7 @@ def import_reference():
         ns.ds_ehem = importlib.import_module("dataloaders.encode_dataset_ehem")
         ns.ds_ehem_mul = importlib.import_module("dataloaders.encode_dataset_ehem_mullevel")
         ns.ds_oct = importlib.import_module("dataloaders.encode_dataset")
+        ns.ds_oct_mul = importlib.import_module("dataloaders.encode_dataset_mullevel")
     finally:
         os.chdir(cwd)
     return ns

@@ -80,6 +80,7 @@ SIGNATURES = {
     "scp_coding_order": (_i, [C.POINTER(_i64), _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "scp_gather_windows": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "scp_gather_rows8": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "scp_pad_gather_seqs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "scp_pmf_to_cdf": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scp_range_encode": (_i64, [_vp, _i64, _vp, _i64]),
     "scp_range_encode_cdf": (_i64, [_vp, _vp, _i64, _i, _vp, _i64]),

@@ -60,6 +60,35 @@ __global__ void __launch_bounds__(256) k_gather_windows(const GWin* __restrict__
     }
 }
 
+// OctAttention sequences (encode.py:23-82 / encode_dataset.py:31-55): [pad rows ; nodes of one row file] per sequence, the
+// pad rows being (level 0, octant 0, occupancy 255) with zero positions and node id -1; ancestor positions are shifted so
+// that one scale 2^-21 serves sequences of different depth (pos / 2^max_level == (pos << (21 - max_level)) / 2^21 exactly)
+struct PSeq { long long dst; long long src; int len; int pad; int shift; int _; };
+
+__global__ void __launch_bounds__(256) k_pad_gather_seqs(const PSeq* __restrict__ seqs, const uint8_t* __restrict__ ctx,
+                                                          const u32* __restrict__ cpos, uint8_t* __restrict__ ctx_out,
+                                                          u32* __restrict__ pos_out, long long* __restrict__ row_of) {
+    const PSeq S = seqs[blockIdx.y];
+    const u32* ci = reinterpret_cast<const u32*>(ctx);
+    u32* co = reinterpret_cast<u32*>(ctx_out);
+    for (int l = blockIdx.x * 256 + threadIdx.x; l < S.len; l += gridDim.x * 256) {
+        const long long t = S.dst + l;
+        const bool real = l >= S.pad;
+        const long long r = S.src + (l - S.pad);
+        if (real) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) co[3 * t + j] = ci[3 * r + j];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) pos_out[12 * t + j] = cpos[12 * r + j] << S.shift;
+        } else {
+            co[3 * t] = 0x00ff0000u; co[3 * t + 1] = 0x0000ff00u; co[3 * t + 2] = 0xff0000ffu;   // 4 x (0,0,255)
+#pragma unroll
+            for (int j = 0; j < 12; ++j) pos_out[12 * t + j] = 0u;
+        }
+        if (row_of) row_of[t] = real ? r : -1;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_gather_rows8(const u64* __restrict__ in, const long long* __restrict__ idx,
                                                        long long n, u64* __restrict__ out) {
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) out[i] = in[idx[i]];
@@ -316,6 +345,29 @@ int scp_gather_windows(const uint8_t* d_ctx, const float* d_pos, const int64_t* 
     k_gather_windows<<<grid, 256, 0, st>>>(d_w, d_ctx, d_pos, d_ctx_out, d_pos_out, (long long*)d_row_even, (long long*)d_row_odd);
     SCP_LAUNCHED();
     SCP_CUDA(cudaFreeAsync(d_w, st));
+    return SCP_OK;
+}
+
+int scp_pad_gather_seqs(const uint8_t* d_ctx, const uint32_t* d_ctx_pos, const int64_t* h_dst_start, const int64_t* h_src_start,
+                        const int32_t* h_len, const int32_t* h_shift, int n_seq, int pad, uint8_t* d_ctx_out,
+                        uint32_t* d_pos_out, int64_t* d_row_of, void* stream) {
+    SCP_REQUIRE(d_ctx && d_ctx_pos && h_dst_start && h_src_start && h_len && h_shift && d_ctx_out && d_pos_out && n_seq >= 0 &&
+                pad >= 0, "scp_pad_gather_seqs: bad argument");
+    if (n_seq == 0) return SCP_OK;
+    cudaStream_t st = as_stream(stream);
+    std::vector<PSeq> seqs(n_seq);
+    int maxlen = 0;
+    for (int i = 0; i < n_seq; ++i) {
+        SCP_REQUIRE(h_len[i] >= pad && h_shift[i] >= 0 && h_shift[i] < 32, "scp_pad_gather_seqs: sequence %d (len >= pad, shift 0..31)", i);
+        seqs[i] = PSeq{h_dst_start[i], h_src_start[i], h_len[i], pad, h_shift[i], 0};
+        maxlen = std::max(maxlen, h_len[i]);
+    }
+    PSeq* d_s = nullptr;
+    SCP_CUDA(upload_async((void**)&d_s, seqs.data(), seqs.size() * sizeof(PSeq), st));
+    dim3 grid((unsigned)std::min<long long>(cdiv(maxlen, 256), 64), (unsigned)n_seq);
+    k_pad_gather_seqs<<<grid, 256, 0, st>>>(d_s, d_ctx, d_ctx_pos, d_ctx_out, d_pos_out, (long long*)d_row_of);
+    SCP_LAUNCHED();
+    SCP_CUDA(cudaFreeAsync(d_s, st));
     return SCP_OK;
 }
 

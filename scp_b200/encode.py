@@ -71,28 +71,48 @@ def compress_ehem(batch, outputfile, model, args, mullevel=MULLEVEL):
     return real_rate / pt_num, elapsed
 
 
-def compress(batch, outputfile, model, args):
-    """encode.py:23-82 (OctAttention, non level-wise, window = context_size)."""
+def _octattn_intervals(model, data, pos, max_tokens=1 << 19):
+    """(c_low, c_high) of every real node of the blocks a reference ``EncodeDataset`` yields (each block =
+    ``context_size-1`` pad rows followed by the nodes of the whole sequence, of one sub-octree, or of one level), in block
+    order.  All windows of all blocks go through the model as ragged batches (encode.py:43-58 runs them one by one)."""
+    cs = model.cfg.model.context_size
+    ctxs, ipos, offs, keep = [], [], [0], []
+    for d, p in zip(data, pos):
+        d, p = _unbatch(d).cuda(), _unbatch(p).cuda()
+        L = d.shape[0]
+        ctxs.append(torch.stack((d[..., 1], d[..., 2], d[..., 0]), -1).to(torch.uint8))    # -> (level, octant, occ)
+        ipos.append(torch.round(p.double() * (1 << 21)).to(torch.int32))                   # exact: pos = int / 2^max_level
+        keep.append(torch.arange(offs[-1] + cs - 1, offs[-1] + L, device=d.device))         # rows behind the pads
+        offs += [offs[-1] + min(a + cs, L) for a in range(0, L, cs)]
+    ctx, ipos, keep = torch.cat(ctxs), torch.cat(ipos), torch.cat(keep)
+    sym = ctx[:, 3, 2].to(torch.int16).contiguous()
+    interval = torch.empty((ctx.shape[0], 2), dtype=torch.int32, device=ctx.device)
+    w0 = 0
+    while w0 < len(offs) - 1:
+        w1 = w0 + 1
+        while w1 < len(offs) - 1 and offs[w1 + 1] - offs[w0] <= max_tokens:
+            w1 += 1
+        lo, hi = offs[w0], offs[w1]
+        logits = model.forward_ragged(ctx[lo:hi].contiguous(), ipos[lo:hi].contiguous(), [o - lo for o in offs[w0:w1 + 1]],
+                                      1.0 / float(1 << 21))
+        coder.pmf_to_cdf(logits, sym=sym[lo:hi].contiguous(), is_logits=True, out={"interval": interval[lo:hi]})
+        w0 = w1
+    return interval[keep]
+
+
+def _compress_octattn(batch, outputfile, model, args):
     if getattr(args, "sequential", False):
         raise NotImplementedError("--sequential (stride-1 windows) is not part of the accelerated path")
     model.eval()
     ids, pos, data, oct_seq, pt_num, bin_num = batch
-    outputfile += '.bin'
     oct_len = int(_unbatch(oct_seq).shape[0])
-    cs = model.cfg.model.context_size
     t0 = time.time()
-    intervals = []
-    for d, p in zip(data, pos):
-        d, p = _unbatch(d).cuda(), _unbatch(p).cuda()
-        L = d.shape[0]
-        offs = list(range(0, L, cs)) + [L]
-        ctx = torch.stack((d[..., 1], d[..., 2], d[..., 0]), -1).to(torch.uint8)
-        ipos = torch.round(p.double() * (1 << 21)).to(torch.int32)
-        logits = model.forward_ragged(ctx, ipos, offs, 1.0 / float(1 << 21))
-        sym = d[:, 3, 0].to(torch.int16).contiguous()
-        iv = coder.pmf_to_cdf(logits, sym=sym, is_logits=True, want_interval=True)["interval"]
-        intervals.append(iv[cs - 1:] if len(data) == 1 else iv[cs - 1:])
-    interval = torch.cat(intervals)[:oct_len]
+    # Rows behind each block's pads, blocks back to back = BFS order of the row file(s): what encode_mullevel.py:60-70
+    # codes (`[:-1023]` per block, then `[:oct_len]`), and what encode.py:59-70 codes for its single whole-sequence block.
+    # With --level_wise encode.py:59-68 stacks the blocks WITHOUT dropping the 1023 surplus rows of each, so its PMF rows
+    # are shifted against the symbols from the second level on (SURVEY 8b "known reference defects", fixed only in
+    # encode_mullevel.py:60): that misalignment is not reproduced, level-wise blocks are coded aligned.
+    interval = _octattn_intervals(model, data, pos)[:oct_len]
     torch.cuda.synchronize()
     elapsed = time.time() - t0
     stream = coder.range_encode(interval.cpu().numpy())
@@ -103,6 +123,21 @@ def compress(batch, outputfile, model, args):
     real_rate = len(stream) * 8
     _report(outputfile, elapsed, int(pt_num), oct_len, real_rate)
     return real_rate / int(pt_num), elapsed
+
+
+def compress(batch, outputfile, model, args):
+    """encode.py:23-82 (OctAttention; windows of ``context_size`` over [pads ; nodes]); writes ``<outputfile>.bin``."""
+    return _compress_octattn(batch, outputfile + '.bin', model, args)
+
+
+def compress_mullevel(batch, outputfile, model, args):
+    """encode_mullevel.py:23-85: same coding, one block per sub-octree (or per level of each), stream named
+    ``<outputfile>[_spher|_cylin]_<blocks>_<bin_num>_0.bin`` (:65-70)."""
+    if getattr(args, "spher", False):
+        outputfile += '_spher'
+    elif getattr(args, "cylin", False):
+        outputfile += '_cylin'
+    return _compress_octattn(batch, outputfile + '_' + str(len(batch[2])) + '_' + str(int(batch[5])) + '_0.bin', model, args)
 
 
 def make_cfg(model_name, data_type):
@@ -126,6 +161,12 @@ def build_model(args):
 
 
 def main(args, mullevel=MULLEVEL):
+    """encode.py:236-311 / encode_mullevel.py:160-233.  Under ``torchrun`` (WORLD_SIZE > 1) the file list is partitioned
+    frame-wise over the ranks (rank r encodes files r, r+R, ...: ``partition.frames_for_rank``), one GPU per rank, no
+    collective on the data path; the per-frame report rows are summed into one table at the end and rank 0 prints /
+    appends the summary the single-process run writes."""
+    from . import partition
+    rank, world, _ = partition.init_from_env()
     model = build_model(args)
     test_files = args.test_files
     if '*' in test_files[0]:
@@ -138,33 +179,44 @@ def main(args, mullevel=MULLEVEL):
         else:
             testset = EncodeEHEMDataset(test_files, 8192, args.type, True, args.lidar_level, args.cylin,
                                         args.spher or args.spher_circle, args.spher_circle, False, args.preproc_path)
+    elif mullevel:                                                  # encode_mullevel.py:13,186
+        from .dataloaders.encode_dataset_mullevel import EncodeDataset as DSM
+        testset = DSM(test_files, 1024, args.type, args.level_wise, args.lidar_level, args.spher, args.preproc_path)
     else:
         testset = EncodeDataset(test_files, 1024, args.type, args.level_wise, args.lidar_level, args.spher, args.preproc_path)
-    bpps, times, psnr, chamfer = [], [], [], []
+    mine = partition.frames_for_rank(len(test_files), rank, world)
+    rows = []
     print("Encoding with", args.model)
-    for i, cur_file in enumerate(test_files):
+    for k, i in enumerate(mine):
+        cur_file = test_files[i]
         print("Encoding ", cur_file, i, '/', len(test_files))
         batch = default_collate([testset[i]])       # DataLoader(batch_size=1) of encode.py:266: leading batch axis of 1
         name = (cur_file.split('/')[-2] + Path(cur_file).stem) if args.type == 'kitti' and cur_file.count('/') >= 2 else Path(cur_file).stem
         if args.model == "EHEM":
             bpp, t = compress_ehem(batch[:-2], test_output_path + name, model, args, mullevel)
+        elif mullevel:
+            bpp, t = compress_mullevel(batch[:-2], test_output_path + Path(cur_file).stem, model, args)
         else:
             bpp, t = compress(batch[:-2], test_output_path + Path(cur_file).stem, model, args)
-        bpps.append(bpp)
-        times.append(t)
-        psnr.append(float(batch[-1]))            # encode.py:288-291: per-frame and running means
-        chamfer.append(float(batch[-2]))
-        print(psnr[-1], bpps[-1], chamfer[-1], times[-1])
-        print(sum(psnr) / (i + 1), sum(bpps) / (i + 1), sum(chamfer) / (i + 1), sum(times) / (i + 1))
-    print('bpps:', bpps)
-    print('sample number:', len(bpps))
-    print('times:', float(np.array(times).mean()))
-    print('chamfer_dist:', float(np.array(chamfer).mean()))
-    print('PSNR:', sum(psnr) / len(psnr))
-    with open(f"test_results_{'mul' if mullevel else 'same'}_{args.type}_{args.lidar_level}.txt", 'a') as f:
-        f.write(f"{'mul' if mullevel else 'same'} {args.lidar_level} {args.test_files} {args.ckpt_path}\nsample number: {len(bpps)}\n"
-                f"times: {float(np.array(times).mean())}\nbpp: {float(np.array(bpps).mean())}\n"
-                f"chamfer_dist: {float(np.array(chamfer).mean())}\nPSNR: {sum(psnr) / len(psnr)}\n\n")
+        rows.append((bpp, t, float(batch[-2]), float(batch[-1])))    # bpp, seconds, chamfer, psnr
+        print(rows[-1][3], rows[-1][0], rows[-1][2], rows[-1][1])    # encode.py:288-291: per-frame and running means
+        print(*(sum(r[c] for r in rows) / (k + 1) for c in (3, 0, 2, 1)))
+    table = partition.gather_frame_table(mine, rows, len(test_files), 4, partition.table_device()).cpu().numpy()
+    bpps, times, chamfer, psnr = (table[:, c].tolist() for c in range(4))
+    if rank == 0:
+        print('bpps:', bpps)
+        print('sample number:', len(bpps))
+        print('times:', float(np.array(times).mean()))
+        print('chamfer_dist:', float(np.array(chamfer).mean()))
+        print('PSNR:', sum(psnr) / len(psnr))
+        with open(f"test_results_{'mul' if mullevel else 'same'}_{args.type}_{args.lidar_level}.txt", 'a') as f:
+            f.write(f"{'mul' if mullevel else 'same'} {args.lidar_level} {args.test_files} {args.ckpt_path}\nsample number: {len(bpps)}\n"
+                    f"times: {float(np.array(times).mean())}\nbpp: {float(np.array(bpps).mean())}\n"
+                    f"chamfer_dist: {float(np.array(chamfer).mean())}\nPSNR: {sum(psnr) / len(psnr)}\n\n")
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     return bpps
 
 

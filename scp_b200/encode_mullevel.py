@@ -7,7 +7,7 @@ def compress_ehem(batch, outputfile, model, args):
     return _enc.compress_ehem(batch, outputfile, model, args, mullevel=True)
 
 
-compress = _enc.compress
+compress = _enc.compress_mullevel      # encode_mullevel.py:23-85
 get_args = _enc.get_args
 
 

@@ -69,9 +69,12 @@ class Encoder:
     # -- stage 1: octrees ---------------------------------------------------------------------
     def _jobs(self, n_frames):
         qf = KITTI_QS if self.kind == "kitti" else FORD_QS
+        clip = self.level if self.is_ehem else 255          # encode_dataset*.py (OctAttention) do not clip levels
         if self.mullevel:
-            return [j for f in range(n_frames) for j in octree.mullevel_jobs(f, self.level, self.kind)], 3
-        clip = self.level if self.is_ehem else 255          # encode_dataset.py (OctAttention) does not clip levels
+            jobs = [j for f in range(n_frames) for j in octree.mullevel_jobs(f, self.level, self.kind)]
+            for j in jobs:
+                j.lidar_level = clip
+            return jobs, 3
         return [octree.JobSpec(f, qf(self.level), None, lidar_level=clip) for f in range(n_frames)], 1
 
     def build_context(self, xyz, frame_offsets):
@@ -128,30 +131,39 @@ class Encoder:
             w0 = w1
 
     def _octattn_logits_to_intervals(self, t, infos, per_frame, interval_row):
-        """encode.py:23-82 (non level-wise): per frame one sequence [1023 pad rows ; nodes] cut into windows of 1024."""
+        """encode.py:23-82 (non level-wise) / encode_mullevel.py:23-85: every row file (the frame's octree, or each of its
+        three sub-octrees) is one sequence [1023 pad rows ; nodes] cut into windows of 1024; positions are divided by
+        2^(deepest level of that file) (encode_dataset.py:38,48).  All sequences of all frames of the batch are assembled by
+        one launch (scp_pad_gather_seqs) and run through the model as ragged batches of windows."""
         ctx, cpos, sym = t["ctx"], t["ctx_pos"], t["sym"]
         dev = ctx.device
         cs = self.context
-        for f in range(len(infos) // per_frame):
-            fi = infos[f * per_frame:(f + 1) * per_frame]
-            r0, n = fi[0].row_start, sum(i.n_rows for i in fi)
-            max_level = max(i.depth for i in fi)
-            padc = torch.zeros((cs - 1, 4, 3), dtype=torch.uint8, device=dev)
-            padc[:, :, 2] = 255
-            seq_ctx = torch.cat([padc, ctx[r0:r0 + n]])
-            seq_pos = torch.cat([torch.zeros((cs - 1, 4, 3), dtype=torch.int32, device=dev), cpos[r0:r0 + n]])
-            row_of = torch.cat([torch.full((cs - 1,), -1, dtype=torch.int64, device=dev),
-                                torch.arange(r0, r0 + n, dtype=torch.int64, device=dev)])
-            L = seq_ctx.shape[0]
-            offs = list(range(0, L, cs)) + [L]
-            step = max(1, self.max_tokens // cs)
-            for a in range(0, len(offs) - 1, step):
-                o = offs[a:a + step + 1]
-                lo, hi = o[0], o[-1]
-                logits = self.model.forward_ragged(seq_ctx[lo:hi].contiguous(), seq_pos[lo:hi].contiguous(),
-                                                   [x - lo for x in o], 1.0 / float(1 << max_level))
-                coder.pmf_to_cdf(logits, sym=sym, is_logits=True, row_of=row_of[lo:hi].contiguous(),
-                                 out={"interval": interval_row})
+        lens = np.array([i.n_rows + cs - 1 for i in infos], np.int32)
+        src = np.array([i.row_start for i in infos], np.int64)
+        dst = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        # deepest level present in the file's rows (the mullevel files lose their last row, Octree.py:259-262)
+        deepest = [max(l + 1 for l, n in enumerate(i.level_rows) if n > 0) if i.n_rows else 1 for i in infos]
+        shift = np.array([21 - d for d in deepest], np.int32)
+        T = int(dst[-1])
+        seq_ctx = torch.empty((T, 4, 3), dtype=torch.uint8, device=dev)
+        seq_pos = torch.empty((T, 4, 3), dtype=torch.int32, device=dev)
+        row_of = torch.empty((T,), dtype=torch.int64, device=dev)
+        _lib.check(self.lib.scp_pad_gather_seqs(_lib.ptr(ctx), _lib.ptr(cpos), _lib.ptr(dst), _lib.ptr(src), _lib.ptr(lens),
+                                                _lib.ptr(shift), len(infos), cs - 1, _lib.ptr(seq_ctx), _lib.ptr(seq_pos),
+                                                _lib.ptr(row_of), _lib.stream_ptr()), "scp_pad_gather_seqs")
+        offs = [0]
+        for a, n in zip(dst[:-1], lens):
+            offs += [int(a) + min(w + cs, int(n)) for w in range(0, int(n), cs)]
+        w0 = 0
+        while w0 < len(offs) - 1:
+            w1 = w0 + 1
+            while w1 < len(offs) - 1 and offs[w1 + 1] - offs[w0] <= self.max_tokens:
+                w1 += 1
+            lo, hi = offs[w0], offs[w1]
+            logits = self.model.forward_ragged(seq_ctx[lo:hi], seq_pos[lo:hi], [o - lo for o in offs[w0:w1 + 1]],
+                                               1.0 / float(1 << 21))
+            coder.pmf_to_cdf(logits, sym=sym, is_logits=True, row_of=row_of[lo:hi], out={"interval": interval_row})
+            w0 = w1
 
     @torch.no_grad()
     def encode_context(self, ctx, pos, level_sizes, level_restart=None):

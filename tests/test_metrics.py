@@ -13,7 +13,7 @@ from conftest import golden
 from oracle import metrics_np as om
 from oracle import octree_np as onp
 
-CASES = {"k12s": "spher", "k14c": "cylin", "k16m": "spher", "f17s": "spher", "k10c": "cylin"}
+CASES = {"k12s": "spher", "k14c": "cylin", "k16m": "spher", "f17s": "spher", "k10c": "cylin", "k14s": "spher"}
 
 
 def _pc(name):
@@ -25,6 +25,18 @@ def _pc(name):
 def test_oracle_chamfer_matches_reference(name):
     m = golden("metrics.npz")
     assert om.dist_chamfer(_pc(name), m[name + "_q"]) == pytest.approx(float(m[name + "_chamfer"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_psnr_matches_pc_error(name):
+    """The D1 PSNR restatement against the reference's own tool: ``pt.pcerror`` -> utils/pc_error (mpeg-pcc-dmetric 0.13.5)
+    -> ``utils.get_psnr`` on (original cloud, proc_pc / mul_proc_pc cloud), oracle/make_golden.py::gen_metrics.  The tool
+    prints six significant digits."""
+    m = golden("metrics.npz")
+    peak = 30000.0 if name == "f17s" else 59.70
+    mse, psnr = om.d1_psnr(_pc(name), m[name + "_q"], peak)
+    assert mse == pytest.approx(float(m[name + "_mseF"]), rel=2e-5)
+    assert psnr == pytest.approx(float(m[name + "_psnr"]), abs=1.5e-4)
 
 
 def test_oracle_dequantise_matches_reference_cloud():
@@ -102,6 +114,8 @@ def test_chamfer_matches_reference_golden(name):
     assert mse == pytest.approx(o_mse, rel=1e-12) and psnr == pytest.approx(o_psnr, rel=1e-12)
     ch, ps = metrics.distortion(pc, q, peak)
     assert ch == pytest.approx(want, rel=1e-12) and ps == pytest.approx(o_psnr, rel=1e-12)
+    # ... and against the reference's pc_error run itself (six printed digits)
+    assert mse == pytest.approx(float(m[name + "_mseF"]), rel=2e-5) and psnr == pytest.approx(float(m[name + "_psnr"]), abs=1.5e-4)
 
 
 def _jobs(name, g):

@@ -80,3 +80,17 @@ def test_octattn_orchestration_vs_reference_logits(tag):
     ref = torch.from_numpy(g[f"{tag}_logits_s2"])
     assert out.shape == ref.shape
     assert (torch.softmax(out, 1) - torch.softmax(ref, 1)).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["n37", "n600"])
+def test_explained_parity_criterion_on_emulated_ops(tag):
+    """tests/parity_explain.py itself (the criterion the -m gpu model tests apply), run on the CPU emulation."""
+    from parity_explain import check_explained_parity
+    from scp_b200 import weights as W
+    from scp_b200.models import EHEM
+    g = golden("ehem_logits.npz")
+    m = EHEM(cfg_ehem(), ops=EmuOps())
+    rep = check_explained_parity(m, W.synth_state_dict(W.ehem_spec(19), 0, True),
+                                 torch.from_numpy(g[f"{tag}_data"].astype(np.int64)), torch.from_numpy(g[f"{tag}_pos"]),
+                                 g[f"{tag}_logits1"], g[f"{tag}_logits2"], what=tag)
+    assert rep["arith_max"] < 1e-4 and len(rep["stages"]) == 3 and rep["direct_max"] < 1e-4

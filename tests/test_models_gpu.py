@@ -1,10 +1,12 @@
 """CUDA EHEM / OctAttention forward against the golden logits of the unmodified reference (CPU fp32).
-Tolerance (BASELINE.json north_star): PMF max-abs <= 1e-3 for the fp32 path."""
+Tolerance (BASELINE.json north_star): PMF max-abs <= 1e-3 for the fp32 path, on every row; the only discontinuity of the
+model (kNN ties) is handled by the explained-rows criterion of tests/parity_explain.py, not by an allowance."""
 import numpy as np
 import pytest
 import torch
 
 from conftest import golden
+from parity_explain import check_explained_parity
 from test_models_cpu import cfg_ehem, cfg_oct
 
 pytestmark = pytest.mark.gpu
@@ -15,74 +17,62 @@ def pmf_err(a, b):
     return (torch.softmax(a.float().cpu(), -1) - torch.softmax(torch.as_tensor(b).float(), -1)).abs().max().item()
 
 
-def pmf_rows(a, b):
-    """Per-row max-abs PMF error: (median, fraction of rows above PMF_TOL, max)."""
-    e = (torch.softmax(a.float().cpu(), -1) - torch.softmax(torch.as_tensor(b).float(), -1)).abs().max(-1)[0]
-    if e.numel() == 0:
-        return 0.0, 0.0, 0.0
-    return e.median().item(), (e > PMF_TOL).float().mean().item(), e.max().item()
-
-
-def assert_parity(a, b, what=""):
-    """fp32 parity bound of BASELINE.json (1e-3) on every row, except that a kNN near-tie (two candidates whose
-    distances differ by float32 rounding noise of the learned features) may flip one neighbour and move the PMFs of
-    the rows attending to it by a few 1e-3: at most 2 % of the rows, never above 2e-2."""
-    med, frac, mx = pmf_rows(a, b)
-    print(what, "pmf err median %.2e  rows>1e-3 %.3f%%  max %.2e" % (med, 100 * frac, mx))
-    assert med < 2e-4 and frac <= 0.02 and mx < 2e-2, (what, med, frac, mx)
-
-
 @pytest.fixture(scope="module")
 def ehem():
     from scp_b200.models import EHEM
     return EHEM(cfg_ehem()).cuda()
 
 
-@pytest.mark.parametrize("tag", ["n1", "n2", "n37", "j600", "j1100"])
-def test_ehem_vs_reference_logits(ehem, tag):
-    """Direct parity with the unmodified reference (inputs without exact kNN distance ties)."""
+@pytest.fixture(scope="module")
+def sd():
+    from scp_b200 import weights as W
+    return W.synth_state_dict(W.ehem_spec(19), 0, True)
+
+
+@pytest.mark.parametrize("tag", ["n1", "n2", "n37", "j600", "j1100", "n600", "n1100"])
+def test_ehem_vs_reference_logits(ehem, sd, tag):
+    """EHEM.forward against the unmodified reference's logits, by the explained-rows criterion of tests/parity_explain.py:
+    (A) every PMF row within 1e-3 of the oracle run on the device's neighbour sets, (B) those sets are k-nearest sets up to
+    float32 ties, (C) windows without near-ties match the reference's own logits within 1e-3 on every row.  ``j*`` = jittered
+    (tie-free) positions, ``n*`` = octree grid positions (exact ties at the k-th neighbour on ~1-3 % of the rows)."""
     g = golden("ehem_logits.npz")
-    data = torch.from_numpy(g[f"{tag}_data"].astype(np.int64))[None].cuda()
-    pos = torch.from_numpy(g[f"{tag}_pos"])[None].cuda()
-    l1, l2 = ehem(data, pos)
+    data = torch.from_numpy(g[f"{tag}_data"].astype(np.int64))
+    pos = torch.from_numpy(g[f"{tag}_pos"])
+    l1, l2 = ehem(data[None].cuda(), pos[None].cuda())
     assert tuple(l1.shape[1:]) == g[f"{tag}_logits1"].shape and tuple(l2.shape[1:]) == g[f"{tag}_logits2"].shape
-    assert_parity(l1[0], g[f"{tag}_logits1"], tag + " group1")
-    if l2.shape[1]:
-        assert_parity(l2[0], g[f"{tag}_logits2"], tag + " group2")
+    check_explained_parity(ehem, sd, data, pos, g[f"{tag}_logits1"], g[f"{tag}_logits2"], what=tag)
 
 
-def test_ehem_full_window_vs_reference(ehem):
+@pytest.mark.parametrize("jitter", [True, False])
+def test_ehem_full_window_vs_reference(ehem, sd, jitter):
+    """One full 8192-token context window (the bench's window size), jittered and gridded positions."""
     g = golden("ehem_logits_full.npz")
     j = golden("ehem_logits_full_jit.npz")
-    data = torch.from_numpy(g["data"].astype(np.int64))[None].cuda()
-    l1, l2 = ehem(data, torch.from_numpy(j["pos"])[None].cuda())
-    assert_parity(l1[0, ::16], j["logits1_s16"], "full 8192 window (tie-free) group1 vs reference")
-    assert_parity(l2[0, ::16], j["logits2_s16"], "full 8192 window (tie-free) group2 vs reference")
+    data = torch.from_numpy(g["data"].astype(np.int64))
+    pos = torch.from_numpy(j["pos"] if jitter else g["pos"])
+    r = j if jitter else g
+    check_explained_parity(ehem, sd, data, pos, r["logits1_s16"], r["logits2_s16"], ref_slice=slice(None, None, 16),
+                           what="full 8192 window, " + ("jittered" if jitter else "grid") + " positions")
 
 
-@pytest.mark.parametrize("tag", ["n600", "n1100", "full"])
-def test_ehem_gridded_positions_vs_oracle_canonical_ties(ehem, tag):
-    """Octree positions lie on a grid: ~1% of the 3-D kNN rows have EXACT distance ties at the k-th neighbour and
-    the reference's pick is torch.topk's internal order.  scp_knn uses a canonical rule (exact float64 distance,
-    lowest index first); with that rule in the oracle the CUDA path agrees to the fp32 tolerance, and the
-    deviation from the raw reference run is reported (it equals what the reference itself shows when only its
-    tie order is permuted)."""
-    from oracle import ehem_torch as O
-    from scp_b200 import weights as W
-    if tag == "full":
-        g = golden("ehem_logits_full.npz")
-        data, pos, r1, r2, sl = g["data"], g["pos"], g["logits1_s16"], g["logits2_s16"], slice(None, None, 16)
-    else:
-        g = golden("ehem_logits.npz")
-        data, pos, r1, r2, sl = g[f"{tag}_data"], g[f"{tag}_pos"], g[f"{tag}_logits1"], g[f"{tag}_logits2"], slice(None)
-    d = torch.from_numpy(data.astype(np.int64))
-    p = torch.from_numpy(pos)
-    l1, l2 = ehem(d[None].cuda(), p[None].cuda())
-    o1, o2 = O.ehem_forward(W.synth_state_dict(W.ehem_spec(19), 0, True), d, p, knn=O.knn_canonical)
-    assert_parity(l1[0], o1, tag + " group1 vs oracle(canonical ties)")
-    assert_parity(l2[0], o2, tag + " group2 vs oracle(canonical ties)")
-    print(tag, "max pmf deviation from the raw reference run (its torch.topk tie order):", pmf_err(l1[0][sl], r1), pmf_err(l2[0][sl], r2))
-    assert pmf_err(l1[0][sl], r1) < 5e-2 and pmf_err(l2[0][sl], r2) < 5e-2
+def test_ehem_ragged_batch_equals_single_windows(ehem):
+    """Batch invariance (what the encoder's ragged batches and the decoder's level-wise calls rely on): a window's logits do
+    not depend on what else is in the call -- bit-identical."""
+    g = golden("ehem_logits.npz")
+    tags = ["n2", "n600", "n37", "j1100"]
+    ctxs, poss, offs, single = [], [], [0], []
+    for t in tags:
+        d = torch.from_numpy(g[f"{t}_data"].astype(np.int64))
+        p = torch.from_numpy(g[f"{t}_pos"])
+        single.append(ehem(d[None].cuda(), p[None].cuda()))
+        d8, pt = d.to(torch.uint8), p.T
+        if len(d8) % 2:
+            pad = torch.zeros_like(d8[:1]); pad[:, :, 2] = 255
+            d8 = torch.cat([d8, pad]); pt = torch.cat([pt, torch.zeros_like(pt[:1])])
+        ctxs.append(d8); poss.append(pt); offs.append(offs[-1] + len(d8))
+    l1, l2 = ehem.forward_ragged(torch.cat(ctxs).cuda(), torch.cat(poss).contiguous().cuda(), offs)
+    for (s1, s2), a, b in zip(single, offs[:-1], offs[1:]):
+        assert torch.equal(l1[a // 2:b // 2], s1[0]) and torch.equal(l2[a // 2:a // 2 + s2.shape[1]], s2[0])
 
 
 @pytest.mark.parametrize("tag", ["w0", "w3", "tail"])

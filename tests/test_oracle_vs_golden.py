@@ -6,7 +6,7 @@ import pytest
 from oracle import octree_np as onp
 from conftest import golden
 
-CASES = ["k12s", "k14c", "k16m", "f17s", "k10c"]
+CASES = ["k12s", "k14c", "k16m", "f17s", "k10c", "k14s"]
 MPATHS = [[0, 0], [0, 1], [1]]
 
 
@@ -63,8 +63,9 @@ def test_level_split_matches_reference(name):
     assert np.array_equal(oct_seq, g["ds_oct_seq"].astype(np.int64))
 
 
-def test_octattn_dataset_matches_reference():
-    g = golden("octree_k12s.npz")
+@pytest.mark.parametrize("name", ["k12s", "k14s"])
+def test_octattn_dataset_matches_reference(name):
+    g = golden(f"octree_{name}.npz")
     ids, pos, data, _ = onp.octattn_dataset(g["rows"].astype(np.int64), 1024)
     assert np.array_equal(ids, g["oct_ids"])
     assert np.array_equal(data, g["oct_data"].astype(np.int64))
