@@ -255,6 +255,10 @@ int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b
 int scp_set_auto_engine(int use_tf32);
 /* Drops the cached hi/lo splits of weight matrices (call after weights changed in place). */
 void scp_gemm_cache_clear(void);
+/* Drops the cached splits of ONE weight matrix (keyed by its device pointer).  The cache cannot see contents: the host
+ * side (scp_b200/ops.py) calls this whenever the tensor behind a pointer is a different object or was modified in place
+ * since its split was taken. */
+void scp_gemm_cache_drop(const float* d_w);
 /* 1 if the tcgen05 engine can take this shape (alignment rules in DESIGN.md). */
 int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K);
 
@@ -315,7 +319,8 @@ int scp_copy_cols(const float* d_src, int64_t lds, int64_t row_step, int64_t row
 
 /* OctAttention embedding (oct_attention.py:52-79,85-99 + attention_model.py:20-22): both streams
  * embed / embed_unknown [n, 600] incl. *sqrt(600) and the sinusoidal PE (row = position inside the sequence).
- * ctx bytes are (level,octant,occ); ctx_pos u32 [n,4,3]; pos_scale = 1/2^max_level (encode_dataset.py:48). */
+ * ctx bytes are (level,octant,occ); ctx_pos u32 [n,4,3]; pos_scale = 1/2^max_level (encode_dataset.py:48).
+ * d_pe may be NULL: cfg.model.pos_embed False, no PositionalEncoding module (attention_model.py:142-144,147-149). */
 int scp_octattn_embed(const uint8_t* d_ctx, const uint32_t* d_ctx_pos, float pos_scale, int level_base,
                       int max_octree_level, const scp_seqs* seqs,
                       const float* d_occ_enc, const float* d_level_enc, const float* d_octant_enc,

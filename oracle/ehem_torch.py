@@ -185,7 +185,7 @@ def octattn_forward(sd, data, pos, train_type="kitti", max_octree_level=12, head
     ou[:, -1] = sd["occ_enc.weight"][255]
     rest = torch.cat((sd["level_enc.weight"][level], sd["octant_enc.weight"][octant],
                       F.linear(pos, sd["abs_pos_enc.weight"], sd["abs_pos_enc.bias"])), 2)
-    pe = sd["transformer_encoder.position_enc.pe"][:csz]
+    pe = sd["transformer_encoder.position_enc.pe"][:csz] if "transformer_encoder.position_enc.pe" in sd else 0.0   # cfg.model.pos_embed (attention_model.py:142-149)
     e = torch.cat((oe, rest), 2).reshape(csz, 600) * math.sqrt(600) + pe
     u = torch.cat((ou, rest), 2).reshape(csz, 600) * math.sqrt(600) + pe
     mask = sd["mask"][:csz, :csz]

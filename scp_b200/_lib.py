@@ -91,6 +91,7 @@ SIGNATURES = {
     "scp_linear": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp]),
     "scp_set_auto_engine": (_i, [_i]),
     "scp_gemm_cache_clear": (None, []),
+    "scp_gemm_cache_drop": (None, [_vp]),
     "scp_set_knn_engine": (_i, [_i]),
     "scp_set_attn_engine": (_i, [_i]),
     "scp_linear_tf32_supported": (_i, [_i64, _i64, _i64, _i, _i]),

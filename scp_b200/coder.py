@@ -1,5 +1,6 @@
 """Host wrappers: coding order (A7), softmax->CDF (A13), range coder (A14).  See include/scp_b200.h."""
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -7,16 +8,26 @@ import torch
 from . import _lib
 
 
-def coding_order(level_sizes, context_size, occ, mullevel=False, level_restart=None):
+def coding_order(level_sizes, context_size, occ, mullevel=False, level_restart=None, reference_single_node_defect=None):
     """encode.py:109-136 / encode_mullevel.py:106-133.  occ: CUDA uint8 [N] occupancy bytes 1..255.
-    Returns (order int64 [N], symbols int16 [N]) on the device."""
+    Returns (order int64 [N], symbols int16 [N]) on the device.
+
+    A level that holds a single node is coded on its own (encode.py:120-124).  encode_mullevel.py:120 adds the running
+    node offset; encode.py:123 forgets it, so for a single-node level BELOW the root the reference's single-octree
+    encoder codes the root's row a second time and never codes that node -- a stream no decoder can invert.  That
+    defect is not reproduced: the node itself is coded (what encode_mullevel.py does) and ``Decoder`` reads it back.
+    ``reference_single_node_defect=True`` (or SCP_REF_SINGLE_NODE_DEFECT=1) restores the reference's order for
+    byte-level comparisons with its output on such frames."""
     lib = _lib.require_device()
     n = int(sum(level_sizes))
     order = torch.zeros(n, dtype=torch.int64, device=occ.device)
     sym = torch.zeros(n, dtype=torch.int16, device=occ.device)
     sizes = (C.c_int64 * len(level_sizes))(*[int(s) for s in level_sizes])
     restart = None if level_restart is None else np.ascontiguousarray(np.asarray(level_restart, np.uint8))
-    _lib.check(lib.scp_coding_order(sizes, _lib.ptr(restart), len(level_sizes), context_size, int(mullevel), _lib.ptr(occ),
+    if reference_single_node_defect is None:
+        reference_single_node_defect = os.environ.get("SCP_REF_SINGLE_NODE_DEFECT", "0") == "1"
+    add_base = 1 if (mullevel or not reference_single_node_defect) else 0
+    _lib.check(lib.scp_coding_order(sizes, _lib.ptr(restart), len(level_sizes), context_size, add_base, _lib.ptr(occ),
                                     _lib.ptr(order), _lib.ptr(sym), _lib.stream_ptr()), "scp_coding_order")
     return order, sym
 

@@ -722,6 +722,17 @@ void gemm_cache_clear() {
     g_wsplit_h.clear();
 }
 
+// drops the cached splits of one weight matrix (any shape registered under this pointer)
+void gemm_cache_drop(const void* w) {
+    std::lock_guard<std::mutex> g(g_wmu);
+    for (auto it = g_wsplit.begin(); it != g_wsplit.end();) {
+        if (it->first.p == w) { cudaFree(it->second); it = g_wsplit.erase(it); } else ++it;
+    }
+    for (auto it = g_wsplit_h.begin(); it != g_wsplit_h.end();) {
+        if (it->first.p == w) { cudaFree(it->second); it = g_wsplit_h.erase(it); } else ++it;
+    }
+}
+
 // fp16 split: [hi N*K halfs | lo N*K halfs | pad to 16 bytes | scale, 1/scale (floats)]
 static int get_weight_split_f16(const float* w, int N, int K, cudaStream_t st, __half** out, const float** oscale) {
     std::lock_guard<std::mutex> g(g_wmu);

@@ -66,41 +66,57 @@ __host__ __device__ __forceinline__ int knn_tile_order(int i, int t0, int nt) {
     return L > R ? t0 - m - 1 - j : t0 + own + m + j;
 }
 
-// max|X| of the call -> scales[0] = 2^e with max * 2^e in [2^7, 2^8), scales[1] = 2 * 2^(-2e) (the factor of the Gram term)
-__global__ void __launch_bounds__(256) k_knn_absmax(const float* __restrict__ X, long long ldx, int d, long long n, unsigned* __restrict__ mx) {
+// max|X| of every SEQUENCE -> scales[2s] = 2^e with max * 2^e in [2^7, 2^8), scales[2s+1] = 2 * 2^(-2e) (the factor of the
+// Gram term).  One scale per sequence (context window), not per call: the fp16 hi/lo parts of a window -- and with them its
+// approximate candidate lists -- must not depend on which other windows share the ragged batch (the encoder batches the
+// windows of whole frames, the decoder one level at a time, and both must see identical neighbour sets).
+// One block per 128-row tile of the tile tables; 8 warps x 16 rows.
+__global__ void __launch_bounds__(256) k_knn_absmax(const float* __restrict__ X, long long ldx, int d,
+                                                     const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
+                                                     const int* __restrict__ tile_start, unsigned* __restrict__ mx) {
+    const int s = tile_seq[blockIdx.x];
+    const long long base = seq_off[s] + tile_start[blockIdx.x];
+    const int rows = (int)min((long long)KT_BM, seq_off[s + 1] - base);
     float m = 0.f;
-    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += (long long)gridDim.x * 8)
-        for (int c = threadIdx.x & 31; c < d; c += 32) m = fmaxf(m, fabsf(X[r * ldx + c]));
+    for (int r = threadIdx.x >> 5; r < rows; r += 8)
+        for (int c = threadIdx.x & 31; c < d; c += 32) m = fmaxf(m, fabsf(X[(base + r) * ldx + c]));
     m = warp_max(m);
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(mx, __float_as_uint(m));       // non-negative floats order like their bits
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(mx + s, __float_as_uint(m));   // non-negative floats order like their bits
 }
-__global__ void k_knn_scale(const unsigned* __restrict__ mx, float* __restrict__ scales) {
-    const float m = __uint_as_float(*mx);
+__global__ void __launch_bounds__(256) k_knn_scale(const unsigned* __restrict__ mx, int n_seq, float* __restrict__ scales) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= n_seq) return;
+    const float m = __uint_as_float(mx[s]);
     int e = 0;
     if (m > 0.f && m < 3e38f) { frexpf(m, &e); e = 8 - e; }
     e = max(-60, min(60, e));
-    scales[0] = ldexpf(1.0f, e);
-    scales[1] = ldexpf(2.0f, -2 * e);
+    scales[2 * s] = ldexpf(1.0f, e);
+    scales[2 * s + 1] = ldexpf(2.0f, -2 * e);
 }
 
-__global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X, long long ldx, int d, long long n,
-                                                     const float* __restrict__ scales, __half* __restrict__ hi,
-                                                     __half* __restrict__ lo, float* __restrict__ xx) {
+__global__ void __launch_bounds__(256) k_split_rows(const float* __restrict__ X, long long ldx, int d, long long row0,
+                                                     const long long* __restrict__ seq_off, const int* __restrict__ tile_seq,
+                                                     const int* __restrict__ tile_start, const float* __restrict__ scales,
+                                                     __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ xx) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= n) return;
-    const float sc = scales[0];
-    float s = 0.f;
-    for (int c = lane; c < d; c += 32) {
-        const float v = X[row * ldx + c];
-        const float vs = v * sc;
-        const __half h = __float2half_rn(vs);
-        hi[row * d + c] = h;
-        lo[row * d + c] = __float2half_rn(vs - __half2float(h));
-        s = fmaf(v, v, s);
+    const int sq = tile_seq[blockIdx.x];
+    const long long base = seq_off[sq] + tile_start[blockIdx.x];
+    const int rows = (int)min((long long)KT_BM, seq_off[sq + 1] - base);
+    const float sc = scales[2 * sq];
+    for (int r = threadIdx.x >> 5; r < rows; r += 8) {
+        const long long g = base + r, row = g - row0;               // global row; row inside the call's buffers
+        float s = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = X[g * ldx + c];
+            const float vs = v * sc;
+            const __half h = __float2half_rn(vs);
+            hi[row * d + c] = h;
+            lo[row * d + c] = __float2half_rn(vs - __half2float(h));
+            s = fmaf(v, v, s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) xx[row] = s;
     }
-    s = warp_sum(s);
-    if (lane == 0) xx[row] = s;
 }
 
 __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUtensorMap tmHi,
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
                 if (lane == 0) mbar_arrive(a_ready);
             }
             const float xq = rowv ? xx[gbase - row0 + q] : 0.f;
-            const float two_g = __ldg(scales + 1);                       // 2 / scale^2: the Gram tile is of the scaled rows
+            const float two_g = __ldg(scales + 2 * s + 1);                       // 2 / scale^2: the Gram tile is of the scaled rows
             for (int e = 0; e < kc; ++e) hq[32 * e] = make_float2(-INFINITY, __int_as_float(-1));
             float th = (rowv && dbg == 0) ? -INFINITY : INFINITY;          // rows past the window never take a candidate
             const int nt = (n + KT_BN - 1) / KT_BN;
@@ -424,14 +440,16 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     SCP_CUDA(malloc_async((void**)&hi, (size_t)total * d * 2 + 1024, st));
     SCP_CUDA(malloc_async((void**)&lo, (size_t)total * d * 2 + 1024, st));
     SCP_CUDA(malloc_async((void**)&xx, (size_t)total * 4 + 1024, st));
-    SCP_CUDA(malloc_async((void**)&scales, 64, st));
-    SCP_CUDA(cudaMemsetAsync(scales, 0, 64, st));
-    k_knn_absmax<<<(unsigned)std::min<long long>(cdiv(total, 8), 2368), 256, 0, st>>>(d_x + row0 * ldx, ldx, d, total,
-                                                                                     reinterpret_cast<unsigned*>(scales) + 4);
+    // per sequence: [n_seq][2] floats (scale, Gram factor) then [n_seq] running maxima
+    const size_t sc_bytes = (size_t)n_seq * 12 + 64;
+    SCP_CUDA(malloc_async((void**)&scales, sc_bytes, st));
+    SCP_CUDA(cudaMemsetAsync(scales, 0, sc_bytes, st));
+    unsigned* mx = reinterpret_cast<unsigned*>(scales + 2 * (size_t)n_seq);
+    k_knn_absmax<<<n_work, 256, 0, st>>>(d_x, ldx, d, d_off, d_tile_seq, d_tile_start, mx);
     SCP_LAUNCHED();
-    k_knn_scale<<<1, 1, 0, st>>>(reinterpret_cast<unsigned*>(scales) + 4, scales);
+    k_knn_scale<<<(unsigned)cdiv(n_seq, 256), 256, 0, st>>>(mx, n_seq, scales);
     SCP_LAUNCHED();
-    k_split_rows<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x + row0 * ldx, ldx, d, total, scales, hi, lo, xx);
+    k_split_rows<<<n_work, 256, 0, st>>>(d_x, ldx, d, row0, d_off, d_tile_seq, d_tile_start, scales, hi, lo, xx);
     SCP_LAUNCHED();
     CUtensorMap mh, ml;
     // the split buffers are transient: encode their maps every call (pointer reuse would alias a cached map only

@@ -38,6 +38,7 @@ namespace scp {
 int linear_tf32(const float* x, long long ldx, const float* w, const float* bias, const float* res, long long ldr,
                 float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st, int split);   // gemm_tc.cu
 void gemm_cache_clear();
+void gemm_cache_drop(const void* w);
 bool knn_tc_ok(int d, int k);                                                                      // knn_tc.cu
 int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n_seq, const long long* d_off,
            const int* d_tile_seq, const int* d_tile_start, int n_work, int k, int* d_idx, cudaStream_t st);
@@ -751,7 +752,7 @@ __global__ void __launch_bounds__(256) k_octattn_embed(const uint8_t* __restrict
             const float x = (float)p[0] * pos_scale, y = (float)p[1] * pos_scale, z = (float)p[2] * pos_scale;
             v = vu = pw[o * 3] * x + pw[o * 3 + 1] * y + pw[o * 3 + 2] * z + pb[o];
         }
-        const float pos = pe[(long long)j * 600 + c];
+        const float pos = pe ? pe[(long long)j * 600 + c] : 0.f;       // cfg.model.pos_embed False: no PositionalEncoding module
         E[tok * 600 + c] = v * scale + pos;
         EU[tok * 600 + c] = vu * scale + pos;
     }
@@ -937,6 +938,7 @@ void scp_seqs_destroy(scp_seqs* s) {
 int64_t scp_seqs_total(const scp_seqs* s) { return s ? s->total : -1; }
 
 void scp_gemm_cache_clear(void) { gemm_cache_clear(); }
+void scp_gemm_cache_drop(const float* d_w) { gemm_cache_drop(d_w); }
 
 int scp_set_knn_engine(int use_tensor_cores) { int old = g_knn_tc; g_knn_tc = use_tensor_cores ? 1 : 0; return old; }
 
@@ -1137,8 +1139,8 @@ int scp_octattn_embed(const uint8_t* d_ctx, const uint32_t* d_ctx_pos, float pos
                       int max_octree_level, const scp_seqs* seqs, const float* d_occ_enc, const float* d_level_enc,
                       const float* d_octant_enc, const float* d_pos_w, const float* d_pos_b, const float* d_pe,
                       float* d_embed, float* d_embed_unknown, void* stream) {
-    SCP_REQUIRE(d_ctx && d_ctx_pos && seqs && d_occ_enc && d_level_enc && d_octant_enc && d_pos_w && d_pos_b && d_pe &&
-                d_embed && d_embed_unknown, "scp_octattn_embed: null argument");
+    SCP_REQUIRE(d_ctx && d_ctx_pos && seqs && d_occ_enc && d_level_enc && d_octant_enc && d_pos_w && d_pos_b &&
+                d_embed && d_embed_unknown, "scp_octattn_embed: null argument");      // d_pe may be NULL (pos_embed False)
     if (seqs->n_tile == 0) return SCP_OK;
     k_octattn_embed<<<seqs->n_tile, 256, 0, as_stream(stream)>>>(d_ctx, d_ctx_pos, pos_scale, level_base, max_octree_level,
                                                                  seqs->d_off, seqs->d_tile_seq, seqs->d_tile_start, d_occ_enc,

@@ -226,9 +226,6 @@ class Decoder:
                     ctx, ctx_model, pos_norm = self._tree_level_inputs(state[f], L, n, frs[f].pos_mm[lv0[f]: lv0[f] + n], pos_eps_last)
                     N = ctx.shape[0]
                     n_code = N - 1 if (drop_last and L == n) else N
-                    if n_code == 1 and L > 1 and not self.mullevel:
-                        raise NotImplementedError("single-node level below the root: encode.py:123 codes the root again instead "
-                                                  "of this node (reference defect), the stream is not decodable")
                     ctxs[f] = ctx
                     items.append((decs[f], ctx_model, pos_norm, n_code))
                 syms = self._decode_level_batch(items)

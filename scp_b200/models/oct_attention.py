@@ -24,11 +24,27 @@ class OctAttention(nn.Module):
         m = cfg.model
         self.embed = 4 * (m.occ_embed_dim + m.level_embed_dim + m.octant_embed_dim + m.abs_pos_embed_dim)
         assert self.embed == 600 and m.head_num * 150 == 600, "kernels are specialised for the reference's 4 x 150 heads"
+        self.pos_embed = bool(getattr(m, "pos_embed", True))
         self.spec = W.octattn_spec(m.context_size, self.embed, m.hidden_dimension, m.layer_num, m.token_num,
-                                   m.max_octree_level)
+                                   m.max_octree_level, self.pos_embed)
         for (name, shape, kind), t in zip(self.spec, W.synth_state_dict(self.spec, seed, sharpen).values()):
             _register(self, name, t, kind in _BUFFER_KINDS)
         self._ops = ops
+        self._sd = None
+
+    def load_state_dict(self, *a, **k):
+        self._sd = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._sd = None
+        return super()._apply(fn, *a, **k)
+
+    def _prepare(self):
+        """Stable per-weight tensor objects: the operator layer keys its split-weight cache on them (scp_b200/ops.py)."""
+        if self._sd is None:
+            self._sd = {k: v.detach() for k, v in self.state_dict().items()}
+        return self._sd
 
     @property
     def ops(self):
@@ -41,7 +57,7 @@ class OctAttention(nn.Module):
         """ctx uint8 [T,4,3] (level, octant, occ), ctx_pos int32 [T,4,3] ancestor cell origins,
         pos_scale = 1/2^max_level (encode_dataset.py:48).  Returns logits [T,255]."""
         ops = self.ops
-        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        sd = self._prepare()
         m = self.cfg.model
         T = ctx.shape[0]
         seqs = ops.seqs(offsets)

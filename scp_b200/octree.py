@@ -133,18 +133,19 @@ class OctreeBuilder:
         return out
 
     def stage_bytes(self):
-        """Algorithmic bytes of each stage of the last plan+emit (SURVEY.md section 8d figures x the units the stage really
-        processes): quantise reads 12 B per frame point once and writes 8 B per (point, job) key; the sort moves
-        (1 + 2P) * 8 B per key that takes part in it, plus, for jobs with a morton_path, two reads of all keys and one
-        write of the kept ones for the compaction in front of it; heads 8 B per sorted key; emit 28 B, occupancy 6 B and
-        context 60 B per node."""
+        """Algorithmic bytes of each stage of the last plan+emit, STRICTLY SURVEY.md section 8d's per-unit figures times the
+        units the stage processes: quantise reads 12 B per frame point once and writes 8 B per (point, job) key; the sort
+        moves (1 + 2P) * 8 B per key that takes part in it (P = ceil((3*depth+1)/8) digit passes of the 8-bit model; the
+        morton_path compaction in front of it is NOT credited); tree emission ("tree") 28 B per node for everything between
+        the sorted keys and the node records (head levels, emission, occupancy); context gather 60 B per node.  The
+        ``heads`` / ``emit`` / ``occupancy`` entries split the tree figure over the three timers for information only
+        (28 B/node is charged once, to ``tree``)."""
         n_frame_pts = int(self._keep.shape[0])
         n_keys = sum(i.n_points for i in self.infos)
         kept, N = self.total_kept, self.total_rows
         P = (3 * max(i.depth for i in self.infos) + 1 + 7) // 8
-        filt = (16 * n_keys + 8 * kept) if kept != n_keys else 0
-        return {"quantise": 12 * n_frame_pts + 8 * n_keys, "sort": filt + (1 + 2 * P) * 8 * kept, "heads": 8 * kept,
-                "emit": 28 * N, "occupancy": 6 * N, "context": 60 * N}
+        return {"quantise": 12 * n_frame_pts + 8 * n_keys, "sort": (1 + 2 * P) * 8 * kept, "tree": 28 * N, "context": 60 * N,
+                "emit": 28 * N}
 
     def stage_ms(self):
         arr = (C.c_float * 6)()

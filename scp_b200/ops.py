@@ -5,6 +5,7 @@ Tensors are views into caller-owned buffers: every op takes (tensor, column offs
 arguments through ``View`` so that concatenations are written in place instead of copied."""
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -69,12 +70,33 @@ class _Rec:
             self.ops.prof.append((self.tag, self.flops, self.nbytes, self.e0, self.e1))
 
 
+# The library caches the hi/lo splits of every weight matrix under its device pointer and cannot see contents.  This table
+# ties each cached pointer to the tensor OBJECT and in-place version it was split from; ``CudaOps.linear`` drops the cache
+# entry when either changed (a new tensor at a recycled address, ``load_state_dict`` copying into the same storage).
+_WEIGHT_SEEN = {}
+
+
+def _weight_is_current(lib, w):
+    key = w.data_ptr()
+    ent = _WEIGHT_SEEN.get(key)
+    if ent is not None and ent[0]() is w and ent[1] == w._version:
+        return
+    lib.scp_gemm_cache_drop(C.c_void_p(key))
+    if len(_WEIGHT_SEEN) > 4096:                                   # forget dead tensors
+        for k in [k for k, (r, _) in _WEIGHT_SEEN.items() if r() is None]:
+            del _WEIGHT_SEEN[k]
+    _WEIGHT_SEEN[key] = (weakref.ref(w), w._version)
+
+
 class CudaOps:
     name = "cuda"
 
     def __init__(self, engine=None):
         self.lib = _lib.require_device()
         self.engine = ENGINE[engine or os.environ.get("SCP_GEMM", "auto")]
+        # 3xFP16 engine: activations are converted unscaled (cvt.rn.satfinite), so |x| must stay below 65504 (weights carry
+        # their own power-of-two scale).  SCP_CHECK_RANGE=1 verifies every Linear input (one reduction + sync per call)
+        self.check_range = os.environ.get("SCP_CHECK_RANGE", "0") == "1"
         self.prof = None          # bench.py: list of (kernel tag, flops, bytes, start event, end event)
         self.event_pool = []      # pre-created timing events (creating them inside the timed region is slow)
 
@@ -122,6 +144,13 @@ class CudaOps:
         rp, ldr = (None, 0) if res is None else self._p(res)
         N, K = w.shape
         assert x[2] == K and y[2] == N, (x[2], K, y[2], N)
+        _weight_is_current(self.lib, w)
+        if self.check_range:
+            t, col, n = x
+            m = float(t[row_off::row_step, col:col + n][:M].abs().max()) if M else 0.0
+            if not m < 6.0e4:
+                raise _lib.ScpError(f"scp_linear: activation magnitude {m:.3g} exceeds the fp16 range of the 3xFP16 engine "
+                                    f"(set SCP_AUTO_ENGINE=1 for 3xTF32)")
         with self._rec("linear", 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (2 if res is not None else 1))):
             _lib.check(self.lib.scp_linear(xp, ldx, _lib.ptr(w), _lib.ptr(b), rp, ldr, yp, ldy, M, N, K, ACT[act],
                                            self.engine if engine is None else ENGINE[engine], _lib.stream_ptr()),
@@ -198,7 +227,7 @@ class CudaOps:
                                               seqs.handle, _lib.ptr(p["occ_enc.weight"]), _lib.ptr(p["level_enc.weight"]),
                                               _lib.ptr(p["octant_enc.weight"]), _lib.ptr(p["abs_pos_enc.weight"]),
                                               _lib.ptr(p["abs_pos_enc.bias"]),
-                                              _lib.ptr(p["transformer_encoder.position_enc.pe"]), _lib.ptr(e),
+                                              _lib.ptr(p.get("transformer_encoder.position_enc.pe")), _lib.ptr(e),
                                               _lib.ptr(eu), _lib.stream_ptr()), "scp_octattn_embed")
 
     def octattn_attention(self, qu, k, ku, v, vu, heads, head_dim, seqs, out, out_u):
@@ -208,6 +237,13 @@ class CudaOps:
         op, ldo = self._p(out)
         oup, ldo2 = self._p(out_u)
         assert ldo == ldo2
+        # algorithmic flops: causal QK^T and PV of the shared score matrix (the reference materialises the full S x S
+        # scores and two PV products, attention_model.py:72-93)
+        fl = sum(2.0 * n * n * heads * head_dim for n in seqs.lengths)
+        with self._rec("octattn_attention", fl, 4.0 * 7 * seqs.total * heads * head_dim):
+            self._octattn_attention(p, ld, heads, head_dim, seqs, op, oup, ldo)
+
+    def _octattn_attention(self, p, ld, heads, head_dim, seqs, op, oup, ldo):
         _lib.check(self.lib.scp_octattn_attention(p[0][0], p[1][0], p[2][0], p[3][0], p[4][0], ld, heads, head_dim,
                                                   seqs.handle, op, oup, ldo, _lib.stream_ptr()),
                    "scp_octattn_attention")

@@ -86,7 +86,7 @@ def ehem_spec(max_level=19):
 
 
 def octattn_spec(context_size=1024, embed=600, hidden=300, layers=3, token_num=255,
-                 max_octree_level=12):
+                 max_octree_level=12, pos_embed=True):
     out = [("mask", (context_size, context_size), "causal_mask")]
     for i in range(layers):
         p = f"transformer_encoder.layers.{i}"
@@ -97,8 +97,9 @@ def octattn_spec(context_size=1024, embed=600, hidden=300, layers=3, token_num=2
                 (f"{p}.linear2.weight", (embed, hidden), "linear_w"), (f"{p}.linear2.bias", (embed,), "linear_b"),
                 (f"{p}.norm1.weight", (embed,), "ln_w"), (f"{p}.norm1.bias", (embed,), "ln_b"),
                 (f"{p}.norm2.weight", (embed,), "ln_w"), (f"{p}.norm2.bias", (embed,), "ln_b")]
-    out += [("transformer_encoder.position_enc.pe", (context_size, embed), "sin_pe"),
-            ("occ_enc.weight", (token_num + 1, 128), "embed"),
+    if pos_embed:                                   # attention_model.py:142-144: the module exists only with cfg.model.pos_embed
+        out += [("transformer_encoder.position_enc.pe", (context_size, embed), "sin_pe")]
+    out += [("occ_enc.weight", (token_num + 1, 128), "embed"),
             ("level_enc.weight", (max_octree_level + 1, 6), "embed"),
             ("octant_enc.weight", (9, 4), "embed"),
             ("abs_pos_enc.weight", (12, 3), "linear_w"), ("abs_pos_enc.bias", (12,), "linear_b"),

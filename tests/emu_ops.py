@@ -143,10 +143,10 @@ class EmuOps:
         pos = ctx_pos.reshape(-1, 4, 3).float() * pos_scale
         rest = torch.cat([p["level_enc.weight"][lvl], p["octant_enc.weight"][c[:, :, 1]],
                           F.linear(pos, p["abs_pos_enc.weight"], p["abs_pos_enc.bias"])], 2)
-        pe = p["transformer_encoder.position_enc.pe"]
+        pe = p.get("transformer_encoder.position_enc.pe")          # absent with cfg.model.pos_embed False
         for a, b in zip(seqs.offsets[:-1], seqs.offsets[1:]):
             for o, dst in ((occ, e), (occ_u, eu)):
-                dst[a:b] = torch.cat([o[a:b], rest[a:b]], 2).reshape(b - a, 600) * math.sqrt(600) + pe[:b - a]
+                dst[a:b] = torch.cat([o[a:b], rest[a:b]], 2).reshape(b - a, 600) * math.sqrt(600) + (pe[:b - a] if pe is not None else 0.0)
 
     def octattn_attention(self, qu, k, ku, v, vu, heads, hd, seqs, out, out_u):
         QU, K, KU, Vv, VU = (_v(t) for t in (qu, k, ku, v, vu))

@@ -69,3 +69,52 @@ def test_f16x3_dynamic_range(xs, ws, tol):
     rel = ((got - ref).abs() / row_scale).max().item()
     print("xs", xs, "ws", ws, "max err / sum|terms|", rel)
     assert rel < tol          # activations of 1e-3 and below sit on the fp16 subnormal step: absolute 3e-8 per term
+
+
+def test_weight_split_cache_follows_the_weights():
+    """The hi/lo weight splits are cached per weight matrix (csrc/gemm_tc.cu).  The cache entry must die with the weights:
+    (a) a new tensor that the caching allocator places at the address of a freed one, (b) an in-place update
+    (``load_state_dict`` copies into the same storage), for both entropy models."""
+    from scp_b200.ops import CudaOps, V
+    from test_models_cpu import cfg_ehem, cfg_oct
+    ops = CudaOps()
+    torch.manual_seed(0)
+    x = torch.randn(256, 256, device="cuda")
+    seen = set()
+    for i in range(4):                                            # (a) same shape, freed and re-allocated
+        w = torch.randn(128, 256, device="cuda") * (i + 1)
+        seen.add(w.data_ptr())
+        y = torch.empty(256, 128, device="cuda")
+        ops.linear(V(x), w, None, V(y))
+        ref = (x.double() @ w.double().T).float()
+        assert (y - ref).abs().max() <= 2e-5 * ref.abs().max(), i
+        del w
+    w = torch.randn(128, 256, device="cuda")
+    y = torch.empty(256, 128, device="cuda")
+    ops.linear(V(x), w, None, V(y))
+    w.mul_(-3.0)                                                  # (b) in place
+    ops.linear(V(x), w, None, V(y))
+    ref = (x.double() @ w.double().T).float()
+    assert (y - ref).abs().max() <= 2e-5 * ref.abs().max()
+    from scp_b200 import weights as W
+    from scp_b200.models import EHEM, OctAttention
+    g = torch.Generator().manual_seed(1)
+    for cls, cfg, spec in ((OctAttention, cfg_oct(), W.octattn_spec()), (EHEM, cfg_ehem(), W.ehem_spec(19))):
+        m = cls(cfg).cuda()
+        if cls is EHEM:
+            data = torch.stack((torch.randint(1, 12, (1, 64, 4), generator=g), torch.randint(1, 9, (1, 64, 4), generator=g),
+                                torch.randint(0, 255, (1, 64, 4), generator=g)), -1).cuda()
+            pos = torch.rand((1, 3, 64), generator=g).cuda()
+        else:
+            data = torch.stack((torch.randint(0, 255, (1, 64, 4), generator=g), torch.randint(1, 12, (1, 64, 4), generator=g),
+                                torch.randint(1, 9, (1, 64, 4), generator=g)), -1).cuda()
+            pos = torch.rand((1, 64, 4, 3), generator=g).cuda()
+        run = lambda mod: [t.clone() for t in (lambda o: o if isinstance(o, tuple) else (o,))(mod(data.clone(), pos))]
+        before = run(m)
+        m.load_state_dict(W.synth_state_dict(spec, seed=5, sharpen=True))        # in-place copy into the same storage
+        after = run(m)
+        fresh = cls(cfg, seed=5).cuda()
+        want = run(fresh)
+        assert not torch.equal(before[0], after[0])
+        for a, b in zip(after, want):
+            assert torch.equal(a, b), cls.__name__

@@ -94,3 +94,24 @@ def test_explained_parity_criterion_on_emulated_ops(tag):
                                  torch.from_numpy(g[f"{tag}_data"].astype(np.int64)), torch.from_numpy(g[f"{tag}_pos"]),
                                  g[f"{tag}_logits1"], g[f"{tag}_logits2"], what=tag)
     assert rep["arith_max"] < 1e-4 and len(rep["stages"]) == 3 and rep["direct_max"] < 1e-4
+
+
+def test_octattn_without_positional_encoding():
+    """cfg.model.pos_embed False (attention_model.py:142-149): no ``position_enc.pe`` in the state_dict (a reference checkpoint
+    trained that way loads strictly) and nothing is added to the embeddings."""
+    from oracle import ehem_torch as O
+    from scp_b200 import weights as W
+    from scp_b200.models import OctAttention
+    cfg = cfg_oct()
+    cfg.model.pos_embed = False
+    m = OctAttention(cfg, ops=EmuOps())
+    assert "transformer_encoder.position_enc.pe" not in m.state_dict() and len(m.state_dict()) == 52
+    g = golden("octattn_logits.npz")
+    data = torch.from_numpy(g["w3_data"].astype(np.int64))[:300]
+    pos = torch.from_numpy(g["w3_pos"])[:300]
+    out = m(data[None].clone(), pos[None])[0]
+    sd = W.synth_state_dict(W.octattn_spec(pos_embed=False), 0, True)
+    ref = O.octattn_forward(sd, data, pos)
+    assert (torch.softmax(out, 1) - torch.softmax(ref, 1)).abs().max() < 1e-4
+    with_pe = O.octattn_forward(W.synth_state_dict(W.octattn_spec(), 0, True), data, pos)
+    assert (torch.softmax(out, 1) - torch.softmax(with_pe, 1)).abs().max() > 1e-3

@@ -122,6 +122,21 @@ def test_knn(ops, d, lens, grid, tensor_cores):
         assert (got - ref).abs().max() < 1e-4 * max(1.0, ref.max().item())
 
 
+@pytest.mark.parametrize("d", [144, 192])
+def test_knn_is_independent_of_the_rest_of_the_batch(ops, d):
+    """Lossless decoding needs the encoder (windows of whole frames in one ragged call) and the decoder (one level per call)
+    to see identical neighbour sets: the indices of a window must not change when windows with a 4000x larger value range
+    share the call (the fp16 hi/lo split of the Gram tiles is scaled per window, csrc/knn_tc.cu)."""
+    cu, _ = ops
+    g = torch.Generator().manual_seed(d)
+    a = torch.randn(1500, d, generator=g) * 0.01
+    big = torch.randn(3000, d, generator=g) * 40.0
+    alone = cu.knn(V(a.cuda()), cu.seqs([0, 1500]), 20).cpu()
+    x = torch.cat([big[:2000], a, big[2000:]]).cuda()
+    inside = cu.knn(V(x), cu.seqs([0, 2000, 3500, 4500]), 20).cpu()
+    assert torch.equal(inside[2000:3500] - 2000, alone)
+
+
 def test_edge_gather(ops):
     cu, em = ops
     n, k = 900, 20

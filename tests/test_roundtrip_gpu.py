@@ -83,6 +83,29 @@ def test_round_trip_cylin_small():
     _round_trip(12, "cylin", False, pts)
 
 
+def test_round_trip_single_node_levels_below_the_root():
+    """A tight cluster far from the sensor: the levels below the root hold ONE node each.  encode.py:123 codes the root's
+    row again for such a level (no running offset) and never codes the node itself -- undecodable; here the node itself is
+    coded (what encode_mullevel.py:120 does) and the round trip is lossless.  ``reference_single_node_defect=True`` still
+    gives the reference's order."""
+    from scp_b200 import coder
+    r = np.random.default_rng(0)
+    pts = (np.array([[60.0, 40.0, -1.0, 0.0]]) + np.concatenate([r.uniform(-0.4, 0.4, (300, 3)), np.zeros((300, 1))], 1)).astype(np.float32)
+    res, dec, trees = _round_trip(12, "spher", False, pts)
+    from scp_b200.encoder import Encoder
+    from scp_b200.models import EHEM
+    enc = Encoder(EHEM(cfg_ehem()).cuda(), 12, "spher", mullevel=False)
+    b, t, _ = enc.build_context(torch.from_numpy(pts).cuda(), [0, len(pts)])
+    level_rows = b.infos[0].level_rows
+    assert level_rows[0] == 1 and 1 in level_rows[1:], level_rows          # the case under test
+    occ = b.emit(("occ",))["occ"]
+    fixed, _ = coder.coding_order(level_rows, 8192, occ, mullevel=False)
+    ref, _ = coder.coding_order(level_rows, 8192, occ, mullevel=False, reference_single_node_defect=True)
+    first = 1 + level_rows[1:].index(1)
+    row = sum(level_rows[:first])
+    assert int(fixed[row]) == row and int(ref[row]) == 0 and sorted(fixed.tolist()) == list(range(sum(level_rows)))
+
+
 def test_round_trip_full_size_k12():
     """BASELINE.json configs[0] at full size: 120 k points, spherical level 12 (~77 k nodes): lossless."""
     from scp_b200 import synth
