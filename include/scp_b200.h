@@ -110,9 +110,11 @@ int scp_octree_finish(scp_octree* t, void* stream);
 /* Device time (ms) of the stages of the last plan+emit, measured with CUDA events on `stream`:
  * [0] quantise+keys [1] radix sort [2] heads/count [3] emit nodes [4] occupancy [5] context gather */
 int scp_octree_stage_ms(scp_octree* t, float out[6]);
-/* Tree builder used by scp_octree_emit: 0 = all levels in one pass over the sorted keys (default), 1 = one pass per level,
- * bottom-up (same outputs, bit for bit; kept as the validated alternative design).  Returns the old value. */
-int scp_set_tree_builder(int by_level);
+/* Tree builder used by scp_octree_emit (same outputs, bit for bit): 0 = node records, all levels in one pass over the sorted
+ * keys; 1 = node records, one pass per level, bottom-up; 2 (default) = like 0, except that a request for the encoder's outputs
+ * only (occ, sym, ctx, pos_norm, voxel_key) is served by two passes over the sorted keys without node records
+ * ([3] = occupancy pass, [4] = 0, [5] = row pass in scp_octree_stage_ms).  Returns the old value. */
+int scp_set_tree_builder(int mode);
 
 /* Standalone pieces of the above, exposed for tests / profiling --------------------------- */
 /* Segmented LSD radix sort of 64-bit keys (8-bit digits, decoupled look-back), in place.

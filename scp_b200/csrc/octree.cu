@@ -37,7 +37,7 @@ constexpr u64 SENTINEL = ~0ull;
 
 struct Tile { int job; int begin; int count; int first; };
 
-struct FrameDev { u32 rho_max_bits; u32 zmin_enc; };
+struct FrameDev { u32 rho_max_bits; u32 zmin_enc; u32 zmax_enc; u32 _pad; };
 
 struct JobDev {
     int frame, path_len, path_bits, drop_last;
@@ -54,6 +54,7 @@ struct JobDev {
     u32 qmax;
     u32 overflow;
     int depth;
+    int depth_known;             // 1: `depth` was derived from the frame statistics BEFORE quantising (fused quantise path)
     int n_kept;                  // keys that take part in the sort (after the morton_path filter); = n_points without a filter
     int n_voxels, n_nodes, n_rows;
     int level_count[MAXL + 1];   // nodes on level L at [L-1]
@@ -106,7 +107,7 @@ __device__ __forceinline__ float rho_of(float x, float y, float z, int mode) {
 
 __global__ void k_init_frames(FrameDev* fr, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { fr[i].rho_max_bits = 0u; fr[i].zmin_enc = 0xffffffffu; }
+    if (i < n) { fr[i].rho_max_bits = 0u; fr[i].zmin_enc = 0xffffffffu; fr[i].zmax_enc = 0u; }
 }
 
 __global__ void __launch_bounds__(TPB) k_frame_stats(const float* __restrict__ xyz, int stride,
@@ -115,17 +116,19 @@ __global__ void __launch_bounds__(TPB) k_frame_stats(const float* __restrict__ x
     Tile t = tiles[blockIdx.x];
     const float* p = xyz + (frame_begin[t.job] + t.begin) * (long long)stride;
     float rmax = 0.f;
-    u32 zmin = 0xffffffffu;
+    u32 zmin = 0xffffffffu, zmax = 0u;
     for (int i = threadIdx.x; i < t.count; i += TPB) {
         float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
         rmax = fmaxf(rmax, rho_of(x, y, z, mode));
-        zmin = min(zmin, enc_ordered(z));
+        const u32 ze = enc_ordered(z);
+        zmin = min(zmin, ze); zmax = max(zmax, ze);
     }
     u32 rb = __reduce_max_sync(0xffffffffu, __float_as_uint(rmax));
-    u32 zb = __reduce_min_sync(0xffffffffu, zmin);
+    u32 zb = __reduce_min_sync(0xffffffffu, zmin), zt = __reduce_max_sync(0xffffffffu, zmax);
     if ((threadIdx.x & 31) == 0) {
         atomicMax(&fr[t.job].rho_max_bits, rb);
         atomicMin(&fr[t.job].zmin_enc, zb);
+        atomicMax(&fr[t.job].zmax_enc, zt);
     }
 }
 
@@ -133,7 +136,7 @@ __global__ void k_job_setup(JobDev* jobs, int n_jobs, const FrameDev* fr, int mo
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     JobDev& J = jobs[j];
-    J.qmax = 0; J.overflow = 0; J.depth = 0; J.n_kept = J.n_points;
+    J.qmax = 0; J.overflow = 0; J.depth = 0; J.depth_known = 0; J.n_kept = J.n_points;
     for (int l = 0; l <= MAXL; ++l) { J.pos_min[l] = 0xffffffffu; J.pos_max[l] = 0u; }
     if (mode == SCP_MODE_CART) {
         J.bin_num = 0.f;
@@ -163,6 +166,27 @@ __global__ void k_job_setup(JobDev* jobs, int n_jobs, const FrameDev* fr, int mo
     J.margin[0] = 1e-7;
     J.margin[1] = 1.5e-6 * J.inv_step[1] + 1e-7;
     J.margin[2] = (mode == SCP_MODE_SPHER) ? 1.5e-6 * J.inv_step[2] + 1e-7 : 1e-7;
+    // Depth of the octree (Octree.py:58: bit length of the largest quantised coordinate over all three axes, BEFORE any
+    // morton_path filter) from the frame statistics alone, so that the fused quantise kernel can apply the filter -- which
+    // tests bits depth-1-j of the radial coordinate -- before it spends any work on a point:
+    //   radial axis: rint(rho / qs) is monotone in rho, so its maximum is rint(rho_max / qs), attained;
+    //   cylindrical z axis: likewise rint((z_max - z_min) / qs);
+    //   angular axes: phi <= float32(2 pi), theta <= float32(pi), and the steps are float32(2 pi | pi) / (bin_num - 1)
+    //   rounded to float32, so q <= (bin_num - 1) * (1 + 2^-24) rounds to at most bin_num - 1 (bin_num <= 2^21).
+    // lo = largest attained coordinate, hi = upper bound; when both have the same bit length the depth is known.  Otherwise
+    // (bin_num - 1 a power of two and the radial maximum one short of it) depth_known stays 0 and the host takes the
+    // two-kernel path (quantise everything, then filter).
+    {
+        const double rmax = (double)rho_max;
+        long long lo = (long long)rint(rmax / J.step[0]);
+        if (mode == SCP_MODE_CYLIN) {
+            const double zspan = (double)dec_ordered(fr[J.frame].zmax_enc) - J.off[2];
+            lo = max(lo, (long long)rint(zspan / J.step[2]));
+        }
+        const long long hi = max(lo, (long long)bm1);
+        const int dl = lo > 0 ? 64 - __clzll(lo) : 0, dh = hi > 0 ? 64 - __clzll(hi) : 0;
+        if (dl == dh && dl >= 1 && dl <= MAXL && lo < (1ll << 21)) { J.depth = dl; J.depth_known = 1; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -321,6 +345,194 @@ __global__ void __launch_bounds__(TPB) k_quantise_frames(const float* __restrict
     }
 }
 
+// Fused coordinate transform + quantise + morton_path filter + compaction (all jobs of a frame in one pass over its points).
+// Needs every job's depth up front (JobDev::depth_known, see k_job_setup).  Per point the float32 transform is evaluated once;
+// per job the radial coordinate is quantised first and the morton_path test (Octree.py:188: bits depth-1-j of the radial
+// coordinate equal path[j]) rejects the point before the angular coordinates, the rounding-margin tests and the Morton spread
+// are touched -- the second and third sub-octree of encode_mullevel keep 5 % and 0.4 % of a sweep.  Kept keys are staged in
+// shared memory and appended to the job's key array at an offset reserved with ONE atomicAdd per (block, job): their order in
+// front of the sort is irrelevant (equal keys are indistinguishable), so no ordered scan over the tiles is needed and the
+// separate filter-count / compaction kernels (two more reads of every key) disappear.
+// `par_pmax`: number of digit passes of the longest job; a job with fewer passes starts in the other ping-pong buffer so that
+// all jobs end in the same one (see k_onesweep).
+__device__ __forceinline__ int sort_passes(int depth) { return (3 * depth + 7) >> 3; }
+
+struct QJob {                 // per-job constants of one block (shared memory)
+    double inv0, inv1, inv2, off2, m0, m1, m2;
+    double s0, s1, s2;
+    long long key_begin;
+    int fshift, fval, plen, job;
+    int to_b, _pad;
+};
+
+constexpr int QHALF = TILE / 2;            // points per flush of the staged keys
+__global__ void __launch_bounds__(TPB, 4) k_quantise_fused(const float* __restrict__ xyz, int stride,
+                                                            const Tile* __restrict__ ftiles, const long long* __restrict__ frame_begin,
+                                                            const int* __restrict__ fj_start, const int* __restrict__ fj,
+                                                            JobDev* jobs, u64* __restrict__ keys_a, u64* __restrict__ keys_b,
+                                                            int mode, int pmax) {
+    __shared__ u64 s_keys[QF_MAXJ][QHALF];                              // kept keys of the current half tile, per job
+    __shared__ QJob s_j[QF_MAXJ];
+    __shared__ unsigned short s_slow[QHALF * QF_MAXJ];                  // (job slot << 12) | point inside the tile
+    __shared__ int s_nslow;
+    __shared__ u32 s_cnt[QF_MAXJ], s_base[QF_MAXJ];
+    const Tile t = ftiles[blockIdx.x];
+    const int f = t.job;
+    const int j0 = fj_start[f], nj = fj_start[f + 1] - j0;
+    const float* p = xyz + (frame_begin[f] + t.begin) * (long long)stride;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < nj) {
+        const int jid = fj[j0 + threadIdx.x];
+        const JobDev& J = jobs[jid];
+        QJob q;
+        q.inv0 = J.inv_step[0]; q.inv1 = J.inv_step[1]; q.inv2 = J.inv_step[2]; q.off2 = J.off[2];
+        q.m0 = J.margin[0]; q.m1 = J.margin[1]; q.m2 = J.margin[2];
+        q.s0 = J.step[0]; q.s1 = J.step[1]; q.s2 = J.step[2];
+        q.key_begin = J.key_begin; q.job = jid;
+        // Octree.py:188: bit depth-1-j of the radial coordinate == path[j]; bits below bit 0 read as 0
+        const int cmp = min(J.path_len, J.depth);
+        int v = 0, tail_ok = 1;
+        for (int j = 0; j < J.path_len; ++j) {
+            const int b = (J.path_bits >> j) & 1;
+            if (j < cmp) v = (v << 1) | b; else tail_ok &= (b == 0);
+        }
+        q.plen = tail_ok ? cmp : -1;
+        q.fshift = J.depth - cmp;
+        q.fval = v;
+        q.to_b = (pmax - sort_passes(J.depth)) & 1;
+        q._pad = 0;
+        s_j[threadIdx.x] = q;
+    }
+    u32 qmax[QF_MAXJ], ovf[QF_MAXJ];
+#pragma unroll
+    for (int s = 0; s < QF_MAXJ; ++s) { qmax[s] = 0; ovf[s] = 0; }
+    auto passes = [&](const QJob& q, long long q0) -> bool {          // radial filter on the exactly rounded coordinate
+        if (q.plen == 0) return true;
+        if (q.plen < 0) return false;
+        return (q0 >> q.fshift) == (long long)q.fval;
+    };
+    // stages the kept keys of this warp: one shared-memory atomicAdd per (warp, job) reserves the run
+    auto emit = [&](int slot, bool keep, long long q0l, long long q1l, long long q2l) {
+        const u32 peers = __ballot_sync(0xffffffffu, keep);
+        if (peers == 0) return;                                        // warp-uniform
+        const int leader = __ffs(peers) - 1;
+        u32 base = 0;
+        if (lane == leader) base = atomicAdd(&s_cnt[slot], (u32)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (!keep) return;
+        u32 o = 0;
+        if ((((unsigned long long)q0l | (unsigned long long)q1l | (unsigned long long)q2l) >> 21) != 0ull) { o = 1; q0l = q1l = q2l = 0; }
+        const u32 q0 = (u32)q0l, q1 = (u32)q1l, q2 = (u32)q2l;
+        s_keys[slot][base + __popc(peers & ((1u << lane) - 1u))] = (spread3(q0) << 2) | (spread3(q1) << 1) | spread3(q2);
+        const u32 qm = max(q0, max(q1, q2));
+#pragma unroll
+        for (int s = 0; s < QF_MAXJ; ++s) if (s == slot) { qmax[s] = max(qmax[s], qm); ovf[s] |= o; }
+    };
+    for (int h0 = 0; h0 < t.count; h0 += QHALF) {
+        const int hend = min(t.count, h0 + QHALF);
+        if (threadIdx.x < QF_MAXJ) s_cnt[threadIdx.x] = 0;
+        if (threadIdx.x == 0) s_nslow = 0;
+        __syncthreads();
+        for (int i0 = h0; i0 < hend; i0 += TPB) {
+            const int i = i0 + threadIdx.x;
+            const bool valid = i < hend;
+            float x = 0.f, y = 0.f, z = 1.f;
+            if (valid) {
+                if (i + 2 * TPB < t.count) prefetch_l2(p + (long long)(i + 2 * TPB) * stride);
+                x = p[(long long)i * stride]; y = p[(long long)i * stride + 1]; z = p[(long long)i * stride + 2];
+            }
+            const float rho = rho_of(x, y, z, mode);
+            const double drho = (double)rho;
+            u32 want = 0;                                               // jobs that keep this point (radial test only)
+            long long q0s[QF_MAXJ];
+#pragma unroll
+            for (int slot = 0; slot < QF_MAXJ; ++slot) {
+                q0s[slot] = 0;
+                if (slot >= nj || !valid) continue;
+                const QJob& q = s_j[slot];
+                const double u0 = drho * q.inv0, r0 = rint(u0);
+                if (0.5 - fabs(u0 - r0) > q.m0) {
+                    q0s[slot] = (long long)r0;
+                    if (passes(q, q0s[slot])) want |= 1u << slot;
+                } else {
+                    s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)((slot << 12) | i);   // within the margin of a .5 boundary
+                }
+            }
+            float phi = 0.f, third = 0.f;
+            bool clear = false;
+            if (want) {                                                 // the expensive part only for points somebody keeps
+                const float xe = __fadd_rn(x, 1e-9f);
+                phi = atan2f(y, xe);
+                if (phi < 0.f) phi = __fadd_rn(phi, 6.2831854820251465f);
+                third = (mode == SCP_MODE_SPHER) ? acosf(__fdiv_rn(z, rho)) : z;
+                clear = (phi > 1e-3f) && (phi < 6.28f);                 // keep clear of the 0 / 2*pi fold
+            }
+#pragma unroll
+            for (int slot = 0; slot < QF_MAXJ; ++slot) {
+                if (slot >= nj) break;
+                const QJob& q = s_j[slot];
+                bool keep = false;
+                long long q1 = 0, q2 = 0;
+                if ((want >> slot) & 1u) {
+                    const double u1 = (double)phi * q.inv1, u2 = ((double)third - q.off2) * q.inv2;
+                    const double r1 = rint(u1), r2 = rint(u2);
+                    if (clear && (0.5 - fabs(u1 - r1) > q.m1) && (0.5 - fabs(u2 - r2) > q.m2)) { keep = true; q1 = (long long)r1; q2 = (long long)r2; }
+                    else s_slow[atomicAdd(&s_nslow, 1)] = (unsigned short)((slot << 12) | i);
+                }
+                emit(slot, keep, q0s[slot], q1, q2);
+            }
+        }
+        __syncthreads();
+        // exact float64 path for the (point, job) pairs near a rounding boundary, densely packed over the threads
+        const int nslow = s_nslow;
+        for (int e0 = 0; e0 < nslow; e0 += TPB) {
+            const int e = e0 + threadIdx.x;
+            bool keep = false;
+            int slot = -1;
+            long long q0 = 0, q1 = 0, q2 = 0;
+            if (e < nslow) {
+                slot = s_slow[e] >> 12;
+                const int i = s_slow[e] & 0xfff;
+                const QJob& q = s_j[slot];
+                const float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
+                quantise_exact(x, y, z, mode, q.s0, q.s1, q.s2, q.off2, q0, q1, q2);
+                keep = passes(q, q0);
+            }
+#pragma unroll
+            for (int sl = 0; sl < QF_MAXJ; ++sl) {
+                if (sl >= nj) break;
+                emit(sl, keep && slot == sl, q0, q1, q2);
+            }
+        }
+        __syncthreads();
+        // one atomicAdd per (block, job, half) reserves the run in the job's key array; coalesced copy out
+        if (threadIdx.x < nj) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd((u32*)&jobs[s_j[threadIdx.x].job].n_kept, s_cnt[threadIdx.x]) : 0u;
+        __syncthreads();
+        for (int slot = 0; slot < nj; ++slot) {
+            const QJob& q = s_j[slot];
+            u64* dst = (q.to_b ? keys_b : keys_a) + q.key_begin + s_base[slot];
+            const int c = (int)s_cnt[slot];
+            for (int i = threadIdx.x; i < c; i += TPB) dst[i] = s_keys[slot][i];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int s = 0; s < QF_MAXJ; ++s) {
+        if (s >= nj) break;
+        const u32 qm = __reduce_max_sync(0xffffffffu, qmax[s]), ov = __reduce_max_sync(0xffffffffu, ovf[s]);
+        if (lane == 0) {
+            JobDev& J = jobs[s_j[s].job];
+            if (qm) atomicMax(&J.qmax, qm);
+            if (ov) atomicMax(&J.overflow, 1u);
+        }
+    }
+}
+
+__global__ void k_job_prepare_fused(JobDev* jobs, int n_jobs) {      // the kept-key counters start at zero
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_jobs) jobs[j].n_kept = 0;
+}
+
 __global__ void k_job_depth(JobDev* jobs, int n_jobs) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
@@ -334,33 +546,27 @@ __global__ void k_job_depth(JobDev* jobs, int n_jobs) {
 // ------------------------------------------------------------------------------------------
 constexpr u32 FLAG_AGG = 1u << 30, FLAG_INC = 1u << 31, VAL_MASK = (1u << 30) - 1;
 
-// also applies the morton_path filter of Octree.py:188 by rewriting rejected keys to SENTINEL
-__global__ void __launch_bounds__(TPB) k_sort_hist(u64* __restrict__ keys, const Tile* __restrict__ tiles,
-                                                    const JobDev* __restrict__ jobs, u32* __restrict__ hist,
-                                                    int P, int apply_filter) {
+// Digit histograms of every job (the "1" of the sort's (1 + 2P) * 8 B/key).  pmax > 0: per-job pass schedule -- a job whose keys
+// need fewer digit passes than the longest job starts in the other ping-pong buffer (see k_onesweep).
+__global__ void __launch_bounds__(TPB) k_sort_hist(const u64* __restrict__ keys_a, const u64* __restrict__ keys_b,
+                                                    const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+                                                    u32* __restrict__ hist, int P, int pmax) {
     __shared__ u32 sh[8 * 256];
     Tile t = tiles[blockIdx.x];
     const JobDev& J = jobs[t.job];
-    for (int i = threadIdx.x; i < P * 256; i += TPB) sh[i] = 0;
+    const int cnt = min(t.count, J.n_kept - t.begin);
+    if (cnt <= 0) return;                                  // block-uniform
+    const int pj = pmax > 0 ? sort_passes(J.depth) : P;
+    for (int i = threadIdx.x; i < pj * 256; i += TPB) sh[i] = 0;
     __syncthreads();
-    u64* src = keys + J.key_begin + t.begin;
-    const int n = J.depth, plen = apply_filter ? J.path_len : 0, pbits = J.path_bits;
-    for (int i = threadIdx.x; i < t.count; i += TPB) {
-        u64 k = src[i];
-        if (plen > 0 && k != SENTINEL) {
-            bool keep = true;
-            for (int j = 0; j < plen; ++j) {
-                int b = n - 1 - j;
-                int bit = b >= 0 ? (int)((k >> (3 * b + 2)) & 1) : 0;
-                keep &= (bit == ((pbits >> j) & 1));
-            }
-            if (!keep) { k = SENTINEL; src[i] = k; }
-        }
-        for (int p = 0; p < P; ++p) atomicAdd(&sh[p * 256 + (u32)((k >> (8 * p)) & 0xff)], 1u);
+    const u64* src = ((pmax > 0 && ((pmax - pj) & 1)) ? keys_b : keys_a) + J.key_begin + t.begin;
+    for (int i = threadIdx.x; i < cnt; i += TPB) {
+        const u64 k = src[i];
+        for (int p = 0; p < pj; ++p) atomicAdd(&sh[p * 256 + (u32)((k >> (8 * p)) & 0xff)], 1u);
     }
     __syncthreads();
     u32* h = hist + (size_t)t.job * P * 256;
-    for (int i = threadIdx.x; i < P * 256; i += TPB)
+    for (int i = threadIdx.x; i < pj * 256; i += TPB)
         if (sh[i]) atomicAdd(&h[i], sh[i]);
 }
 
@@ -452,10 +658,13 @@ __global__ void __launch_bounds__(256) k_scan_hist(u32* hist) {   // one block p
     h[threadIdx.x] = base + inc - v;
 }
 
-__global__ void __launch_bounds__(TPB, 4) k_onesweep(const u64* __restrict__ in, u64* __restrict__ out,
+// pmax > 0 selects the per-job pass schedule: a job of depth d needs ceil(3d/8) digit passes; it skips the passes beyond
+// that and starts in buffer B when (pmax - its passes) is odd, so that after pmax launches every job's sorted keys lie in the
+// same buffer ((pmax & 1) ? B : A).  pmax == 0: all jobs take all P passes from A (scp_segmented_sort_u64, fallback path).
+__global__ void __launch_bounds__(TPB, 4) k_onesweep(u64* __restrict__ buf_a, u64* __restrict__ buf_b,
                                                    const Tile* __restrict__ tiles, int n_tiles,
                                                    const JobDev* __restrict__ jobs, const u32* __restrict__ hist,
-                                                   int P, int pass, u32* desc, u32* ticket, u32* err) {
+                                                   int P, int pass, int pmax, u32* desc, u32* ticket, u32* err) {
     __shared__ u64 s_keys[SORT_TILE];
     __shared__ u32 s_whist[8][257];
     __shared__ u32 s_dstart[256];
@@ -471,6 +680,14 @@ __global__ void __launch_bounds__(TPB, 4) k_onesweep(const u64* __restrict__ in,
     const JobDev& J = jobs[tl.job];
     tl.count = min(tl.count, J.n_kept - tl.begin);       // compacted jobs: the tail tiles are empty and nobody looks back at them
     if (tl.count <= 0) return;
+    int par = pass & 1;
+    if (pmax > 0) {
+        const int pj = sort_passes(J.depth);
+        if (pass >= pj) return;                          // block-uniform: this job's keys are sorted already
+        par = (pass + pmax - pj) & 1;
+    }
+    const u64* in = par ? buf_b : buf_a;
+    u64* out = par ? buf_a : buf_b;
     const u64* src = in + J.key_begin + tl.begin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int shift = pass * 8;
@@ -584,14 +801,18 @@ __device__ __forceinline__ void load_heads(const u64* __restrict__ src, int tbeg
     }
 }
 
+// One histogram per CHUNK = the WKEYS (256) consecutive sorted keys a warp owns (8 chunks per tile): with the exclusive prefix
+// over a job's chunks (k_level_scan) every warp of the later passes knows the BFS rank of its first node on every level
+// without any block-level scan.
+constexpr int CHUNKS = TILE / WKEYS;         // 8
 __global__ void __launch_bounds__(TPB) k_head_hist(const u64* __restrict__ keys, const Tile* __restrict__ tiles,
-                                                    const JobDev* __restrict__ jobs, u32* __restrict__ tile_hist) {
-    __shared__ u32 sh[NBINS];
+                                                    const JobDev* __restrict__ jobs, u32* __restrict__ chunk_hist) {
+    __shared__ u32 sh[CHUNKS][NBINS];
     const Tile t = tiles[blockIdx.x];
     const JobDev& J = jobs[t.job];
-    if (threadIdx.x < NBINS) sh[threadIdx.x] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < NBINS) sh[warp][lane] = 0;
+    __syncwarp();
     // keys past n_kept were filtered out before the sort (tail tiles are empty)
     const int cnt = min(t.count, J.n_kept - t.begin);
     if (cnt > 0) {
@@ -601,34 +822,36 @@ __global__ void __launch_bounds__(TPB) k_head_hist(const u64* __restrict__ keys,
 #pragma unroll
         for (int it = 0; it < WITER; ++it) {
             const u32 peers = __match_any_sync(0xffffffffu, h[it]);
-            if (h[it] > 0 && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sh[h[it]], (u32)__popc(peers));
+            if (h[it] > 0 && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sh[warp][h[it]], (u32)__popc(peers));
         }
     }
-    __syncthreads();
-    if (threadIdx.x < NBINS) tile_hist[(size_t)blockIdx.x * NBINS + threadIdx.x] = sh[threadIdx.x];
+    __syncwarp();
+    if (lane < NBINS) chunk_hist[((size_t)blockIdx.x * CHUNKS + warp) * NBINS + lane] = sh[warp][lane];
 }
 
 // K5: one warp per job: exclusive scan of the tile histograms, level counts and offsets
 __global__ void k_level_scan(JobDev* jobs, int n_jobs, const int* __restrict__ job_tile_begin,
-                             u32* tile_hist /* in: counts, out: exclusive prefix inside the job */) {
+                             u32* chunk_hist /* in: counts, out: exclusive prefix inside the job */) {
     int j = blockIdx.x;
     JobDev& J = jobs[j];
     __shared__ u32 tot[32];
     int b = threadIdx.x;
     u32 run = 0;
     if (b < NBINS) {
-        const int t0 = job_tile_begin[j], t1 = job_tile_begin[j + 1];
+        // only the chunks that hold sorted keys (compacted jobs keep a fraction of their points)
+        const int t0 = job_tile_begin[j] * CHUNKS;
+        const int t1 = min(job_tile_begin[j + 1] * CHUNKS, t0 + (J.n_kept + WKEYS - 1) / WKEYS);
         int t = t0;
-        for (; t + 4 <= t1; t += 4) {                   // four independent loads in flight
-            u32 c[4];
+        for (; t + 8 <= t1; t += 8) {                   // eight independent loads in flight
+            u32 c[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) c[q] = tile_hist[(size_t)(t + q) * NBINS + b];
+            for (int q = 0; q < 8; ++q) c[q] = chunk_hist[(size_t)(t + q) * NBINS + b];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { tile_hist[(size_t)(t + q) * NBINS + b] = run; run += c[q]; }
+            for (int q = 0; q < 8; ++q) { chunk_hist[(size_t)(t + q) * NBINS + b] = run; run += c[q]; }
         }
         for (; t < t1; ++t) {
-            u32 c = tile_hist[(size_t)t * NBINS + b];
-            tile_hist[(size_t)t * NBINS + b] = run;
+            u32 c = chunk_hist[(size_t)t * NBINS + b];
+            chunk_hist[(size_t)t * NBINS + b] = run;
             run += c;
         }
     }
@@ -720,7 +943,7 @@ __global__ void __launch_bounds__(TPB) k_emit_nodes(const u64* __restrict__ keys
     if (threadIdx.x <= MAXL) {
         int L = threadIdx.x;       // L = 0: voxel counter
         u32 s = 0;
-        const u32* tb = tile_base + (size_t)(t.first + t.begin / TILE) * NBINS;   // tiles may be a compacted list
+        const u32* tb = tile_base + (size_t)(t.first + t.begin / TILE) * CHUNKS * NBINS;   // first chunk of the tile (tiles may be a compacted list)
         if (L == 0) { for (int h = 1; h < NBINS; ++h) s += tb[h]; }
         else if (L <= n) { for (int h = 1; h <= L; ++h) s += tb[h]; }
         s_base[L] = s;
@@ -1318,6 +1541,270 @@ __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles,
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K6/K7 fused ("lean" outputs: occ, sym, ctx, pos_norm): two passes over the SORTED KEYS, no node records at all.
+// ------------------------------------------------------------------------------------------
+// A node on level L is the run of sorted keys that share their first L-1 octal digits; it is "opened" by the first key of the
+// run, i.e. by every key whose head level h is <= L.  With the per-level ballots of a warp a key knows, for EVERY level at
+// once, the BFS rank of the node it opens there (rank of heads) and of the node that contains it (heads at or before it,
+// minus one) -- so parents, ancestors and children never have to be looked up through stored indices:
+//   pass 1 (k_tree_occ)  occupancy byte of every node = OR over the digits of the keys that open one of its children: a
+//                        segmented OR over the warp (segments = parents), plain byte stores for parents whose run lies
+//                        inside the warp, atomicOr on the aligned word for the <= 2 runs per level cut by the warp border;
+//                        also the voxel extremes that give every level's (min, max) coordinate for the normalisation.
+//   pass 2 (k_tree_rows) for every (key, level >= h): the final row -- occupancy of the node and of its three ancestors
+//                        (four byte gathers at ranks known from the ballots, L1-resident), level / octant bytes and the
+//                        normalised position from the key's own coordinates; the nodes a warp opens on one level are
+//                        consecutive rows, written through a per-warp staging tile as coalesced words.
+// Traffic: 2 x 8 B/key + 1 B/node (+ atomics) + the 27 B/node of outputs, against the 28 + 60 B/node of the record-based
+// design (k_emit_nodes / k_occupancy / k_context, kept for the outputs that need parent indices and ancestor positions).
+// Warp-autonomous: a warp owns one chunk (WKEYS = 256 consecutive sorted keys, 8 rounds of 32); the rank of its first node on
+// every level comes from the chunk prefix table (k_head_hist / k_level_scan), the running ranks stay in warp-uniform
+// registers -- no block-level scan, no __syncthreads inside the key loop.
+// Register layout "lane = level": lane L keeps the ballot of level L (lanes that open a node there; lane 0: new voxels) and
+// the running rank base[L] of the chunk, so the per-level state is two registers, the update after a round is ONE add per
+// lane, and the level loops are ordinary runtime loops (an unrolled 21-level body overflowed the instruction cache: half of
+// the stall samples of the first version were "no instruction").  b[L] / base[L] reach all lanes by a shuffle from lane L.
+__device__ __forceinline__ u32 tree_ballots(int h, int n, int lane, int& wmin) {
+    const int hh = h == 0 ? 99 : h;
+    wmin = __reduce_min_sync(0xffffffffu, hh);
+    const u32 b0 = __ballot_sync(0xffffffffu, h > 0);
+    u32 bvec = lane == 0 ? b0 : 0u;
+    for (int L = max(wmin, 1); L <= n; ++L) {                           // warp-uniform bounds
+        const u32 b = __ballot_sync(0xffffffffu, hh <= L);
+        if (lane == L) bvec = b;
+    }
+    return bvec;
+}
+
+// lane L: nodes the job opened on level L in front of this chunk (lane 0: voxels)
+__device__ __forceinline__ u32 chunk_bases(const u32* __restrict__ cb, int n, int lane) {
+    const u32 c = (lane >= 1 && lane < NBINS) ? __ldg(cb + lane) : 0u;   // lane h: heads of level h in front of the chunk
+    u32 inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+    const u32 vox = __shfl_sync(0xffffffffu, inc, NBINS - 1);
+    return lane == 0 ? vox : (lane <= n ? inc : 0u);
+}
+
+__global__ void __launch_bounds__(TPB) k_tree_occ(const u64* __restrict__ keys, const Tile* __restrict__ tiles, JobDev* jobs,
+                                                   const u32* __restrict__ chunk_base, uint8_t* __restrict__ occ_all,
+                                                   u64* __restrict__ vox_key) {
+    __shared__ u32 s_mm[4];
+    __shared__ int s_ls[MAXL + 2];
+    const Tile t = tiles[blockIdx.x];
+    JobDev& J = jobs[t.job];
+    const int n = J.depth;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 ltmask = (1u << lane) - 1u, lemask = (2u << lane) - 1u;
+    if (threadIdx.x <= MAXL + 1) s_ls[threadIdx.x] = J.level_start[threadIdx.x];
+    if (threadIdx.x >= 64 && threadIdx.x < 68) s_mm[threadIdx.x - 64] = (threadIdx.x & 1) ? 0u : 0xffffffffu;
+    __syncthreads();
+    const u64* src = keys + J.key_begin;
+    const long long node0 = J.node_start;
+    uint8_t* occ = occ_all + node0;
+    u32* occ32 = reinterpret_cast<u32*>(occ_all);
+    const int n_vox = J.n_voxels;
+    u32 cmin = 0xffffffffu, cmax = 0u, emin = 0xffffffffu, emax = 0u;
+    const int cnt = min(t.count, J.n_kept - t.begin);          // keys past n_kept were filtered out before the sort
+    const int wbeg = warp * WKEYS;
+    if (wbeg < cnt) {
+        u32 basev = chunk_bases(chunk_base + ((size_t)(t.first + t.begin / TILE) * CHUNKS + warp) * NBINS, n, lane);
+        const int g0 = t.begin + wbeg;
+        u64 carry = (lane == 0 && g0 > 0) ? __ldg(src + g0 - 1) : 0ull;
+        u64 knext = wbeg + lane < cnt ? __ldg(src + g0 + lane) : SENTINEL;
+        for (int it = 0; it < WITER; ++it) {
+            const int idx = wbeg + it * 32 + lane;
+            if (wbeg + it * 32 >= cnt) break;                   // warp-uniform
+            const u64 k = knext;
+            if (it + 1 < WITER) knext = idx + 32 < cnt ? __ldg(src + t.begin + idx + 32) : SENTINEL;
+            u64 prev = __shfl_up_sync(0xffffffffu, k, 1);
+            if (lane == 0) prev = carry;
+            const int h = idx < cnt ? head_level(k, prev, g0 + it * 32 + lane == 0, n) : 0;
+            carry = __shfl_sync(0xffffffffu, k, 31);
+            int wmin;
+            const u32 bvec = tree_ballots(h, n, lane, wmin);
+            const u32 b0 = __shfl_sync(0xffffffffu, bvec, 0);
+            const u32 vbase = __shfl_sync(0xffffffffu, basev, 0);
+            if (h > 0) {
+                const u32 v = vbase + __popc(b0 & ltmask);
+                if (vox_key) vox_key[J.vox_start + v] = k;
+                // x & m is monotone in x, so every level's min / max node coordinate follows from the voxel extremes
+                const u32 x = compact3(k >> 2), y = compact3(k >> 1), z = compact3(k);
+                const u32 lo = min(x, min(y, z)), hi = max(x, max(y, z));
+                cmin = min(cmin, lo); cmax = max(cmax, hi);
+                if ((int)v != n_vox - 1) { emin = min(emin, lo); emax = max(emax, hi); }
+            }
+            // children on level Lc (Lc = n+1: the voxels) add their digit bit to their parent on level Lc-1
+            for (int Lc = max(wmin, 2); Lc <= n + 1; ++Lc) {     // warp-uniform bounds
+                const u32 bc = Lc <= n ? __shfl_sync(0xffffffffu, bvec, Lc) : b0;
+                if (bc == 0) continue;                           // warp-uniform
+                const u32 bp = __shfl_sync(0xffffffffu, bvec, Lc - 1);   // parents opened in these 32 keys = segment starts
+                const u32 pbase = __shfl_sync(0xffffffffu, basev, Lc - 1);
+                u32 v = ((bc >> lane) & 1u) ? (1u << ((u32)(k >> (3 * (n + 1 - Lc))) & 7u)) : 0u;
+                const u32 below = bp & lemask;
+                const int seg0 = below ? 31 - __clz(below) : 0;  // first lane of my parent's run inside these 32 keys
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 up = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane - o >= seg0) v |= up;
+                }
+                const bool last = (lane == 31) || ((bp >> (lane + 1)) & 1u);
+                if (last && v) {
+                    const u32 pr = pbase + __popc(below) - 1u;                 // the parent that contains this key
+                    const long long idx2 = (long long)s_ls[Lc - 2] + pr;
+                    if (below != 0 && lane != 31) occ[idx2] = (uint8_t)v;      // run inside these 32 keys: complete
+                    else { const long long g = node0 + idx2; atomicOr(occ32 + (g >> 2), v << (8 * (int)(g & 3))); }
+                }
+            }
+            basev += __popc(bvec);                               // every lane advances its own level
+        }
+    }
+    cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
+    emin = __reduce_min_sync(0xffffffffu, emin); emax = __reduce_max_sync(0xffffffffu, emax);
+    if (lane == 0 && cmin != 0xffffffffu) {
+        atomicMin(&s_mm[0], cmin); atomicMax(&s_mm[1], cmax); atomicMin(&s_mm[2], emin); atomicMax(&s_mm[3], emax);
+    }
+    __syncthreads();
+    if (threadIdx.x >= 1 && threadIdx.x <= n) {                 // see k_emit_nodes
+        const int L = threadIdx.x;
+        const u32 m = ~((1u << (n - L + 1)) - 1u);
+        const bool excl = J.drop_last && L == n;
+        const u32 mn = excl ? s_mm[2] : s_mm[0], mx = excl ? s_mm[3] : s_mm[1];
+        if (mn != 0xffffffffu) {
+            atomicMin(&J.pos_min[L - 1], mn & m);
+            atomicMax(&J.pos_max[L - 1], mx & m);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TPB, 3) k_tree_rows(const u64* __restrict__ keys, const Tile* __restrict__ tiles,
+                                                       const JobDev* __restrict__ jobs, const u32* __restrict__ chunk_base,
+                                                       const uint8_t* __restrict__ occ_all, scp_octree_out O) {
+    __shared__ int s_ls[MAXL + 2];
+    __shared__ double s_mn[MAXL + 1], s_den[MAXL + 1], s_inv[MAXL + 1];
+    __shared__ u32 s_thr[MAXL + 1], s_lv[MAXL + 1];
+    __shared__ u32 s_stage[TPB / 32][2][96];
+    const Tile t = tiles[blockIdx.x];
+    const JobDev& J = jobs[t.job];
+    const int n = J.depth;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 ltmask = (1u << lane) - 1u, lemask = (2u << lane) - 1u;
+    if (threadIdx.x <= MAXL + 1) s_ls[threadIdx.x] = J.level_start[threadIdx.x];
+    if (threadIdx.x >= 64 + 1 && threadIdx.x <= 64 + n) {
+        const int L = threadIdx.x - 64;
+        const double den = (double)(J.pos_max[L - 1] - J.pos_min[L - 1]) + ((L == n && !J.pos_eps_last) ? 0.0 : 1e-9);
+        s_mn[L] = (double)J.pos_min[L - 1]; s_den[L] = den; s_inv[L] = 1.0 / den;
+        s_thr[L] = den > 0.0 ? 16u : 0xffffffffu;
+        // level bytes of (great-grandparent, grandparent, parent, self): 0 = missing; the last level is clipped to lidar_level
+        u32 lv = 0;                                                // (encode_dataset_ehem.py:86)
+        for (int q = 0; q < 4; ++q) {
+            int Lk = max(L - (3 - q), 0);
+            if (L == n && n > J.lidar_level) Lk = min(Lk, J.lidar_level);
+            lv |= (u32)Lk << (8 * q);
+        }
+        s_lv[L] = lv;
+    }
+    __syncthreads();
+    const u64* src = keys + J.key_begin;
+    const uint8_t* __restrict__ occ = occ_all + J.node_start;
+    const long long row0 = J.row_start;
+    const int n_rows = J.n_rows;
+    const int cnt = min(t.count, J.n_kept - t.begin);
+    const int wbeg = warp * WKEYS;
+    if (wbeg >= cnt) return;                                      // warp-uniform; no block-level synchronisation below
+    u32 basev = chunk_bases(chunk_base + ((size_t)(t.first + t.begin / TILE) * CHUNKS + warp) * NBINS, n, lane);
+    const int g0 = t.begin + wbeg;
+    u64 carry = (lane == 0 && g0 > 0) ? __ldg(src + g0 - 1) : 0ull;
+    u64 knext = wbeg + lane < cnt ? __ldg(src + g0 + lane) : SENTINEL;
+    u32* sc = s_stage[warp][0];
+    float* sp = reinterpret_cast<float*>(s_stage[warp][1]);
+    for (int it = 0; it < WITER; ++it) {
+        const int idx = wbeg + it * 32 + lane;
+        if (wbeg + it * 32 >= cnt) break;                         // warp-uniform
+        const u64 k = knext;
+        if (it + 1 < WITER) knext = idx + 32 < cnt ? __ldg(src + t.begin + idx + 32) : SENTINEL;
+        u64 prev = __shfl_up_sync(0xffffffffu, k, 1);
+        if (lane == 0) prev = carry;
+        const int h = idx < cnt ? head_level(k, prev, g0 + it * 32 + lane == 0, n) : 0;
+        carry = __shfl_sync(0xffffffffu, k, 31);
+        int wmin;
+        const u32 bvec = tree_ballots(h, n, lane, wmin);
+        const u32 x = compact3(k >> 2), y = compact3(k >> 1), z = compact3(k);
+        // ranks of the nodes that CONTAIN this key on the three levels above the current one (shifted down every level)
+        u32 b1 = 0, b2 = 0, b3 = 0, r1 = 0, r2 = 0, r3 = 0;       // level L-1, L-2, L-3: ballot and base
+        {
+            const int L0 = max(wmin, 1);
+            if (L0 - 1 >= 1) { b1 = __shfl_sync(0xffffffffu, bvec, L0 - 1); r1 = __shfl_sync(0xffffffffu, basev, L0 - 1); }
+            if (L0 - 2 >= 1) { b2 = __shfl_sync(0xffffffffu, bvec, L0 - 2); r2 = __shfl_sync(0xffffffffu, basev, L0 - 2); }
+            if (L0 - 3 >= 1) { b3 = __shfl_sync(0xffffffffu, bvec, L0 - 3); r3 = __shfl_sync(0xffffffffu, basev, L0 - 3); }
+        }
+        for (int L = max(wmin, 1); L <= n; ++L) {                  // warp-uniform bounds
+            const u32 bl = __shfl_sync(0xffffffffu, bvec, L);
+            const u32 rl = __shfl_sync(0xffffffffu, basev, L);
+            if (bl != 0) {                                        // warp-uniform
+                const bool mine = (bl >> lane) & 1u;
+                const u32 ci = __popc(bl & ltmask);               // my node among the nodes opened on level L by these 32 keys
+                const long long lrow = (long long)s_ls[L - 1] + rl;                  // row (inside the job) of the first one
+                const int nw = (int)max(0ll, min((long long)__popc(bl), (long long)n_rows - lrow)); // minus the dropped last row
+                if (nw > 0) {                                     // warp-uniform
+                    if (mine) {
+                        const u32 self = ((u32)__ldg(occ + lrow + ci) - 1u) & 0xffu;
+                        // (occ-1) of ggp | gp << 8 | parent << 16 | self << 24; a missing ancestor reads 255 (occ 256)
+                        u32 occp = self << 24;
+                        occp |= (L >= 2 ? ((u32)__ldg(occ + s_ls[L - 2] + r1 + __popc(b1 & lemask) - 1u) - 1u) & 0xffu : 0xffu) << 16;
+                        occp |= (L >= 3 ? ((u32)__ldg(occ + s_ls[L - 3] + r2 + __popc(b2 & lemask) - 1u) - 1u) & 0xffu : 0xffu) << 8;
+                        occp |= (L >= 4 ? ((u32)__ldg(occ + s_ls[L - 4] + r3 + __popc(b3 & lemask) - 1u) - 1u) & 0xffu : 0xffu);
+                        // bit j of (coordinate >> sh3) is the octant bit of the ancestor j levels up (sh3 = lowest bit of the own cell)
+                        const int sh3 = n - L + 1;
+                        const u32 W = (((x >> sh3) & 0xfu) << 8) | (((y >> sh3) & 0xfu) << 4) | ((z >> sh3) & 0xfu);
+                        u32 OC = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = 3 - q, Lk = L - j;
+                            u32 o = ((((W >> j) & 0x111u) * 0x124u) >> 8 & 7u) + 1u;   // 4*xbit + 2*ybit + zbit + 1
+                            if (Lk <= 1) o = (Lk == 1) ? 1u : 0u;                       // root: octant 1; missing: 0
+                            OC |= o << (8 * q);
+                        }
+                        const u32 LV = s_lv[L];
+                        sc[3 * ci] = __byte_perm(__byte_perm(LV, OC, 0x1040), occp, 0x3410);
+                        sc[3 * ci + 1] = __byte_perm(__byte_perm(LV, OC, 0x6205), occp, 0x3250);
+                        sc[3 * ci + 2] = __byte_perm(__byte_perm(LV, OC, 0x0730), occp, 0x7216);
+                        if (O.pos_norm) {
+                            const u32 m = ~((1u << sh3) - 1u);                          // the node's own cell origin
+                            const double mn = s_mn[L], den = s_den[L], inv = s_inv[L];
+                            const u32 thr = s_thr[L];
+                            sp[3 * ci] = norm_pos(x & m, mn, den, inv, thr);
+                            sp[3 * ci + 1] = norm_pos(y & m, mn, den, inv, thr);
+                            sp[3 * ci + 2] = norm_pos(z & m, mn, den, inv, thr);
+                        }
+                        if ((int)ci < nw) {
+                            if (O.occ) O.occ[row0 + lrow + ci] = (uint8_t)(self + 1u);
+                            if (O.sym) O.sym[row0 + lrow + ci] = (int16_t)self;
+                        }
+                    }
+                    // the nodes opened on level L are nw consecutive rows: compacted in the staging tile, stored coalesced
+                    __syncwarp();
+                    const int nvw = 3 * nw;
+                    if (O.ctx) {
+                        u32* dst = reinterpret_cast<u32*>(O.ctx + 12 * (row0 + lrow));
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) if (32 * j + lane < nvw) dst[32 * j + lane] = sc[32 * j + lane];
+                    }
+                    if (O.pos_norm) {
+                        float* dst = O.pos_norm + 3 * (row0 + lrow);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) if (32 * j + lane < nvw) dst[32 * j + lane] = sp[32 * j + lane];
+                    }
+                    __syncwarp();
+                }
+            }
+            b3 = b2; r3 = r2; b2 = b1; r2 = r1; b1 = bl; r1 = rl;  // level L becomes "one level up" of the next one
+        }
+        basev += __popc(bvec);                                     // every lane advances its own level
+    }
+}
+
 }  // namespace scp
 
 // ==========================================================================================
@@ -1355,8 +1842,9 @@ static void build_tiles(const std::vector<long long>& counts, int tile, std::vec
 }
 
 // keys -> sorted (ping-pong with tmp).  hist_ready: the digit histograms were already produced (k_compact_hist).
+// pmax > 0: per-job pass schedule (keys of job j start in `keys` or `tmp` as k_quantise_fused left them), P == pmax.
 static int run_sort(u64* keys, u64* tmp, const Tile* d_tiles, int n_tiles, const JobDev* d_jobs, int n_jobs, int P,
-                    bool hist_ready, DevBuf& hist, DevBuf& desc, DevBuf& misc, cudaStream_t st, u64** result) {
+                    bool hist_ready, int pmax, DevBuf& hist, DevBuf& desc, DevBuf& misc, cudaStream_t st, u64** result) {
     if (P <= 0 || n_tiles == 0) { *result = keys; return SCP_OK; }
     if (int e = desc.reserve((size_t)P * n_tiles * 256 * 4)) return e;
     if (int e = misc.reserve(64 * 4)) return e;
@@ -1365,28 +1853,34 @@ static int run_sort(u64* keys, u64* tmp, const Tile* d_tiles, int n_tiles, const
     if (!hist_ready) {
         if (int e = hist.reserve((size_t)n_jobs * P * 256 * 4)) return e;
         SCP_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)n_jobs * P * 256 * 4, st));
-        k_sort_hist<<<n_tiles, TPB, 0, st>>>(keys, d_tiles, d_jobs, hist.as<u32>(), P, 0);
+        k_sort_hist<<<n_tiles, TPB, 0, st>>>(keys, tmp, d_tiles, d_jobs, hist.as<u32>(), P, pmax);
         SCP_LAUNCHED();
     }
     k_scan_hist<<<n_jobs * P, 256, 0, st>>>(hist.as<u32>());
     SCP_LAUNCHED();
-    u64* a = keys; u64* b = tmp;
     for (int p = 0; p < P; ++p) {
-        k_onesweep<<<n_tiles, TPB, 0, st>>>(a, b, d_tiles, n_tiles, d_jobs, hist.as<u32>(), P, p, desc.as<u32>(),
+        k_onesweep<<<n_tiles, TPB, 0, st>>>(keys, tmp, d_tiles, n_tiles, d_jobs, hist.as<u32>(), P, p, pmax, desc.as<u32>(),
                                             misc.as<u32>() + 1 + p, misc.as<u32>());
         SCP_LAUNCHED();
-        std::swap(a, b);
     }
-    *result = a;
+    *result = (P & 1) ? tmp : keys;
     return SCP_OK;
 }
 
-static int tree_builder_default() { const char* e = getenv("SCP_TREE"); return (e && !strcmp(e, "level")) ? 1 : 0; }
+// 0 = node records, all levels in one pass (k_emit_nodes + k_occupancy + k_context*); 1 = node records, one pass per level
+// (k_level_pass); 2 (default) = as 0, but the lean outputs (occ, sym, ctx, pos_norm) come from the two key passes
+// k_tree_occ / k_tree_rows without node records.  env SCP_TREE = records | level | keys
+static int tree_builder_default() {
+    const char* e = getenv("SCP_TREE");
+    if (e && !strcmp(e, "level")) return 1;
+    if (e && !strcmp(e, "records")) return 0;
+    return 2;
+}
 static int g_tree_builder = tree_builder_default();
 
 extern "C" {
 
-int scp_set_tree_builder(int by_level) { int old = g_tree_builder; g_tree_builder = by_level ? 1 : 0; return old; }
+int scp_set_tree_builder(int mode) { int old = g_tree_builder; g_tree_builder = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return old; }
 
 scp_octree* scp_octree_create(void) { return new scp_octree(); }
 
@@ -1448,7 +1942,7 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     if (int e = t->frames.reserve((size_t)n_frames * sizeof(FrameDev))) return e;
     if (int e = t->frame_begin.reserve((size_t)n_frames * 8)) return e;
     if (int e = t->jobs.reserve((size_t)n_jobs * sizeof(JobDev))) return e;
-    if (int e = t->tile_hist.reserve((size_t)nt_p * NBINS * 4)) return e;
+    if (int e = t->tile_hist.reserve((size_t)nt_p * CHUNKS * NBINS * 4)) return e;
     if (int e = t->job_tile_begin.reserve((size_t)(n_jobs + 1) * 4)) return e;
     Tile* d_ftiles = t->tiles_pts.as<Tile>();
     t->nt_frame = nt_f;
@@ -1480,6 +1974,36 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
         std::vector<int> fill(fj_start.begin(), fj_start.end() - 1);
         for (int j = 0; j < n_jobs; ++j) fj[fill[h_jobs[j].frame]++] = j;
     }
+    // Fused path (spherical / cylindrical): depth from the frame statistics, then ONE kernel does transform + quantise +
+    // morton_path filter + compaction for all jobs of a frame; the sort follows with a per-job pass schedule.
+    bool fused = mode != SCP_MODE_CART && max_per_frame >= 1 && max_per_frame <= QF_MAXJ && !getenv("SCP_QUANT_OLD");
+    int max_depth = 0, any_filter = 0;
+    if (fused) {
+        SCP_CUDA(cudaMemcpyAsync(t->hjobs.data(), d_jobs, n_jobs * sizeof(JobDev), cudaMemcpyDeviceToHost, st));
+        SCP_CUDA(cudaStreamSynchronize(st));
+        for (int j = 0; j < n_jobs; ++j) {
+            fused = fused && t->hjobs[j].depth_known;
+            max_depth = std::max(max_depth, t->hjobs[j].depth);
+        }
+    }
+    if (fused) {
+        SCP_REQUIRE(max_depth >= 1 && max_depth <= MAXL, "octree depth %d outside [1,%d]", max_depth, MAXL);
+        t->P = (3 * max_depth + 7) / 8;
+        t->max_depth = max_depth;
+        int *d_fjs = nullptr, *d_fj = nullptr;
+        SCP_CUDA(upload_async((void**)&d_fjs, fj_start.data(), (size_t)(n_frames + 1) * 4, st));
+        SCP_CUDA(upload_async((void**)&d_fj, fj.data(), (size_t)n_jobs * 4, st));
+        k_job_prepare_fused<<<(int)cdiv(n_jobs, 128), 128, 0, st>>>(d_jobs, n_jobs);
+        SCP_LAUNCHED();
+        k_quantise_fused<<<nt_f, TPB, 0, st>>>(d_xyz, point_stride, d_ftiles, t->frame_begin.as<long long>(), d_fjs, d_fj, d_jobs,
+                                               t->keys_a.as<u64>(), t->keys_b.as<u64>(), mode, t->P);
+        SCP_LAUNCHED();
+        SCP_CUDA(cudaFreeAsync(d_fjs, st));
+        SCP_CUDA(cudaFreeAsync(d_fj, st));
+        SCP_CUDA(cudaEventRecord(t->ev[1], st));
+        if (int e = run_sort(t->keys_a.as<u64>(), t->keys_b.as<u64>(), t->tiles_sort.as<Tile>(), nt_s, d_jobs, n_jobs, t->P,
+                             false, t->P, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
+    } else {
     if (mode != SCP_MODE_CART && max_per_frame >= 2 && max_per_frame <= QF_MAXJ) {
         int *d_fjs = nullptr, *d_fj = nullptr;
         SCP_CUDA(upload_async((void**)&d_fjs, fj_start.data(), (size_t)(n_frames + 1) * 4, st));
@@ -1498,14 +2022,14 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     SCP_CUDA(cudaEventRecord(t->ev[1], st));
     SCP_CUDA(cudaMemcpyAsync(t->hjobs.data(), d_jobs, n_jobs * sizeof(JobDev), cudaMemcpyDeviceToHost, st));
     SCP_CUDA(cudaStreamSynchronize(st));
-    int max_depth = 0, any_filter = 0;
+    max_depth = 0;
     for (int j = 0; j < n_jobs; ++j) {
         if (t->hjobs[j].overflow) { set_error("job %d: quantised coordinate outside [0, 2^21)", j); return SCP_ERR_RANGE; }
         max_depth = std::max(max_depth, t->hjobs[j].depth);
         any_filter |= t->hjobs[j].path_len > 0;
     }
     SCP_REQUIRE(max_depth >= 1 && max_depth <= MAXL, "octree depth %d outside [1,%d]", max_depth, MAXL);
-    t->P = (3 * max_depth + 1 + 7) / 8;
+    t->P = (3 * max_depth + 7) / 8;
     t->max_depth = max_depth;
     if (any_filter) {
         // jobs with a morton_path (mullevel): drop the rejected keys before sorting
@@ -1527,10 +2051,11 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
         SCP_CUDA(cudaFreeAsync(d_stb, st));
         SCP_CUDA(cudaFreeAsync(d_kept, st));
         if (int e = run_sort(t->keys_b.as<u64>(), t->keys_a.as<u64>(), t->tiles_sort.as<Tile>(), nt_s, d_jobs, n_jobs, t->P,
-                             true, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
+                             true, 0, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
     } else {
         if (int e = run_sort(t->keys_a.as<u64>(), t->keys_b.as<u64>(), t->tiles_sort.as<Tile>(), nt_s, d_jobs, n_jobs, t->P,
-                             false, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
+                             false, 0, t->hist, t->desc, t->misc, st, &t->sorted)) return e;
+    }
     }
     SCP_CUDA(cudaEventRecord(t->ev[2], st));
     k_head_hist<<<nt_p, TPB, 0, st>>>(t->sorted, d_ptiles, d_jobs, t->tile_hist.as<u32>());
@@ -1545,6 +2070,14 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     SCP_CUDA(cudaMemcpyAsync(&err, t->misc.p, 4, cudaMemcpyDeviceToHost, st));
     SCP_CUDA(cudaStreamSynchronize(st));
     if (err) { set_error("radix sort look-back timed out"); return SCP_ERR_INTERNAL; }
+    for (int j = 0; j < n_jobs; ++j) {
+        if (t->hjobs[j].overflow) { set_error("job %d: quantised coordinate outside [0, 2^21)", j); return SCP_ERR_RANGE; }
+        if (t->hjobs[j].depth_known && (t->hjobs[j].qmax >> t->hjobs[j].depth) != 0u) {
+            set_error("job %d: a quantised coordinate (%u) exceeds the depth %d derived from the frame statistics", j, t->hjobs[j].qmax,
+                      t->hjobs[j].depth);
+            return SCP_ERR_INTERNAL;
+        }
+    }
     t->total_nodes = t->total_rows = t->total_vox = 0;
     std::vector<long long> ncount(n_jobs);
     for (int j = 0; j < n_jobs; ++j) {
@@ -1616,6 +2149,31 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     SCP_REQUIRE(t && d_out && t->planned, "scp_octree_emit: plan first");
     cudaStream_t st = as_stream(stream);
     const long long N = t->total_nodes + 1;
+    const bool lean_out = !d_out->level && !d_out->octant && !d_out->parent && !d_out->pos && !d_out->ctx_pos && !d_out->rows_i64;
+    if (g_tree_builder == 2 && lean_out) {
+        // key passes: no node records
+        const int nt_e = (int)t->h_tiles_emit.size();
+        if (int e = t->n_occ.reserve(N + 8)) return e;
+        if (int e = t->tiles_emit.reserve((size_t)(nt_e + 1) * sizeof(Tile))) return e;
+        SCP_CUDA(cudaMemcpyAsync(t->tiles_emit.p, t->h_tiles_emit.data(), nt_e * sizeof(Tile), cudaMemcpyHostToDevice, st));
+        SCP_CUDA(cudaMemsetAsync(t->n_occ.p, 0, (size_t)N + 8, st));
+        JobDev* dj = t->jobs.as<JobDev>();
+        SCP_CUDA(cudaEventRecord(t->ev[4], st));
+        if (nt_e) {
+            k_tree_occ<<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), t->n_occ.as<uint8_t>(),
+                                             reinterpret_cast<u64*>(d_out->voxel_key));
+            SCP_LAUNCHED();
+        }
+        SCP_CUDA(cudaEventRecord(t->ev[5], st));
+        SCP_CUDA(cudaEventRecord(t->ev[6], st));
+        if (nt_e && (d_out->occ || d_out->sym || d_out->ctx || d_out->pos_norm)) {
+            k_tree_rows<<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), t->n_occ.as<uint8_t>(), *d_out);
+            SCP_LAUNCHED();
+        }
+        SCP_CUDA(cudaEventRecord(t->ev[7], st));
+        t->emitted = true;
+        return SCP_OK;
+    }
     if (int e = t->n_lo.reserve(N * 2)) return e;
     if (int e = t->n_occ.reserve(N)) return e;
     if (int e = t->n_parent.reserve(N * 4)) return e;
@@ -1674,8 +2232,7 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     }
     SCP_CUDA(cudaEventRecord(t->ev[6], st));
     if (nt_n) {
-        const bool lean = !d_out->level && !d_out->octant && !d_out->parent && !d_out->pos && !d_out->ctx_pos && !d_out->rows_i64;
-        if (lean) k_context_lean<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
+        if (lean_out) k_context_lean<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
         else k_context<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
         SCP_LAUNCHED();
     }
@@ -1726,7 +2283,7 @@ int scp_segmented_sort_u64(uint64_t* d_keys, uint64_t* d_tmp, const int64_t* h_s
             cudaMemcpyAsync(dt.p, tiles.data(), tiles.size() * sizeof(Tile), cudaMemcpyHostToDevice, st) != cudaSuccess) {
             set_error("scp_segmented_sort_u64: upload failed"); rc = SCP_ERR_CUDA; break;
         }
-        rc = run_sort((u64*)d_keys, (u64*)d_tmp, dt.as<Tile>(), (int)tiles.size(), dj.as<JobDev>(), n_seg, P, false, hist, desc,
+        rc = run_sort((u64*)d_keys, (u64*)d_tmp, dt.as<Tile>(), (int)tiles.size(), dj.as<JobDev>(), n_seg, P, false, 0, hist, desc,
                       misc, st, &res);
         if (rc) break;
         long long total = h_seg_offsets[n_seg] - h_seg_offsets[0];

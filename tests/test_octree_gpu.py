@@ -175,11 +175,15 @@ def test_plan_errors_are_reported():
         octree.OctreeBuilder().plan(pts, [0, 0], [octree.JobSpec(0, 1.0, None)], "cart")
 
 
-@pytest.mark.parametrize("mul,level,mode", [(False, 12, "spher"), (True, 16, "spher"), (False, 14, "cylin")])
-def test_level_pass_tree_builder_is_bit_identical(mul, level, mode):
-    """The bottom-up builder (one pass per level: k_level_pass, scp_set_tree_builder(1)) and the default one (all levels in
-    one pass over the sorted keys: k_emit_nodes + k_occupancy) produce identical outputs, ragged batch included
-    (a 1-point frame, frames that end inside a 32-key group, full-size frames)."""
+@pytest.mark.parametrize("mul,level,mode", [(False, 12, "spher"), (True, 16, "spher"), (False, 14, "cylin"), (True, 14, "cylin")])
+def test_tree_builders_and_quantise_paths_are_bit_identical(mul, level, mode):
+    """Three tree builders -- node records in one pass over the sorted keys (0: k_emit_nodes + k_occupancy + k_context*), node
+    records level by level (1: k_level_pass), and the record-free key passes that serve the encoder's outputs (2, default:
+    k_tree_occ + k_tree_rows) -- and two front ends -- the fused transform + quantise + morton_path filter + compaction kernel
+    with the per-job sort schedule (default) and the older quantise-all / filter / compact / sort sequence (SCP_QUANT_OLD=1)
+    -- produce identical outputs, ragged batch included (a 1-point frame, frames that end inside a 32-key group, full-size
+    frames)."""
+    import os
     from scp_b200 import _lib, octree, synth
     lib = _lib.require_device()
     frames = [synth.make_frame("kitti", s, level, mode, guard=True, n_points=n)[0]
@@ -192,17 +196,21 @@ def test_level_pass_tree_builder_is_bit_identical(mul, level, mode):
         jobs = [octree.JobSpec(i, synth.KITTI_QS(level), None, lidar_level=level) for i in range(len(frames))]
     names = ("occ", "level", "octant", "parent", "pos", "ctx", "pos_norm", "ctx_pos", "voxel_key", "sym")
     res = []
-    for by_level in (0, 1):
-        old = lib.scp_set_tree_builder(by_level)
+    for builder, old_quant in ((0, True), (1, True), (2, True), (0, False), (2, False)):
+        old = lib.scp_set_tree_builder(builder)
+        if old_quant:
+            os.environ["SCP_QUANT_OLD"] = "1"
         try:
             b = octree.OctreeBuilder().plan(allp, offs, jobs, mode)
             out = b.emit(names)
-            lean = b.emit(("occ", "sym", "ctx", "pos_norm"))
+            lean = b.emit(("occ", "sym", "ctx", "pos_norm", "voxel_key"))
             res.append(({k: v.cpu().numpy() for k, v in out.items()}, {k: v.cpu().numpy() for k, v in lean.items()},
-                        [(i.depth, i.n_rows, i.n_voxels, tuple(i.level_rows), tuple(i.pos_mm)) for i in b.infos]))
+                        [(i.depth, i.n_rows, i.n_voxels, tuple(i.level_rows), tuple(i.pos_mm)) for i in b.infos], b.total_kept))
         finally:
             lib.scp_set_tree_builder(old)
-    assert res[0][2] == res[1][2]
-    for a, c in ((res[0][0], res[1][0]), (res[0][1], res[1][1])):
-        for k in a:
-            assert np.array_equal(a[k], c[k], equal_nan=True), k
+            os.environ.pop("SCP_QUANT_OLD", None)
+    for r in res[1:]:
+        assert res[0][2] == r[2] and res[0][3] == r[3]
+        for a, c in ((res[0][0], r[0]), (res[0][1], r[1])):
+            for k in a:
+                assert np.array_equal(a[k], c[k], equal_nan=True), k
