@@ -112,8 +112,9 @@ int scp_octree_finish(scp_octree* t, void* stream);
 int scp_octree_stage_ms(scp_octree* t, float out[6]);
 /* Tree builder used by scp_octree_emit (same outputs, bit for bit): 0 = node records, all levels in one pass over the sorted
  * keys; 1 = node records, one pass per level, bottom-up; 2 (default) = like 0, except that a request for the encoder's outputs
- * only (occ, sym, ctx, pos_norm, voxel_key) is served by two passes over the sorted keys without node records
- * ([3] = occupancy pass, [4] = 0, [5] = row pass in scp_octree_stage_ms).  Returns the old value. */
+ * only (occ, sym, ctx, pos_norm, voxel_key) is served by ONE warp-autonomous pass over the sorted keys that writes occupancy
+ * bytes and node records together (no first-child array, no separate occupancy kernel; [3] = that pass, [4] = 0 in
+ * scp_octree_stage_ms), followed by the context gather.  Returns the old value. */
 int scp_set_tree_builder(int mode);
 
 /* Standalone pieces of the above, exposed for tests / profiling --------------------------- */

@@ -1305,18 +1305,14 @@ __global__ void __launch_bounds__(TPB) k_occupancy(const Tile* __restrict__ tile
 // K7b: K=4 ancestor context + level-normalised positions (+ optional reference-layout expansion)
 //   Octree.py:102-137 gen_K_parent_seq ; encode_dataset_ehem.py:54,66-72,85-93
 // ------------------------------------------------------------------------------------------
-// float32((x - mn) / den) exactly as numpy computes it (float64 divide, then one rounding to float32) without the divide:
-// q' = (x - mn) * (1/den) is within 2 ulp(float64) of the correctly rounded quotient, so both round to the same float32
-// unless q' lies within a few ulp of the midpoint of two float32 values (low 29 mantissa bits = 0x10000000); only then
-// (probability 2^-25) the divide is executed -- out of line, so that its ~25 instructions are not if-converted into the
-// common path.  `thr` = 16, or 0xffffffff to force the divide (den == 0: single-cell level without the 1e-9).
-__device__ __noinline__ float norm_pos_exact(double d, double den) { return (float)(d / den); }
-__device__ __forceinline__ float norm_pos(u32 x, double mn, double den, double inv, u32 thr) {
-    const double d = (double)x - mn;
-    const double q = d * inv;
-    const u32 m = ((u32)__double2loint(q) + 0x10000008u) & 0x1fffffffu;     // <= 16  <=>  |low29 - 0x10000000| <= 8
-    if (m <= thr) return norm_pos_exact(d, den);
-    return (float)q;
+// float32((x - mn) / den) of encode_dataset_ehem.py:70-72 without float64: x - mn = d and max - min = D are integers below
+// 2^21, den = D + 1e-9 (or D for the last level of a mullevel sub-octree).  The reference's float64 quotient d / den rounded
+// to float32 equals the correctly rounded float32 quotient d / D: the 1e-9 moves the quotient by a relative 1e-9 / D, less
+// than its distance 2^-25 / D from the nearest float32 rounding midpoint (d / D with D < 2^21 has at most 21 significant
+// quotient bits, so it is never ON a midpoint), and the intermediate float64 rounding (2^-53) is smaller still.  D = 0 (a
+// single-cell level): 0 / 1e-9 = 0 with the epsilon, 0 / 0 = NaN without -- `zero` carries that value.
+__device__ __forceinline__ float norm_pos_f(u32 x, u32 mn, float D, float zero) {
+    return D > 0.f ? __fdiv_rn(__uint2float_rn(x - mn), D) : zero;
 }
 
 // Lean variant for the encoder's outputs (occ, sym, ctx, pos_norm): own record + 3 dependent (parent, occupancy) gathers;
@@ -1326,17 +1322,25 @@ __device__ __forceinline__ float norm_pos(u32 x, double mn, double den, double i
 // byte permutes for the 12 context bytes, the divide out of line.  Four nodes per thread keep four gather chains in flight.
 __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
                                                           NodeArrays A, scp_octree_out O) {
-    __shared__ double s_mn[MAXL + 1], s_den[MAXL + 1], s_inv[MAXL + 1];
-    __shared__ u32 s_thr[MAXL + 1];
+    __shared__ u32 s_mn[MAXL + 1], s_lv[MAXL + 1];
+    __shared__ float s_D[MAXL + 1], s_zero[MAXL + 1];
     __shared__ u32 s_stage[TPB / 32][2][96];
     const Tile t = tiles[blockIdx.x];
     const JobDev& J = jobs[t.job];
     const int n = J.depth;
     if (threadIdx.x >= 1 && threadIdx.x <= n) {
         const int L = threadIdx.x;
-        const double den = (double)(J.pos_max[L - 1] - J.pos_min[L - 1]) + ((L == n && !J.pos_eps_last) ? 0.0 : 1e-9);
-        s_mn[L] = (double)J.pos_min[L - 1]; s_den[L] = den; s_inv[L] = 1.0 / den;
-        s_thr[L] = den > 0.0 ? 16u : 0xffffffffu;
+        s_mn[L] = J.pos_min[L - 1];
+        s_D[L] = (float)(J.pos_max[L - 1] - J.pos_min[L - 1]);
+        s_zero[L] = (L == n && !J.pos_eps_last) ? __int_as_float(0x7fc00000) : 0.f;
+        // level bytes of (great-grandparent, grandparent, parent, self): 0 = missing; the last level is clipped to lidar_level
+        u32 lv = 0;                                               // (encode_dataset_ehem.py:86)
+        for (int q = 0; q < 4; ++q) {
+            int Lk = max(L - (3 - q), 0);
+            if (L == n && n > J.lidar_level) Lk = min(Lk, J.lidar_level);
+            lv |= (u32)Lk << (8 * q);
+        }
+        s_lv[L] = lv;
     }
     __syncthreads();
     const long long node0 = J.node_start, row0 = J.row_start;
@@ -1345,8 +1349,6 @@ __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict_
     const u32* __restrict__ a_par = A.parent + node0;
     const u64* __restrict__ a_pos = A.pos + node0;
     const int cnt = min(t.count, J.n_rows - t.begin);             // the dropped last row (Octree.py:259-262)
-    const int lidar_level = J.lidar_level;
-    const bool clip = n > lidar_level;                            // encode_dataset_ehem.py:86 can only bite then
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int u = 0; u < NPT; ++u) {                                        // warm-up: round 1 (round 0 is loaded right away)
@@ -1417,29 +1419,23 @@ __global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict_
                 u32 px, py, pz;
                 unpack_pos(pp[u], A.morton, px, py, pz);
                 const u32 W = (((px >> sh3) & 0xfu) << 8) | (((py >> sh3) & 0xfu) << 4) | ((pz >> sh3) & 0xfu);
-                u32 OC = 0, LV = 0;
+                u32 OC = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int j = 3 - k, Lk = Lu - j;
                     u32 o = ((((W >> j) & 0x111u) * 0x124u) >> 8 & 7u) + 1u;       // 4*xbit + 2*ybit + zbit + 1
                     if (Lk <= 1) o = (Lk == 1) ? 1u : 0u;                           // root: octant 1; missing: 0
                     OC |= o << (8 * k);
-                    LV |= (u32)max(Lk, 0) << (8 * k);
                 }
-                if (clip && Lu == n) {                                              // encode_dataset_ehem.py:86
-                    u32 c = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) c |= min((LV >> (8 * k)) & 0xffu, (u32)lidar_level) << (8 * k);
-                    LV = c;
-                }
+                const u32 LV = s_lv[Lu];
                 // 12 context bytes (level, octant, occ-1) x 4 from the three byte-planes
                 w0 = __byte_perm(__byte_perm(LV, OC, 0x1040), occp[u], 0x3410);
                 w1 = __byte_perm(__byte_perm(LV, OC, 0x6205), occp[u], 0x3250);
                 w2 = __byte_perm(__byte_perm(LV, OC, 0x0730), occp[u], 0x7216);
                 if (O.pos_norm) {
-                    const double mn = s_mn[Lu], den = s_den[Lu], inv = s_inv[Lu];
-                    const u32 thr = s_thr[Lu];
-                    f0 = norm_pos(px, mn, den, inv, thr); f1 = norm_pos(py, mn, den, inv, thr); f2 = norm_pos(pz, mn, den, inv, thr);
+                    const u32 mn = s_mn[Lu];
+                    const float D = s_D[Lu], zero = s_zero[Lu];
+                    f0 = norm_pos_f(px, mn, D, zero); f1 = norm_pos_f(py, mn, D, zero); f2 = norm_pos_f(pz, mn, D, zero);
                 }
             }
             u32* sc = s_stage[warp][0];
@@ -1542,25 +1538,21 @@ __global__ void __launch_bounds__(TPB) k_context(const Tile* __restrict__ tiles,
 }
 
 // ------------------------------------------------------------------------------------------
-// K6/K7 fused ("lean" outputs: occ, sym, ctx, pos_norm): two passes over the SORTED KEYS, no node records at all.
+// K6 + K7a in one pass over the SORTED KEYS (tree builder 2, the default for the encoder's outputs occ / sym / ctx / pos_norm).
 // ------------------------------------------------------------------------------------------
 // A node on level L is the run of sorted keys that share their first L-1 octal digits; it is "opened" by the first key of the
 // run, i.e. by every key whose head level h is <= L.  With the per-level ballots of a warp a key knows, for EVERY level at
 // once, the BFS rank of the node it opens there (rank of heads) and of the node that contains it (heads at or before it,
-// minus one) -- so parents, ancestors and children never have to be looked up through stored indices:
-//   pass 1 (k_tree_occ)  occupancy byte of every node = OR over the digits of the keys that open one of its children: a
-//                        segmented OR over the warp (segments = parents), plain byte stores for parents whose run lies
-//                        inside the warp, atomicOr on the aligned word for the <= 2 runs per level cut by the warp border;
-//                        also the voxel extremes that give every level's (min, max) coordinate for the normalisation.
-//   pass 2 (k_tree_rows) for every (key, level >= h): the final row -- occupancy of the node and of its three ancestors
-//                        (four byte gathers at ranks known from the ballots, L1-resident), level / octant bytes and the
-//                        normalised position from the key's own coordinates; the nodes a warp opens on one level are
-//                        consecutive rows, written through a per-warp staging tile as coalesced words.
-// Traffic: 2 x 8 B/key + 1 B/node (+ atomics) + the 27 B/node of outputs, against the 28 + 60 B/node of the record-based
-// design (k_emit_nodes / k_occupancy / k_context, kept for the outputs that need parent indices and ancestor positions).
+// minus one).  k_tree_occ<RECORDS> uses that twice per (key, level): the occupancy byte of a node = OR over the digits of the
+// keys that open one of its children -- a segmented OR over the warp (segments = parents), plain byte stores for parents
+// whose run lies inside the 32 keys, atomicOr on the aligned word for the <= 2 runs per level cut by the border -- and, with
+// RECORDS, the node record (level | octant, parent index, cell origin) the context kernel gathers from.  No first-child
+// array, no voxel-digit array, no separate occupancy kernel (k_emit_nodes + k_occupancy: 28 + 6 B/node more traffic and a
+// dependent level -> first_child -> children load chain).  The voxel extremes that give every level's (min, max) coordinate
+// for the normalisation come out of the same pass.
 // Warp-autonomous: a warp owns one chunk (WKEYS = 256 consecutive sorted keys, 8 rounds of 32); the rank of its first node on
-// every level comes from the chunk prefix table (k_head_hist / k_level_scan), the running ranks stay in warp-uniform
-// registers -- no block-level scan, no __syncthreads inside the key loop.
+// every level comes from the chunk prefix table (k_head_hist / k_level_scan) -- no block-level scan, no __syncthreads
+// inside the key loop.
 // Register layout "lane = level": lane L keeps the ballot of level L (lanes that open a node there; lane 0: new voxels) and
 // the running rank base[L] of the chunk, so the per-level state is two registers, the update after a round is ONE add per
 // lane, and the level loops are ordinary runtime loops (an unrolled 21-level body overflowed the instruction cache: half of
@@ -1587,23 +1579,32 @@ __device__ __forceinline__ u32 chunk_bases(const u32* __restrict__ cb, int n, in
     return lane == 0 ? vox : (lane <= n ? inc : 0u);
 }
 
+template <bool RECORDS>
 __global__ void __launch_bounds__(TPB) k_tree_occ(const u64* __restrict__ keys, const Tile* __restrict__ tiles, JobDev* jobs,
-                                                   const u32* __restrict__ chunk_base, uint8_t* __restrict__ occ_all,
-                                                   u64* __restrict__ vox_key) {
+                                                   const u32* __restrict__ chunk_base, NodeArrays A, u64* __restrict__ vox_key) {
     __shared__ u32 s_mm[4];
-    __shared__ int s_ls[MAXL + 2];
+    __shared__ u32 s_ls[MAXL + 2];
+    __shared__ u64 s_keep[MAXL + 2];        // packed-position bits that survive on level L (cell size 2^(n-L+1))
     const Tile t = tiles[blockIdx.x];
     JobDev& J = jobs[t.job];
     const int n = J.depth;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 ltmask = (1u << lane) - 1u, lemask = (2u << lane) - 1u;
-    if (threadIdx.x <= MAXL + 1) s_ls[threadIdx.x] = J.level_start[threadIdx.x];
+    if (threadIdx.x <= MAXL + 1) s_ls[threadIdx.x] = (u32)J.level_start[threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x <= 32 + MAXL) {
+        const int L = threadIdx.x - 32;
+        const u32 m = (L >= 1 && L <= n) ? (~((1u << (n - L + 1)) - 1u)) & 0x1fffffu : 0u;
+        s_keep[L] = pack_pos(m, m, m);
+    }
     if (threadIdx.x >= 64 && threadIdx.x < 68) s_mm[threadIdx.x - 64] = (threadIdx.x & 1) ? 0u : 0xffffffffu;
     __syncthreads();
     const u64* src = keys + J.key_begin;
     const long long node0 = J.node_start;
-    uint8_t* occ = occ_all + node0;
-    u32* occ32 = reinterpret_cast<u32*>(occ_all);
+    uint8_t* occ = A.occ + node0;
+    u32* occ32 = reinterpret_cast<u32*>(A.occ);
+    uint16_t* r_lo = A.lo + node0;
+    u32* r_par = A.parent + node0;
+    u64* r_pos = A.pos + node0;
     const int n_vox = J.n_voxels;
     u32 cmin = 0xffffffffu, cmax = 0u, emin = 0xffffffffu, emax = 0u;
     const int cnt = min(t.count, J.n_kept - t.begin);          // keys past n_kept were filtered out before the sort
@@ -1626,24 +1627,40 @@ __global__ void __launch_bounds__(TPB) k_tree_occ(const u64* __restrict__ keys, 
             const u32 bvec = tree_ballots(h, n, lane, wmin);
             const u32 b0 = __shfl_sync(0xffffffffu, bvec, 0);
             const u32 vbase = __shfl_sync(0xffffffffu, basev, 0);
+            u64 P = 0;
             if (h > 0) {
                 const u32 v = vbase + __popc(b0 & ltmask);
                 if (vox_key) vox_key[J.vox_start + v] = k;
                 // x & m is monotone in x, so every level's min / max node coordinate follows from the voxel extremes
                 const u32 x = compact3(k >> 2), y = compact3(k >> 1), z = compact3(k);
+                if (RECORDS) P = pack_pos(x, y, z);
                 const u32 lo = min(x, min(y, z)), hi = max(x, max(y, z));
                 cmin = min(cmin, lo); cmax = max(cmax, hi);
                 if ((int)v != n_vox - 1) { emin = min(emin, lo); emax = max(emax, hi); }
+                if (RECORDS && h == 1) { r_lo[0] = (uint16_t)(1u | (1u << 8)); r_par[0] = 0u; r_pos[0] = 0ull; }   // root: level 1, octant 1
             }
-            // children on level Lc (Lc = n+1: the voxels) add their digit bit to their parent on level Lc-1
+            // children on level Lc (Lc = n+1: the voxels) add their digit bit to their parent on level Lc-1; the children
+            // that are nodes (Lc <= n) also get their record: level | octant, parent index, cell origin
             for (int Lc = max(wmin, 2); Lc <= n + 1; ++Lc) {     // warp-uniform bounds
                 const u32 bc = Lc <= n ? __shfl_sync(0xffffffffu, bvec, Lc) : b0;
                 if (bc == 0) continue;                           // warp-uniform
                 const u32 bp = __shfl_sync(0xffffffffu, bvec, Lc - 1);   // parents opened in these 32 keys = segment starts
                 const u32 pbase = __shfl_sync(0xffffffffu, basev, Lc - 1);
-                u32 v = ((bc >> lane) & 1u) ? (1u << ((u32)(k >> (3 * (n + 1 - Lc))) & 7u)) : 0u;
+                const bool head = (bc >> lane) & 1u;
+                const u32 dig = (u32)(k >> (3 * (n + 1 - Lc))) & 7u;
+                u32 v = head ? (1u << dig) : 0u;
                 const u32 below = bp & lemask;
                 const int seg0 = below ? 31 - __clz(below) : 0;  // first lane of my parent's run inside these 32 keys
+                const u32 pr = (u32)s_ls[Lc - 2] + pbase + __popc(below) - 1u;      // the parent that contains this key
+                if (RECORDS && Lc <= n) {
+                    const u32 cbase = __shfl_sync(0xffffffffu, basev, Lc);
+                    if (head) {
+                        const u32 r = (u32)s_ls[Lc - 1] + cbase + __popc(bc & ltmask);
+                        r_lo[r] = (uint16_t)((u32)Lc | ((dig + 1u) << 8));
+                        r_par[r] = pr;
+                        r_pos[r] = P & s_keep[Lc];
+                    }
+                }
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const u32 up = __shfl_up_sync(0xffffffffu, v, o);
@@ -1651,10 +1668,8 @@ __global__ void __launch_bounds__(TPB) k_tree_occ(const u64* __restrict__ keys, 
                 }
                 const bool last = (lane == 31) || ((bp >> (lane + 1)) & 1u);
                 if (last && v) {
-                    const u32 pr = pbase + __popc(below) - 1u;                 // the parent that contains this key
-                    const long long idx2 = (long long)s_ls[Lc - 2] + pr;
-                    if (below != 0 && lane != 31) occ[idx2] = (uint8_t)v;      // run inside these 32 keys: complete
-                    else { const long long g = node0 + idx2; atomicOr(occ32 + (g >> 2), v << (8 * (int)(g & 3))); }
+                    if (below != 0 && lane != 31) occ[pr] = (uint8_t)v;        // run inside these 32 keys: complete
+                    else { const long long g = node0 + pr; atomicOr(occ32 + (g >> 2), v << (8 * (int)(g & 3))); }
                 }
             }
             basev += __popc(bvec);                               // every lane advances its own level
@@ -1675,133 +1690,6 @@ __global__ void __launch_bounds__(TPB) k_tree_occ(const u64* __restrict__ keys, 
             atomicMin(&J.pos_min[L - 1], mn & m);
             atomicMax(&J.pos_max[L - 1], mx & m);
         }
-    }
-}
-
-__global__ void __launch_bounds__(TPB, 3) k_tree_rows(const u64* __restrict__ keys, const Tile* __restrict__ tiles,
-                                                       const JobDev* __restrict__ jobs, const u32* __restrict__ chunk_base,
-                                                       const uint8_t* __restrict__ occ_all, scp_octree_out O) {
-    __shared__ int s_ls[MAXL + 2];
-    __shared__ double s_mn[MAXL + 1], s_den[MAXL + 1], s_inv[MAXL + 1];
-    __shared__ u32 s_thr[MAXL + 1], s_lv[MAXL + 1];
-    __shared__ u32 s_stage[TPB / 32][2][96];
-    const Tile t = tiles[blockIdx.x];
-    const JobDev& J = jobs[t.job];
-    const int n = J.depth;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 ltmask = (1u << lane) - 1u, lemask = (2u << lane) - 1u;
-    if (threadIdx.x <= MAXL + 1) s_ls[threadIdx.x] = J.level_start[threadIdx.x];
-    if (threadIdx.x >= 64 + 1 && threadIdx.x <= 64 + n) {
-        const int L = threadIdx.x - 64;
-        const double den = (double)(J.pos_max[L - 1] - J.pos_min[L - 1]) + ((L == n && !J.pos_eps_last) ? 0.0 : 1e-9);
-        s_mn[L] = (double)J.pos_min[L - 1]; s_den[L] = den; s_inv[L] = 1.0 / den;
-        s_thr[L] = den > 0.0 ? 16u : 0xffffffffu;
-        // level bytes of (great-grandparent, grandparent, parent, self): 0 = missing; the last level is clipped to lidar_level
-        u32 lv = 0;                                                // (encode_dataset_ehem.py:86)
-        for (int q = 0; q < 4; ++q) {
-            int Lk = max(L - (3 - q), 0);
-            if (L == n && n > J.lidar_level) Lk = min(Lk, J.lidar_level);
-            lv |= (u32)Lk << (8 * q);
-        }
-        s_lv[L] = lv;
-    }
-    __syncthreads();
-    const u64* src = keys + J.key_begin;
-    const uint8_t* __restrict__ occ = occ_all + J.node_start;
-    const long long row0 = J.row_start;
-    const int n_rows = J.n_rows;
-    const int cnt = min(t.count, J.n_kept - t.begin);
-    const int wbeg = warp * WKEYS;
-    if (wbeg >= cnt) return;                                      // warp-uniform; no block-level synchronisation below
-    u32 basev = chunk_bases(chunk_base + ((size_t)(t.first + t.begin / TILE) * CHUNKS + warp) * NBINS, n, lane);
-    const int g0 = t.begin + wbeg;
-    u64 carry = (lane == 0 && g0 > 0) ? __ldg(src + g0 - 1) : 0ull;
-    u64 knext = wbeg + lane < cnt ? __ldg(src + g0 + lane) : SENTINEL;
-    u32* sc = s_stage[warp][0];
-    float* sp = reinterpret_cast<float*>(s_stage[warp][1]);
-    for (int it = 0; it < WITER; ++it) {
-        const int idx = wbeg + it * 32 + lane;
-        if (wbeg + it * 32 >= cnt) break;                         // warp-uniform
-        const u64 k = knext;
-        if (it + 1 < WITER) knext = idx + 32 < cnt ? __ldg(src + t.begin + idx + 32) : SENTINEL;
-        u64 prev = __shfl_up_sync(0xffffffffu, k, 1);
-        if (lane == 0) prev = carry;
-        const int h = idx < cnt ? head_level(k, prev, g0 + it * 32 + lane == 0, n) : 0;
-        carry = __shfl_sync(0xffffffffu, k, 31);
-        int wmin;
-        const u32 bvec = tree_ballots(h, n, lane, wmin);
-        const u32 x = compact3(k >> 2), y = compact3(k >> 1), z = compact3(k);
-        // ranks of the nodes that CONTAIN this key on the three levels above the current one (shifted down every level)
-        u32 b1 = 0, b2 = 0, b3 = 0, r1 = 0, r2 = 0, r3 = 0;       // level L-1, L-2, L-3: ballot and base
-        {
-            const int L0 = max(wmin, 1);
-            if (L0 - 1 >= 1) { b1 = __shfl_sync(0xffffffffu, bvec, L0 - 1); r1 = __shfl_sync(0xffffffffu, basev, L0 - 1); }
-            if (L0 - 2 >= 1) { b2 = __shfl_sync(0xffffffffu, bvec, L0 - 2); r2 = __shfl_sync(0xffffffffu, basev, L0 - 2); }
-            if (L0 - 3 >= 1) { b3 = __shfl_sync(0xffffffffu, bvec, L0 - 3); r3 = __shfl_sync(0xffffffffu, basev, L0 - 3); }
-        }
-        for (int L = max(wmin, 1); L <= n; ++L) {                  // warp-uniform bounds
-            const u32 bl = __shfl_sync(0xffffffffu, bvec, L);
-            const u32 rl = __shfl_sync(0xffffffffu, basev, L);
-            if (bl != 0) {                                        // warp-uniform
-                const bool mine = (bl >> lane) & 1u;
-                const u32 ci = __popc(bl & ltmask);               // my node among the nodes opened on level L by these 32 keys
-                const long long lrow = (long long)s_ls[L - 1] + rl;                  // row (inside the job) of the first one
-                const int nw = (int)max(0ll, min((long long)__popc(bl), (long long)n_rows - lrow)); // minus the dropped last row
-                if (nw > 0) {                                     // warp-uniform
-                    if (mine) {
-                        const u32 self = ((u32)__ldg(occ + lrow + ci) - 1u) & 0xffu;
-                        // (occ-1) of ggp | gp << 8 | parent << 16 | self << 24; a missing ancestor reads 255 (occ 256)
-                        u32 occp = self << 24;
-                        occp |= (L >= 2 ? ((u32)__ldg(occ + s_ls[L - 2] + r1 + __popc(b1 & lemask) - 1u) - 1u) & 0xffu : 0xffu) << 16;
-                        occp |= (L >= 3 ? ((u32)__ldg(occ + s_ls[L - 3] + r2 + __popc(b2 & lemask) - 1u) - 1u) & 0xffu : 0xffu) << 8;
-                        occp |= (L >= 4 ? ((u32)__ldg(occ + s_ls[L - 4] + r3 + __popc(b3 & lemask) - 1u) - 1u) & 0xffu : 0xffu);
-                        // bit j of (coordinate >> sh3) is the octant bit of the ancestor j levels up (sh3 = lowest bit of the own cell)
-                        const int sh3 = n - L + 1;
-                        const u32 W = (((x >> sh3) & 0xfu) << 8) | (((y >> sh3) & 0xfu) << 4) | ((z >> sh3) & 0xfu);
-                        u32 OC = 0;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int j = 3 - q, Lk = L - j;
-                            u32 o = ((((W >> j) & 0x111u) * 0x124u) >> 8 & 7u) + 1u;   // 4*xbit + 2*ybit + zbit + 1
-                            if (Lk <= 1) o = (Lk == 1) ? 1u : 0u;                       // root: octant 1; missing: 0
-                            OC |= o << (8 * q);
-                        }
-                        const u32 LV = s_lv[L];
-                        sc[3 * ci] = __byte_perm(__byte_perm(LV, OC, 0x1040), occp, 0x3410);
-                        sc[3 * ci + 1] = __byte_perm(__byte_perm(LV, OC, 0x6205), occp, 0x3250);
-                        sc[3 * ci + 2] = __byte_perm(__byte_perm(LV, OC, 0x0730), occp, 0x7216);
-                        if (O.pos_norm) {
-                            const u32 m = ~((1u << sh3) - 1u);                          // the node's own cell origin
-                            const double mn = s_mn[L], den = s_den[L], inv = s_inv[L];
-                            const u32 thr = s_thr[L];
-                            sp[3 * ci] = norm_pos(x & m, mn, den, inv, thr);
-                            sp[3 * ci + 1] = norm_pos(y & m, mn, den, inv, thr);
-                            sp[3 * ci + 2] = norm_pos(z & m, mn, den, inv, thr);
-                        }
-                        if ((int)ci < nw) {
-                            if (O.occ) O.occ[row0 + lrow + ci] = (uint8_t)(self + 1u);
-                            if (O.sym) O.sym[row0 + lrow + ci] = (int16_t)self;
-                        }
-                    }
-                    // the nodes opened on level L are nw consecutive rows: compacted in the staging tile, stored coalesced
-                    __syncwarp();
-                    const int nvw = 3 * nw;
-                    if (O.ctx) {
-                        u32* dst = reinterpret_cast<u32*>(O.ctx + 12 * (row0 + lrow));
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) if (32 * j + lane < nvw) dst[32 * j + lane] = sc[32 * j + lane];
-                    }
-                    if (O.pos_norm) {
-                        float* dst = O.pos_norm + 3 * (row0 + lrow);
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) if (32 * j + lane < nvw) dst[32 * j + lane] = sp[32 * j + lane];
-                    }
-                    __syncwarp();
-                }
-            }
-            b3 = b2; r3 = r2; b2 = b1; r2 = r1; b1 = bl; r1 = rl;  // level L becomes "one level up" of the next one
-        }
-        basev += __popc(bvec);                                     // every lane advances its own level
     }
 }
 
@@ -1868,8 +1756,8 @@ static int run_sort(u64* keys, u64* tmp, const Tile* d_tiles, int n_tiles, const
 }
 
 // 0 = node records, all levels in one pass (k_emit_nodes + k_occupancy + k_context*); 1 = node records, one pass per level
-// (k_level_pass); 2 (default) = as 0, but the lean outputs (occ, sym, ctx, pos_norm) come from the two key passes
-// k_tree_occ / k_tree_rows without node records.  env SCP_TREE = records | level | keys
+// (k_level_pass); 2 (default) = as 0, but the lean outputs (occ, sym, ctx, pos_norm) come from
+// k_tree_occ (occupancy + records in one warp-autonomous key pass) + k_context_lean.  env SCP_TREE = records | level | keys
 static int tree_builder_default() {
     const char* e = getenv("SCP_TREE");
     if (e && !strcmp(e, "level")) return 1;
@@ -2151,23 +2039,32 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     const long long N = t->total_nodes + 1;
     const bool lean_out = !d_out->level && !d_out->octant && !d_out->parent && !d_out->pos && !d_out->ctx_pos && !d_out->rows_i64;
     if (g_tree_builder == 2 && lean_out) {
-        // key passes: no node records
-        const int nt_e = (int)t->h_tiles_emit.size();
+        // one key pass writes occupancy + node records; the lean context kernel gathers from them
+        const int nt_e = (int)t->h_tiles_emit.size(), nt_n = (int)t->h_tiles_node.size();
+        if (int e = t->n_lo.reserve(N * 2)) return e;
         if (int e = t->n_occ.reserve(N + 8)) return e;
+        if (int e = t->n_parent.reserve(N * 4)) return e;
+        if (int e = t->n_pos.reserve(N * 8)) return e;
         if (int e = t->tiles_emit.reserve((size_t)(nt_e + 1) * sizeof(Tile))) return e;
+        if (int e = t->tiles_node.reserve((size_t)(nt_n + 1) * sizeof(Tile))) return e;
         SCP_CUDA(cudaMemcpyAsync(t->tiles_emit.p, t->h_tiles_emit.data(), nt_e * sizeof(Tile), cudaMemcpyHostToDevice, st));
+        SCP_CUDA(cudaMemcpyAsync(t->tiles_node.p, t->h_tiles_node.data(), nt_n * sizeof(Tile), cudaMemcpyHostToDevice, st));
         SCP_CUDA(cudaMemsetAsync(t->n_occ.p, 0, (size_t)N + 8, st));
+        NodeArrays A{t->n_lo.as<uint16_t>(), t->n_occ.as<uint8_t>(), t->n_parent.as<u32>(), t->n_pos.as<u64>(), nullptr, nullptr, 0};
         JobDev* dj = t->jobs.as<JobDev>();
+        const bool rows = d_out->occ || d_out->sym || d_out->ctx || d_out->pos_norm;
         SCP_CUDA(cudaEventRecord(t->ev[4], st));
         if (nt_e) {
-            k_tree_occ<<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), t->n_occ.as<uint8_t>(),
-                                             reinterpret_cast<u64*>(d_out->voxel_key));
+            if (rows) k_tree_occ<true><<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), A,
+                                                              reinterpret_cast<u64*>(d_out->voxel_key));
+            else k_tree_occ<false><<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), A,
+                                                          reinterpret_cast<u64*>(d_out->voxel_key));
             SCP_LAUNCHED();
         }
         SCP_CUDA(cudaEventRecord(t->ev[5], st));
         SCP_CUDA(cudaEventRecord(t->ev[6], st));
-        if (nt_e && (d_out->occ || d_out->sym || d_out->ctx || d_out->pos_norm)) {
-            k_tree_rows<<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), t->n_occ.as<uint8_t>(), *d_out);
+        if (nt_n && rows) {
+            k_context_lean<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), dj, A, *d_out);
             SCP_LAUNCHED();
         }
         SCP_CUDA(cudaEventRecord(t->ev[7], st));

@@ -178,8 +178,8 @@ def test_plan_errors_are_reported():
 @pytest.mark.parametrize("mul,level,mode", [(False, 12, "spher"), (True, 16, "spher"), (False, 14, "cylin"), (True, 14, "cylin")])
 def test_tree_builders_and_quantise_paths_are_bit_identical(mul, level, mode):
     """Three tree builders -- node records in one pass over the sorted keys (0: k_emit_nodes + k_occupancy + k_context*), node
-    records level by level (1: k_level_pass), and the record-free key passes that serve the encoder's outputs (2, default:
-    k_tree_occ + k_tree_rows) -- and two front ends -- the fused transform + quantise + morton_path filter + compaction kernel
+    records level by level (1: k_level_pass), and the warp-autonomous key pass that writes occupancy and records together for
+    the encoder's outputs (2, default: k_tree_occ + k_context_lean) -- and two front ends -- the fused transform + quantise + morton_path filter + compaction kernel
     with the per-job sort schedule (default) and the older quantise-all / filter / compact / sort sequence (SCP_QUANT_OLD=1)
     -- produce identical outputs, ragged batch included (a 1-point frame, frames that end inside a 32-key group, full-size
     frames)."""
