@@ -117,8 +117,11 @@ __global__ void __launch_bounds__(TPB) k_frame_stats(const float* __restrict__ x
     const float* p = xyz + (frame_begin[t.job] + t.begin) * (long long)stride;
     float rmax = 0.f;
     u32 zmin = 0xffffffffu, zmax = 0u;
+    const bool v4 = stride == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;      // KITTI rows (x, y, z, intensity): one 16-byte load
     for (int i = threadIdx.x; i < t.count; i += TPB) {
-        float x = p[(long long)i * stride], y = p[(long long)i * stride + 1], z = p[(long long)i * stride + 2];
+        float x, y, z;
+        if (v4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i); x = v.x; y = v.y; z = v.z; }
+        else { x = p[(long long)i * stride]; y = p[(long long)i * stride + 1]; z = p[(long long)i * stride + 2]; }
         rmax = fmaxf(rmax, rho_of(x, y, z, mode));
         const u32 ze = enc_ordered(z);
         zmin = min(zmin, ze); zmax = max(zmax, ze);
@@ -380,6 +383,7 @@ __global__ void __launch_bounds__(TPB, 4) k_quantise_fused(const float* __restri
     const int f = t.job;
     const int j0 = fj_start[f], nj = fj_start[f + 1] - j0;
     const float* p = xyz + (frame_begin[f] + t.begin) * (long long)stride;
+    const bool v4 = stride == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;      // KITTI rows (x, y, z, intensity): one 16-byte load
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < nj) {
         const int jid = fj[j0 + threadIdx.x];
@@ -439,7 +443,8 @@ __global__ void __launch_bounds__(TPB, 4) k_quantise_fused(const float* __restri
             float x = 0.f, y = 0.f, z = 1.f;
             if (valid) {
                 if (i + 2 * TPB < t.count) prefetch_l2(p + (long long)(i + 2 * TPB) * stride);
-                x = p[(long long)i * stride]; y = p[(long long)i * stride + 1]; z = p[(long long)i * stride + 2];
+                if (v4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i); x = v.x; y = v.y; z = v.z; }
+                else { x = p[(long long)i * stride]; y = p[(long long)i * stride + 1]; z = p[(long long)i * stride + 2]; }
             }
             const float rho = rho_of(x, y, z, mode);
             const double drho = (double)rho;
@@ -1320,8 +1325,9 @@ __device__ __forceinline__ float norm_pos_f(u32 x, u32 mn, float D, float zero) 
 // more low bits cleared, its octant is the coordinate bit triple of its level).  The kernel is instruction-issue bound
 // (ncu: ~300 instructions per node before this version), hence the bit tricks: all four octants from one 12-bit word,
 // byte permutes for the 12 context bytes, the divide out of line.  Four nodes per thread keep four gather chains in flight.
-__global__ void __launch_bounds__(TPB, 4) k_context_lean(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
-                                                          NodeArrays A, scp_octree_out O) {
+template <int NPT, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_context_lean(const Tile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+                                                             NodeArrays A, scp_octree_out O) {
     __shared__ u32 s_mn[MAXL + 1], s_lv[MAXL + 1];
     __shared__ float s_D[MAXL + 1], s_zero[MAXL + 1];
     __shared__ u32 s_stage[TPB / 32][2][96];
@@ -1580,7 +1586,7 @@ __device__ __forceinline__ u32 chunk_bases(const u32* __restrict__ cb, int n, in
 }
 
 template <bool RECORDS>
-__global__ void __launch_bounds__(TPB) k_tree_occ(const u64* __restrict__ keys, const Tile* __restrict__ tiles, JobDev* jobs,
+__global__ void __launch_bounds__(TPB, 4) k_tree_occ(const u64* __restrict__ keys, const Tile* __restrict__ tiles, JobDev* jobs,
                                                    const u32* __restrict__ chunk_base, NodeArrays A, u64* __restrict__ vox_key) {
     __shared__ u32 s_mm[4];
     __shared__ u32 s_ls[MAXL + 2];
@@ -1711,8 +1717,8 @@ struct scp_octree {
     DevBuf pass_desc, tiles_pass;
     int n_jobs = 0, mode = 0, P = 0, nt_frame = 0;
     long long total_keys = 0, total_nodes = 0, total_rows = 0, total_vox = 0;
-    bool planned = false, emitted = false;
-    cudaEvent_t ev[8] = {};
+    bool planned = false, emitted = false, host_gap = false;
+    cudaEvent_t ev[10] = {};        // [8], [9]: around the host synchronisation inside the quantise stage (fused path)
     bool ev_ok = false;
     u64* sorted = nullptr;
 };
@@ -1765,6 +1771,14 @@ static int tree_builder_default() {
     return 2;
 }
 static int g_tree_builder = tree_builder_default();
+
+static int launch_context_lean(int nt_n, const Tile* tiles, const JobDev* jobs, NodeArrays A, const scp_octree_out& O, cudaStream_t st) {
+    // two nodes per thread at 40 registers, six blocks per SM: measured 1.35 ms per 131 M nodes against 1.75 ms with four nodes
+    // per thread at 64 registers / four blocks (the gather chains are latency-bound: resident warps beat unrolling)
+    k_context_lean<2, 6><<<nt_n, TPB, 0, st>>>(tiles, jobs, A, O);
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
 
 extern "C" {
 
@@ -1866,7 +1880,9 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     // morton_path filter + compaction for all jobs of a frame; the sort follows with a per-job pass schedule.
     bool fused = mode != SCP_MODE_CART && max_per_frame >= 1 && max_per_frame <= QF_MAXJ && !getenv("SCP_QUANT_OLD");
     int max_depth = 0, any_filter = 0;
+    t->host_gap = false;
     if (fused) {
+        SCP_CUDA(cudaEventRecord(t->ev[8], st));
         SCP_CUDA(cudaMemcpyAsync(t->hjobs.data(), d_jobs, n_jobs * sizeof(JobDev), cudaMemcpyDeviceToHost, st));
         SCP_CUDA(cudaStreamSynchronize(st));
         for (int j = 0; j < n_jobs; ++j) {
@@ -1881,6 +1897,8 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
         int *d_fjs = nullptr, *d_fj = nullptr;
         SCP_CUDA(upload_async((void**)&d_fjs, fj_start.data(), (size_t)(n_frames + 1) * 4, st));
         SCP_CUDA(upload_async((void**)&d_fj, fj.data(), (size_t)n_jobs * 4, st));
+        SCP_CUDA(cudaEventRecord(t->ev[9], st));
+        t->host_gap = true;
         k_job_prepare_fused<<<(int)cdiv(n_jobs, 128), 128, 0, st>>>(d_jobs, n_jobs);
         SCP_LAUNCHED();
         k_quantise_fused<<<nt_f, TPB, 0, st>>>(d_xyz, point_stride, d_ftiles, t->frame_begin.as<long long>(), d_fjs, d_fj, d_jobs,
@@ -2055,17 +2073,16 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
         const bool rows = d_out->occ || d_out->sym || d_out->ctx || d_out->pos_norm;
         SCP_CUDA(cudaEventRecord(t->ev[4], st));
         if (nt_e) {
-            if (rows) k_tree_occ<true><<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), A,
-                                                              reinterpret_cast<u64*>(d_out->voxel_key));
-            else k_tree_occ<false><<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), A,
-                                                          reinterpret_cast<u64*>(d_out->voxel_key));
+            // instruction-issue bound (80 % issue active): four blocks per SM at 56 registers measured faster than five or six
+            u64* vk = reinterpret_cast<u64*>(d_out->voxel_key);
+            if (rows) k_tree_occ<true><<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), A, vk);
+            else k_tree_occ<false><<<nt_e, TPB, 0, st>>>(t->sorted, t->tiles_emit.as<Tile>(), dj, t->tile_hist.as<u32>(), A, vk);
             SCP_LAUNCHED();
         }
         SCP_CUDA(cudaEventRecord(t->ev[5], st));
         SCP_CUDA(cudaEventRecord(t->ev[6], st));
         if (nt_n && rows) {
-            k_context_lean<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), dj, A, *d_out);
-            SCP_LAUNCHED();
+            if (int e = launch_context_lean(nt_n, t->tiles_node.as<Tile>(), dj, A, *d_out, st)) return e;
         }
         SCP_CUDA(cudaEventRecord(t->ev[7], st));
         t->emitted = true;
@@ -2129,9 +2146,8 @@ int scp_octree_emit(scp_octree* t, const scp_octree_out* d_out, void* stream) {
     }
     SCP_CUDA(cudaEventRecord(t->ev[6], st));
     if (nt_n) {
-        if (lean_out) k_context_lean<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
-        else k_context<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out);
-        SCP_LAUNCHED();
+        if (lean_out) { if (int e = launch_context_lean(nt_n, t->tiles_node.as<Tile>(), d_jobs, A, *d_out, st)) return e; }
+        else { k_context<<<nt_n, TPB, 0, st>>>(t->tiles_node.as<Tile>(), d_jobs, A, *d_out); SCP_LAUNCHED(); }
     }
     SCP_CUDA(cudaEventRecord(t->ev[7], st));
     t->emitted = true;
@@ -2151,6 +2167,11 @@ int scp_octree_stage_ms(scp_octree* t, float out[6]) {
     SCP_CUDA(cudaEventSynchronize(t->ev[7]));
     const int a[6] = {0, 1, 2, 4, 5, 6}, b[6] = {1, 2, 3, 5, 6, 7};
     for (int i = 0; i < 6; ++i) SCP_CUDA(cudaEventElapsedTime(&out[i], t->ev[a[i]], t->ev[b[i]]));
+    if (t->host_gap) {                   // the device is idle while the host reads the job depths: not kernel time
+        float gap = 0.f;
+        SCP_CUDA(cudaEventElapsedTime(&gap, t->ev[8], t->ev[9]));
+        out[0] -= gap;
+    }
     return SCP_OK;
 }
 
