@@ -48,6 +48,12 @@ bool swin_attn_tc_ok(long long ldq, long long ldk, long long ldv, long long ldo,
 int swin_attn_tc(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, const float* qb,
                  const float* kb, const float* vb, const float* relpos, int heads, const long long* d_off, const int* d_win_seq,
                  const int* d_win_idx, int n_win, int shift, float* out, long long ldo, cudaStream_t st);
+bool octattn_h_ok(long long ld, long long ldo, int head_dim, const void* qu, const void* k, const void* ku, const void* v,
+                  const void* vu, const void* o, const void* ou);                                          // octattn_h.cu
+int octattn_attn_h(const float* qu, const float* k, const float* ku, const float* v, const float* vu, long long ld, int heads,
+                   const long long* h_off, int n_seq, const long long* d_off, const int* d_tile_seq, const int* d_tile_start,
+                   int n_tile, const int* d_tile128_seq, const int* d_tile128_start, int n_tile128, float* out, float* out_u,
+                   long long ldo, cudaStream_t st);
 int swin_attn_h(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, const float* qb,
                 const float* kb, const float* vb, const float* relpos, int heads, const long long* d_off, const int* d_win_seq,
                 const int* d_win_idx, int n_win, int shift, float* out, long long ldo, cudaStream_t st);          // attn_h.cu
@@ -1156,6 +1162,12 @@ int scp_octattn_attention(const float* d_qu, const float* d_k, const float* d_ku
     SCP_REQUIRE(d_qu && d_k && d_ku && d_v && d_vu && seqs && d_out && d_out_u, "scp_octattn_attention: null argument");
     SCP_REQUIRE(head_dim > 0 && head_dim <= 150 && heads > 0, "scp_octattn_attention: head_dim must be <= 150");
     if (seqs->n_tile == 0) return SCP_OK;
+    // engine: 1 (default) = tcgen05 / TMEM / TMA flash kernel (octattn_h.cu), 0 = fp32 SIMT kernel (kept as the A/B reference)
+    static const int engine = getenv("SCP_OCTATTN_ENGINE") ? atoi(getenv("SCP_OCTATTN_ENGINE")) : 1;
+    if (engine == 1 && octattn_h_ok(ld, ldo, head_dim, d_qu, d_k, d_ku, d_v, d_vu, d_out, d_out_u))
+        return octattn_attn_h(d_qu, d_k, d_ku, d_v, d_vu, ld, heads, seqs->h_off.data(), seqs->n_seq, seqs->d_off, seqs->d_tile_seq,
+                              seqs->d_tile_start, seqs->n_tile, seqs->d_tile128_seq, seqs->d_tile128_start, seqs->n_tile128,
+                              d_out, d_out_u, ldo, as_stream(stream));
     dim3 grid(seqs->n_tile * 4, heads);
     k_octattn_attn<<<grid, 128, 0, as_stream(stream)>>>(d_qu, d_k, d_ku, d_v, d_vu, ld, heads, head_dim, seqs->d_off,
                                                         seqs->d_tile_seq, seqs->d_tile_start, d_out, d_out_u, ldo);
