@@ -97,53 +97,109 @@ __global__ void __launch_bounds__(256) k_gather_rows8(const u64* __restrict__ in
 // ------------------------------------------------------------------------------------------
 // A13 logits/PMF -> uint16 CDF
 // ------------------------------------------------------------------------------------------
-constexpr int CDF_R = 64;        // rows per block == threads per block
+constexpr int CDF_R = 64;        // rows per block
+constexpr int CDF_T = 256;       // threads per block: 8 warps load + softmax 8 rows each, 64 threads run the sequential cumsums
 constexpr int CDF_LD = 257;      // padded row stride: (257*r + i) % 32 is conflict-free both ways
 
-__global__ void __launch_bounds__(CDF_R) k_pmf_to_cdf(const float* __restrict__ in, long long n, int is_logits,
+// Phase 1 (all 8 warps): a warp streams one row at a time -- 255 floats, lane + 32 j, fully coalesced -- and, for logits, does
+// the softmax in registers (max and sum by xor-shuffle trees, IEEE divide), then parks the PMF row in shared memory.
+// Phase 2 (64 threads, one per row): np.cumsum in float32 is a strictly sequential chain of 254 additions per row
+// (numpyAc.py:111) and has to stay one to be bit-exact; the other warps of the block idle through it, the other resident
+// blocks of the SM cover it.  With only the (c_low, c_high) interval requested -- the encoder's path -- the running sum is
+// kept in a register and sampled at the symbol, nothing is written back.
+// Phase 3: normalise (float32 divide by the last sum), float64 x 65281 + rint + int16 wrap (numpyAc.py:80-107).
+__global__ void __launch_bounds__(CDF_T) k_pmf_to_cdf(const float* __restrict__ in, long long n, int is_logits,
                                                        const long long* __restrict__ row_of, const int16_t* __restrict__ sym,
                                                        uint16_t* __restrict__ cdf, u32* __restrict__ interval,
                                                        float* __restrict__ pmf) {
     extern __shared__ float s[];                 // [CDF_R][CDF_LD]
+    __shared__ long long s_orow[CDF_R];
     const long long row0 = (long long)blockIdx.x * CDF_R;
     const int rows = (int)min((long long)CDF_R, n - row0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* src = in + row0 * 255;
-    for (int i = threadIdx.x; i < rows * 255; i += CDF_R) {
-        int r = i / 255, c = i - r * 255;
-        s[r * CDF_LD + c] = src[i];
-    }
-    __syncthreads();
-    if (is_logits) {                              // torch.softmax(output, 2)  (encode.py:126-127)
-        for (int r = warp; r < rows; r += CDF_R / 32) {
-            float* x = s + r * CDF_LD;
-            float m = -INFINITY;
-            for (int c = lane; c < 255; c += 32) m = fmaxf(m, x[c]);
-            m = warp_max(m);
-            float e[8];
-            float sum = 0.f;
+    if (threadIdx.x < rows) s_orow[threadIdx.x] = row_of ? row_of[row0 + threadIdx.x] : row0 + threadIdx.x;
+    // four rows per warp in flight: all 32 loads are issued before the first softmax (one row at a time left the warp waiting
+    // ~1 us of DRAM latency per row)
+    constexpr int RB = 4;
+    for (int r0 = warp * RB; r0 < rows; r0 += (CDF_T / 32) * RB) {
+        float e[RB][8];
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            const float* x = in + (row0 + r0 + q) * 255;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                int c = lane + 32 * j;
-                e[j] = c < 255 ? expf(x[c] - m) : 0.f;
-                sum += e[j];
-            }
-            sum = warp_sum(sum);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int c = lane + 32 * j;
-                if (c < 255) x[c] = __fdiv_rn(e[j], sum);
+                const int c = lane + 32 * j;
+                e[q][j] = (r0 + q < rows && c < 255) ? __ldg(x + c) : -INFINITY;
             }
         }
-        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < RB; ++q) {
+            if (r0 + q >= rows) break;                // warp-uniform
+            if (is_logits) {                          // torch.softmax(output, 2)  (encode.py:126-127)
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m = fmaxf(m, e[q][j]);
+                m = warp_max(m);
+                // 2^((x - max) log2 e) on the special-function unit and one reciprocal per row: the softmax was 80 % of the
+                // kernel's instructions with expf / IEEE divides (0.16 ms of issue time per 514 k rows); the PMF differs from
+                // torch.softmax by ~1e-7 either way, and encoder and decoder run this same kernel
+                const float ml = m * 1.4426950408889634f;
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float p;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(fmaf(e[q][j], 1.4426950408889634f, -ml)));
+                    e[q][j] = lane + 32 * j < 255 ? p : 0.f;
+                    sum += e[q][j];
+                }
+                sum = warp_sum(sum);
+                const float inv = __frcp_rn(sum);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) e[q][j] *= inv;
+            }
+            float* dst = s + (r0 + q) * CDF_LD;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = lane + 32 * j;
+                if (c < 255) dst[c] = e[q][j];
+            }
+        }
     }
+    __syncthreads();
     if (pmf) {
-        for (int i = threadIdx.x; i < rows * 255; i += CDF_R) {
+        for (int i = threadIdx.x; i < rows * 255; i += CDF_T) {
             int r = i / 255, c = i - r * 255;
-            long long orow = row_of ? row_of[row0 + r] : row0 + r;
+            const long long orow = s_orow[r];
             if (orow < 0) continue;
             pmf[orow * 255 + c] = s[r * CDF_LD + c];
         }
+    }
+    if (!cdf) {
+        // interval only: sequential float32 cumsum in a register, sampled at sym-1, sym and the end
+        if (interval && threadIdx.x < rows) {
+            const long long orow = s_orow[threadIdx.x];
+            if (orow >= 0) {
+                const float* x = s + threadIdx.x * CDF_LD;
+                int sy = sym[orow];
+                sy = sy < 0 ? 0 : (sy > 254 ? 254 : sy);
+                float acc = x[0];
+                float c_lo = 0.f, c_hi = acc;                     // cumsum[sy-1] (unused for sy == 0), cumsum[sy]
+#pragma unroll 8
+                for (int c = 1; c < 255; ++c) {
+                    if (c == sy) c_lo = acc;
+                    acc = __fadd_rn(acc, x[c]);
+                    if (c == sy) c_hi = acc;
+                }
+                const float last = acc;
+                const double Fl = sy == 0 ? 0.0 : (double)__fdiv_rn(c_lo, last);
+                const u32 lo = (u32)(((long long)rint(Fl * 65281.0) + sy) & 0xffff);
+                u32 hi = 0x10000u;                                // numpyAc_backend.cpp:277
+                if (sy != 254) hi = (u32)(((long long)rint((double)__fdiv_rn(c_hi, last) * 65281.0) + sy + 1) & 0xffff);
+                interval[2 * orow] = lo;
+                interval[2 * orow + 1] = hi;
+            }
+        }
+        return;
     }
     // np.cumsum(pdf, axis=1) in float32: strictly sequential adds (numpyAc.py:111)
     if (threadIdx.x < rows) {
@@ -154,7 +210,7 @@ __global__ void __launch_bounds__(CDF_R) k_pmf_to_cdf(const float* __restrict__ 
     }
     __syncthreads();
     // cdfF/cdfF[:, -1:] (float32) -> float64 [0, f...] * 65281 -> rint -> int16 wrap -> + arange(256)
-    for (int i = threadIdx.x; i < rows * 128; i += CDF_R) {
+    for (int i = threadIdx.x; i < rows * 128; i += CDF_T) {
         int r = i >> 7, c2 = (i & 127) * 2;
         const float* x = s + r * CDF_LD;
         const float last = x[254];
@@ -166,16 +222,14 @@ __global__ void __launch_bounds__(CDF_R) k_pmf_to_cdf(const float* __restrict__ 
             long long q = (long long)rint(F * 65281.0) + c;
             v[k] = (u32)(q & 0xffff);
         }
-        if (cdf) {
-            long long orow = row_of ? row_of[row0 + r] : row0 + r;
-            if (orow < 0) continue;
-            reinterpret_cast<u32*>(cdf + orow * 256)[c2 >> 1] = v[0] | (v[1] << 16);
-        }
+        const long long orow = s_orow[r];
+        if (orow < 0) continue;
+        reinterpret_cast<u32*>(cdf + orow * 256)[c2 >> 1] = v[0] | (v[1] << 16);
     }
     if (interval && threadIdx.x < rows) {
         const float* x = s + threadIdx.x * CDF_LD;
         const float last = x[254];
-        long long orow = row_of ? row_of[row0 + threadIdx.x] : row0 + threadIdx.x;
+        const long long orow = s_orow[threadIdx.x];
         if (orow < 0) return;
         int sy = sym[orow];
         sy = sy < 0 ? 0 : (sy > 254 ? 254 : sy);
@@ -391,7 +445,7 @@ int scp_pmf_to_cdf(const float* d_in, int64_t n, int is_logits, const int64_t* d
         SCP_CUDA(cudaFuncSetAttribute(k_pmf_to_cdf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_done = true;
     }
-    k_pmf_to_cdf<<<(unsigned)cdiv(n, CDF_R), CDF_R, smem, as_stream(stream)>>>(
+    k_pmf_to_cdf<<<(unsigned)cdiv(n, CDF_R), CDF_T, smem, as_stream(stream)>>>(
         d_in, n, is_logits, (const long long*)d_row_of, d_sym, d_cdf, d_interval, d_pmf);
     SCP_LAUNCHED();
     return SCP_OK;
