@@ -35,7 +35,8 @@ constexpr int NBINS = 24;             // head-level histogram bins (0 = not a ne
 constexpr int MAXL = SCP_MAX_DEPTH;   // 21
 constexpr u64 SENTINEL = ~0ull;
 
-struct Tile { int job; int begin; int count; int first; };
+struct Tile { int job; int begin; int count; int first; long long kb = 0; int pj = 0; int _pad = 0; };
+// sort tiles only: kb = first key of the job, pj = digit passes of the job under the per-job schedule (0: all passes)
 
 struct FrameDev { u32 rho_max_bits; u32 zmin_enc; u32 zmax_enc; u32 _pad; };
 
@@ -561,10 +562,10 @@ __global__ void __launch_bounds__(TPB) k_sort_hist(const u64* __restrict__ keys_
     const JobDev& J = jobs[t.job];
     const int cnt = min(t.count, J.n_kept - t.begin);
     if (cnt <= 0) return;                                  // block-uniform
-    const int pj = pmax > 0 ? sort_passes(J.depth) : P;
+    const int pj = t.pj > 0 ? t.pj : P;
     for (int i = threadIdx.x; i < pj * 256; i += TPB) sh[i] = 0;
     __syncthreads();
-    const u64* src = ((pmax > 0 && ((pmax - pj) & 1)) ? keys_b : keys_a) + J.key_begin + t.begin;
+    const u64* src = ((t.pj > 0 && ((pmax - pj) & 1)) ? keys_b : keys_a) + t.kb + t.begin;
     for (int i = threadIdx.x; i < cnt; i += TPB) {
         const u64 k = src[i];
         for (int p = 0; p < pj; ++p) atomicAdd(&sh[p * 256 + (u32)((k >> (8 * p)) & 0xff)], 1u);
@@ -663,9 +664,8 @@ __global__ void __launch_bounds__(256) k_scan_hist(u32* hist) {   // one block p
     h[threadIdx.x] = base + inc - v;
 }
 
-// pmax > 0 selects the per-job pass schedule: a job of depth d needs ceil(3d/8) digit passes; it skips the passes beyond
-// that and starts in buffer B when (pmax - its passes) is odd, so that after pmax launches every job's sorted keys lie in the
-// same buffer ((pmax & 1) ? B : A).  pmax == 0: all jobs take all P passes from A (scp_segmented_sort_u64, fallback path).
+// Tiles with pj > 0 follow the per-job pass schedule (see below; result in (pmax & 1) ? B : A), tiles with pj == 0 take all P
+// passes starting from A (scp_segmented_sort_u64, fallback path).
 __global__ void __launch_bounds__(TPB, 4) k_onesweep(u64* __restrict__ buf_a, u64* __restrict__ buf_b,
                                                    const Tile* __restrict__ tiles, int n_tiles,
                                                    const JobDev* __restrict__ jobs, const u32* __restrict__ hist,
@@ -683,29 +683,36 @@ __global__ void __launch_bounds__(TPB, 4) k_onesweep(u64* __restrict__ buf_a, u6
     if (t >= n_tiles) return;
     Tile tl = tiles[t];
     const JobDev& J = jobs[tl.job];
-    tl.count = min(tl.count, J.n_kept - tl.begin);       // compacted jobs: the tail tiles are empty and nobody looks back at them
-    if (tl.count <= 0) return;
-    int par = pass & 1;
-    if (pmax > 0) {
-        const int pj = sort_passes(J.depth);
-        if (pass >= pj) return;                          // block-uniform: this job's keys are sorted already
-        par = (pass + pmax - pj) & 1;
-    }
-    const u64* in = par ? buf_b : buf_a;
-    u64* out = par ? buf_a : buf_b;
-    const u64* src = in + J.key_begin + tl.begin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int shift = pass * 8;
     const int wbase = warp * (32 * SORT_ITEMS);
+    // per-job schedule (tl.pj > 0): a job of depth d needs pj = ceil(3d/8) passes; it skips the rest and starts in buffer B when
+    // (pmax - pj) is odd, so that after pmax launches every job's sorted keys lie in the same buffer
+    if (tl.pj > 0 && pass >= tl.pj) return;              // block-uniform: this job's keys are sorted already
+    const int par = tl.pj > 0 ? ((pass + pmax - tl.pj) & 1) : (pass & 1);
+    // The keys are addressed from the tile record alone (ticket -> tile -> keys): going through the job record for the key
+    // offset (ticket -> tile -> job -> keys) put a fourth dependent L2 / DRAM latency at the head of every tile.  n_kept (a
+    // device-side count) arrives in parallel; slots behind it hold stale keys of the job's own region and become SENTINEL.
+    const int n_kept = J.n_kept;
     u64 key[SORT_ITEMS];
-    u32 rank[SORT_ITEMS];
+    {
+        const u64* sa = (par ? buf_b : buf_a) + tl.kb + tl.begin;
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        int idx = wbase + i * 32 + lane;
-        key[i] = idx < tl.count ? src[idx] : SENTINEL;
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const int idx = wbase + i * 32 + lane;
+            key[i] = idx < tl.count ? sa[idx] : SENTINEL;
+        }
     }
+    tl.count = min(tl.count, n_kept - tl.begin);         // compacted jobs: the tail tiles are empty and nobody looks back at them
+    if (tl.count <= 0) return;
+    u64* out = par ? buf_a : buf_b;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) if (wbase + i * 32 + lane >= tl.count) key[i] = SENTINEL;
+    u32 rank[SORT_ITEMS];
     // the 16 match operations are independent of the histogram chain below: issue them back to back (each has ~40 cycles
-    // of latency; inside the read-modify-write loop they were the largest stall of the kernel)
+    // of latency; inside the read-modify-write loop they were the largest stall of the kernel).  (Replacing the chain by one
+    // shared-memory atomicAdd per digit group, whose return value is the count of the warp's earlier items, measured slower:
+    // 2.16 against 1.63 ms for the seven passes.)
     u32 peers[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
@@ -762,7 +769,7 @@ __global__ void __launch_bounds__(TPB, 4) k_onesweep(u64* __restrict__ buf_a, u6
         }
     }
     __syncthreads();
-    u64* dst = out + J.key_begin;
+    u64* dst = out + tl.kb;
     for (int s = threadIdx.x; s < tl.count; s += TPB) {
         u64 k = s_keys[s];
         u32 dg = (u32)((k >> shift) & 0xff);
@@ -1851,6 +1858,7 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
     Tile* d_ptiles = d_ftiles + nt_f;
     SCP_CUDA(cudaMemcpyAsync(d_ftiles, ftiles.data(), nt_f * sizeof(Tile), cudaMemcpyHostToDevice, st));
     SCP_CUDA(cudaMemcpyAsync(d_ptiles, t->h_tiles_pts.data(), nt_p * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    for (Tile& tl : t->h_tiles_sort) tl.kb = t->hjobs[tl.job].key_begin;
     SCP_CUDA(cudaMemcpyAsync(t->tiles_sort.p, t->h_tiles_sort.data(), nt_s * sizeof(Tile), cudaMemcpyHostToDevice, st));
     SCP_CUDA(cudaMemcpyAsync(t->frame_begin.p, fbegin.data(), n_frames * 8, cudaMemcpyHostToDevice, st));
     SCP_CUDA(cudaMemcpyAsync(t->jobs.p, t->hjobs.data(), n_jobs * sizeof(JobDev), cudaMemcpyHostToDevice, st));
@@ -1894,6 +1902,8 @@ int scp_octree_plan(scp_octree* t, const float* d_xyz, int point_stride, const i
         SCP_REQUIRE(max_depth >= 1 && max_depth <= MAXL, "octree depth %d outside [1,%d]", max_depth, MAXL);
         t->P = (3 * max_depth + 7) / 8;
         t->max_depth = max_depth;
+        for (Tile& tl : t->h_tiles_sort) tl.pj = (3 * t->hjobs[tl.job].depth + 7) / 8;      // per-job pass schedule
+        SCP_CUDA(cudaMemcpyAsync(t->tiles_sort.p, t->h_tiles_sort.data(), nt_s * sizeof(Tile), cudaMemcpyHostToDevice, st));
         int *d_fjs = nullptr, *d_fj = nullptr;
         SCP_CUDA(upload_async((void**)&d_fjs, fj_start.data(), (size_t)(n_frames + 1) * 4, st));
         SCP_CUDA(upload_async((void**)&d_fj, fj.data(), (size_t)n_jobs * 4, st));
@@ -2190,6 +2200,7 @@ int scp_segmented_sort_u64(uint64_t* d_keys, uint64_t* d_tmp, const int64_t* h_s
     }
     std::vector<Tile> tiles;
     build_tiles(cnt, SORT_TILE, tiles, nullptr);
+    for (Tile& tl : tiles) tl.kb = jobs[tl.job].key_begin;
     DevBuf dj, dt, hist, desc, misc;
     int rc = SCP_OK;
     u64* res = nullptr;
