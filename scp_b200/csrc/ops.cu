@@ -227,6 +227,56 @@ __global__ void __launch_bounds__(256) k_layernorm_v4(const float* __restrict__ 
     }
 }
 
+// same for any C = 4 * n4 <= 128 * NV (OctAttention: C = 600, NV = 5): lanes past the end of the row hold zeros
+template <int NV>
+__global__ void __launch_bounds__(256) k_layernorm_v4g(const float* __restrict__ X, long long ldx, const float* __restrict__ R,
+                                                        long long ldr, const float* __restrict__ g, const float* __restrict__ b,
+                                                        float* __restrict__ Y, long long ldy, long long M, int C, float eps) {
+    const int lane = threadIdx.x & 31, n4 = C >> 2;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float4 v[NV];
+    const float4* x4 = reinterpret_cast<const float4*>(X + row * ldx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = lane + 32 * i < n4 ? __ldcs(x4 + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (R) {
+        const float4* r4 = reinterpret_cast<const float4*>(R + row * ldr);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (lane + 32 * i < n4) {
+                const float4 r = __ldcs(r4 + lane + 32 * i);
+                v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w;
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < n4) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    }
+    const float rs = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+    float4* y4 = reinterpret_cast<float4*>(Y + row * ldy);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < n4) {
+            const float4 gg = __ldg(g4 + lane + 32 * i), bb = __ldg(b4 + lane + 32 * i);
+            float4 o;
+            o.x = v[i].x * rs * gg.x + bb.x; o.y = v[i].y * rs * gg.y + bb.y;
+            o.z = v[i].z * rs * gg.z + bb.z; o.w = v[i].w * rs * gg.w + bb.w;
+            y4[lane + 32 * i] = o;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // EHEM embedding
 // ------------------------------------------------------------------------------------------
@@ -989,7 +1039,7 @@ int scp_layernorm(const float* d_x, int64_t ldx, const float* d_res, int64_t ldr
     SCP_REQUIRE(d_x && d_gamma && d_beta && d_y && C > 0 && C <= 640, "scp_layernorm: bad argument (C<=640)");
     if (M == 0) return SCP_OK;
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    const bool v4 = (C == 256 || C == 512) && ldx % 4 == 0 && ldy % 4 == 0 && al(d_x) && al(d_y) && al(d_gamma) && al(d_beta) &&
+    const bool v4 = C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && al(d_x) && al(d_y) && al(d_gamma) && al(d_beta) &&
                     (!d_res || (ldr % 4 == 0 && al(d_res)));
     if (v4 && C == 256) {
         k_layernorm_v4<2><<<(unsigned)cdiv(M, 8), 256, 0, as_stream(stream)>>>(d_x, ldx, d_res, ldr, d_gamma, d_beta, d_y, ldy, M, eps);
@@ -998,6 +1048,11 @@ int scp_layernorm(const float* d_x, int64_t ldx, const float* d_res, int64_t ldr
     }
     if (v4 && C == 512) {
         k_layernorm_v4<4><<<(unsigned)cdiv(M, 8), 256, 0, as_stream(stream)>>>(d_x, ldx, d_res, ldr, d_gamma, d_beta, d_y, ldy, M, eps);
+        SCP_LAUNCHED();
+        return SCP_OK;
+    }
+    if (v4) {                                    // other widths (OctAttention: 600) on the float4 path too
+        k_layernorm_v4g<5><<<(unsigned)cdiv(M, 8), 256, 0, as_stream(stream)>>>(d_x, ldx, d_res, ldr, d_gamma, d_beta, d_y, ldy, M, C, eps);
         SCP_LAUNCHED();
         return SCP_OK;
     }

@@ -43,7 +43,15 @@ class OctAttention(nn.Module):
     def _prepare(self):
         """Stable per-weight tensor objects: the operator layer keys its split-weight cache on them (scp_b200/ops.py)."""
         if self._sd is None:
-            self._sd = {k: v.detach() for k, v in self.state_dict().items()}
+            sd = {k: v.detach() for k, v in self.state_dict().items()}
+            for i in range(self.cfg.model.layer_num):
+                a = f"transformer_encoder.layers.{i}.attn"
+                # one GEMM per stream: [key; value] of the known stream, [key; query; value] of the unknown stream
+                sd[f"{a}.kv.weight"] = torch.cat([sd[f"{a}.mlp_key.weight"], sd[f"{a}.mlp_value.weight"]], 0).contiguous()
+                sd[f"{a}.kv.bias"] = torch.cat([sd[f"{a}.mlp_key.bias"], sd[f"{a}.mlp_value.bias"]], 0).contiguous()
+                sd[f"{a}.kqv.weight"] = torch.cat([sd[f"{a}.mlp_key.weight"], sd[f"{a}.mlp_query.weight"], sd[f"{a}.mlp_value.weight"]], 0).contiguous()
+                sd[f"{a}.kqv.bias"] = torch.cat([sd[f"{a}.mlp_key.bias"], sd[f"{a}.mlp_query.bias"], sd[f"{a}.mlp_value.bias"]], 0).contiguous()
+            self._sd = sd
         return self._sd
 
     @property
@@ -72,10 +80,9 @@ class OctAttention(nn.Module):
             p = f"transformer_encoder.layers.{i}"
             # K, V of the known stream; K, Q, V of the unknown stream (attention_model.py:65-70), one buffer so
             # that all five operands share a row stride
-            ALL = ops.empty(T, 3000, like)
-            for col, nm, src in ((0, "mlp_key", E), (600, "mlp_value", E), (1200, "mlp_key", EU),
-                                 (1800, "mlp_query", EU), (2400, "mlp_value", EU)):
-                ops.linear(V(src), sd[f"{p}.attn.{nm}.weight"], sd[f"{p}.attn.{nm}.bias"], V(ALL, col, 600))
+            ALL = ops.empty(T, 3000, like)          # columns: K | V of the known stream, K | Q | V of the unknown stream
+            ops.linear(V(E), sd[f"{p}.attn.kv.weight"], sd[f"{p}.attn.kv.bias"], V(ALL, 0, 1200))
+            ops.linear(V(EU), sd[f"{p}.attn.kqv.weight"], sd[f"{p}.attn.kqv.bias"], V(ALL, 1200, 1800))
             A, AU = ops.empty(T, 600, like), ops.empty(T, 600, like)
             ops.octattn_attention(V(ALL, 1800, 600), V(ALL, 0, 600), V(ALL, 1200, 600), V(ALL, 600, 600),
                                   V(ALL, 2400, 600), m.head_num, 150, seqs, V(A), V(AU))
