@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(TPB) k_frame_stats(const float* __restrict__ x
     float rmax = 0.f;
     u32 zmin = 0xffffffffu, zmax = 0u;
     const bool v4 = stride == 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;      // KITTI rows (x, y, z, intensity): one 16-byte load
+#pragma unroll 4
     for (int i = threadIdx.x; i < t.count; i += TPB) {
         float x, y, z;
         if (v4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i); x = v.x; y = v.y; z = v.z; }
