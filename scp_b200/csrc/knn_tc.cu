@@ -35,6 +35,18 @@ constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 64;                      // K blo
 // (ncu: 0.8 IPC per SM).  Half the TMEM (256 columns: one accumulator stage) and a 3-stage ring (one candidate tile) per
 // CTA let a second CTA share the SM: two epilogue warps per scheduler, and each CTA's MMAs / TMA run under the other's
 // epilogue.
+// Round-2 timeline (clock64 stamps of CTA 0, `SCP_KNN_TRACE=1`; profiles/r02_knn_timeline.md) and the three single-CTA restructurings
+// it led to, all measured SLOWER on the bench frames and therefore not kept:
+//  * a (128-query, 64-candidate) tile takes 2200 cycles per SM for 36 MMAs; 1430 with the scan switched off -- that IS the tensor
+//    pipe for this shape: N = 64 TS-form MMAs issued by ONE thread retire every 48-57 cycles (whatever the accumulator order),
+//    by the two issuers of two co-resident CTAs (or two issuing warps of one CTA) every 40, never at the nominal 32;
+//  * 256 query rows per CTA sharing every candidate tile (half the L2 bytes) changes nothing: L2 -> shared memory is not the
+//    limiter (34 B/clk per SM at the rate above, cap ~42), and one issuer made it slower;
+//  * four accumulator stages + two epilogue teams with a heap each (candidate tiles alternate between the teams, thresholds
+//    shared, heaps merged at the end; two issuing warps) decouples the MMAs from the slowest epilogue warp and reaches the same
+//    1430 without the scan, but every row then pays its accepts against two half-informed heaps: 44 ms per step against 36.
+// What is left between 1430 and 2200 is the accept path itself (per-lane heap sift-downs, 150-250 dependent cycles per round,
+// rounds = the maximum over the lanes of a warp).
 constexpr int KT_STAGES = 3, KT_ACC = 1;
 constexpr int KT_EXTRA = 8;                                    // approximate top-(k+8) is re-ranked exactly
 constexpr int KT_MAXD = 192;                                   // A_hi + A_lo: 2 x 96 TMEM columns (two fp16 per column)
@@ -124,7 +136,8 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
                                                     const __half* __restrict__ xhi, const __half* __restrict__ xlo,
                                                     const float* __restrict__ scales, const float* __restrict__ xx, const long long* __restrict__ seq_off,
                                                     const int* __restrict__ tile_seq, const int* __restrict__ tile_start,
-                                                    int n_work, long long row0, int d, int kc, int* __restrict__ idx_out, int dbg) {
+                                                    int n_work, long long row0, int d, int kc, int* __restrict__ idx_out, int dbg,
+                                                    long long* __restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + KT_OFF_BAR);
@@ -186,6 +199,8 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
         const uint32_t idesc = (1u << 4) | ((uint32_t)(KT_BN >> 3) << 17) | ((uint32_t)(KT_BM >> 4) << 24);     // f16 x f16 -> f32
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0, a_phase = 0;
+        int tr_n = 0;                                      // development aid (SCP_KNN_TRACE=1): clock stamps of CTA 0
+        const bool TR = trace && blockIdx.x == 0;
         for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
             const int s = tile_seq[wk];
             const int n = (int)(seq_off[s + 1] - seq_off[s]);
@@ -193,17 +208,23 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
             mbar_wait(a_ready, a_phase);                                // this work item's query rows are in TMEM
             a_phase ^= 1;
             for (int ci = 0; ci < nt; ++ci) {
+                if (TR && lane == 0 && tr_n < 900) trace[tr_n++] = clock64();            // tile: before the accumulator wait
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
+                if (TR && lane == 0 && tr_n < 900) trace[tr_n++] = clock64();            // tile: accumulator free
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * KT_BN);
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(&full[stage], phase);
+                    if (TR && lane == 0 && tr_n < 900 && (kb == 0 || kb == n_kb - 1)) trace[tr_n++] = clock64();   // first / last K block landed
                     tc_fence_after();
                     const uint8_t* b = smem + stage * KT_STAGE_BYTES;
                     const uint64_t dbh = make_smem_desc(b), dbl = make_smem_desc(b + KT_TILE_BYTES);
                     const uint32_t ah = tmem_base + KT_T_AH + (uint32_t)(kb * 32), al = tmem_base + KT_T_AL + (uint32_t)(kb * 32);
+                    const int kk_n = min(4, (d - kb * KT_BK + 15) >> 4);     // d = 144: the last K block holds 16 channels, the rest of
+                                                                             // the box is TMA zero fill -- no MMAs for it
                     if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {                     // 16 fp16 = 8 TMEM columns of A = 2 descriptor units of B
+                            if (kk >= kk_n) break;
                             const uint64_t o = (uint64_t)(2 * kk);
                             tc_mma_f16_ts(d_tmem, ah + 8u * kk, dbh + o, idesc, (kb | kk) ? 1u : 0u);
                             tc_mma_f16_ts(d_tmem, al + 8u * kk, dbh + o, idesc, 1u);
@@ -226,6 +247,8 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
         float2* hq = reinterpret_cast<float2*>(smem + KT_OFF_HS) + w * (32 * 32) + lane;  // heap (score, candidate), entry e at hq[32 e]
         const uint32_t t_lane = tmem_base + ((uint32_t)(w * 32) << 16);
         int acc = 0; uint32_t acc_phase = 0;
+        const bool ETR = trace && blockIdx.x == 0 && w == 0 && lane == 0;
+        int e_n = 0;
         for (int wk = blockIdx.x; wk < n_work; wk += gridDim.x) {
             const int s = tile_seq[wk];
             const long long gbase = seq_off[s];
@@ -276,7 +299,9 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
                     nx0 = c0_next + lane < n ? __ldg(xw + c0_next + lane) : INFINITY;
                     nx1 = c0_next + lane + 32 < n ? __ldg(xw + c0_next + lane + 32) : INFINITY;
                 }
+                if (ETR && e_n < 900) trace[1024 + e_n++] = clock64();                  // tile: before the score wait
                 mbar_wait(&tfull[acc], acc_phase);
+                if (ETR && e_n < 900) trace[1024 + e_n++] = clock64();                  // tile: scores ready
                 tc_fence_after();
                 uint32_t r[2][32];
                 tc_ld32_nowait(t_lane + (uint32_t)(acc * KT_BN), r[0]);
@@ -285,6 +310,7 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
                 tc_fence_before();                                         // scores are in registers: the stage can be refilled
                 __syncwarp();
                 if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);
+                if (ETR && e_n < 900) trace[1024 + e_n++] = clock64();                  // tile: scores in registers, stage returned
                 if (++acc == KT_ACC) { acc = 0; acc_phase ^= 1; }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -342,6 +368,7 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
                     }
                 }
                 c0 = c0_next;
+                if (ETR && e_n < 900) trace[1024 + e_n++] = clock64();                  // tile: scanned
             }
             if (rowv) {                                                    // kc survivors (unordered) for the exact re-rank
                 int* dst = idx_out + (gbase - row0 + q) * 32;
@@ -462,8 +489,28 @@ int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     const int grid = std::min(n_work, 2 * n_sm);                      // two resident CTAs per SM
     const int dbg = getenv("SCP_KNN_DBG") ? atoi(getenv("SCP_KNN_DBG")) : 0;          // timing experiments only
-    k_knn_tc<<<grid, 256, KT_SMEM, st>>>(mh, ml, hi, lo, scales, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, dbg);
+    static long long* d_trace = nullptr;
+    static const bool want_trace = getenv("SCP_KNN_TRACE") != nullptr;
+    if (want_trace && !d_trace) cudaMalloc(&d_trace, 2048 * 8);
+    if (want_trace) cudaMemsetAsync(d_trace, 0, 2048 * 8, st);
+    k_knn_tc<<<grid, 256, KT_SMEM, st>>>(mh, ml, hi, lo, scales, xx, d_off, d_tile_seq, d_tile_start, n_work, row0, d, kc, cand, dbg,
+                                         want_trace ? d_trace : nullptr);
     SCP_LAUNCHED();
+    if (want_trace) {                                    // development aid: per-tile timeline of CTA 0 (MMA warp / epilogue warp 0)
+        static long long hh[2048];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hh, d_trace, sizeof(hh), cudaMemcpyDeviceToHost);
+        auto avg = [&](int base, int stride, int a, int b, int t0, int t1) {
+            double s = 0; int n = 0;
+            for (int t = t0; t < t1; ++t) { const long long x = hh[base + t * stride + a], y = hh[base + t * stride + b]; if (x && y) { s += (double)(y - x); ++n; } }
+            return n ? s / n : 0.0;
+        };
+        for (int lo_t = 2; lo_t < 200; lo_t += 66)
+            fprintf(stderr, "knn trace d=%d tiles %d-%d: MMA warp  acc-wait %.0f  kb0-wait %.0f  kb0->kbL %.0f  period %.0f | epilogue  score-wait %.0f  ld %.0f  scan %.0f  period %.0f\n",
+                    d, lo_t, lo_t + 66, avg(0, 4, 0, 1, lo_t, lo_t + 66), avg(0, 4, 1, 2, lo_t, lo_t + 66), avg(0, 4, 2, 3, lo_t, lo_t + 66),
+                    avg(0, 4, 0, 4, lo_t, lo_t + 66), avg(1024, 4, 0, 1, lo_t, lo_t + 66), avg(1024, 4, 1, 2, lo_t, lo_t + 66),
+                    avg(1024, 4, 2, 3, lo_t, lo_t + 66), avg(1024, 4, 0, 4, lo_t, lo_t + 66));
+    }
     k_knn_rerank<<<(unsigned)cdiv(total, 8), 256, 0, st>>>(d_x, ldx, d, row0, total, cand, 32, k, d_idx);
     SCP_LAUNCHED();
     SCP_CUDA(cudaFreeAsync(cand, st));
