@@ -39,6 +39,40 @@ __device__ __forceinline__ float tc_erf(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
     return copysignf(fmaf(-p * t, e, 1.0f), x);
 }
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two IEEE-rounded results, bit-identical to the scalar
+// instructions).  The GELU epilogue of the N = 1024 layer is issue-bound (ncu: 58 % issue-active, eligible warps not selected
+// 0.65 per issue): the pair form needs ~8 issue slots per element instead of ~18.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// GELU of two values, operation for operation the scalar 0.5 v (1 + tc_erf(v / sqrt 2)) above (the polynomial is evaluated with
+// negated coefficients, which negates every intermediate exactly, so that -p t needs no separate sign flip)
+__device__ __forceinline__ f32x2 tc_gelu2(f32x2 v) {
+    const f32x2 x = mul2(v, pk2(0.70710678118654752440f, 0.70710678118654752440f));
+    float x0, x1;
+    upk2(x, x0, x1);
+    const f32x2 ax = pk2(fabsf(x0), fabsf(x1));
+    float d0, d1, t0, t1;
+    upk2(fma2(pk2(0.3275911f, 0.3275911f), ax, pk2(1.0f, 1.0f)), d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+    const f32x2 t = pk2(t0, t1);
+    f32x2 p = fma2(pk2(-1.061405429f, -1.061405429f), t, pk2(1.453152027f, 1.453152027f));
+    p = fma2(p, t, pk2(-1.421413741f, -1.421413741f));
+    p = fma2(p, t, pk2(0.284496736f, 0.284496736f));
+    p = fma2(p, t, pk2(-0.254829592f, -0.254829592f));                       // = -p of the scalar form
+    float a0, a1, e0, e1;
+    upk2(mul2(mul2(ax, ax), pk2(-1.4426950408889634f, -1.4426950408889634f)), a0, a1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    float r0, r1;
+    upk2(fma2(mul2(p, t), pk2(e0, e1), pk2(1.0f, 1.0f)), r0, r1);
+    const f32x2 erf1 = add2(pk2(1.0f, 1.0f), pk2(copysignf(r0, x0), copysignf(r1, x1)));
+    return mul2(mul2(pk2(0.5f, 0.5f), v), erf1);
+}
 __device__ __forceinline__ float tc_act(float v, int act) {
     switch (act) {
         case SCP_ACT_LEAKY001: return v > 0.f ? v : 0.01f * v;
@@ -519,12 +553,13 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 const bool have = n0 < N && row0 < M;
                 const bool vec = have && vec_ok && n0 + 32 <= N;
                 float4 q[8], b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int n_row = (int)(M - row0 < 32 ? (M - row0 > 0 ? M - row0 : 0) : 32);       // rows of this warp's quarter inside the matrix
                 if (R) {
+                    const float* rp = R + (row0 + sub_r) * ldr + n0 + sub_c;
+                    const long long rstep = 4 * ldr;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const long long row = row0 + it * 4 + sub_r;
-                        q[it] = (vec && row < M) ? __ldcs(reinterpret_cast<const float4*>(R + row * ldr + n0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    for (int it = 0; it < 8; ++it, rp += rstep)
+                        q[it] = (vec && it * 4 + sub_r < n_row) ? __ldcs(reinterpret_cast<const float4*>(rp)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (bias && vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + sub_c));
                 if (ETR && e_n < 960) trace[1024 + e_n++] = clock64();                  // chunk: before the accumulator wait
@@ -534,8 +569,13 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 tc_ld32(t_row + (uint32_t)c0, r);
                 if (ETR && e_n < 960) trace[1024 + e_n++] = clock64();                  // chunk: scores in registers
                 if (H) {
+                    const f32x2 osc2 = pk2(osc, osc);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * osc);      // exact: power of two
+                    for (int j = 0; j < 32; j += 2) {                                                        // exact: power of two
+                        float a, b;
+                        upk2(mul2(pk2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), osc2), a, b);
+                        r[j] = __float_as_uint(a); r[j + 1] = __float_as_uint(b);
+                    }
                 }
                 if (c0 + 64 >= BN) {                          // last chunk of this warp: the TMEM stage can go back now
                     tc_fence_before();
@@ -551,24 +591,36 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                     // the activation is chosen ONCE per chunk: a `switch (act)` per element was a third of the epilogue's
                     // instructions, and the eight epilogue warps set the pace of the K = 256 layers (MMA-warp trace: ~4500 of
                     // 9000 cycles per tile spent waiting for an accumulator to come back)
-                    auto store_rows = [&](auto actf) {
-#pragma unroll
-                        for (int it = 0; it < 8; ++it) {
+                    // (packed pairs: FADD2 / FMUL2 / FFMA2, same roundings as the scalar form)
+                    const f32x2 b01 = pk2(b4.x, b4.y), b23 = pk2(b4.z, b4.w);
+                    auto store_rows = [&](auto actf2) {
+                        float* yp = Y + (row0 + sub_r) * ldy + n0 + sub_c;       // one 64-bit address, then a constant step per iteration
+                        const long long ystep = 4 * ldy;
+                        auto row4 = [&](int it, float* dst) {
                             const int rr = it * 4 + sub_r;
-                            const long long row = row0 + rr;
-                            if (row < M) {
-                                float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((((sub_c >> 2) ^ rr) & 7) << 2));
-                                v.x = actf(v.x + b4.x); v.y = actf(v.y + b4.y); v.z = actf(v.z + b4.z); v.w = actf(v.w + b4.w);
-                                if (R) { v.x += q[it].x; v.y += q[it].y; v.z += q[it].z; v.w += q[it].w; }
-                                __stcs(reinterpret_cast<float4*>(Y + row * ldy + n0 + sub_c), v);
-                            }
+                            float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((((sub_c >> 2) ^ rr) & 7) << 2));
+                            f32x2 lo2 = actf2(add2(pk2(v.x, v.y), b01)), hi2 = actf2(add2(pk2(v.z, v.w), b23));
+                            if (R) { lo2 = add2(lo2, pk2(q[it].x, q[it].y)); hi2 = add2(hi2, pk2(q[it].z, q[it].w)); }
+                            upk2(lo2, v.x, v.y); upk2(hi2, v.z, v.w);
+                            __stcs(reinterpret_cast<float4*>(dst), v);
+                        };
+                        if (n_row == 32) {                      // warp-uniform; ONE basic block: the eight rows' dependent chains (LDS -> ~14
+                                                                // packed ops + 2 MUFU -> STG, ~180 cycles each) interleave instead of running
+                                                                // one after the other behind a per-row bounds branch
+#pragma unroll
+                            for (int it = 0; it < 8; ++it, yp += ystep) row4(it, yp);
+                        } else {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it, yp += ystep)
+                                if (it * 4 + sub_r < n_row) row4(it, yp);
                         }
                     };
+                    auto each = [](f32x2 v, auto f) { float a, b; upk2(v, a, b); return pk2(f(a), f(b)); };
                     switch (act) {                          // warp-uniform
-                        case SCP_ACT_GELU: store_rows([](float v) { return 0.5f * v * (1.0f + tc_erf(v * 0.70710678118654752440f)); }); break;
-                        case SCP_ACT_LEAKY001: store_rows([](float v) { return v > 0.f ? v : 0.01f * v; }); break;
-                        case SCP_ACT_RELU: store_rows([](float v) { return fmaxf(v, 0.f); }); break;
-                        default: store_rows([](float v) { return v; }); break;
+                        case SCP_ACT_GELU: store_rows([](f32x2 v) { return tc_gelu2(v); }); break;
+                        case SCP_ACT_LEAKY001: store_rows([&](f32x2 v) { return each(v, [](float x) { return x > 0.f ? x : 0.01f * x; }); }); break;
+                        case SCP_ACT_RELU: store_rows([&](f32x2 v) { return each(v, [](float x) { return fmaxf(x, 0.f); }); }); break;
+                        default: store_rows([](f32x2 v) { return v; }); break;
                     }
                     __syncwarp();
                     if (ETR && e_n < 960) trace[1024 + e_n++] = clock64();              // chunk: stored
