@@ -256,6 +256,9 @@ int scp_linear(const float* d_x, int64_t ldx, const float* d_w, const float* d_b
                int64_t M, int N, int K, int act, int engine, void* stream);
 /* What SCP_GEMM_AUTO means: 0 = fp32 SIMT everywhere, 1 = tcgen05 3xTF32 for the large layers. Returns the old value. */
 int scp_set_auto_engine(int use_tf32);
+/* CTAs per thread-block cluster of the K <= 256 tensor-core layers with many rows (1, 2 or 4; default 2, SCP_GEMM_CL): the CTAs of
+   a cluster share the weight stream by TMA multicast.  Results do not depend on it (same MMAs, same order).  Returns the old value. */
+int scp_set_gemm_cluster(int ctas);
 /* Drops the cached hi/lo splits of weight matrices (call after weights changed in place). */
 void scp_gemm_cache_clear(void);
 /* Drops the cached splits of ONE weight matrix (keyed by its device pointer).  The cache cannot see contents: the host

@@ -90,6 +90,7 @@ SIGNATURES = {
     "scp_seqs_total": (_i64, [_vp]),
     "scp_linear": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp]),
     "scp_set_auto_engine": (_i, [_i]),
+    "scp_set_gemm_cluster": (_i, [_i]),
     "scp_gemm_cache_clear": (None, []),
     "scp_gemm_cache_drop": (None, [_vp]),
     "scp_set_knn_engine": (_i, [_i]),

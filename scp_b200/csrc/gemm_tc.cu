@@ -347,7 +347,14 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
 // exact inverse, read from `oscale`), the activations are taken as they are -- |x| < 65504 converts with saturation,
 // and what falls below the fp16 subnormal step (2^-24) is an ABSOLUTE error of 3e-8 per product term, far below the
 // 2^-22 relative error of the split itself for the O(1) activations of this model.
-template <int BN, int STAGES, bool H>
+//
+// CL > 1 (A-stationary order only): a thread-block CLUSTER of CL CTAs walks the N tiles of CL different M blocks in lock-step and
+// shares the weight stream -- every CTA fetches 1/CL of each W_hi / W_lo tile and TMA-multicasts it into the same stage of all
+// CL CTAs.  The K <= 256 layers are bound by L2 bandwidth, not by the tensor pipe: every 128-row M block streams the whole
+// weight matrix (hi + lo) from L2, 4.3 GB per call of the N = 1024 layer against 2.5 GB of activations, and the kernel time
+// follows the L2 byte count at ~7.5 TB/s with or without the output stores (tools/exp_gemm_time.py, SCP_GEMM_DBG runs of
+// round 2).  A stage may be refilled when the MMAs of ALL CL CTAs have read it: empty[] counts CL multicast commits.
+template <int BN, int STAGES, bool H, int CL = 1>
 __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ CUtensorMap tmBlo,
@@ -380,7 +387,16 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
     // its fp32 A block (128 KB at K = 256) for each of the 6-8 N tiles of the layer, which made the K = 256 layers
     // L2 -> shared-memory bound (8.4 TB/s of L2 reads) and kept the splitter warps as busy as the tensor pipe.
     const long long n_mblk = (M + BM - 1) / BM;
+    const int cl_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
     auto tile_of = [&](long long it, int& m_blk, int& n_blk) -> bool {
+        if (CL > 1) {
+            // cluster c takes the M blocks [CL (c + r n_clusters), +CL) in round r; a block past the end (odd tail) is a phantom:
+            // its TMA boxes are zero-filled and its stores masked, and the CTA keeps the cluster's barriers in step
+            const long long first = ((long long)(blockIdx.x / CL) + (it / n_tiles_n) * (gridDim.x / CL)) * CL;
+            m_blk = (int)(first + cl_rank); n_blk = (int)(it % n_tiles_n);
+            return first < n_mblk;
+        }
         if (a_stationary) {
             const long long m = (long long)blockIdx.x + (it / n_tiles_n) * gridDim.x;
             m_blk = (int)m; n_blk = (int)(it % n_tiles_n);
@@ -397,7 +413,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBlo)) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 4); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); mbar_init(&ready[s], 4); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -408,6 +424,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                        // every CTA's barriers exist before a peer's TMA or commit signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -423,8 +440,14 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                     mbar_expect_tx(&full[stage], load_a ? STAGE_BYTES : 2 * B_BYTES);
                     if (load_a) tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
                     if (H && load_a) tma_load_2d(a + BM * 128, &tmA, &full[stage], kb * BK + 32, m_blk * BM);   // second 32-wide fp32 box
+                    if (CL > 1) {                          // this CTA's 1/CL of the weight tile, to every CTA of the cluster
+                        constexpr int ROWS = BN / CL;
+                        tma_load_2d_mc(a + OFF_B + cl_rank * ROWS * 128, &tmB, &full[stage], kb * BK, n_blk * BN + cl_rank * ROWS, CL_MASK);
+                        tma_load_2d_mc(a + OFF_BLO + cl_rank * ROWS * 128, &tmBlo, &full[stage], kb * BK, n_blk * BN + cl_rank * ROWS, CL_MASK);
+                    } else {
                     tma_load_2d(a + OFF_B, &tmB, &full[stage], kb * BK, n_blk * BN);
                     tma_load_2d(a + OFF_BLO, &tmBlo, &full[stage], kb * BK, n_blk * BN);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -465,6 +488,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                             tc_mma_tf32_ts(d_tmem, ah + 8u * k, dbl + o, idesc, 1u);
                         }
                     }
+                    if (CL > 1) tc_commit_mc(&empty[stage], CL_MASK);   // ... in every CTA of the cluster (their TMA writes this stage too)
+                    else
                     tc_commit(&empty[stage]);              // frees the smem stage and its TMEM A slot when these MMAs retire
                     if (kb == n_kb - 1) tc_commit(&tfull[acc]);   // accumulator ready for the epilogue
                 }
@@ -647,6 +672,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                        // no CTA leaves while a peer may still multicast into it or signal its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -849,6 +875,43 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     return SCP_OK;
 }
 
+int g_gemm_cluster = getenv("SCP_GEMM_CL") ? atoi(getenv("SCP_GEMM_CL")) : 2;     // CTAs per cluster of the K <= 256 layers (1 | 2 | 4)
+
+// Cluster launch of the A-stationary kernel (CL CTAs share the weight stream by TMA multicast).  `mb` / `mbl` have boxes of
+// BN / CL rows.  Returns SCP_OK, or a negative value when the cluster cannot be scheduled (the caller falls back to CL = 1).
+template <int BN, int STAGES, int CL>
+static int launch_ts_cl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, const float* res,
+                        long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st, const float* oscale) {
+    constexpr int smem = STAGES * (128 * 256 + 2 * BN * 128) + 1024 + 512 + 8 * 32 * 32 * 4;
+    auto kern = k_gemm_x3_ts<BN, STAGES, true, CL>;
+    static int n_clusters = 0;                              // co-resident clusters of CL CTAs (one CTA per SM)
+    if (!n_clusters) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); n_clusters = -1; }
+        else {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(CL * 64); q.blockDim = dim3(512); q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            q.attrs = at; q.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n_clusters = -1; }
+            else n_clusters = n;
+        }
+    }
+    if (n_clusters <= 0) return -1;
+    const long long n_mblk = cdiv(M, 128);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(CL * std::min<long long>(cdiv(n_mblk, CL), n_clusters)));
+    cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    long long* no_trace = nullptr;
+    SCP_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, oscale, 1, no_trace));
+    SCP_LAUNCHED();
+    return SCP_OK;
+}
+
 template <int BN, int STAGES, bool H>
 static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbl, const float* bias, const float* res,
                      long long ldr, float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st,
@@ -906,6 +969,18 @@ int linear_tf32(const float* x, long long ldx, const float* w, const float* bias
         const float* osc = nullptr;
         if (int e = get_weight_split_f16(w, N, K, st, &wh, &osc)) return e;
         const int BN = N > 64 ? 128 : 64;
+        // K <= 256 layers with many M blocks: clusters share the weight stream (SCP_GEMM_CL = 1 | 2 | 4; default 2)
+        const int cl = g_gemm_cluster;
+        static int n_sm = 0;
+        if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+        if (BN == 128 && cl > 1 && K <= 256 && N % 128 == 0 && N >= 256 && cdiv(M, 128) >= 2 * n_sm) {
+            const int rows = 128 / (cl >= 4 ? 4 : 2);
+            if (int e = get_tensor_map_2d_t(wh, K, N, K, rows, 1, &mb)) return e;
+            if (int e = get_tensor_map_2d_t(wh + (long long)N * K, K, N, K, rows, 1, &mbl)) return e;
+            const int r = cl >= 4 ? launch_ts_cl<128, 3, 4>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st, osc)
+                                  : launch_ts_cl<128, 3, 2>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st, osc);
+            if (r >= 0) return r;                            // < 0: clusters cannot be scheduled here -> single-CTA kernel below
+        }
         if (int e = get_tensor_map_2d_t(wh, K, N, K, BN, 1, &mb)) return e;
         if (int e = get_tensor_map_2d_t(wh + (long long)N * K, K, N, K, BN, 1, &mbl)) return e;
         if (BN == 128) return launch_ts<128, 3, true>(ma, mb, mbl, bias, res, ldr, y, ldy, M, N, K, act, st, osc);

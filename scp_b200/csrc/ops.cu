@@ -39,6 +39,7 @@ int linear_tf32(const float* x, long long ldx, const float* w, const float* bias
                 float* y, long long ldy, long long M, int N, int K, int act, cudaStream_t st, int split);   // gemm_tc.cu
 void gemm_cache_clear();
 void gemm_cache_drop(const void* w);
+extern int g_gemm_cluster;
 bool knn_tc_ok(int d, int k);                                                                      // knn_tc.cu
 int knn_tc(const float* d_x, long long ldx, int d, const long long* h_off, int n_seq, const long long* d_off,
            const int* d_tile_seq, const int* d_tile_start, int n_work, int k, int* d_idx, cudaStream_t st);
@@ -1001,6 +1002,8 @@ int scp_set_knn_engine(int use_tensor_cores) { int old = g_knn_tc; g_knn_tc = us
 int scp_set_attn_engine(int mode) { int old = g_attn_tc; g_attn_tc = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return old; }
 
 int scp_set_auto_engine(int mode) { int old = g_auto_tf32; g_auto_tf32 = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return old; }
+
+int scp_set_gemm_cluster(int ctas) { int old = g_gemm_cluster; g_gemm_cluster = ctas >= 4 ? 4 : (ctas >= 2 ? 2 : 1); return old; }
 
 int scp_linear_tf32_supported(int64_t ldx, int64_t ldy, int64_t M, int N, int K) {
     return linear_tf32_ok(ldx, ldy, M, N, K, nullptr, nullptr, nullptr) ? 1 : 0;

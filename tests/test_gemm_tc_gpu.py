@@ -118,3 +118,34 @@ def test_weight_split_cache_follows_the_weights():
         assert not torch.equal(before[0], after[0])
         for a, b in zip(after, want):
             assert torch.equal(a, b), cls.__name__
+
+
+@pytest.mark.parametrize("M,N,K,act,res", [(70001, 768, 256, "none", False), (75000, 1024, 256, "gelu", False),
+                                           (90000, 256, 256, "none", True), (60000, 512, 192, "leaky", False)])
+def test_cluster_multicast_is_bit_identical(M, N, K, act, res):
+    """K <= 256 layers with many rows run in thread-block clusters that share the weight stream by TMA multicast (csrc/gemm_tc.cu,
+    CL = 2 or 4): same MMAs in the same order as the single-CTA kernel, so the result must not change by a bit -- including the
+    phantom M block of an odd tail and rows past M."""
+    from scp_b200.ops import CudaOps
+    cu = CudaOps(engine="f16x3")
+    cu.lib.scp_gemm_cache_clear()
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) * 0.1).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    r = torch.randn(M, N, generator=g).cuda() if res else None
+    outs = []
+    for cl in (1, 2, 4):
+        old = cu.lib.scp_set_gemm_cluster(cl)
+        y = torch.full((M + 300, N), float("nan"), device="cuda")
+        cu.linear(V(x), w, b, V(y[:M]), act=act, res=V(r) if res else None)
+        torch.cuda.synchronize()
+        cu.lib.scp_set_gemm_cluster(old)
+        assert torch.isnan(y[M:]).all()                      # nothing written past the last row
+        outs.append(y[:M].clone())
+    ref = x.double() @ w.double().T + b.double()
+    ref = {"none": lambda t: t, "leaky": lambda t: torch.nn.functional.leaky_relu(t, 0.01), "gelu": torch.nn.functional.gelu}[act](ref)
+    if res:
+        ref = ref + r.double()
+    assert (outs[0].double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
