@@ -368,14 +368,23 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
     constexpr int OFF_B = A_BYTES, OFF_BLO = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 512, T_A = 256;
     static_assert(2 * BN <= 256 && STAGES * 64 <= 256, "TMEM budget");
+    // A-stationary order: the ring is cut into stages of ONE operand K block each -- an A block (fp32, only for the first N tile of
+    // an M block) or a [W_hi | W_lo] block -- instead of [A | W_hi | W_lo] stages whose A third stays empty for 5-7 of every 6-8
+    // tiles.  Same shared memory, twice the stages in flight: the mainloop of the K <= 256 layers was bound by the latency of
+    // the weight stream (one K block every ~950 cycles whether 12 MMAs or 4 were issued on it, and whether or not clusters halved
+    // the L2 reads: three 32 KB loads in flight against ~2500 cycles from TMA issue to the stage's release).
+    constexpr int AS_STAGE_BYTES = A_BYTES > 2 * B_BYTES ? A_BYTES : 2 * B_BYTES;
+    constexpr int AS_STAGES = (STAGES * STAGE_BYTES) / AS_STAGE_BYTES;
+    constexpr int NBAR = AS_STAGES > STAGES ? AS_STAGES : STAGES;
+    static_assert((3 * NBAR + 4) * 8 + 8 <= 512, "barrier block");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;
+    uint64_t* empty = full + NBAR;
+    uint64_t* tfull = empty + NBAR;
     uint64_t* tempty = tfull + 2;
-    uint64_t* ready = tempty + 2;                        // A_hi / A_lo of the stage are in TMEM (4 splitter warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + STAGES);
+    uint64_t* ready = tempty + 2;                        // A_hi / A_lo of the stage (A-stationary: of K block kb) are in TMEM (4 splitter warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + NBAR);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles_n = (N + BN - 1) / BN;
@@ -413,7 +422,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBlo)) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); mbar_init(&ready[s], 4); }
+        for (int s = 0; s < NBAR; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); mbar_init(&ready[s], 4); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -428,7 +437,40 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 && a_stationary) {
+        int stage = 0; uint32_t phase = 0;                  // all lanes run the loop, the elected lane issues (uniform operands)
+        int m_blk, n_blk;
+        for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
+            for (int kb = 0; kb < n_kb; ++kb) {
+                if (n_blk == 0) {                           // the M block's activations: one stage per K block, consumed by the splitters
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* a = smem + stage * AS_STAGE_BYTES;
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[stage], A_BYTES);
+                        tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
+                        if (H) tma_load_2d(a + BM * 128, &tmA, &full[stage], kb * BK + 32, m_blk * BM);      // second 32-wide fp32 box
+                    }
+                    __syncwarp();
+                    if (++stage == AS_STAGES) { stage = 0; phase ^= 1; }
+                }
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* b = smem + stage * AS_STAGE_BYTES;
+                if (elect_one()) {
+                    mbar_expect_tx(&full[stage], 2 * B_BYTES);
+                    if (CL > 1) {                          // this CTA's 1/CL of the weight tile, to every CTA of the cluster
+                        constexpr int ROWS = BN / CL;
+                        tma_load_2d_mc(b + cl_rank * ROWS * 128, &tmB, &full[stage], kb * BK, n_blk * BN + cl_rank * ROWS, CL_MASK);
+                        tma_load_2d_mc(b + B_BYTES + cl_rank * ROWS * 128, &tmBlo, &full[stage], kb * BK, n_blk * BN + cl_rank * ROWS, CL_MASK);
+                    } else {
+                        tma_load_2d(b, &tmB, &full[stage], kb * BK, n_blk * BN);
+                        tma_load_2d(b + B_BYTES, &tmBlo, &full[stage], kb * BK, n_blk * BN);
+                    }
+                }
+                __syncwarp();
+                if (++stage == AS_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 0) {
         int stage = 0; uint32_t phase = 0;                  // all lanes run the loop, the elected lane issues (uniform operands)
         int m_blk, n_blk;
         for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
@@ -452,6 +494,57 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+        }
+    } else if (warp == 1 && a_stationary) {
+        // all lanes run the loop (warp-uniform operands -> uniform registers), the elected lane issues; see tc.cuh elect_one()
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);                        // f16 x f16 -> f32
+        int stage = 0; uint32_t phase = 0, mb_phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        int m_blk, n_blk;
+        int tr_n = 0;                                      // development aid (SCP_GEMM_TRACE=1): clock stamps of CTA 0's MMA warp
+        const bool TR = trace && blockIdx.x == 0;
+        for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
+            if (TR && lane == 0 && tr_n < 480) trace[tr_n++] = clock64();            // tile: before the accumulator wait
+            mbar_wait(&tempty[acc], acc_phase ^ 1);
+            if (TR && lane == 0 && tr_n < 480) trace[tr_n++] = clock64();            // tile: accumulator free
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                if (n_blk == 0) {
+                    // A_hi / A_lo of this K block are in TMEM: the splitters have read the A stage, hand it back to the producer
+                    // (in EVERY CTA of the cluster: the stage's next use may be a weight block that the peers multicast into it)
+                    mbar_wait(&ready[kb], mb_phase);
+                    // -- and through a multicast COMMIT, not a plain remote arrive: the arrivals of this CTA must reach a peer's
+                    // barrier in the order of the stage's uses, and the commits of its earlier weight blocks are still in flight)
+                    if (elect_one()) {
+                        if (CL > 1) tc_commit_mc(&empty[stage], CL_MASK);
+                        else mbar_arrive(&empty[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == AS_STAGES) { stage = 0; phase ^= 1; }
+                }
+                mbar_wait(&full[stage], phase);
+                if (TR && lane == 0 && tr_n < 480) trace[tr_n++] = clock64();        // K block: operands ready
+                tc_fence_after();
+                const uint8_t* b = smem + stage * AS_STAGE_BYTES;
+                const uint64_t db = make_smem_desc(b), dbl = make_smem_desc(b + B_BYTES);
+                const uint32_t ah = tmem_base + T_A + (uint32_t)(kb * 64), al = ah + 32u;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {          // 16 fp16 = 8 TMEM columns of A = 2 descriptor units of B per MMA
+                        const uint64_t o = (uint64_t)(2 * k);
+                        tc_mma_f16_ts(d_tmem, ah + 8u * k, db + o, idesc, (kb | k) ? 1u : 0u);
+                        tc_mma_f16_ts(d_tmem, al + 8u * k, db + o, idesc, 1u);
+                        tc_mma_f16_ts(d_tmem, ah + 8u * k, dbl + o, idesc, 1u);
+                    }
+                    if (CL > 1) tc_commit_mc(&empty[stage], CL_MASK);   // in every CTA of the cluster (their TMA writes this stage too)
+                    else tc_commit(&empty[stage]);         // frees the stage when these MMAs retire
+                    if (kb == n_kb - 1) tc_commit(&tfull[acc]);   // accumulator ready for the epilogue
+                }
+                __syncwarp();
+                if (++stage == AS_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (n_blk == n_tiles_n - 1) mb_phase ^= 1;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp == 1) {
         // all lanes run the loop (warp-uniform operands -> uniform registers), the elected lane issues; see tc.cuh elect_one()
@@ -497,6 +590,50 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else if (warp >= 4 && warp < 8 && a_stationary) {
+        // splitter, A-stationary order: only the first N tile of an M block has A stages; thread = row of the A tile
+        if constexpr (H) {
+            const int row = (warp - 4) * 32 + lane;
+            const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + T_A;
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            int m_blk, n_blk;
+            for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
+                if (n_blk == 0) {
+                    // (the resident A of the previous M block was read by the MMAs of its last tile: this warp has seen that
+                    // tile's accumulator complete, below)
+                    for (int kb = 0; kb < n_kb; ++kb) {
+                        mbar_wait(&full[stage], phase);
+                        const uint8_t* a = smem + stage * AS_STAGE_BYTES + row * 128;
+                        uint32_t hi[32], lo[32];
+                        // 64 fp32 of the row (two boxes) -> 32 + 32 packed fp16 pairs, even k in the low half
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const float4 v = *reinterpret_cast<const float4*>(a + (c >> 3) * (BM * 128) + (((c & 7) ^ (row & 7)) << 4));
+                            split_f16x2(v.x, v.y, hi[2 * c], lo[2 * c]);
+                            split_f16x2(v.z, v.w, hi[2 * c + 1], lo[2 * c + 1]);
+                        }
+                        tc_st32(t_lane + (uint32_t)(kb * 64), hi);
+                        tc_st32(t_lane + (uint32_t)(kb * 64) + 32u, lo);
+                        tc_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ready[kb]);           // (release: the stage's shared-memory reads are done as well)
+                        if (++stage == AS_STAGES) { stage = 0; phase ^= 1; }      // the A stage ...
+                        if (++stage == AS_STAGES) { stage = 0; phase ^= 1; }      // ... and the weight stage behind it
+                    }
+                } else {
+                    for (int kb = 0; kb < n_kb; ++kb)
+                        if (++stage == AS_STAGES) { stage = 0; phase ^= 1; }
+                }
+                // Follow EVERY tile's accumulator barrier: a parity wait only tells "the phase before the current one is over", so a
+                // warp that skipped the five later tiles of an M block and then waited for the last one would be let through by the
+                // first (and overwrite the resident A under the MMAs that still read it).
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
         }
     } else if (warp >= 4 && warp < 8) {
         // splitter: thread = row of the A tile; its 128 bytes sit in 8 swizzled 16-byte chunks of the row's line
