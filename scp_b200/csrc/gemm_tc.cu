@@ -471,25 +471,19 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
             }
         }
     } else if (warp == 0) {
+        // streaming order (K > 256, or too few M blocks): every tile loads [A | W_hi | W_lo] stages
         int stage = 0; uint32_t phase = 0;                  // all lanes run the loop, the elected lane issues (uniform operands)
         int m_blk, n_blk;
         for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
-            const bool load_a = !a_stationary || n_blk == 0;
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* a = smem + stage * STAGE_BYTES;
                 if (elect_one()) {
-                    mbar_expect_tx(&full[stage], load_a ? STAGE_BYTES : 2 * B_BYTES);
-                    if (load_a) tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
-                    if (H && load_a) tma_load_2d(a + BM * 128, &tmA, &full[stage], kb * BK + 32, m_blk * BM);   // second 32-wide fp32 box
-                    if (CL > 1) {                          // this CTA's 1/CL of the weight tile, to every CTA of the cluster
-                        constexpr int ROWS = BN / CL;
-                        tma_load_2d_mc(a + OFF_B + cl_rank * ROWS * 128, &tmB, &full[stage], kb * BK, n_blk * BN + cl_rank * ROWS, CL_MASK);
-                        tma_load_2d_mc(a + OFF_BLO + cl_rank * ROWS * 128, &tmBlo, &full[stage], kb * BK, n_blk * BN + cl_rank * ROWS, CL_MASK);
-                    } else {
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_2d(a, &tmA, &full[stage], kb * BK, m_blk * BM);
+                    if (H) tma_load_2d(a + BM * 128, &tmA, &full[stage], kb * BK + 32, m_blk * BM);   // second 32-wide fp32 box
                     tma_load_2d(a + OFF_B, &tmB, &full[stage], kb * BK, n_blk * BN);
                     tma_load_2d(a + OFF_BLO, &tmBlo, &full[stage], kb * BK, n_blk * BN);
-                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -566,7 +560,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                 tc_fence_after();
                 const uint8_t* a = smem + stage * STAGE_BYTES;
                 const uint64_t db = make_smem_desc(a + OFF_B), dbl = make_smem_desc(a + OFF_BLO);
-                const uint32_t ah = tmem_base + T_A + (uint32_t)((a_stationary ? kb : stage) * 64), al = ah + 32u;
+                const uint32_t ah = tmem_base + T_A + (uint32_t)(stage * 64), al = ah + 32u;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {          // 8 tf32 / 16 fp16 = 8 TMEM columns of A = 2 descriptor units of B per MMA
@@ -640,23 +634,10 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
         const int row = (warp - 4) * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp - 4) * 32) << 16) + T_A;
         int stage = 0; uint32_t phase = 0;
-        int acc = 0, prev_acc = 0; uint32_t acc_phase = 0, prev_phase = 0;
         int m_blk, n_blk;
         for (long long it = 0; tile_of(it, m_blk, n_blk); ++it) {
-            const bool split_a = !a_stationary || n_blk == 0;
-            if (a_stationary && n_blk == 0 && it > 0) {
-                // the resident A of the previous M block is still read by the MMAs of its last tile: wait for that accumulator
-                mbar_wait(&tfull[prev_acc], prev_phase);
-                tc_fence_after();
-            }
             for (int kb = 0; kb < n_kb; ++kb) {
                 mbar_wait(&full[stage], phase);
-                if (!split_a) {                            // weights only: nothing to split, keep the barrier phases in step
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_relaxed(&ready[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    continue;
-                }
                 const uint8_t* a = smem + stage * STAGE_BYTES + row * 128;
                 uint32_t hi[32], lo[32];
                 if (H) {
@@ -679,8 +660,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                     lo[4 * c + 3] = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(hi[4 * c + 3]));
                 }
                 }
-                tc_st32(t_lane + (uint32_t)((a_stationary ? kb : stage) * 64), hi);
-                tc_st32(t_lane + (uint32_t)((a_stationary ? kb : stage) * 64) + 32u, lo);
+                tc_st32(t_lane + (uint32_t)(stage * 64), hi);
+                tc_st32(t_lane + (uint32_t)(stage * 64) + 32u, lo);
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
@@ -688,8 +669,6 @@ __global__ void __launch_bounds__(512, 1) k_gemm_x3_ts(const __grid_constant__ C
                                                                          // generic memory to publish, and a release arrive costs a MEMBAR
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            prev_acc = acc; prev_phase = acc_phase;
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else if (warp >= 8) {
         // epilogue: as in k_gemm_tf32, one 32-column chunk at a time (128-register budget)

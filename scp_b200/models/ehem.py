@@ -119,7 +119,7 @@ class EHEM(nn.Module):
             cur = dst
         return out
 
-    def _swin_layer(self, pre, h, seqs, shift, query=None):
+    def _swin_layer(self, pre, h, seqs, shift, query=None, dst=None):
         ops, P = self.ops, self._prep
         sd = P["sd"]
         T = h.shape[0]
@@ -148,7 +148,7 @@ class EHEM(nn.Module):
         ops.layernorm(V(h2), sd[f"{pre}.layernorm_after.weight"], sd[f"{pre}.layernorm_after.bias"], V(ln))
         mid = ops.empty(T, 1024, h)
         ops.linear(V(ln), sd[f"{pre}.intermediate.dense.weight"], sd[f"{pre}.intermediate.dense.bias"], V(mid), act="gelu")
-        h3 = ops.empty(T, 256, h)
+        h3 = ops.empty(T, 256, h) if dst is None else dst            # dst: a [T,256] column slice of the concatenated states
         ops.linear(V(mid), sd[f"{pre}.output.dense.weight"], sd[f"{pre}.output.dense.bias"], V(h3), res=V(h2))
         return h3
 
@@ -170,10 +170,10 @@ class EHEM(nn.Module):
         fine = seqs
         for i, depth in enumerate(depths):
             for j in range(depth):
-                h = self._swin_layer(f"{enc}.layers.{i}.blocks.{j}", h, seqs, 0 if j % 2 == 0 else W.SWIN_WINDOW // 2, query)
-            if i == 0:
-                ops.copy_cols(V(h), V(out, 0, 256))
-            else:
+                # the last block of stage 0 writes its output straight into the first 256 columns of `out` (no copy)
+                h = self._swin_layer(f"{enc}.layers.{i}.blocks.{j}", h, seqs, 0 if j % 2 == 0 else W.SWIN_WINDOW // 2, query,
+                                     dst=out[:, 0:256] if (i == 0 and j == depth - 1) else None)
+            if i > 0:
                 ops.upsample_cols(V(h), seqs, fine, i, V(out, 256 * i, 256))
             if i < len(depths) - 1:
                 pre = f"{enc}.layers.{i}.downsample"
@@ -268,8 +268,7 @@ class EHEM(nn.Module):
         self._mlp("pre_attn_mlp", V(feat_a), V(PRE, 16, 240), row_step=2, row_off=0, rows=H)
         CROSS = ops.empty(H, 1280, pos)
         ops.copy_cols(V(feat_a), V(CROSS, 1024, 256), row_step=2, row_off=1, rows=H)
-        fa2 = ops.empty(H, 256, pos)
-        ops.copy_cols(V(feat_a), V(fa2), row_step=2, row_off=1, rows=H)
+        fa2 = CROSS[:, 1024:1280]                                 # the odd tokens' ancestor features: query stream of the cross encoder
         self._swin_encoder("swin_cross_transformer", W.EHEM_CROSS_DEPTHS, PRE, half, CROSS, query=fa2)
         logits2 = ops.empty(H, 255, pos)
         self._mlp("prob_pred_mlp2", V(CROSS), V(logits2))
