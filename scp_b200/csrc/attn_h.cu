@@ -22,6 +22,7 @@
 // matrices, from which the chunks arrive by TMA in the K-major 128B-swizzled layout.  Staging the chunks with loader warps
 // inside the kernel (as attn_tc.cu does) re-converts every chunk for each of the four query blocks of a window and, with
 // the three loader warps that fit next to a second CTA, set the pace of the whole kernel (measured: 8.7 k cycles per chunk).
+#include <algorithm>
 #include <stdlib.h>
 #include <cuda_fp16.h>
 #include "tc.cuh"
@@ -129,7 +130,12 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
                                                                 const float* __restrict__ qb, const float* __restrict__ relpos,
                                                                 int heads, const long long* __restrict__ seq_off,
                                                                 const int* __restrict__ win_seq, const int* __restrict__ win_idx,
-                                                                int shift, float* __restrict__ O, long long ldo) {
+                                                                int shift, float* __restrict__ O, long long ldo, int n_win) {
+    // PERSISTENT: the grid is a multiple of `heads` CTAs (two per SM); CTA c keeps head c % heads (its relative-position table is
+    // loaded once) and walks the (window, query block) pairs c / heads, + gridDim.x / heads, ...  TMEM, barriers and the table
+    // are set up once per CTA instead of once per 128 queries (the set-up was ~9000 of the ~30 000 cycles of a work item).  Every
+    // chunk barrier completes an even number of phases per work item (4), so the parities of the chunk loop repeat unchanged;
+    // q_full (1 phase per item) and o_ready (7) carry the item count.
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* s_bias = reinterpret_cast<float*>(sm + AH_OFF_BIAS);
@@ -145,18 +151,23 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int h = blockIdx.x % heads, qblk = blockIdx.x / heads;
-    const int gw = blockIdx.y;
-    const int s = win_seq[gw], w = win_idx[gw];
-    const long long base = seq_off[s];
-    const int S = (int)(seq_off[s + 1] - base);
-    const int Sp = ((S + AH_WS - 1) / AH_WS) * AH_WS;
-    const bool last_win = (w == Sp / AH_WS - 1) && shift > 0;
-    // rolled position of this block's first query row; blocks are 128-aligned inside the 512-aligned padded sequence,
-    // so a block never wraps and it has real (stored) rows iff its first row is real
-    int q_start = w * AH_WS + qblk * AH_BQ + shift;
-    if (q_start >= Sp) q_start -= Sp;
-    if (q_start >= S) return;                                              // CTA-uniform, before any barrier / TMEM use
+    const int h = blockIdx.x % heads;
+    const int pair0 = blockIdx.x / heads, pair_step = gridDim.x / heads, n_pairs = n_win * (AH_WS / AH_BQ);
+    // work item `pair`: window gw, query block qblk.  Returns false for a block without real (stored) rows: blocks are
+    // 128-aligned inside the 512-aligned padded sequence, so a block never wraps and has real rows iff its first row is real
+    struct Item { int gw, qblk, S, q_start; long long base; bool last_win; };
+    auto item_of = [&](int pair, Item& I) -> bool {
+        I.gw = pair / (AH_WS / AH_BQ); I.qblk = pair % (AH_WS / AH_BQ);
+        const int s = win_seq[I.gw], w = win_idx[I.gw];
+        I.base = seq_off[s];
+        I.S = (int)(seq_off[s + 1] - I.base);
+        const int Sp = ((I.S + AH_WS - 1) / AH_WS) * AH_WS;
+        I.last_win = (w == Sp / AH_WS - 1) && shift > 0;
+        int q_start = w * AH_WS + I.qblk * AH_BQ + shift;                  // rolled position of the block's first query row
+        if (q_start >= Sp) q_start -= Sp;
+        I.q_start = q_start;
+        return q_start < I.S;
+    };
 
     if (warp == 8) {
         if (lane == 0) {
@@ -187,7 +198,15 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
         const int quarter = warp & 3, half = warp >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+        Item I;
+        uint32_t it = 0;                                                   // work items of this CTA so far
+        for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+        if (!item_of(pair, I)) continue;
+        const long long base = I.base;
+        const int S = I.S, q_start = I.q_start, qblk = I.qblk;
+        const bool last_win = I.last_win;
         {   // half a Q row -> TMEM: 1/sqrt(64) and log2(e) folded in (softmax(x) = 2^(x log2e - max) / sum), fp16 hi/lo pairs
+            // (the S MMAs of the previous item, the last readers of Q, retired before its last softmax chunk started)
             const int u = q_start + row;
             const float4* src = reinterpret_cast<const float4*>(u < S ? Q + (base + u) * ldq + h * AH_HD : qb + h * AH_HD) + half * 8;
             uint32_t hi[16], lo[16];
@@ -292,10 +311,18 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
                 *reinterpret_cast<float4*>(dst + d) = make_float4(__uint_as_float(o[d]) * inv, __uint_as_float(o[d + 1]) * inv,
                                                                    __uint_as_float(o[d + 2]) * inv, __uint_as_float(o[d + 3]) * inv);
         }
+        tc_fence_before();                                                 // O has been read: the next item's PV(0) may overwrite it
+        ++it;                                                              // (ordered by that item's q_full arrival)
+        }
     } else if (warp == 8) {
         // ---------------- MMA issuer: all lanes run the loop, the elected lane issues (tc.cuh elect_one) ----------------
         const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(AH_BQ >> 4) << 24);     // f16 x f16 -> f32, N = 64
-        mbar_wait(q_full, 0);
+        Item I;
+        uint32_t it = 0;
+        for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+        if (!item_of(pair, I)) continue;
+        mbar_wait(q_full, it & 1);                                         // Q of this item in TMEM, O of the previous one read
+        tc_fence_after();
 #pragma unroll 1
         for (int i = 0; i <= AH_NC; ++i) {
             if (i < AH_NC) {                                               // S(i) = Q K_i^T  (after PV(i-2) in program order,
@@ -321,7 +348,7 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
                 const int j = i - 1, b = j & 1, n = j >> 1;
                 mbar_wait(&v_full[b], n & 1);
                 mbar_wait(&p_full[b], n & 1);
-                if (j > 0) mbar_wait(o_ready, (j - 1) & 1);
+                if (j > 0) mbar_wait(o_ready, (it + (uint32_t)(j - 1)) & 1);      // 7 phases per item
                 tc_fence_after();
                 const uint8_t* vs_ = sm + AH_OFF_V + b * AH_STAGE;
                 const uint32_t p_tmem = tmem + AH_T_SP + (uint32_t)(b * 64);
@@ -340,6 +367,8 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
                 __syncwarp();
             }
         }
+        ++it;
+        }
     } else {
         // ---------------- TMA producer (warp 9): chunk i of the window = padded rows [gw*512 + 64 i, +64) ----------------
         if (lane == 0) {
@@ -348,26 +377,34 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmVh)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmVl)) : "memory");
         }
+        Item I;
+        uint32_t it = 0;
+        for (int pair = pair0; pair < n_pairs; pair += pair_step) {
+        if (!item_of(pair, I)) continue;
+        const int gw = I.gw;
 #pragma unroll 1
         for (int i = 0; i < AH_NC; ++i) {
             const int b = i & 1, n = i >> 1;
             const int prow = gw * AH_WS + i * AH_BK;
             uint8_t* kdst = sm + AH_OFF_K + b * AH_STAGE;
             uint8_t* vdst = sm + AH_OFF_V + b * AH_STAGE;
-            if (n > 0) mbar_wait(&s_full[b], (n - 1) & 1);               // S(i-2) retired: K stage b is free
+            // the stage's previous user: chunk i-2 of this item, or chunk 6 + b of the previous item (its 4th phase: parity 1)
+            if (n > 0 || it > 0) mbar_wait(&s_full[b], (n - 1) & 1);     // S(i-2) retired: K stage b is free
             if (elect_one()) {
                 mbar_expect_tx(&k_full[b], AH_STAGE);
                 tma_load_2d(kdst, &tmKh, &k_full[b], h * AH_HD, prow);
                 tma_load_2d(kdst + AH_TILE, &tmKl, &k_full[b], h * AH_HD, prow);
             }
             __syncwarp();
-            if (n > 0) mbar_wait(&pv_done[b], (n - 1) & 1);              // PV(i-2) retired: V stage b is free
+            if (n > 0 || it > 0) mbar_wait(&pv_done[b], (n - 1) & 1);    // PV(i-2) retired: V stage b is free
             if (elect_one()) {
                 mbar_expect_tx(&v_full[b], AH_STAGE);
                 tma_load_2d(vdst, &tmVh, &v_full[b], prow, h * AH_HD);
                 tma_load_2d(vdst + AH_TILE, &tmVl, &v_full[b], prow, h * AH_HD);
             }
             __syncwarp();
+        }
+        ++it;
         }
     }
     tc_fence_before();
@@ -395,9 +432,13 @@ int swin_attn_h(const float* q, long long ldq, const float* k, long long ldk, co
     if (int e = get_tensor_map_2d_f16(k_lo, cols, rows, (int)cols, 64, &mkl)) return e;
     if (int e = get_tensor_map_2d_f16(vt_hi, rows, cols, (int)rows, 64, &mvh)) return e;
     if (int e = get_tensor_map_2d_f16(vt_lo, rows, cols, (int)rows, 64, &mvl)) return e;
-    dim3 grid((AH_WS / AH_BQ) * heads, n_win);
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    const long long n_items = (long long)n_win * (AH_WS / AH_BQ) * heads;
+    const int slots = std::max(heads, (2 * n_sm / heads) * heads);            // two resident CTAs per SM, a multiple of `heads`
+    const int grid = (int)std::min<long long>(n_items, slots);
     k_swin_attn_h<<<grid, AH_THREADS, AH_SMEM, st>>>(q, ldq, mkh, mkl, mvh, mvl, qb, relpos, heads, d_off, d_win_seq, d_win_idx,
-                                                     shift, out, ldo);
+                                                     shift, out, ldo, n_win);
     SCP_LAUNCHED();
     SCP_CUDA(cudaFreeAsync(buf, st));
     return SCP_OK;
