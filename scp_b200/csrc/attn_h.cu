@@ -57,14 +57,35 @@ __device__ __forceinline__ float ah_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// named barrier of one row quarter (64 threads); the id is an immediate so that ptxas reserves 5 barriers, not all 16
-__device__ __forceinline__ void ah_pair_sync(int quarter) {
-    switch (quarter) {
-        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-    }
+// 16 lanes x 64 columns: register 4 n + {0,1} = (lane l / 4, column 8 n + 2 (l % 4) + {0,1}), 4 n + {2,3} = the same of lane l / 4 + 8
+__device__ __forceinline__ void ah_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void ah_st_16x256b_x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x8.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+          "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+          "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+// 16 lanes x 32 columns: register 2 n + k = (lane l / 4 + 8 k, column 4 n + l % 4)
+__device__ __forceinline__ void ah_st_16x128b_x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void ah_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -139,7 +160,6 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* s_bias = reinterpret_cast<float*>(sm + AH_OFF_BIAS);
-    float* s_xch = reinterpret_cast<float*>(sm + AH_OFF_XCH);      // [2 slots][2 halves][128 rows] pair exchange
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AH_OFF_BAR);
     uint64_t* k_full = bars;            // [2] K chunk landed                                   (TMA, expect_tx)
     uint64_t* v_full = bars + 2;        // [2] V chunk landed                                   (TMA, expect_tx)
@@ -191,13 +211,18 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 8) {
-        // ---------------- softmax + output: TWO threads per query row ----------------
-        // row = 32 (warp & 3) + lane (the TMEM lane quarter of both warps); half = warp >> 2 owns score columns
-        // [32 half, +32) of every chunk and output dims [32 half, +32).  The two threads agree on the chunk maximum through
-        // a shared-memory slot + a 64-thread named barrier; the row sum is joined at the end.
-        const int quarter = warp & 3, half = warp >> 2;
-        const int row = quarter * 32 + lane;
-        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+        // ---------------- softmax + output: a warp owns 16 query rows, FOUR threads per row ----------------
+        // rows = TMEM lanes 32 (warp & 3) + 16 (warp >> 2) + [0, 16).  Scores are read with tcgen05.ld.16x256b (layout verified with
+        // tools/exp/tmem_layout.cu): thread = (g = lane / 4, q = lane % 4) holds, for n = 0..7, columns 8 n + 2 q + {0, 1} of row g
+        // (registers 4 n + 0, 1) and of row g + 8 (registers 4 n + 2, 3).  A row's maximum and sum are quad reductions (two
+        // shuffles) -- the earlier two-threads-per-row form exchanged them through shared memory and a named barrier between two
+        // warps of different schedulers, and that wait was the largest item of the ~2500-cycle softmax chain.  The pair
+        // (column 2 w, 2 w + 1) is exactly one packed fp16 word of P, and tcgen05.st.16x128b puts register 2 n + k at
+        // (row g + 8 k, word 4 n + q): P_hi / P_lo go back without any exchange, and no other warp touches these 16 lanes.
+        const int quarter = warp & 3, rh = warp >> 2;
+        const int g = lane >> 2, q4 = lane & 3;
+        const int rowA = quarter * 32 + rh * 16 + g;                       // rowB = rowA + 8
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32 + rh * 16) << 16);
         Item I;
         uint32_t it = 0;                                                   // work items of this CTA so far
         for (int pair = pair0; pair < n_pairs; pair += pair_step) {
@@ -205,68 +230,71 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
         const long long base = I.base;
         const int S = I.S, q_start = I.q_start, qblk = I.qblk;
         const bool last_win = I.last_win;
-        {   // half a Q row -> TMEM: 1/sqrt(64) and log2(e) folded in (softmax(x) = 2^(x log2e - max) / sum), fp16 hi/lo pairs
+        const int uA = q_start + rowA, uB = uA + 8;
+        {   // two Q rows -> TMEM: 1/sqrt(64) and log2(e) folded in (softmax(x) = 2^(x log2e - max) / sum), fp16 hi/lo pairs
             // (the S MMAs of the previous item, the last readers of Q, retired before its last softmax chunk started)
-            const int u = q_start + row;
-            const float4* src = reinterpret_cast<const float4*>(u < S ? Q + (base + u) * ldq + h * AH_HD : qb + h * AH_HD) + half * 8;
+            const float* srcA = (uA < S ? Q + (base + uA) * ldq + h * AH_HD : qb + h * AH_HD) + 2 * q4;
+            const float* srcB = (uB < S ? Q + (base + uB) * ldq + h * AH_HD : qb + h * AH_HD) + 2 * q4;
             uint32_t hi[16], lo[16];
+            const float qs = 0.125f * AH_LOG2E;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float4 v = __ldg(src + c);
-                const float qs = 0.125f * AH_LOG2E;
-                ah_split2(v.x * qs, v.y * qs, hi[2 * c], lo[2 * c]);
-                ah_split2(v.z * qs, v.w * qs, hi[2 * c + 1], lo[2 * c + 1]);
+            for (int n = 0; n < 8; ++n) {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(srcA + 8 * n));
+                const float2 c = __ldg(reinterpret_cast<const float2*>(srcB + 8 * n));
+                ah_split2(a.x * qs, a.y * qs, hi[2 * n], lo[2 * n]);
+                ah_split2(c.x * qs, c.y * qs, hi[2 * n + 1], lo[2 * n + 1]);
             }
-            tc_st16(trow + AH_T_QH + (uint32_t)(half * 16), hi);
-            tc_st16(trow + AH_T_QL + (uint32_t)(half * 16), lo);
+            ah_st_16x128b_x8(tbase + AH_T_QH, hi);
+            ah_st_16x128b_x8(tbase + AH_T_QL, lo);
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(q_full);
         }
-        float m_run = -INFINITY, l_run = 0.f;
-        const int pi = qblk * AH_BQ + row;                                 // window position of this row
+        float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;         // running maxima; PARTIAL row sums of this thread's columns
+        const int piA = qblk * AH_BQ + rowA;                               // window position of row A (row B: + 8)
 #pragma unroll 1
         for (int i = 0; i < AH_NC; ++i) {
-            const int b = i & 1, n = i >> 1;
-            const uint32_t t_sp = trow + AH_T_SP + (uint32_t)(b * 64);
-            mbar_wait(&s_full[b], n & 1);
+            const int b = i & 1, n_ = i >> 1;
+            const uint32_t t_sp = tbase + AH_T_SP + (uint32_t)(b * 64);
+            mbar_wait(&s_full[b], n_ & 1);
             tc_fence_after();
             uint32_t r[32];
-            tc_ld32(t_sp + (uint32_t)(half * 32), r);
-            // swin_transformer.py:620: -100 on the other half of the last (rolled) window.  A whole chunk is on one side, so
-            // the offset is folded into the running-max bookkeeping instead of being added to all scores.
-            const bool masked = last_win && ((pi < AH_WS / 2) != (i < AH_NC / 2));
+            ah_ld_16x256b_x8(t_sp, r);
+            tc_wait_ld();
+            // swin_transformer.py:620: -100 on the other half of the last (rolled) window.  A whole chunk is on one side (and so is
+            // a 128-row query block), so the offset is folded into the running-max bookkeeping instead of being added to all scores.
+            const bool masked = last_win && ((piA < AH_WS / 2) != (i < AH_NC / 2));
             const float moff = masked ? -100.0f * AH_LOG2E : 0.0f;
-            const float* bp = s_bias + (pi - i * AH_BK - half * 32 + AH_WS - 1);
-            float cmax = -INFINITY;
+            const float* bpA = s_bias + (piA - i * AH_BK + AH_WS - 1 - 2 * q4);    // bias of (row, key column c) = bp[-c]
+            float cA = -INFINITY, cB = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float v = __uint_as_float(r[j]) + bp[-j];
-                r[j] = __float_as_uint(v);
-                cmax = fmaxf(cmax, v);
+            for (int n = 0; n < 8; ++n) {
+                const float a0 = __uint_as_float(r[4 * n]) + bpA[-8 * n], a1 = __uint_as_float(r[4 * n + 1]) + bpA[-8 * n - 1];
+                const float b0 = __uint_as_float(r[4 * n + 2]) + bpA[8 - 8 * n], b1 = __uint_as_float(r[4 * n + 3]) + bpA[8 - 8 * n - 1];
+                r[4 * n] = __float_as_uint(a0); r[4 * n + 1] = __float_as_uint(a1);
+                r[4 * n + 2] = __float_as_uint(b0); r[4 * n + 3] = __float_as_uint(b1);
+                cA = fmaxf(cA, fmaxf(a0, a1)); cB = fmaxf(cB, fmaxf(b0, b1));
             }
-            // chunk maximum of the whole row: exchange with the partner thread (slot alternates per chunk, one barrier).  After
-            // the barrier both threads hold their S columns in registers, so P may overwrite the chunk in place.
-            float* slot = s_xch + (i & 1) * 256;
-            slot[half * 128 + row] = cmax;
-            ah_pair_sync(quarter);
-            cmax = fmaxf(cmax, slot[(half ^ 1) * 128 + row]);
-            const float mx = fmaxf(m_run, cmax + moff);
-            const float alpha = ah_ex2(m_run - mx);                        // 0 on the first chunk (m_run = -inf)
-            m_run = mx;
-            const float sub = mx - moff;
-            float sum = 0.f;
-            uint32_t lo[16];
+            cA = fmaxf(cA, __shfl_xor_sync(0xffffffffu, cA, 1)); cB = fmaxf(cB, __shfl_xor_sync(0xffffffffu, cB, 1));
+            cA = fmaxf(cA, __shfl_xor_sync(0xffffffffu, cA, 2)); cB = fmaxf(cB, __shfl_xor_sync(0xffffffffu, cB, 2));
+            const float mxA = fmaxf(mA, cA + moff), mxB = fmaxf(mB, cB + moff);
+            const float alA = ah_ex2(mA - mxA), alB = ah_ex2(mB - mxB);    // 0 on the first chunk (m = -inf)
+            mA = mxA; mB = mxB;
+            const float subA = mxA - moff, subB = mxB - moff;
+            float sA = 0.f, sB = 0.f;
+            uint32_t ph[16], pl[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float p0 = ah_ex2(__uint_as_float(r[2 * j]) - sub), p1 = ah_ex2(__uint_as_float(r[2 * j + 1]) - sub);
-                sum += p0 + p1;
-                ah_split2(p0, p1, r[j], lo[j]);                            // r[0..16) becomes P_hi (pairs of keys, even key low)
+            for (int n = 0; n < 8; ++n) {
+                const float a0 = ah_ex2(__uint_as_float(r[4 * n]) - subA), a1 = ah_ex2(__uint_as_float(r[4 * n + 1]) - subA);
+                const float b0 = ah_ex2(__uint_as_float(r[4 * n + 2]) - subB), b1 = ah_ex2(__uint_as_float(r[4 * n + 3]) - subB);
+                sA += a0 + a1; sB += b0 + b1;
+                ah_split2(a0, a1, ph[2 * n], pl[2 * n]);                   // word 4 n + q of row A: keys 8 n + 2 q, + 1 (even key low)
+                ah_split2(b0, b1, ph[2 * n + 1], pl[2 * n + 1]);
             }
-            l_run = fmaf(l_run, alpha, sum);
-            tc_st16(t_sp + (uint32_t)(half * 16), r);
-            tc_st16(t_sp + 32u + (uint32_t)(half * 16), lo);
+            lA = fmaf(lA, alA, sA); lB = fmaf(lB, alB, sB);
+            ah_st_16x128b_x8(t_sp, ph);                                    // P_hi over columns [0, 32) of the chunk it came from,
+            ah_st_16x128b_x8(t_sp + 32u, pl);                              // P_lo over [32, 64): only this warp reads these lanes
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -276,16 +304,16 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
                 // row of the warp moved its maximum (alpha == 1 exactly), the common case after the first chunks.
                 mbar_wait(&pv_done[b ^ 1], ((i - 1) >> 1) & 1);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+                if (__any_sync(0xffffffffu, alA != 1.0f || alB != 1.0f)) {
+                    uint32_t o[32];
+                    ah_ld_16x256b_x8(tbase + AH_T_O, o);
+                    tc_wait_ld();
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        uint32_t o16[16];
-                        ah_ld16(trow + AH_T_O + (uint32_t)(half * 32 + 16 * q), o16);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int d = 0; d < 16; ++d) o16[d] = __float_as_uint(__uint_as_float(o16[d]) * alpha);
-                        tc_st16(trow + AH_T_O + (uint32_t)(half * 32 + 16 * q), o16);
+                    for (int n = 0; n < 8; ++n) {
+                        o[4 * n] = __float_as_uint(__uint_as_float(o[4 * n]) * alA); o[4 * n + 1] = __float_as_uint(__uint_as_float(o[4 * n + 1]) * alA);
+                        o[4 * n + 2] = __float_as_uint(__uint_as_float(o[4 * n + 2]) * alB); o[4 * n + 3] = __float_as_uint(__uint_as_float(o[4 * n + 3]) * alB);
                     }
+                    ah_st_16x256b_x8(tbase + AH_T_O, o);
                     tc_wait_st();
                 }
                 tc_fence_before();
@@ -295,21 +323,25 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
         }
         mbar_wait(&pv_done[(AH_NC - 1) & 1], ((AH_NC - 1) >> 1) & 1);      // PV of the last chunk
         tc_fence_after();
-        // row sum = both halves (same running maximum, so the partial sums simply add)
-        float* slot = s_xch + 512;
-        slot[half * 128 + row] = l_run;
-        ah_pair_sync(quarter);
-        const float l_tot = l_run + slot[(half ^ 1) * 128 + row];
+        // row sums: the four threads of a row hold partial sums under the same running maximum
+        lA += __shfl_xor_sync(0xffffffffu, lA, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+        lA += __shfl_xor_sync(0xffffffffu, lA, 2); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
         uint32_t o[32];
-        tc_ld32(trow + AH_T_O + (uint32_t)(half * 32), o);
-        const int u = q_start + row;
-        if (u < S) {
-            const float inv = 1.0f / l_tot;
-            float* dst = O + (base + u) * ldo + h * AH_HD + half * 32;
+        ah_ld_16x256b_x8(tbase + AH_T_O, o);
+        tc_wait_ld();
+        if (uA < S) {
+            const float inv = 1.0f / lA;
+            float* dst = O + (base + uA) * ldo + h * AH_HD + 2 * q4;
 #pragma unroll
-            for (int d = 0; d < 32; d += 4)
-                *reinterpret_cast<float4*>(dst + d) = make_float4(__uint_as_float(o[d]) * inv, __uint_as_float(o[d + 1]) * inv,
-                                                                   __uint_as_float(o[d + 2]) * inv, __uint_as_float(o[d + 3]) * inv);
+            for (int n = 0; n < 8; ++n)
+                *reinterpret_cast<float2*>(dst + 8 * n) = make_float2(__uint_as_float(o[4 * n]) * inv, __uint_as_float(o[4 * n + 1]) * inv);
+        }
+        if (uB < S) {
+            const float inv = 1.0f / lB;
+            float* dst = O + (base + uB) * ldo + h * AH_HD + 2 * q4;
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                *reinterpret_cast<float2*>(dst + 8 * n) = make_float2(__uint_as_float(o[4 * n + 2]) * inv, __uint_as_float(o[4 * n + 3]) * inv);
         }
         tc_fence_before();                                                 // O has been read: the next item's PV(0) may overwrite it
         ++it;                                                              // (ordered by that item's q_full arrival)
