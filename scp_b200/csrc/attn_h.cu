@@ -268,10 +268,13 @@ __global__ void __launch_bounds__(AH_THREADS, 2) k_swin_attn_h(const float* __re
             const float moff = masked ? -100.0f * AH_LOG2E : 0.0f;
             const float* bpA = s_bias + (piA - i * AH_BK + AH_WS - 1 - 2 * q4);    // bias of (row, key column c) = bp[-c]
             float cA = -INFINITY, cB = -INFINITY;
+            float e0 = bpA[8], e1 = bpA[7];                                // row B = row A + 8 sees row A's bias of the previous n
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                const float a0 = __uint_as_float(r[4 * n]) + bpA[-8 * n], a1 = __uint_as_float(r[4 * n + 1]) + bpA[-8 * n - 1];
-                const float b0 = __uint_as_float(r[4 * n + 2]) + bpA[8 - 8 * n], b1 = __uint_as_float(r[4 * n + 3]) + bpA[8 - 8 * n - 1];
+                const float d0 = bpA[-8 * n], d1 = bpA[-8 * n - 1];
+                const float a0 = __uint_as_float(r[4 * n]) + d0, a1 = __uint_as_float(r[4 * n + 1]) + d1;
+                const float b0 = __uint_as_float(r[4 * n + 2]) + e0, b1 = __uint_as_float(r[4 * n + 3]) + e1;
+                e0 = d0; e1 = d1;
                 r[4 * n] = __float_as_uint(a0); r[4 * n + 1] = __float_as_uint(a1);
                 r[4 * n + 2] = __float_as_uint(b0); r[4 * n + 3] = __float_as_uint(b1);
                 cA = fmaxf(cA, fmaxf(a0, a1)); cB = fmaxf(cB, fmaxf(b0, b1));
