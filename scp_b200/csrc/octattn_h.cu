@@ -16,8 +16,8 @@
 // the chunks at or below the diagonal are visited (2 qb + 2 of them for query block qb).
 // TMEM map (512 columns, one CTA per SM): Q_hi [0,96) | Q_lo [96,192) | S/P buffer b at [192 + 64 b, +64): S fp32, then
 //                         P_hi [+0,+32) P_lo [+32,+64) | O [320,480)
-// Warp roles (320 threads): warps 0-7 softmax / output (two threads per query row: TMEM lane quarter = warp & 3, column
-// half = warp >> 2), warp 8 MMA issuer + TMEM owner, warp 9 TMA producer.
+// Warp roles (320 threads): warps 0-7 softmax / output (a warp owns 16 query rows = TMEM lanes 32 (warp & 3) + 16 (warp >> 2) + [0,16),
+// four threads per row), warp 8 MMA issuer + TMEM owner, warp 9 TMA producer.
 // K and V are prepared once per launch by k_octattn_prep (fp16 hi/lo split, V transposed, sequences padded to 64-key tiles).
 #include <stdlib.h>
 #include <vector>
@@ -53,21 +53,41 @@ __device__ __forceinline__ float oh_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ void oh_pair_sync(int quarter) {
-    switch (quarter) {
-        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-    }
-}
-__device__ __forceinline__ void oh_ld16(uint32_t taddr, uint32_t* r) {
+// 16 lanes x 64 columns: register 4 n + {0,1} = (lane l / 4, column 8 n + 2 (l % 4) + {0,1}), 4 n + {2,3} = the same of lane l / 4 + 8
+__device__ __forceinline__ void oh_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+// the same for 32 columns
+__device__ __forceinline__ void oh_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void oh_st_16x256b_x4(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+// 16 lanes x 32 columns: register 2 n + k = (lane l / 4 + 8 k, column 4 n + l % 4)
+__device__ __forceinline__ void oh_st_16x128b_x8(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 
 // K / V preparation: block = (64-token tile of a sequence, head).  The padded row of token j of a sequence is
@@ -126,7 +146,6 @@ __global__ void __launch_bounds__(OH_THREADS, 1) k_octattn_attn_h(const float* _
                                                                    float* __restrict__ O, float* __restrict__ OU, long long ldo) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* s_xch = reinterpret_cast<float*>(sm + OH_OFF_XCH);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OH_OFF_BAR);
     uint64_t* k_full = bars;            // [2] K chunk landed                                   (TMA, expect_tx)
     uint64_t* v_full = bars + 2;        // [2] V chunk landed                                   (TMA, expect_tx)
@@ -167,81 +186,106 @@ __global__ void __launch_bounds__(OH_THREADS, 1) k_octattn_attn_h(const float* _
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 8) {
-        // ---------------- softmax + output: TWO threads per query row ----------------
-        const int quarter = warp & 3, half = warp >> 2;
-        const int row = quarter * 32 + lane;
-        const int u = q0 + row;                                            // query index inside the sequence
-        const bool valid = u < S;
-        const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+        // ---------------- softmax + output: a warp owns 16 query rows, FOUR threads per row (see attn_h.cu) ----------------
+        // rows = TMEM lanes 32 (warp & 3) + 16 (warp >> 2) + [0, 16); thread (g = lane / 4, q = lane % 4) holds, of rows g and g + 8,
+        // the columns 8 n + 2 q + {0, 1} of every 64-column piece (tcgen05.ld.16x256b): row maxima, row sums and the two diagonal
+        // dot products are quad reductions (two shuffles) instead of a shared-memory exchange between two warps, and a register
+        // pair is one packed fp16 word of P / Q that tcgen05.st.16x128b puts back in the operand layout of the TS-form MMA.
+        const int quarter = warp & 3, rh = warp >> 2;
+        const int g = lane >> 2, q4 = lane & 3;
+        const int rowA = quarter * 32 + rh * 16 + g;                       // rowB = rowA + 8
+        const int uA = q0 + rowA, uB = uA + 8;                             // query indices inside the sequence
+        const bool vA = uA < S, vB = uB < S;
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32 + rh * 16) << 16);
         const float qs = rsqrtf((float)OH_HD) * OH_LOG2E;                  // 1/sqrt(150) and log2(e): scores live in the log2 domain
-        float dk = 0.f, dku = 0.f;                                         // this half's part of QU . K_own and QU . KU_own
-        {   // half a Q row (dims [96 half, +96), zero behind dim 150) -> TMEM as fp16 hi/lo pairs
-            uint32_t hi[48], lo[48];
-            const float* qrow = QU + (base + u) * ld + h * OH_HD;
-            const float* krow = K + (base + u) * ld + h * OH_HD;
-            const float* kurow = KU + (base + u) * ld + h * OH_HD;
+        float dkA = 0.f, dkuA = 0.f, dkB = 0.f, dkuB = 0.f;                // this thread's part of QU . K_own and QU . KU_own
+        {   // two Q rows (192 padded dims, zero behind dim 150) -> TMEM as fp16 hi/lo pairs, 32 words (64 dims) at a time
+            const float* qA = QU + (base + uA) * ld + h * OH_HD;
+            const float* kA = K + (base + uA) * ld + h * OH_HD;
+            const float* kuA = KU + (base + uA) * ld + h * OH_HD;
+            const float* qB = QU + (base + uB) * ld + h * OH_HD;
+            const float* kB = K + (base + uB) * ld + h * OH_HD;
+            const float* kuB = KU + (base + uB) * ld + h * OH_HD;
+#pragma unroll 1
+            for (int p = 0; p < 3; ++p) {
+                uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int c = 0; c < 48; ++c) {
-                const int d = half * 96 + 2 * c;
-                float2 q = make_float2(0.f, 0.f);
-                if (valid && d < OH_HD) {
-                    q = __ldg(reinterpret_cast<const float2*>(qrow + d));
-                    const float2 a = __ldg(reinterpret_cast<const float2*>(krow + d)), b = __ldg(reinterpret_cast<const float2*>(kurow + d));
-                    dk = fmaf(q.x, a.x, fmaf(q.y, a.y, dk));
-                    dku = fmaf(q.x, b.x, fmaf(q.y, b.y, dku));
+                for (int n = 0; n < 8; ++n) {
+                    const int d = 64 * p + 8 * n + 2 * q4;                 // word 32 p + 4 n + q: dims d, d + 1
+                    float2 a = make_float2(0.f, 0.f), c = a;
+                    if (d < OH_HD) {
+                        if (vA) {
+                            a = __ldg(reinterpret_cast<const float2*>(qA + d));
+                            const float2 x = __ldg(reinterpret_cast<const float2*>(kA + d)), y = __ldg(reinterpret_cast<const float2*>(kuA + d));
+                            dkA = fmaf(a.x, x.x, fmaf(a.y, x.y, dkA));
+                            dkuA = fmaf(a.x, y.x, fmaf(a.y, y.y, dkuA));
+                        }
+                        if (vB) {
+                            c = __ldg(reinterpret_cast<const float2*>(qB + d));
+                            const float2 x = __ldg(reinterpret_cast<const float2*>(kB + d)), y = __ldg(reinterpret_cast<const float2*>(kuB + d));
+                            dkB = fmaf(c.x, x.x, fmaf(c.y, x.y, dkB));
+                            dkuB = fmaf(c.x, y.x, fmaf(c.y, y.y, dkuB));
+                        }
+                    }
+                    oh_split2(a.x * qs, a.y * qs, hi[2 * n], lo[2 * n]);
+                    oh_split2(c.x * qs, c.y * qs, hi[2 * n + 1], lo[2 * n + 1]);
                 }
-                oh_split2(q.x * qs, q.y * qs, hi[c], lo[c]);
+                oh_st_16x128b_x8(tbase + OH_T_QH + (uint32_t)(32 * p), hi);
+                oh_st_16x128b_x8(tbase + OH_T_QL + (uint32_t)(32 * p), lo);
             }
-            tc_st32(trow + OH_T_QH + (uint32_t)(half * 48), reinterpret_cast<const uint32_t(&)[32]>(hi[0]));
-            tc_st16(trow + OH_T_QH + (uint32_t)(half * 48 + 32), hi + 32);
-            tc_st32(trow + OH_T_QL + (uint32_t)(half * 48), reinterpret_cast<const uint32_t(&)[32]>(lo[0]));
-            tc_st16(trow + OH_T_QL + (uint32_t)(half * 48 + 32), lo + 32);
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(q_full);
         }
-        float m_run = -INFINITY, l_run = 0.f;
+        float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;         // running maxima; PARTIAL row sums of this thread's columns
 #pragma unroll 1
         for (int i = 0; i < nc; ++i) {
-            const int b = i & 1, n = i >> 1;
-            const uint32_t t_sp = trow + OH_T_SP + (uint32_t)(b * 64);
-            mbar_wait(&s_full[b], n & 1);
+            const int b = i & 1, n_ = i >> 1;
+            const uint32_t t_sp = tbase + OH_T_SP + (uint32_t)(b * 64);
+            mbar_wait(&s_full[b], n_ & 1);
             tc_fence_after();
             uint32_t r[32];
-            tc_ld32(t_sp + (uint32_t)(half * 32), r);
-            float cmax = -INFINITY;
+            oh_ld_16x256b_x8(t_sp, r);
+            tc_wait_ld();
+            float cA = -INFINITY, cB = -INFINITY;
             if (i * OH_BK + OH_BK <= q0) {                                 // chunk entirely below the block's first row: no mask
 #pragma unroll
-                for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(r[j]));
+                for (int n = 0; n < 8; ++n) {
+                    cA = fmaxf(cA, fmaxf(__uint_as_float(r[4 * n]), __uint_as_float(r[4 * n + 1])));
+                    cB = fmaxf(cB, fmaxf(__uint_as_float(r[4 * n + 2]), __uint_as_float(r[4 * n + 3])));
+                }
             } else {                                                       // strictly-lower triangle: key < query
-                const int jb = i * OH_BK + half * 32;
+                const int jb = i * OH_BK + 2 * q4;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float v = (jb + j < u) ? __uint_as_float(r[j]) : -INFINITY;
-                    r[j] = __float_as_uint(v);
-                    cmax = fmaxf(cmax, v);
+                for (int n = 0; n < 8; ++n) {
+                    const int j = jb + 8 * n;
+                    const float a0 = j < uA ? __uint_as_float(r[4 * n]) : -INFINITY, a1 = j + 1 < uA ? __uint_as_float(r[4 * n + 1]) : -INFINITY;
+                    const float b0 = j < uB ? __uint_as_float(r[4 * n + 2]) : -INFINITY, b1 = j + 1 < uB ? __uint_as_float(r[4 * n + 3]) : -INFINITY;
+                    r[4 * n] = __float_as_uint(a0); r[4 * n + 1] = __float_as_uint(a1);
+                    r[4 * n + 2] = __float_as_uint(b0); r[4 * n + 3] = __float_as_uint(b1);
+                    cA = fmaxf(cA, fmaxf(a0, a1)); cB = fmaxf(cB, fmaxf(b0, b1));
                 }
             }
-            float* slot = s_xch + (i & 1) * 256;
-            slot[half * 128 + row] = cmax;
-            oh_pair_sync(quarter);
-            cmax = fmaxf(cmax, slot[(half ^ 1) * 128 + row]);
-            const float mx = fmaxf(m_run, cmax);
-            const float sub = mx == -INFINITY ? 0.f : mx;                  // a row without any key so far (row 0): all p = 0
-            const float alpha = oh_ex2(m_run - sub);                       // 0 while m_run = -inf
-            m_run = mx;
-            float sum = 0.f;
-            uint32_t lo[16];
+            cA = fmaxf(cA, __shfl_xor_sync(0xffffffffu, cA, 1)); cB = fmaxf(cB, __shfl_xor_sync(0xffffffffu, cB, 1));
+            cA = fmaxf(cA, __shfl_xor_sync(0xffffffffu, cA, 2)); cB = fmaxf(cB, __shfl_xor_sync(0xffffffffu, cB, 2));
+            const float mxA = fmaxf(mA, cA), mxB = fmaxf(mB, cB);
+            const float subA = mxA == -INFINITY ? 0.f : mxA, subB = mxB == -INFINITY ? 0.f : mxB;    // a row without any key so far: all p = 0
+            const float alA = oh_ex2(mA - subA), alB = oh_ex2(mB - subB);  // 0 while m = -inf
+            mA = mxA; mB = mxB;
+            float sA = 0.f, sB = 0.f;
+            uint32_t ph[16], pl[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float p0 = oh_ex2(__uint_as_float(r[2 * j]) - sub), p1 = oh_ex2(__uint_as_float(r[2 * j + 1]) - sub);
-                sum += p0 + p1;
-                oh_split2(p0, p1, r[j], lo[j]);                            // r[0..16) becomes P_hi (pairs of keys, even key low)
+            for (int n = 0; n < 8; ++n) {
+                const float a0 = oh_ex2(__uint_as_float(r[4 * n]) - subA), a1 = oh_ex2(__uint_as_float(r[4 * n + 1]) - subA);
+                const float b0 = oh_ex2(__uint_as_float(r[4 * n + 2]) - subB), b1 = oh_ex2(__uint_as_float(r[4 * n + 3]) - subB);
+                sA += a0 + a1; sB += b0 + b1;
+                oh_split2(a0, a1, ph[2 * n], pl[2 * n]);                   // word 4 n + q of row A: keys 8 n + 2 q, + 1 (even key low)
+                oh_split2(b0, b1, ph[2 * n + 1], pl[2 * n + 1]);
             }
-            l_run = fmaf(l_run, alpha, sum);
-            tc_st16(t_sp + (uint32_t)(half * 16), r);
-            tc_st16(t_sp + 32u + (uint32_t)(half * 16), lo);
+            lA = fmaf(lA, alA, sA); lB = fmaf(lB, alB, sB);
+            oh_st_16x128b_x8(t_sp, ph);
+            oh_st_16x128b_x8(t_sp + 32u, pl);
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -250,15 +294,18 @@ __global__ void __launch_bounds__(OH_THREADS, 1) k_octattn_attn_h(const float* _
                 // PV(i) accumulates into O: bring O to the new maximum first (PV(i-1) must have retired)
                 mbar_wait(&pv_done[b ^ 1], ((i - 1) >> 1) & 1);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+                if (__any_sync(0xffffffffu, alA != 1.0f || alB != 1.0f)) {
 #pragma unroll 1
-                    for (int q = 0; q < 5; ++q) {                          // this half's 80 output columns
-                        uint32_t o16[16];
-                        oh_ld16(trow + OH_T_O + (uint32_t)(half * 80 + 16 * q), o16);
+                    for (int p = 0; p < 5; ++p) {                          // 160 output columns, 32 at a time
+                        uint32_t o[16];
+                        oh_ld_16x256b_x4(tbase + OH_T_O + (uint32_t)(32 * p), o);
                         tc_wait_ld();
 #pragma unroll
-                        for (int d = 0; d < 16; ++d) o16[d] = __float_as_uint(__uint_as_float(o16[d]) * alpha);
-                        tc_st16(trow + OH_T_O + (uint32_t)(half * 80 + 16 * q), o16);
+                        for (int n = 0; n < 4; ++n) {
+                            o[4 * n] = __float_as_uint(__uint_as_float(o[4 * n]) * alA); o[4 * n + 1] = __float_as_uint(__uint_as_float(o[4 * n + 1]) * alA);
+                            o[4 * n + 2] = __float_as_uint(__uint_as_float(o[4 * n + 2]) * alB); o[4 * n + 3] = __float_as_uint(__uint_as_float(o[4 * n + 3]) * alB);
+                        }
+                        oh_st_16x256b_x4(tbase + OH_T_O + (uint32_t)(32 * p), o);
                     }
                     tc_wait_st();
                 }
@@ -269,41 +316,47 @@ __global__ void __launch_bounds__(OH_THREADS, 1) k_octattn_attn_h(const float* _
         }
         mbar_wait(&pv_done[(nc - 1) & 1], ((nc - 1) >> 1) & 1);            // PV of the last chunk
         tc_fence_after();
-        // join the halves: row sum (same running maximum in both threads) and the two diagonal dot products
-        float* slot = s_xch + 512;
-        slot[half * 128 + row] = l_run;
-        slot[256 + half * 128 + row] = dk;
-        slot[512 + half * 128 + row] = dku;
-        oh_pair_sync(quarter);
-        const float l_off = l_run + slot[(half ^ 1) * 128 + row];
-        const float sii = (dk + slot[256 + (half ^ 1) * 128 + row]) * qs;     // known stream: own key with its occupancy
-        const float siu = (dku + slot[512 + (half ^ 1) * 128 + row]) * qs;    // unknown stream: own key without
-        // each stream: maximum over (strictly lower part, own diagonal term), weights of the two parts, normaliser
-        const float M1 = fmaxf(m_run, sii), M2 = fmaxf(m_run, siu);
-        const float wo1 = oh_ex2(m_run - M1), wd1 = oh_ex2(sii - M1), wo2 = oh_ex2(m_run - M2), wd2 = oh_ex2(siu - M2);
-        const float inv1 = 1.0f / fmaf(l_off, wo1, wd1), inv2 = 1.0f / fmaf(l_off, wo2, wd2);
-        const float a1 = wo1 * inv1, d1 = wd1 * inv1, a2 = wo2 * inv2, d2 = wd2 * inv2;
-        const float* vrow = V + (base + u) * ld + h * OH_HD;
-        const float* vurow = VU + (base + u) * ld + h * OH_HD;
-        float* dst = O + (base + u) * ldo + h * OH_HD;
-        float* dstu = OU + (base + u) * ldo + h * OH_HD;
-#pragma unroll 1
-        for (int q = 0; q < 5; ++q) {                                      // this half's output dims [80 half, +80) below 150
-            uint32_t o16[16];
-            oh_ld16(trow + OH_T_O + (uint32_t)(half * 80 + 16 * q), o16);  // .sync.aligned: the WHOLE warp, valid row or not
-            tc_wait_ld();
-            if (valid) {
+        // join the four threads of a row: row sum (same running maximum in all of them) and the two diagonal dot products
 #pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                    const int d = half * 80 + 16 * q + e;
-                    if (d < OH_HD) {
-                        const float2 vv = __ldg(reinterpret_cast<const float2*>(vrow + d)), vu = __ldg(reinterpret_cast<const float2*>(vurow + d));
-                        const float o0 = __uint_as_float(o16[e]), o1 = __uint_as_float(o16[e + 1]);
-                        *reinterpret_cast<float2*>(dst + d) = make_float2(fmaf(o0, a1, d1 * vv.x), fmaf(o1, a1, d1 * vv.y));
-                        *reinterpret_cast<float2*>(dstu + d) = make_float2(fmaf(o0, a2, d2 * vu.x), fmaf(o1, a2, d2 * vu.y));
-                    }
+        for (int o = 1; o <= 2; o <<= 1) {
+            lA += __shfl_xor_sync(0xffffffffu, lA, o); lB += __shfl_xor_sync(0xffffffffu, lB, o);
+            dkA += __shfl_xor_sync(0xffffffffu, dkA, o); dkB += __shfl_xor_sync(0xffffffffu, dkB, o);
+            dkuA += __shfl_xor_sync(0xffffffffu, dkuA, o); dkuB += __shfl_xor_sync(0xffffffffu, dkuB, o);
+        }
+        // each stream: maximum over (strictly lower part, own diagonal term), weights of the two parts, normaliser
+        auto weights = [&](float m_run, float l_off, float dk, float dku, float& a1, float& d1, float& a2, float& d2) {
+            const float sii = dk * qs, siu = dku * qs;                     // known stream: own key with its occupancy; unknown: without
+            const float M1 = fmaxf(m_run, sii), M2 = fmaxf(m_run, siu);
+            const float wo1 = oh_ex2(m_run - M1), wd1 = oh_ex2(sii - M1), wo2 = oh_ex2(m_run - M2), wd2 = oh_ex2(siu - M2);
+            const float inv1 = 1.0f / fmaf(l_off, wo1, wd1), inv2 = 1.0f / fmaf(l_off, wo2, wd2);
+            a1 = wo1 * inv1; d1 = wd1 * inv1; a2 = wo2 * inv2; d2 = wd2 * inv2;
+        };
+        float a1A, d1A, a2A, d2A, a1B, d1B, a2B, d2B;
+        weights(mA, lA, dkA, dkuA, a1A, d1A, a2A, d2A);
+        weights(mB, lB, dkB, dkuB, a1B, d1B, a2B, d2B);
+        auto emit_row = [&](int u, const uint32_t* o, int k, int p, float a1, float d1, float a2, float d2) {
+            const float* vrow = V + (base + u) * ld + h * OH_HD;
+            const float* vurow = VU + (base + u) * ld + h * OH_HD;
+            float* dst = O + (base + u) * ldo + h * OH_HD;
+            float* dstu = OU + (base + u) * ldo + h * OH_HD;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const int d = 32 * p + 8 * n + 2 * q4;
+                if (d < OH_HD) {
+                    const float2 vv = __ldg(reinterpret_cast<const float2*>(vrow + d)), vu = __ldg(reinterpret_cast<const float2*>(vurow + d));
+                    const float o0 = __uint_as_float(o[4 * n + 2 * k]), o1 = __uint_as_float(o[4 * n + 2 * k + 1]);
+                    *reinterpret_cast<float2*>(dst + d) = make_float2(fmaf(o0, a1, d1 * vv.x), fmaf(o1, a1, d1 * vv.y));
+                    *reinterpret_cast<float2*>(dstu + d) = make_float2(fmaf(o0, a2, d2 * vu.x), fmaf(o1, a2, d2 * vu.y));
                 }
             }
+        };
+#pragma unroll 1
+        for (int p = 0; p < 5; ++p) {                                      // output dims [32 p, +32) below 150
+            uint32_t o[16];
+            oh_ld_16x256b_x4(tbase + OH_T_O + (uint32_t)(32 * p), o);     // .sync.aligned: the WHOLE warp, valid rows or not
+            tc_wait_ld();
+            if (vA) emit_row(uA, o, 0, p, a1A, d1A, a2A, d2A);
+            if (vB) emit_row(uB, o, 1, p, a1B, d1B, a2B, d2B);
             __syncwarp();
         }
     } else if (warp == 8) {
