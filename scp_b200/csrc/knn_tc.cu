@@ -45,6 +45,9 @@ constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 64;                      // K blo
 //  * four accumulator stages + two epilogue teams with a heap each (candidate tiles alternate between the teams, thresholds
 //    shared, heaps merged at the end; two issuing warps) decouples the MMAs from the slowest epilogue warp and reaches the same
 //    1430 without the scan, but every row then pays its accepts against two half-informed heaps: 44 ms per step against 36.
+//  * eight epilogue warps with four threads per query row (tcgen05.ld.16x256b, one heap owner per row): no faster on the synthetic
+//    walk, 11 % slower on the bench frames -- the scan and the accept rounds are bound by the SM's issue slots, which more warps
+//    do not add to.
 // What is left between 1430 and 2200 is the accept path itself (per-lane heap sift-downs, 150-250 dependent cycles per round,
 // rounds = the maximum over the lanes of a warp).
 constexpr int KT_STAGES = 3, KT_ACC = 1;
