@@ -579,6 +579,10 @@ def run_ours(args):
     if ref_m:
         parity["reference_run_on_this_box"] = {"n_nodes": ref_m["n_nodes"], "bytes": ref_m["bytes"], "bpp": ref_m["bpp"]}
         parity["nodes_equal"] = ref_m["n_nodes"] == pr.n_nodes
+        if not parity["nodes_equal"]:
+            parity["nodes_note"] = ("the frame is NOT guard-banded: numpy's float32 arctan2 / arccos (SVML, not correctly rounded) put a "
+                                    "handful of the 120 000 points into the neighbouring bin of the correctly rounded CUDA transform "
+                                    "(DESIGN.md 'Float stage'); on guard-banded inputs every integer stage is bit-exact (tests/test_octree_gpu.py)")
         parity["bpp_dev"] = abs(pr.bpp - ref_m["bpp"]) / ref_m["bpp"]
     cores = os.cpu_count() or 1
     if ref_m:
