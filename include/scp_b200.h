@@ -294,6 +294,11 @@ int scp_set_knn_engine(int use_tensor_cores);
  * (BatchNorm eval folded to s,t; monotone so the max commutes exactly). */
 int scp_edge_gather_max(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k, int64_t n,
                         const float* d_bn_scale, const float* d_bn_shift, float* d_out, int64_t ldo, void* stream);
+/* The same, writing the result into a second view as well (d_out2 may be NULL): dgcnn.py:118-150 concatenates every edge-conv
+ * output twice (into the next layer's input and into the final feature), so the copy is made where the values are produced. */
+int scp_edge_gather_max2(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k, int64_t n,
+                         const float* d_bn_scale, const float* d_bn_shift, float* d_out, int64_t ldo, float* d_out2, int64_t ldo2,
+                         void* stream);
 
 /* 1-D shifted-window attention (swin_transformer.py:406-501 + :603-652,:684-697), heads x 64.
  * q [total, *] (ldq) queries, kv-side k,v [total, *] (ldk, ldv): projected tokens of every sequence.  Each

@@ -101,6 +101,7 @@ SIGNATURES = {
     "scp_ehem_embed_occ": (_i, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "scp_knn": (_i, [_vp, _i64, _i, _vp, _i, _vp, _vp]),
     "scp_edge_gather_max": (_i, [_vp, _i64, _i, _vp, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "scp_edge_gather_max2": (_i, [_vp, _i64, _i, _vp, _i, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "scp_swin_attention": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i64, _vp]),
     "scp_pair_concat": (_i, [_vp, _i64, _vp, _vp, _i, _vp, _i64, _vp]),
     "scp_upsample_cols": (_i, [_vp, _i64, _vp, _vp, _i, _i, _vp, _i64, _i, _vp]),

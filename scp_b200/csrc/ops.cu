@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(KS_Q) k_knn_small(const float* __restrict__ X,
 __global__ void __launch_bounds__(256) k_edge_gather(const float* __restrict__ uv, long long lduv, int C,
                                                       const int* __restrict__ idx, int k, long long n,
                                                       const float* __restrict__ bs, const float* __restrict__ bt,
-                                                      float* __restrict__ out, long long ldo) {
+                                                      float* __restrict__ out, long long ldo, float* __restrict__ out2,
+                                                      long long ldo2) {
     const int per = 256 / C;            // points per block iteration (C in {64,128,256})
     const int c = threadIdx.x % C;
     const int pl = threadIdx.x / C;
@@ -592,7 +593,9 @@ __global__ void __launch_bounds__(256) k_edge_gather(const float* __restrict__ u
         }
         const float sel = sc >= 0.f ? mx : mn;
         float v = fmaf(sc, sel + uv[p * lduv + C + c], sh);
-        out[p * ldo + c] = v > 0.f ? v : 0.2f * v;
+        v = v > 0.f ? v : 0.2f * v;
+        out[p * ldo + c] = v;
+        if (out2) out2[p * ldo2 + c] = v;               // the same columns in a second concatenation (dgcnn.py feeds x_k to two cats)
     }
 }
 
@@ -1126,15 +1129,21 @@ int scp_knn(const float* d_x, int64_t ldx, int d, const scp_seqs* seqs, int k, i
     return SCP_OK;
 }
 
-int scp_edge_gather_max(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k, int64_t n,
-                        const float* d_bn_scale, const float* d_bn_shift, float* d_out, int64_t ldo, void* stream) {
+int scp_edge_gather_max2(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k, int64_t n,
+                         const float* d_bn_scale, const float* d_bn_shift, float* d_out, int64_t ldo, float* d_out2, int64_t ldo2,
+                         void* stream) {
     SCP_REQUIRE(d_uv && d_idx && d_bn_scale && d_bn_shift && d_out, "scp_edge_gather_max: null argument");
     SCP_REQUIRE(C == 64 || C == 128 || C == 256, "scp_edge_gather_max: C must be 64, 128 or 256");
     if (n == 0) return SCP_OK;
     k_edge_gather<<<grid_for(n, 256 / C, 148 * 32), 256, 0, as_stream(stream)>>>(d_uv, lduv, C, d_idx, k, n, d_bn_scale,
-                                                                                 d_bn_shift, d_out, ldo);
+                                                                                 d_bn_shift, d_out, ldo, d_out2, ldo2);
     SCP_LAUNCHED();
     return SCP_OK;
+}
+
+int scp_edge_gather_max(const float* d_uv, int64_t lduv, int C, const int32_t* d_idx, int k, int64_t n,
+                        const float* d_bn_scale, const float* d_bn_shift, float* d_out, int64_t ldo, void* stream) {
+    return scp_edge_gather_max2(d_uv, lduv, C, d_idx, k, n, d_bn_scale, d_bn_shift, d_out, ldo, nullptr, 0, stream);
 }
 
 int scp_swin_attention(const float* d_q, int64_t ldq, const float* d_k, int64_t ldk, const float* d_v, int64_t ldv,

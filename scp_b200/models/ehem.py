@@ -215,8 +215,7 @@ class EHEM(nn.Module):
         idx = ops.knn(V(pos), seqs, k)
         uv = ops.empty(T, 128, pos)
         ops.linear(V(pos), P["conv1.w"], None, V(uv), engine="simt")
-        ops.edge_gather_max(V(uv), 64, idx, P["conv1.s"], P["conv1.t"], V(P123, 0, 64))
-        ops.copy_cols(V(P123, 0, 64), V(F2, 0, 64))
+        ops.edge_gather_max(V(uv), 64, idx, P["conv1.s"], P["conv1.t"], V(P123, 0, 64), y2=V(F2, 0, 64))
         idx = ops.knn(V(F2), seqs, k)
         uv = ops.empty(T, 256, pos)
         # conv2 / mlp2 feed kNN #3 (neighbour sets): error-compensated 3xFP16 products keep them at fp32 accuracy (parity,
@@ -224,14 +223,12 @@ class EHEM(nn.Module):
         # the same setting
         geo = os.environ.get("SCP_GEO_ENGINE", "auto")
         ops.linear(V(F2), P["conv2.w"], None, V(uv), engine=geo)
-        ops.edge_gather_max(V(uv), 128, idx, P["conv2.s"], P["conv2.t"], V(P123, 64, 128))
-        ops.copy_cols(V(P123, 64, 128), V(F3, 0, 128))
+        ops.edge_gather_max(V(uv), 128, idx, P["conv2.s"], P["conv2.t"], V(P123, 64, 128), y2=V(F3, 0, 128))
         self._mlp(f"{g}.mlp2", V(F2, 64, 80), V(F3, 128, 64), engine=geo)
         idx = ops.knn(V(F3), seqs, k)
         uv = ops.empty(T, 512, pos)
         ops.linear(V(F3), P["conv3.w"], None, V(uv))
-        ops.edge_gather_max(V(uv), 256, idx, P["conv3.s"], P["conv3.t"], V(P123, 192, 256))
-        ops.copy_cols(V(P123, 192, 256), V(EC2, 0, 256))
+        ops.edge_gather_max(V(uv), 256, idx, P["conv3.s"], P["conv3.t"], V(P123, 192, 256), y2=V(EC2, 0, 256))
         self._mlp(f"{g}.mlp3", V(F3, 128, 64), V(FEAT, 0, 128))
         self._mlp(f"{g}.edge_mlp1", V(P123), V(EC2, 256, 256))
         self._mlp(f"{g}.edge_mlp2", V(EC2), V(FEAT, 128, 128))

@@ -183,13 +183,15 @@ class CudaOps:
             _lib.check(self.lib.scp_knn(xp, ldx, x[2], seqs.handle, k, _lib.ptr(idx), _lib.stream_ptr()), "scp_knn")
         return idx
 
-    def edge_gather_max(self, uv, C_, idx, bn_scale, bn_shift, y):
+    def edge_gather_max(self, uv, C_, idx, bn_scale, bn_shift, y, y2=None):
+        """``y2``: optional second view that receives the same values (the next layer's concatenated input)."""
         up, ldu = self._p(uv)
         yp, ldy = self._p(y)
+        y2p, ldy2 = (None, 0) if y2 is None else self._p(y2)
         n = idx.shape[0]
         with self._rec("edge_gather", 2.0 * n * C_ * idx.shape[1], 4.0 * n * (C_ * (idx.shape[1] + 2) + idx.shape[1])):
-            _lib.check(self.lib.scp_edge_gather_max(up, ldu, C_, _lib.ptr(idx), idx.shape[1], n,
-                                                    _lib.ptr(bn_scale), _lib.ptr(bn_shift), yp, ldy, _lib.stream_ptr()),
+            _lib.check(self.lib.scp_edge_gather_max2(up, ldu, C_, _lib.ptr(idx), idx.shape[1], n,
+                                                     _lib.ptr(bn_scale), _lib.ptr(bn_shift), yp, ldy, y2p, ldy2, _lib.stream_ptr()),
                        "scp_edge_gather_max")
 
     def swin_attention(self, q, k, v, qb, kb, vb, relpos, heads, seqs, shift, y):

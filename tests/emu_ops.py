@@ -81,11 +81,13 @@ class EmuOps:
             idx[a:b] = top.int()
         return idx
 
-    def edge_gather_max(self, uv, C, idx, s, t, y):
+    def edge_gather_max(self, uv, C, idx, s, t, y, y2=None):
         u = _v(uv)
         nb = u[:, :C][idx.long()]                      # [n,k,C]
         sel = torch.where(s >= 0, nb.max(1)[0], nb.min(1)[0])
         _v(y)[:] = F.leaky_relu(s * (sel + u[:, C:2 * C]) + t, 0.2)
+        if y2 is not None:
+            _v(y2)[:] = _v(y)
 
     def swin_attention(self, q, k, v, qb, kb, vb, relpos, heads, seqs, shift, y):
         qv, kv, vv, out = _v(q), _v(k), _v(v), _v(y)

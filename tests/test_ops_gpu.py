@@ -147,8 +147,10 @@ def test_edge_gather(ops):
         t, tc = both(1, C, 6)
         y, yc = torch.zeros(n, C + 8), torch.zeros(n, C + 8, device="cuda")
         em.edge_gather_max(V(uv), C, idx, s[0], t[0], V(y, 8, C))
-        cu.edge_gather_max(V(uvc), C, idx.cuda(), sc[0], tc[0], V(yc, 8, C))
+        y2c = torch.zeros(n, C + 4, device="cuda")
+        cu.edge_gather_max(V(uvc), C, idx.cuda(), sc[0], tc[0], V(yc, 8, C), y2=V(y2c, 4, C))      # second view: same values
         close(yc, y, 1e-6)
+        assert torch.equal(y2c[:, 4:], yc[:, 8:]) and (y2c[:, :4] == 0).all()
 
 
 @pytest.mark.parametrize("tensor_cores", [2, 1, 0])          # 2 = 3xFP16 two CTAs/SM (default), 1 = 3xTF32, 0 = fp32 SIMT
