@@ -283,7 +283,6 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready);
             }
-            const float xq = rowv ? xx[gbase - row0 + q] : 0.f;
             const float two_g = __ldg(scales + 2 * s + 1);                       // 2 / scale^2: the Gram tile is of the scaled rows
             for (int e = 0; e < kc; ++e) hq[32 * e] = make_float2(-INFINITY, __int_as_float(-1));
             float th = (rowv && dbg == 0) ? -INFINITY : INFINITY;          // rows past the window never take a candidate
@@ -326,8 +325,10 @@ __global__ void __launch_bounds__(256, 2) k_knn_tc(const __grid_constant__ CUten
                         const float xcv[4] = {xc.x, xc.y, xc.z, xc.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            // == (2 g - |c|^2) - |q|^2 with one rounding per subtraction (2 g / scale^2 is exact)
-                            const float sc = __fsub_rn(fmaf(two_g, __uint_as_float(r[hh][j4 + e]), -xcv[e]), xq);
+                            // 2 g - |c|^2 (2 g / scale^2 is exact): the score up to the row's own -|q|^2, which does not change
+                            // the order inside a row -- the heap and the threshold live in this shifted scale (the scan is bound
+                            // by issue slots: two instructions per candidate instead of three)
+                            const float sc = fmaf(two_g, __uint_as_float(r[hh][j4 + e]), -xcv[e]);
                             r[hh][j4 + e] = __float_as_uint(sc);
                             smax = fmaxf(smax, sc);
                         }
